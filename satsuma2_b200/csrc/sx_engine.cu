@@ -1,0 +1,829 @@
+// libsatsuma_b200: context, HBM layout, batching and the C ABI (include/satsuma_xcorr.h).
+//
+// Host-side role: what HomologyByXCorr::align_target / Align / FilterMatches do around the
+// kernels in the reference (analysis/HomologyByXCorrSlave.cc:168-300): expand block requests
+// into chunk pairs, make sure every chunk signal needed has a spectrum resident in HBM
+// (target spectra are kept across calls and reused by every query, the reference recomputes
+// them per pair), launch the three kernels per batch, map chunk-local matches to sequence
+// coordinates and hand t_result-compatible records back.
+#include "../../include/satsuma_xcorr.h"
+#include "sx_kernels.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace sx;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(expr)                                                                         \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return fail(_e == cudaErrorMemoryAllocation ? SX_ERR_NOMEM : SX_ERR_CUDA, "%s: %s", #expr, \
+                  cudaGetErrorString(_e));                                               \
+  } while (0)
+
+namespace {
+
+struct ChunkStore {
+  int32_t n = 0;
+  uint8_t *d_bases = nullptr;
+  size_t blob_bytes = 0;
+  std::vector<int64_t> offsets;
+  std::vector<int32_t> lens, starts, seq_ids, seq_sizes;
+};
+
+struct PairReq {
+  int32_t t, q;
+  int32_t fast;
+};
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  int ensure(size_t want) {
+    if (want <= n) return SX_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+    if (e != cudaSuccess) return fail(SX_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e));
+    n = want;
+    return SX_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+template <typename T>
+struct PinBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  int ensure(size_t want) {
+    if (want <= n) return SX_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMallocHost((void **)&p, want * sizeof(T));
+    if (e != cudaSuccess) return fail(SX_ERR_NOMEM, "cudaMallocHost(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e));
+    n = want;
+    return SX_OK;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+}  // namespace
+
+struct sx_ctx {
+  sx_config cfg;
+  int log2n = 0, N = 0;
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool profiling = false;
+  sx_stats stats;
+
+  ChunkStore T, Q;
+  double target_total = 0;
+
+  // signal slots: [0, n_persist) = cached target spectra (slot == target chunk index),
+  // [n_persist, n_persist + n_transient) = per-batch workspace
+  size_t n_persist = 0, n_transient = 0;
+  DevBuf<float2> spec;
+  DevBuf<uint32_t> planes;
+  DevBuf<uint8_t> sbytes;
+  DevBuf<SlotMeta> meta;
+  std::vector<uint8_t> t_valid;  // persistent target slot holds a spectrum
+
+  // per-batch device buffers
+  DevBuf<SigDesc> d_sigs;
+  DevBuf<SpDesc> d_sps;
+  DevBuf<uint2> d_cand_ref;
+  DevBuf<uint16_t> d_cand_pool;
+  DevBuf<ResultRec> d_res;
+  DevBuf<SegRec> d_seg_tap;
+  DevBuf<BatchCounters> d_ctr;
+  DevBuf<double> d_table;
+  DevBuf<float> d_tap;
+  bool have_table = false;
+
+  PinBuf<SigDesc> h_sigs;
+  PinBuf<SpDesc> h_sps;
+  PinBuf<ResultRec> h_res;
+  PinBuf<BatchCounters> h_ctr;
+
+  std::vector<sx_result> last;  // records of the last align call
+
+  Slots slots() const {
+    Slots s;
+    s.spec = spec.p;
+    s.planes = planes.p;
+    s.bytes = sbytes.p;
+    s.meta = meta.p;
+    return s;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+static int pick_log2n(int t_chunk) {
+  int n = 2 * t_chunk, l = 0;
+  while ((1 << l) < n) l++;
+  if ((1 << l) != n) return -1;
+  return l;
+}
+
+extern "C" void sx_default_config(sx_config *c) {
+  memset(c, 0, sizeof(*c));
+  c->abi_version = SX_ABI_VERSION;
+  c->device = 0;
+  c->t_chunk = 4096;
+  c->q_chunk = 4096;
+  c->cutoff = 1.8;
+  c->cutoff_fast = 2.9;
+  c->min_len = 0;
+  c->use_prob_table = 0;
+  c->min_prob = 0.99;
+  c->prob_table_value = 0.9999;
+  c->target_total = 0;
+  c->rc_coord_mode = 0;
+  c->max_batch_pairs = 0;
+  c->spectra_cache_bytes = 0;
+  c->sort_results = 0;
+}
+
+extern "C" int sx_abi_version(void) { return SX_ABI_VERSION; }
+extern "C" const char *sx_last_error(void) { return g_err.c_str(); }
+
+extern "C" int sx_create(const sx_config *cfg, sx_ctx **out) {
+  if (!cfg || !out) return fail(SX_ERR_ARG, "sx_create: null argument");
+  if (cfg->abi_version != SX_ABI_VERSION) return fail(SX_ERR_ARG, "sx_create: ABI version %d != %d", cfg->abi_version, SX_ABI_VERSION);
+  const int l = pick_log2n(cfg->t_chunk);
+  if (l < 0 || !log2n_supported(l))
+    return fail(SX_ERR_ARG, "sx_create: t_chunk=%d unsupported (2*t_chunk must be a power of two in [2048,16384])", cfg->t_chunk);
+  if (cfg->q_chunk < 1 || cfg->q_chunk > 2 * cfg->t_chunk)
+    return fail(SX_ERR_ARG, "sx_create: q_chunk=%d must be in [1, 2*t_chunk]", cfg->q_chunk);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(SX_ERR_CUDA, "sx_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(SX_ERR_ARG, "sx_create: device %d of %d", cfg->device, ndev);
+  CU(cudaSetDevice(cfg->device));
+  sx_ctx *c = new (std::nothrow) sx_ctx();
+  if (!c) return fail(SX_ERR_NOMEM, "sx_create: out of host memory");
+  c->cfg = *cfg;
+  c->log2n = l;
+  c->N = 1 << l;
+  if (c->cfg.max_batch_pairs <= 0) c->cfg.max_batch_pairs = 16384;
+  if (c->cfg.spectra_cache_bytes == 0) c->cfg.spectra_cache_bytes = (int64_t)48 << 30;
+  memset(&c->stats, 0, sizeof(c->stats));
+  c->target_total = cfg->target_total;
+  cudaError_t ce = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess)
+    for (int i = 0; i < 5 && ce == cudaSuccess; i++) ce = cudaEventCreate(&c->ev[i]);
+  if (ce == cudaSuccess) ce = upload_tables();
+  if (ce != cudaSuccess) {
+    delete c;
+    return fail(SX_ERR_CUDA, "sx_create: %s", cudaGetErrorString(ce));
+  }
+  int rc = c->d_ctr.ensure(1);
+  if (rc == SX_OK) rc = c->h_ctr.ensure(1);
+  if (rc != SX_OK) {
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return SX_OK;
+}
+
+extern "C" void sx_destroy(sx_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  cudaStreamSynchronize(c->stream);
+  if (c->T.d_bases) cudaFree(c->T.d_bases);
+  if (c->Q.d_bases) cudaFree(c->Q.d_bases);
+  c->spec.release(); c->planes.release(); c->sbytes.release(); c->meta.release();
+  c->d_sigs.release(); c->d_sps.release(); c->d_cand_ref.release(); c->d_cand_pool.release();
+  c->d_res.release(); c->d_seg_tap.release(); c->d_ctr.release(); c->d_table.release(); c->d_tap.release();
+  c->h_sigs.release(); c->h_sps.release(); c->h_res.release(); c->h_ctr.release();
+  for (int i = 0; i < 5; i++)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int set_store(sx_ctx *c, ChunkStore &S, const char *bases, const int64_t *offsets, const int32_t *lens,
+                     const int32_t *starts, const int32_t *seq_ids, int32_t n, const int32_t *seq_sizes,
+                     int32_t n_seqs, int max_len, const char *what) {
+  if (n < 0 || (n > 0 && (!bases || !offsets || !lens))) return fail(SX_ERR_ARG, "%s: null argument", what);
+  size_t blob = 0;
+  for (int i = 0; i < n; i++) {
+    if (lens[i] < 0 || lens[i] > max_len)
+      return fail(SX_ERR_ARG, "%s: chunk %d has length %d (allowed 0..%d)", what, i, lens[i], max_len);
+    if (offsets[i] < 0) return fail(SX_ERR_ARG, "%s: negative offset", what);
+    blob = std::max(blob, (size_t)offsets[i] + (size_t)lens[i]);
+    if (seq_ids && (seq_ids[i] < 0 || seq_ids[i] >= n_seqs))
+      return fail(SX_ERR_ARG, "%s: chunk %d refers to sequence %d of %d", what, i, seq_ids[i], n_seqs);
+  }
+  if (S.d_bases) cudaFree(S.d_bases);
+  S.d_bases = nullptr;
+  S.n = n;
+  S.blob_bytes = blob;
+  S.offsets.assign(offsets, offsets + n);
+  S.lens.assign(lens, lens + n);
+  if (starts) S.starts.assign(starts, starts + n); else S.starts.assign(n, 0);
+  if (seq_ids) S.seq_ids.assign(seq_ids, seq_ids + n); else S.seq_ids.assign(n, 0);
+  if (seq_sizes && n_seqs > 0) S.seq_sizes.assign(seq_sizes, seq_sizes + n_seqs); else S.seq_sizes.assign(1, 0);
+  if (blob > 0) {
+    CU(cudaMalloc((void **)&S.d_bases, blob + 16));
+    CU(cudaMemcpyAsync(S.d_bases, bases, blob, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stats.h2d_bytes += (int64_t)blob;
+  }
+  return SX_OK;
+}
+
+static size_t slot_bytes(const sx_ctx *c) {
+  const size_t N = (size_t)c->N;
+  return 2 * N * sizeof(float2) + 2 * (N / 32) * sizeof(uint32_t) + N + sizeof(SlotMeta);
+}
+
+static int alloc_slots(sx_ctx *c) {
+  // persistent region for targets if it fits the budget
+  const size_t sb = slot_bytes(c);
+  size_t persist = 0;
+  if (c->cfg.spectra_cache_bytes > 0 && (size_t)c->T.n * sb <= (size_t)c->cfg.spectra_cache_bytes) persist = (size_t)c->T.n;
+  const size_t transient = (size_t)3 * (size_t)c->cfg.max_batch_pairs;
+  const size_t total = persist + transient;
+  const size_t N = (size_t)c->N;
+  int rc;
+  if ((rc = c->spec.ensure(total * 2 * N)) != SX_OK) return rc;
+  if ((rc = c->planes.ensure(total * 2 * (N / 32))) != SX_OK) return rc;
+  if ((rc = c->sbytes.ensure(total * N)) != SX_OK) return rc;
+  if ((rc = c->meta.ensure(total)) != SX_OK) return rc;
+  c->n_persist = persist;
+  c->n_transient = transient;
+  c->t_valid.assign(persist, 0);
+  return SX_OK;
+}
+
+extern "C" int sx_set_targets(sx_ctx *c, const char *bases, const int64_t *offsets, const int32_t *lens,
+                              const int32_t *starts, const int32_t *seq_ids, int32_t n, const int32_t *seq_sizes,
+                              int32_t n_seqs) {
+  if (!c) return fail(SX_ERR_ARG, "sx_set_targets: null context");
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->cfg.device));
+  int rc = set_store(c, c->T, bases, offsets, lens, starts, seq_ids, n, seq_sizes, n_seqs, c->N, "sx_set_targets");
+  if (rc != SX_OK) return rc;
+  if (c->cfg.target_total <= 0) {  // Slave.cc:405-408
+    double tot = 0;
+    for (int32_t s : c->T.seq_sizes) tot += (double)s;
+    c->target_total = tot;
+  }
+  return alloc_slots(c);
+}
+
+extern "C" int sx_set_queries(sx_ctx *c, const char *bases, const int64_t *offsets, const int32_t *lens,
+                              const int32_t *starts, const int32_t *seq_ids, int32_t n, const int32_t *seq_sizes,
+                              int32_t n_seqs) {
+  if (!c) return fail(SX_ERR_ARG, "sx_set_queries: null context");
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->cfg.device));
+  return set_store(c, c->Q, bases, offsets, lens, starts, seq_ids, n, seq_sizes, n_seqs, c->N, "sx_set_queries");
+}
+
+extern "C" int sx_invalidate_spectra(sx_ctx *c) {
+  if (!c) return fail(SX_ERR_ARG, "null context");
+  std::lock_guard<std::mutex> lk(c->mu);
+  std::fill(c->t_valid.begin(), c->t_valid.end(), 0);
+  return SX_OK;
+}
+
+extern "C" int sx_build_prob_table(double target_total, double *table) {
+  // ProbTable::Setup (analysis/ProbTable.cc:15-56): rows p_match = i/511, columns len = 1..2047;
+  // smallest identity (27-step bisection) whose probability is NON-ZERO.  Built with
+  // the host's libm so that it is bit-identical to what the reference builds.
+  if (!table) return fail(SX_ERR_ARG, "sx_build_prob_table: null table");
+  const int rows = 512, cols = 2048;
+  for (int j = 0; j < cols; j++) table[j] = 0.;
+  for (int i = 1; i < rows; i++) {
+    double *row = table + (size_t)i * cols;
+    const double ident_expect = (double)i / ((double)rows - 1);
+    row[0] = 2.;
+    for (int j = 1; j < cols; j++) {
+      double lo = 0, hi = 1;
+      while (hi - lo > 0.00000001) {
+        const double mid = (hi + lo) / 2.0;
+        // GetMatchProbabilityRaw (ProbTable.cc:143-165); built without FMA contraction (-ffp-contract=off)
+        const double s = std::sqrt(ident_expect * (1. - ident_expect) * (double)j);
+        const double m = ident_expect * (double)j;
+        const double x = (double)j * mid;
+        const double cdf = 0.5 * (1. + std::erf((m - x) / s / 1.414213562));
+        const double expect = cdf * target_total;
+        if (std::exp(-expect) != 0.)
+          hi = mid;
+        else
+          lo = mid;
+      }
+      row[j] = (hi + lo) / 2.0;
+    }
+  }
+  return SX_OK;
+}
+
+extern "C" int sx_set_prob_table(sx_ctx *c, const double *table) {
+  if (!c || !table) return fail(SX_ERR_ARG, "sx_set_prob_table: null argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->cfg.device));
+  int rc = c->d_table.ensure((size_t)512 * 2048);
+  if (rc != SX_OK) return rc;
+  CU(cudaMemcpy(c->d_table.p, table, sizeof(double) * 512 * 2048, cudaMemcpyHostToDevice));
+  c->have_table = true;
+  return SX_OK;
+}
+
+extern "C" int sx_set_profiling(sx_ctx *c, int32_t enabled) {
+  if (!c) return fail(SX_ERR_ARG, "null context");
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->profiling = enabled != 0;
+  return SX_OK;
+}
+extern "C" int sx_get_stats(sx_ctx *c, sx_stats *out) {
+  if (!c || !out) return fail(SX_ERR_ARG, "null argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  *out = c->stats;
+  return SX_OK;
+}
+extern "C" int sx_reset_stats(sx_ctx *c) {
+  if (!c) return fail(SX_ERR_ARG, "null context");
+  std::lock_guard<std::mutex> lk(c->mu);
+  memset(&c->stats, 0, sizeof(c->stats));
+  return SX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One device batch.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Batch {
+  std::vector<SigDesc> sigs;
+  std::vector<SpDesc> sps;
+  std::vector<PairReq> pairs;  // batch-local pair index -> chunk indices
+  size_t transient_used = 0;
+  std::unordered_map<int32_t, int32_t> tslot;  // target chunk -> slot (transient mode)
+  std::unordered_map<int32_t, int32_t> qslot;  // query chunk  -> forward slot (rc slot = +1)
+  void clear() {
+    sigs.clear(); sps.clear(); pairs.clear(); tslot.clear(); qslot.clear();
+    transient_used = 0;
+  }
+};
+
+struct TapRequest {
+  float *sig5n = nullptr;   // host, 5N per signal
+  float *xc = nullptr;      // host, N per strand-pair
+  std::vector<int32_t> *cands = nullptr;
+  std::vector<SegRec> *segs = nullptr;
+};
+
+}  // namespace
+
+static ScoreParams score_params(const sx_ctx *c) {
+  ScoreParams p;
+  p.target_total = c->target_total;
+  p.min_prob = c->cfg.min_prob;
+  p.table_value = c->cfg.prob_table_value;
+  p.table = c->d_table.p;
+  p.min_len = c->cfg.min_len;
+  p.use_table = (c->cfg.use_prob_table && c->have_table) ? 1 : 0;
+  return p;
+}
+
+static void to_result(const sx_ctx *c, const ResultRec &r, const PairReq &pr, sx_result *o) {
+  // FilterMatches coordinate mapping (Slave.cc:176-181, 202-212) and RCQuery (Slave.cc:56-60)
+  const ChunkStore &T = c->T, &Q = c->Q;
+  const int32_t qid = Q.seq_ids[pr.q], tid = T.seq_ids[pr.t];
+  const int32_t qsize = Q.seq_sizes[qid];
+  const int32_t tstart = T.starts[pr.t] + r.start_t;
+  int32_t qstart;
+  if (!r.strand) {
+    qstart = Q.starts[pr.q] + r.start_q;
+  } else {
+    const int32_t chunk = c->cfg.rc_coord_mode == 1 ? Q.lens[pr.q] : c->cfg.q_chunk;
+    qstart = r.start_q + qsize - Q.starts[pr.q] - chunk;
+  }
+  memset(o, 0, sizeof(*o));
+  o->query_id = (uint64_t)(int64_t)qid;
+  o->target_id = (uint64_t)(int64_t)tid;
+  o->query_size = (uint64_t)(int64_t)qsize;
+  o->qstart = (uint64_t)(int64_t)qstart;  // int -> unsigned long, sign-extended as in the reference
+  o->tstart = (uint64_t)(int64_t)tstart;
+  o->len = (uint64_t)(int64_t)r.len;
+  o->reverse = (uint8_t)(r.strand ? 1 : 0);
+  o->prob = r.prob;
+  o->ident = r.ident;
+}
+
+static int run_batch(sx_ctx *c, Batch &b, std::vector<sx_result> *results, TapRequest *tap) {
+  const int nsig = (int)b.sigs.size(), nsp = (int)b.sps.size();
+  if (nsp == 0 && nsig == 0) return SX_OK;
+  const size_t N = (size_t)c->N;
+  int rc;
+  if ((rc = c->d_sigs.ensure(std::max(nsig, 1))) != SX_OK) return rc;
+  if ((rc = c->h_sigs.ensure(std::max(nsig, 1))) != SX_OK) return rc;
+  if ((rc = c->d_sps.ensure(std::max(nsp, 1))) != SX_OK) return rc;
+  if ((rc = c->h_sps.ensure(std::max(nsp, 1))) != SX_OK) return rc;
+  if ((rc = c->d_cand_ref.ensure(std::max(nsp, 1))) != SX_OK) return rc;
+  if (c->d_cand_pool.n == 0 && (rc = c->d_cand_pool.ensure(std::max<size_t>((size_t)nsp * 640, 1 << 16))) != SX_OK) return rc;
+  if (c->d_cand_pool.n < (size_t)nsp * 640 && (rc = c->d_cand_pool.ensure((size_t)nsp * 640)) != SX_OK) return rc;
+  if (c->d_res.n == 0) {
+    if ((rc = c->d_res.ensure(std::max<size_t>((size_t)nsp * 8, 1 << 16))) != SX_OK) return rc;
+  }
+  if (nsig) memcpy(c->h_sigs.p, b.sigs.data(), sizeof(SigDesc) * nsig);
+  if (nsp) memcpy(c->h_sps.p, b.sps.data(), sizeof(SpDesc) * nsp);
+  cudaStream_t st = c->stream;
+  if (nsig) CU(cudaMemcpyAsync(c->d_sigs.p, c->h_sigs.p, sizeof(SigDesc) * nsig, cudaMemcpyHostToDevice, st));
+  if (nsp) CU(cudaMemcpyAsync(c->d_sps.p, c->h_sps.p, sizeof(SpDesc) * nsp, cudaMemcpyHostToDevice, st));
+  c->stats.h2d_bytes += (int64_t)(sizeof(SigDesc) * nsig + sizeof(SpDesc) * nsp);
+
+  float *d_sig_tap = nullptr, *d_xc_tap = nullptr;
+  if (tap && (tap->sig5n || tap->xc)) {
+    if ((rc = c->d_tap.ensure((size_t)std::max(nsig, 1) * 5 * N + (size_t)std::max(nsp, 1) * N)) != SX_OK) return rc;
+    if (tap->sig5n) d_sig_tap = c->d_tap.p;
+    if (tap->xc) d_xc_tap = c->d_tap.p + (size_t)std::max(nsig, 1) * 5 * N;
+  }
+  SegRec *d_seg_tap = nullptr;
+  unsigned int seg_tap_cap = 0;
+  if (tap && tap->segs) {
+    if ((rc = c->d_seg_tap.ensure((size_t)1 << 20)) != SX_OK) return rc;
+    d_seg_tap = c->d_seg_tap.p;
+    seg_tap_cap = (unsigned int)c->d_seg_tap.n;
+  }
+
+  const bool prof = c->profiling;
+  const Slots ws = c->slots();
+  const ScoreParams prm = score_params(c);
+  bool need_encode = nsig > 0, need_xcorr = true;
+  unsigned long long n_cand_seen = 0;
+  for (int attempt = 0; attempt < 8; attempt++) {
+    CU(cudaMemsetAsync(c->d_ctr.p, 0, sizeof(BatchCounters), st));
+    if (prof) CU(cudaEventRecord(c->ev[0], st));
+    if (need_encode) {
+      CU(launch_encode_fft(c->log2n, c->d_sigs.p, nsig, ws, d_sig_tap, st));
+      c->stats.kernel_launches += 1;
+    }
+    if (prof) CU(cudaEventRecord(c->ev[1], st));
+    if (nsp && need_xcorr) {
+      CU(launch_xcorr_findtop(c->log2n, c->d_sps.p, nsp, ws, c->cfg.cutoff, c->cfg.cutoff_fast, c->d_cand_pool.p,
+                              (unsigned int)std::min<size_t>(c->d_cand_pool.n, 0xfffffff0u), c->d_cand_ref.p,
+                              c->d_ctr.p, d_xc_tap, st));
+      c->stats.kernel_launches += 1;
+    }
+    if (prof) CU(cudaEventRecord(c->ev[2], st));
+    if (nsp) {
+      CU(launch_scan_score(c->log2n, c->d_sps.p, nsp, ws, c->d_cand_pool.p, c->d_cand_ref.p, prm, c->d_res.p,
+                           (unsigned int)std::min<size_t>(c->d_res.n, 0xfffffff0u), d_seg_tap, seg_tap_cap,
+                           c->d_ctr.p, st));
+      c->stats.kernel_launches += 2;
+    }
+    if (prof) CU(cudaEventRecord(c->ev[3], st));
+    CU(cudaMemcpyAsync(c->h_ctr.p, c->d_ctr.p, sizeof(BatchCounters), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    c->stats.d2h_bytes += (int64_t)sizeof(BatchCounters);
+    if (prof) {
+      float ms = 0;
+      if (need_encode) { cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->stats.ms_encode_fft += ms; }
+      if (nsp && need_xcorr) { cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->stats.ms_xcorr += ms; }
+      if (nsp) { cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->stats.ms_scan_score += ms; }
+      cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]);
+      c->stats.ms_total += ms;
+    }
+    const BatchCounters ctr = *c->h_ctr.p;
+    need_encode = false;  // spectra of this batch are in place now
+    if (need_xcorr) n_cand_seen = ctr.n_candidates;
+    if (ctr.status & ST_CAND_OVERFLOW) {
+      // the candidate pool was too small: grow to what the kernel asked for and redo K2+K3
+      const size_t want = std::max<size_t>((size_t)ctr.cand_used + (ctr.cand_used >> 2), c->d_cand_pool.n * 2);
+      if ((rc = c->d_cand_pool.ensure(want)) != SX_OK) return rc;
+      c->stats.retries++;
+      need_xcorr = true;
+      continue;
+    }
+    if (ctr.status & ST_RES_OVERFLOW) {
+      const size_t want = std::max<size_t>((size_t)ctr.res_used + (ctr.res_used >> 2), c->d_res.n * 2);
+      if ((rc = c->d_res.ensure(want)) != SX_OK) return rc;
+      c->stats.retries++;
+      need_xcorr = false;  // candidates are valid; only the scan is repeated
+      // cand_ref/pool untouched, but the counter block is zeroed: K3 does not need cand_used
+      continue;
+    }
+    if (ctr.status & ST_TAP_OVERFLOW) return fail(SX_ERR_CAPACITY, "segment tap overflow (%u records)", ctr.seg_tap_used);
+
+    // ---- success: account, fetch records -----------------------------------------------------------
+    c->stats.batches++;
+    c->stats.signals += nsig;
+    c->stats.strand_pairs += nsp;
+    c->stats.chunk_pairs += (int64_t)b.pairs.size();
+    c->stats.candidates += (int64_t)n_cand_seen;
+    c->stats.segments += (int64_t)ctr.n_segments;
+    c->stats.matches += (int64_t)ctr.res_used;
+    if (ctr.res_used && results) {
+      if ((rc = c->h_res.ensure(ctr.res_used)) != SX_OK) return rc;
+      CU(cudaMemcpyAsync(c->h_res.p, c->d_res.p, sizeof(ResultRec) * ctr.res_used, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      c->stats.d2h_bytes += (int64_t)(sizeof(ResultRec) * ctr.res_used);
+      ResultRec *r = c->h_res.p;
+      if (c->cfg.sort_results) {
+        // reference emission order: pair, forward before reverse, candidate lag ascending, position ascending
+        std::sort(r, r + ctr.res_used, [](const ResultRec &a, const ResultRec &b2) {
+          if (a.pair != b2.pair) return a.pair < b2.pair;
+          if (a.strand != b2.strand) return a.strand < b2.strand;
+          if (a.shift != b2.shift) return a.shift < b2.shift;
+          return a.start_t < b2.start_t;
+        });
+      }
+      const size_t base = results->size();
+      results->resize(base + ctr.res_used);
+      for (unsigned int i = 0; i < ctr.res_used; i++) to_result(c, r[i], b.pairs[r[i].pair], &(*results)[base + i]);
+    }
+    if (tap) {
+      if (tap->sig5n && nsig) CU(cudaMemcpy(tap->sig5n, d_sig_tap, sizeof(float) * nsig * 5 * N, cudaMemcpyDeviceToHost));
+      if (tap->xc && nsp) CU(cudaMemcpy(tap->xc, d_xc_tap, sizeof(float) * nsp * N, cudaMemcpyDeviceToHost));
+      if (tap->cands && nsp) {
+        std::vector<uint2> refs(nsp);
+        CU(cudaMemcpy(refs.data(), c->d_cand_ref.p, sizeof(uint2) * nsp, cudaMemcpyDeviceToHost));
+        tap->cands->clear();
+        for (int s = 0; s < nsp; s++) {
+          std::vector<uint16_t> tmp(refs[s].y);
+          if (refs[s].y) CU(cudaMemcpy(tmp.data(), c->d_cand_pool.p + refs[s].x, sizeof(uint16_t) * refs[s].y, cudaMemcpyDeviceToHost));
+          for (uint16_t v : tmp) tap->cands->push_back((int32_t)v);
+        }
+      }
+      if (tap->segs) {
+        tap->segs->resize(ctr.seg_tap_used);
+        if (ctr.seg_tap_used) CU(cudaMemcpy(tap->segs->data(), d_seg_tap, sizeof(SegRec) * ctr.seg_tap_used, cudaMemcpyDeviceToHost));
+      }
+    }
+    return SX_OK;
+  }
+  return fail(SX_ERR_CUDA, "device pools kept overflowing after 8 attempts");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batching of pair requests.
+// ------------------------------------------------------------------------------------------------
+static int32_t target_slot(sx_ctx *c, Batch &b, int32_t t) {
+  if (c->n_persist) {
+    if (!c->t_valid[t]) {
+      SigDesc s;
+      s.src = c->T.d_bases + c->T.offsets[t];
+      s.len = c->T.lens[t];
+      s.strand = 0;
+      s.slot = t;
+      s.pad = 0;
+      b.sigs.push_back(s);
+      c->t_valid[t] = 1;
+    }
+    return t;
+  }
+  auto it = b.tslot.find(t);
+  if (it != b.tslot.end()) return it->second;
+  const int32_t slot = (int32_t)(c->n_persist + b.transient_used++);
+  SigDesc s;
+  s.src = c->T.d_bases + c->T.offsets[t];
+  s.len = c->T.lens[t];
+  s.strand = 0;
+  s.slot = slot;
+  s.pad = 0;
+  b.sigs.push_back(s);
+  b.tslot.emplace(t, slot);
+  return slot;
+}
+
+static int32_t query_slot(sx_ctx *c, Batch &b, int32_t q) {
+  auto it = b.qslot.find(q);
+  if (it != b.qslot.end()) return it->second;
+  const int32_t slot = (int32_t)(c->n_persist + b.transient_used);
+  b.transient_used += 2;
+  for (int strand = 0; strand < 2; strand++) {
+    SigDesc s;
+    s.src = c->Q.d_bases + c->Q.offsets[q];
+    s.len = c->Q.lens[q];
+    s.strand = strand;
+    s.slot = slot + strand;
+    s.pad = 0;
+    b.sigs.push_back(s);
+  }
+  b.qslot.emplace(q, slot);
+  return slot;
+}
+
+static int align_list(sx_ctx *c, const PairReq *reqs, int64_t n, sx_result *out, int64_t cap, int64_t *n_out) {
+  if (c->T.n == 0 && n > 0) return fail(SX_ERR_STATE, "align: no targets loaded");
+  if (c->Q.n == 0 && n > 0) return fail(SX_ERR_STATE, "align: no queries loaded");
+  CU(cudaSetDevice(c->cfg.device));
+  c->last.clear();
+  Batch b;
+  const size_t maxpairs = (size_t)c->cfg.max_batch_pairs;
+  for (int64_t i = 0; i < n; i++) {
+    const PairReq &r = reqs[i];
+    if (r.t < 0 || r.t >= c->T.n || r.q < 0 || r.q >= c->Q.n)
+      return fail(SX_ERR_ARG, "align: pair %lld = (target %d, query %d) out of range", (long long)i, r.t, r.q);
+    // worst case this pair needs 3 fresh transient slots
+    if (b.pairs.size() >= maxpairs || b.transient_used + 3 > c->n_transient) {
+      int rc = run_batch(c, b, &c->last, nullptr);
+      if (rc != SX_OK) return rc;
+      b.clear();
+    }
+    const int32_t ts = target_slot(c, b, r.t);
+    const int32_t qs = query_slot(c, b, r.q);
+    const int32_t pidx = (int32_t)b.pairs.size();
+    b.pairs.push_back(r);
+    for (int strand = 0; strand < 2; strand++) {
+      SpDesc sp;
+      sp.t_slot = ts;
+      sp.q_slot = qs + strand;
+      sp.pair = pidx;
+      sp.flags = (strand ? SP_REVERSE : 0) | (r.fast ? SP_FAST : 0);
+      b.sps.push_back(sp);
+    }
+  }
+  int rc = run_batch(c, b, &c->last, nullptr);
+  if (rc != SX_OK) return rc;
+  const int64_t total = (int64_t)c->last.size();
+  if (n_out) *n_out = total;
+  if (total > cap) return fail(SX_ERR_CAPACITY, "align: %lld records, buffer holds %lld", (long long)total, (long long)cap);
+  if (total && out) memcpy(out, c->last.data(), sizeof(sx_result) * (size_t)total);
+  return SX_OK;
+}
+
+extern "C" int sx_align_pairs(sx_ctx *c, const int32_t *pairs, int64_t n, int32_t fast, sx_result *out, int64_t cap,
+                              int64_t *n_out) {
+  if (!c || (n > 0 && !pairs)) return fail(SX_ERR_ARG, "sx_align_pairs: null argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  std::vector<PairReq> reqs((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    reqs[i].t = pairs[2 * i];
+    reqs[i].q = pairs[2 * i + 1];
+    reqs[i].fast = fast ? 1 : 0;
+  }
+  return align_list(c, reqs.data(), n, out, cap, n_out);
+}
+
+extern "C" int sx_align_blocks(sx_ctx *c, const sx_pair *blocks, int32_t n_blocks, sx_result *out, int64_t cap,
+                               int64_t *n_out) {
+  if (!c || (n_blocks > 0 && !blocks)) return fail(SX_ERR_ARG, "sx_align_blocks: null argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  std::vector<PairReq> reqs;
+  for (int32_t bi = 0; bi < n_blocks; bi++) {
+    const sx_pair &p = blocks[bi];
+    if (p.target_from < 0 || p.target_to >= c->T.n || p.query_from < 0 || p.query_to >= c->Q.n)
+      return fail(SX_ERR_ARG, "sx_align_blocks: block %d ranges t[%d,%d] q[%d,%d] out of bounds", bi, p.target_from,
+                  p.target_to, p.query_from, p.query_to);
+    // loop order of align_target (Slave.cc:290-299): queries outer, targets inner
+    for (int32_t q = p.query_from; q <= p.query_to; q++)
+      for (int32_t t = p.target_from; t <= p.target_to; t++) {
+        PairReq r;
+        r.t = t;
+        r.q = q;
+        r.fast = p.fast ? 1 : 0;
+        reqs.push_back(r);
+      }
+  }
+  return align_list(c, reqs.data(), (int64_t)reqs.size(), out, cap, n_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage taps (parity tests).  They run the production kernels on one signal / one strand-pair in
+// the transient slot region and copy the intermediate out.
+// ------------------------------------------------------------------------------------------------
+static int tap_prepare(sx_ctx *c, int32_t target, int32_t query, int32_t strand, int32_t fast, Batch &b) {
+  if (target < 0 || target >= c->T.n || query < 0 || query >= c->Q.n || (strand != 0 && strand != 1))
+    return fail(SX_ERR_ARG, "tap: (target %d, query %d, strand %d) out of range", target, query, strand);
+  if (c->n_transient < 3) return fail(SX_ERR_STATE, "tap: no workspace (call sx_set_targets first)");
+  CU(cudaSetDevice(c->cfg.device));
+  const int32_t base = (int32_t)c->n_persist;
+  SigDesc s;
+  s.src = c->T.d_bases + c->T.offsets[target];
+  s.len = c->T.lens[target];
+  s.strand = 0;
+  s.slot = base;
+  s.pad = 0;
+  b.sigs.push_back(s);
+  s.src = c->Q.d_bases + c->Q.offsets[query];
+  s.len = c->Q.lens[query];
+  s.strand = strand;
+  s.slot = base + 1;
+  b.sigs.push_back(s);
+  SpDesc sp;
+  sp.t_slot = base;
+  sp.q_slot = base + 1;
+  sp.pair = 0;
+  sp.flags = (strand ? SP_REVERSE : 0) | (fast ? SP_FAST : 0);
+  b.sps.push_back(sp);
+  PairReq pr;
+  pr.t = target;
+  pr.q = query;
+  pr.fast = fast;
+  b.pairs.push_back(pr);
+  return SX_OK;
+}
+
+extern "C" int sx_tap_signal(sx_ctx *c, int32_t is_target, int32_t chunk, int32_t strand, float *out5) {
+  if (!c || !out5) return fail(SX_ERR_ARG, "sx_tap_signal: null argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  const ChunkStore &S = is_target ? c->T : c->Q;
+  if (chunk < 0 || chunk >= S.n || (strand != 0 && strand != 1)) return fail(SX_ERR_ARG, "sx_tap_signal: chunk %d out of range", chunk);
+  if (c->n_transient < 1) return fail(SX_ERR_STATE, "tap: no workspace (call sx_set_targets first)");
+  CU(cudaSetDevice(c->cfg.device));
+  Batch b;
+  SigDesc s;
+  s.src = S.d_bases + S.offsets[chunk];
+  s.len = S.lens[chunk];
+  s.strand = strand;
+  s.slot = (int32_t)c->n_persist;
+  s.pad = 0;
+  b.sigs.push_back(s);
+  TapRequest t;
+  t.sig5n = out5;
+  return run_batch(c, b, nullptr, &t);
+}
+
+extern "C" int sx_tap_xcorr(sx_ctx *c, int32_t target, int32_t query, int32_t strand, float *out) {
+  if (!c || !out) return fail(SX_ERR_ARG, "sx_tap_xcorr: null argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  Batch b;
+  int rc = tap_prepare(c, target, query, strand, 0, b);
+  if (rc != SX_OK) return rc;
+  TapRequest t;
+  t.xc = out;
+  return run_batch(c, b, nullptr, &t);
+}
+
+extern "C" int sx_tap_candidates(sx_ctx *c, int32_t target, int32_t query, int32_t strand, int32_t fast, int32_t *idx,
+                                 int32_t cap, int32_t *n_out) {
+  if (!c || !n_out) return fail(SX_ERR_ARG, "sx_tap_candidates: null argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  Batch b;
+  int rc = tap_prepare(c, target, query, strand, fast, b);
+  if (rc != SX_OK) return rc;
+  std::vector<int32_t> cands;
+  TapRequest t;
+  t.cands = &cands;
+  if ((rc = run_batch(c, b, nullptr, &t)) != SX_OK) return rc;
+  *n_out = (int32_t)cands.size();
+  if ((int32_t)cands.size() > cap) return fail(SX_ERR_CAPACITY, "sx_tap_candidates: %zu candidates", cands.size());
+  if (idx && !cands.empty()) memcpy(idx, cands.data(), sizeof(int32_t) * cands.size());
+  return SX_OK;
+}
+
+extern "C" int sx_tap_segments(sx_ctx *c, int32_t target, int32_t query, int32_t strand, int32_t fast, sx_segment *out,
+                               int32_t cap, int32_t *n_out) {
+  if (!c || !n_out) return fail(SX_ERR_ARG, "sx_tap_segments: null argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  Batch b;
+  int rc = tap_prepare(c, target, query, strand, fast, b);
+  if (rc != SX_OK) return rc;
+  std::vector<SegRec> segs;
+  TapRequest t;
+  t.segs = &segs;
+  if ((rc = run_batch(c, b, nullptr, &t)) != SX_OK) return rc;
+  std::sort(segs.begin(), segs.end(), [](const SegRec &a, const SegRec &b2) {
+    if (a.shift != b2.shift) return a.shift < b2.shift;
+    return a.start_t < b2.start_t;
+  });
+  *n_out = (int32_t)segs.size();
+  if ((int32_t)segs.size() > cap) return fail(SX_ERR_CAPACITY, "sx_tap_segments: %zu segments", segs.size());
+  for (size_t i = 0; i < segs.size() && out; i++) {
+    out[i].start_target = segs[i].start_t;
+    out[i].start_query = segs[i].start_t + segs[i].shift;
+    out[i].len = segs[i].len;
+  }
+  return SX_OK;
+}

@@ -1,0 +1,959 @@
+// Hand-written sm_100a kernels for Satsuma2's chunk-pair cross-correlation path.
+//
+//   K1 encode_fft_kernel      (a)+(b)  DNA -> 4-channel entropy-weighted signal -> spectra
+//        replaces CCSignal::SetSequence / ComputeEntropy / SeqToPCM (analysis/CrossCorr.cc:35-134,
+//        179-206), DNAVector::ReverseComplement (analysis/DNAVector.cc:482-521) and the forward
+//        FFTReal::do_fft calls of CrossCorrelation::DoOne (CrossCorr.cc:471-474)
+//   K2 xcorr_findtop_kernel   (c)+(d)  spectral product (+ reference quirk bins), channel sum,
+//        one inverse FFT, half rotation, RMS envelope, threshold, ordered compaction
+//        replaces CrossCorrelation::DoOne / CrossCorrelate (CrossCorr.cc:386-507) and
+//        SeqAnalyzer::FindTop (CrossCorr.cc:878-944)
+//   K3 scan_score_kernel[_generic] (e)  diagonal sliding-window scan + match probability
+//        replaces SeqAnalyzer::MatchUp / DoOne (CrossCorr.cc:583-605, 667-724),
+//        GetMatchProbabilityEx (analysis/AlignProbability.cc:62-127), ProbTable lookup
+//        (analysis/ProbTable.cc:58-74, 105-140) and the filter of FilterMatches
+//        (analysis/HomologyByXCorrSlave.cc:168-219)
+//
+// No tensor cores (nothing here is a dense contraction), no cuFFT, no CPU fallback.
+#include "sx_kernels.h"
+#include "sx_fft.cuh"
+
+#include <math.h>
+#include <string.h>
+
+namespace sx {
+
+// ------------------------------------------------------------------------------------------------
+// Lookup tables.  The IUPAC codec (analysis/DNAVector.cc:13-58): fraction of A,C,G,T per letter,
+// complement letter; match scores (int)(100*DNA_EqualAmb + 0.5) (CrossCorr.cc:547-553).
+// Bytes >= 128 are undefined behaviour in the reference (negative table index); here they are
+// mapped to NUL when a chunk is loaded, so every table has 128 rows.
+// ------------------------------------------------------------------------------------------------
+__constant__ uint16_t c_fcode[128];  // 4 x 4-bit value codes (A,C,G,T): 0:0 1:1 2:1/2 3:1/3 4:1/4
+__constant__ uint8_t c_comp[128];    // complement letter (0 for unknown)
+__constant__ uint8_t c_base2[128];   // 0..3 for A,C,G,T; 4 otherwise; |8 for B,V,H,D (thirds)
+__device__ uint8_t g_score[128 * 128];
+
+static double h_frac[128 * 4];
+static uint8_t h_comp[128];
+static uint8_t h_score[128 * 128];
+static uint16_t h_fcode[128];
+static uint8_t h_base2[128];
+static bool h_tables_ready = false;
+
+static void host_put(int ch, int a, int c, int g, int t, int comp) {
+  static const double val[5] = {0., 1., 0.5, 1. / 3., 0.25};
+  h_fcode[ch] = (uint16_t)(a | (c << 4) | (g << 8) | (t << 12));
+  h_frac[ch * 4 + 0] = val[a];
+  h_frac[ch * 4 + 1] = val[c];
+  h_frac[ch * 4 + 2] = val[g];
+  h_frac[ch * 4 + 3] = val[t];
+  h_comp[ch] = (uint8_t)comp;
+}
+
+static void build_host_tables() {
+  if (h_tables_ready) return;
+  memset(h_frac, 0, sizeof(h_frac));
+  memset(h_comp, 0, sizeof(h_comp));
+  memset(h_fcode, 0, sizeof(h_fcode));
+  host_put('A', 1, 0, 0, 0, 'T');
+  host_put('C', 0, 1, 0, 0, 'G');
+  host_put('G', 0, 0, 1, 0, 'C');
+  host_put('T', 0, 0, 0, 1, 'A');
+  host_put('K', 0, 0, 2, 2, 'M');
+  host_put('M', 2, 2, 0, 0, 'K');
+  host_put('R', 2, 0, 2, 0, 'Y');
+  host_put('Y', 0, 2, 0, 2, 'R');
+  host_put('S', 0, 2, 2, 0, 'S');
+  host_put('W', 2, 0, 0, 2, 'W');
+  host_put('B', 0, 3, 3, 3, 'V');
+  host_put('V', 3, 3, 3, 0, 'B');
+  host_put('H', 3, 3, 0, 3, 'D');
+  host_put('D', 3, 0, 3, 3, 'H');
+  host_put('-', 0, 0, 0, 0, '-');
+  host_put('N', 4, 4, 4, 4, 'N');
+  host_put('X', 4, 4, 4, 4, 'X');
+  for (int i = 0; i < 128; i++) {
+    h_base2[i] = 4;
+    if (i == 'B' || i == 'V' || i == 'H' || i == 'D') h_base2[i] = 4 | 8;
+  }
+  h_base2['A'] = 0;
+  h_base2['C'] = 1;
+  h_base2['G'] = 2;
+  h_base2['T'] = 3;
+  for (int a = 0; a < 128; a++)
+    for (int b = 0; b < 128; b++) {
+      double pa = h_frac[a * 4 + 0] * h_frac[b * 4 + 0];
+      double pc = h_frac[a * 4 + 1] * h_frac[b * 4 + 1];
+      double pg = h_frac[a * 4 + 2] * h_frac[b * 4 + 2];
+      double pt = h_frac[a * 4 + 3] * h_frac[b * 4 + 3];
+      double dot = pa + pc + pg + pt;
+      double amb = (a == b && a != 'N') ? 1. : dot;
+      h_score[a * 128 + b] = (uint8_t)(int)(amb * 100. + 0.5);
+    }
+  h_tables_ready = true;
+}
+
+const double *host_frac_table() { build_host_tables(); return h_frac; }
+const uint8_t *host_comp_table() { build_host_tables(); return h_comp; }
+const uint8_t *host_score_table() { build_host_tables(); return h_score; }
+
+cudaError_t upload_tables() {
+  build_host_tables();
+  cudaError_t e;
+  if ((e = cudaMemcpyToSymbol(c_fcode, h_fcode, sizeof(h_fcode))) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbol(c_comp, h_comp, sizeof(h_comp))) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbol(c_base2, h_base2, sizeof(h_base2))) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbol(g_score, h_score, sizeof(h_score))) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+bool log2n_supported(int log2n) { return log2n >= 11 && log2n <= 14; }
+size_t slot_spec_elems(int log2n) { return (size_t)2 << log2n; }
+
+// fraction of channel c (0..3) for a table entry; exact doubles {0,1,1/2,1/3,1/4}
+__device__ __forceinline__ double frac_of(uint32_t fcode, int c) {
+  const uint32_t v = (fcode >> (4 * c)) & 15u;
+  // 1/3 must be the same double the reference computes (1./3.)
+  return v == 0 ? 0.0 : v == 1 ? 1.0 : v == 2 ? 0.5 : v == 3 ? (1.0 / 3.0) : 0.25;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// =================================================================================================
+// K1: encode + forward transform.  One CTA per chunk signal.
+// =================================================================================================
+template <int LOG2N, int NT>
+__global__ void __launch_bounds__(NT) encode_fft_kernel(const SigDesc *__restrict__ sigs, Slots ws,
+                                                        float *__restrict__ tap) {
+  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, WIN = N / 512, NWARP = NT / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *buf = reinterpret_cast<float2 *>(smem_raw);            // N complex
+  uint8_t *sb = smem_raw + (size_t)N * sizeof(float2);            // N oriented bases
+  float *went = reinterpret_cast<float *>(sb + N);                // 512 window weights
+  uint16_t *s_fcode = reinterpret_cast<uint16_t *>(went + 512);   // 128 x u16
+  __shared__ double s_red[4][NWARP];
+  __shared__ double s_off[4];
+  __shared__ int s_flags;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const SigDesc sd = sigs[blockIdx.x];
+  const int len = sd.len;
+  const uint8_t *__restrict__ src = sd.src;
+
+  if (tid < 128) s_fcode[tid] = c_fcode[tid];
+  if (tid == 0) s_flags = 0;
+  __syncthreads();
+
+  // ---- 1. load (optionally reverse-complement), sanitise, bit-planes ----------------------------
+  uint32_t *planes = ws.planes + (size_t)sd.slot * 2 * NW;
+  uint8_t *gbytes = ws.bytes + (size_t)sd.slot * N;
+  int myflags = 0;
+  for (int k0 = warp * 32; k0 < N; k0 += NT) {
+    const int k = k0 + lane;
+    uint32_t b = 0, code = 4;
+    if (k < len) {
+      b = sd.strand ? src[len - 1 - k] : src[k];
+      if (b >= 128u) b = 0;
+      if (sd.strand) b = c_comp[b];
+      code = c_base2[b];
+      if (code & 4u) myflags |= SLOT_NONACGT;
+      if (code & 8u) myflags |= 2;
+    }
+    sb[k] = (uint8_t)b;
+    gbytes[k] = (uint8_t)b;
+    const uint32_t lo = __ballot_sync(0xffffffffu, (code & 5u) == 1u);  // C or T -> bit0
+    const uint32_t hi = __ballot_sync(0xffffffffu, (code & 6u) == 2u);  // G or T -> bit1
+    if (lane == 0) {
+      planes[k0 >> 5] = lo;
+      planes[NW + (k0 >> 5)] = hi;
+    }
+  }
+  if (myflags) atomicOr(&s_flags, myflags);
+  __syncthreads();
+  const int flags = s_flags;
+
+  // ---- 2. window sums, entropy weights (ComputeEntropy) and channel means (SeqToPCM) ------------
+  double tot[4] = {0., 0., 0., 0.};
+  const int nwin = (len + WIN - 1) / WIN;
+  for (int w = tid; w < nwin; w += NT) {
+    double s4[4] = {0., 0., 0., 0.};
+    const int i0 = w * WIN;
+    int k = 0;
+    for (int j = i0; j < i0 + WIN && j < len; j++, k++) {
+      const uint32_t fc = s_fcode[sb[j]];
+#pragma unroll
+      for (int c = 0; c < 4; c++) s4[c] = __dadd_rn(s4[c], frac_of(fc, c));
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) tot[c] += s4[c];
+    double s = 0.;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const double p = __ddiv_rn(s4[c], (double)k);
+      const double e = (p < 0.001) ? 0.0 : __ddiv_rn(__dmul_rn(p, log(p)), 0.69314718056);
+      s = (c == 0) ? e : __dadd_rn(s, e);
+    }
+    float v = __double2float_rn(-s);
+    if (v < 0.f) v = 0.f;
+    went[w] = v;
+  }
+  // Means: all fractions except 1/3 are dyadic, so partial sums are exact in any order; with
+  // B/V/H/D present fall back to the reference's sequential summation order.
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const double r = warp_sum(tot[c]);
+    if (lane == 0) s_red[c][warp] = r;
+  }
+  __syncthreads();
+  if (tid < 4) {
+    double sum = 0.;
+    if (flags & 2) {
+      for (int i = 0; i < len; i++) sum = __dadd_rn(sum, frac_of(s_fcode[sb[i]], tid));
+    } else {
+      for (int w = 0; w < NWARP; w++) sum += s_red[tid][w];
+    }
+    s_off[tid] = __ddiv_rn(sum, (double)len);
+  }
+  __syncthreads();
+  const bool flat = len < 1024;  // "Skip entropy": weight 1 everywhere (CrossCorr.cc:39-44)
+
+  if (tap != nullptr) {
+    float *te = tap + (size_t)blockIdx.x * 5 * N;
+    for (int k = tid; k < N; k += NT) te[k] = flat ? 1.f : (k < len ? went[k / WIN] : 0.f);
+  }
+
+  // ---- 3. two complex transforms: (A + iC) then (G + iT) -----------------------------------------
+  float acc_re = 0.f, acc_im = 0.f, acc_ny = 0.f;
+  constexpr int PH1 = scrambled_pos<LOG2N>(H - 1), PH = scrambled_pos<LOG2N>(H),
+                PH2 = scrambled_pos<LOG2N>(H + 1);
+#pragma unroll 1
+  for (int pr = 0; pr < 2; pr++) {
+    const double off0 = s_off[2 * pr], off1 = s_off[2 * pr + 1];
+    for (int k = tid; k < N; k += NT) {
+      float2 v = make_float2(0.f, 0.f);
+      if (k < len) {
+        const uint32_t fc = s_fcode[sb[k]];
+        const double e = flat ? 1.0 : (double)went[k / WIN];
+        v.x = __double2float_rn(__dmul_rn(e, __dsub_rn(frac_of(fc, 2 * pr), off0)));
+        v.y = __double2float_rn(__dmul_rn(e, __dsub_rn(frac_of(fc, 2 * pr + 1), off1)));
+      }
+      buf[k] = v;
+      if (tap != nullptr) {
+        float *ts = tap + (size_t)blockIdx.x * 5 * N + (size_t)(1 + 2 * pr) * N;
+        ts[k] = v.x;
+        ts[N + k] = v.y;
+      }
+    }
+    __syncthreads();
+    fft_forward<LOG2N, NT>(buf, tid);
+    // spectra out (scrambled order), 16-byte stores
+    float4 *dst = reinterpret_cast<float4 *>(ws.spec + ((size_t)sd.slot * 2 + pr) * N);
+    const float4 *s4p = reinterpret_cast<const float4 *>(buf);
+    for (int k = tid; k < N / 2; k += NT) dst[k] = s4p[k];
+    if (tid == 0) {
+      // per-channel bins from the packed transform: X_re-channel[k] + X_im-channel[k]
+      //   = (a+b)/2 - i (a-b)/2  with a = Z[k], b = conj(Z[N-k])
+      const float2 a = buf[PH1], z2 = buf[PH2], zn = buf[PH];
+      const float2 b = make_float2(z2.x, -z2.y);
+      const float2 s = cadd(a, b), d = csub(a, b);
+      acc_re += 0.5f * s.x + 0.5f * d.y;
+      acc_im += 0.5f * s.y - 0.5f * d.x;
+      acc_ny += zn.x + zn.y;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    SlotMeta m;
+    m.len = len;
+    m.flags = flags & SLOT_NONACGT;
+    m.q_re = acc_re;
+    m.q_im = acc_im;
+    m.q_nyq = acc_ny;
+    m.pad[0] = m.pad[1] = m.pad[2] = 0;
+    ws.meta[sd.slot] = m;
+  }
+}
+
+// =================================================================================================
+// K2: spectral product + inverse transform + FindTop.  One CTA per strand-pair.
+// =================================================================================================
+template <int LOG2N, int NT>
+__global__ void __launch_bounds__(NT)
+    xcorr_findtop_kernel(const SpDesc *__restrict__ sps, Slots ws, double cutoff, double cutoff_fast,
+                         uint16_t *__restrict__ cand_pool, unsigned int pool_cap, uint2 *__restrict__ cand_ref,
+                         BatchCounters *ctr, float *__restrict__ xc_tap) {
+  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, NB = N / 256, NWARP = NT / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *buf = reinterpret_cast<float2 *>(smem_raw);
+  uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw + (size_t)N * sizeof(float2));  // NW words
+  uint32_t *wpre = mask + NW;                                                            // NW prefix counts
+  __shared__ double s_thr[NB];
+  __shared__ unsigned int s_wtot[NWARP];
+  __shared__ unsigned int s_base;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const SpDesc sp = sps[blockIdx.x];
+  const SlotMeta tm = ws.meta[sp.t_slot];
+
+  // ---- product: P = conj(U1) V1 + conj(U2) V2 (bin order is irrelevant here) ----------------------
+  {
+    const float4 *U1 = reinterpret_cast<const float4 *>(ws.spec + ((size_t)sp.t_slot * 2) * N);
+    const float4 *U2 = U1 + N / 2;
+    const float4 *V1 = reinterpret_cast<const float4 *>(ws.spec + ((size_t)sp.q_slot * 2) * N);
+    const float4 *V2 = V1 + N / 2;
+    float4 *dst = reinterpret_cast<float4 *>(buf);
+#pragma unroll 2
+    for (int k = tid; k < N / 2; k += NT) {
+      const float4 u1 = __ldg(U1 + k), u2 = __ldg(U2 + k), v1 = __ldg(V1 + k), v2 = __ldg(V2 + k);
+      float4 p;
+      p.x = (v1.x * u1.x + v1.y * u1.y) + (v2.x * u2.x + v2.y * u2.y);
+      p.y = (v1.y * u1.x - v1.x * u1.y) + (v2.y * u2.x - v2.x * u2.y);
+      p.z = (v1.z * u1.z + v1.w * u1.w) + (v2.z * u2.z + v2.w * u2.w);
+      p.w = (v1.w * u1.z - v1.z * u1.w) + (v2.w * u2.z - v2.z * u2.w);
+      dst[k] = p;
+    }
+  }
+  __syncthreads();
+  // ---- reference quirk (CrossCorr.cc:480-492): bins H-1 and H keep the TARGET spectrum ------------
+  if (tid == 0) {
+    constexpr int PH1 = scrambled_pos<LOG2N>(H - 1), PH = scrambled_pos<LOG2N>(H),
+                  PH2 = scrambled_pos<LOG2N>(H + 1);
+    buf[PH1] = make_float2(tm.q_re, tm.q_im);
+    buf[PH2] = make_float2(tm.q_re, -tm.q_im);
+    buf[PH] = make_float2(tm.q_nyq, 0.f);
+  }
+  __syncthreads();
+  fft_inverse<LOG2N, NT>(buf, tid);
+
+  // xc[i] = Re x[(i + H) mod N] / N   (rescale + half rotation, CrossCorr.cc:493-505)
+  const float scale = 1.0f / (float)N;
+  auto xc_at = [&](int i) -> float { return buf[(i + H) & (N - 1)].x * scale; };
+
+  if (xc_tap != nullptr) {
+    float *o = xc_tap + (size_t)blockIdx.x * N;
+    for (int i = tid; i < N; i += NT) o[i] = xc_at(i);
+  }
+
+  // ---- FindTop: RMS envelope per 256 lags (float square, double accumulate), threshold ------------
+  const double co = (sp.flags & SP_FAST) ? cutoff_fast : cutoff;
+  for (int b = warp; b < NB; b += NWARP) {
+    double acc = 0.;
+    if (NB > 8) {
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        const float v = xc_at(b * 256 + r * 32 + lane);
+        acc += (double)__fmul_rn(v, v);
+      }
+      acc = warp_sum(acc);
+    }
+    if (lane == 0) s_thr[b] = __dadd_rn(__dmul_rn(__dsqrt_rn(__ddiv_rn(acc, 256.0)), co), 1.0);
+  }
+  __syncthreads();
+  for (int w = warp; w < NW; w += NWARP) {
+    const int i = w * 32 + lane;
+    const bool hit = (double)xc_at(i) > s_thr[i >> 8];
+    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) mask[w] = m;
+  }
+  __syncthreads();
+  // ---- ordered compaction: exclusive scan of per-word popcounts -----------------------------------
+  constexpr int IPT = (NW + NT - 1) / NT;  // words per thread (contiguous)
+  unsigned int cnt[IPT], mine = 0;
+#pragma unroll
+  for (int r = 0; r < IPT; r++) {
+    const int w = tid * IPT + r;
+    cnt[r] = (w < NW) ? __popc(mask[w]) : 0;
+    mine += cnt[r];
+  }
+  unsigned int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_wtot[warp] = incl;
+  __syncthreads();
+  unsigned int wbase = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < NWARP; w++) {
+    if (w < warp) wbase += s_wtot[w];
+    total += s_wtot[w];
+  }
+  if (tid == 0) {
+    unsigned int base = 0xffffffffu;
+    if (total > 0) {
+      base = atomicAdd(&ctr->cand_used, total);
+      if (base + total > pool_cap) {
+        atomicOr(&ctr->status, (unsigned int)ST_CAND_OVERFLOW);
+        base = 0xffffffffu;
+      }
+    } else {
+      base = 0;
+    }
+    s_base = base;
+    cand_ref[blockIdx.x] = make_uint2(base, total);
+    atomicAdd(&ctr->n_candidates, (unsigned long long)total);
+  }
+  __syncthreads();
+  const unsigned int base = s_base;
+  if (base != 0xffffffffu && total > 0) {
+    unsigned int o = base + wbase + (incl - mine);
+#pragma unroll
+    for (int r = 0; r < IPT; r++) {
+      const int w = tid * IPT + r;
+      if (w < NW) {
+        uint32_t m = mask[w];
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          cand_pool[o++] = (uint16_t)(w * 32 + bit);
+        }
+      }
+    }
+  }
+  (void)wpre;
+}
+
+// =================================================================================================
+// Match probability (AlignProbability.cc:11-40, 62-127 / ProbTable.cc:58-74, 105-140), FP64, no
+// FMA contraction so that it matches the reference's x86-64 arithmetic operation by operation
+// (erf/exp come from the CUDA math library: <= 2 ulp from glibc's).
+// Returns true when the segment is kept ("if (prob < m_minProb) continue", Slave.cc:186,194).
+// =================================================================================================
+__device__ __forceinline__ bool score_counts(double matches, double gcT, double gcQ, int len,
+                                             const ScoreParams &prm, double &prob, double &ident) {
+  const double dl = (double)len;
+  ident = __ddiv_rn(matches, dl);
+  const double gc_target = __ddiv_rn(gcT, dl);
+  const double at_target = __dsub_rn(1., gc_target);
+  double r = __dmul_rn(gcQ, gc_target);
+  r = __dadd_rn(r, __dmul_rn(__dsub_rn(dl, gcQ), at_target));
+  const double p_match = __ddiv_rn(__ddiv_rn(r, dl), 2.);
+  if (prm.use_table) {
+    const int index = (int)__dmul_rn(p_match, 511.0);
+    if (index < 1 || index > 511) {
+      prob = 0.;  // reference reads out of bounds for index 0: defined as "reject"
+    } else {
+      const int l = len >= 2048 ? 2047 : len;
+      prob = (ident >= __ldg(prm.table + (size_t)index * 2048 + l)) ? prm.table_value : 0.;
+    }
+  } else {
+    const double s = __dsqrt_rn(__dmul_rn(__dmul_rn(p_match, __dsub_rn(1., p_match)), dl));
+    const double m = __dmul_rn(p_match, dl);
+    const double x = __dmul_rn(dl, ident);
+    const double z = __ddiv_rn(__ddiv_rn(__dsub_rn(m, x), s), 1.414213562);
+    const double cdf = __dmul_rn(0.5, __dadd_rn(1., erf(z)));
+    const double expect = __dmul_rn(cdf, prm.target_total);
+    prob = exp(-expect);
+  }
+  if (len < prm.min_len) return false;
+  return !(prob < prm.min_prob);
+}
+
+__device__ __forceinline__ void emit_result(const SpDesc &sp, int start_t, int shift, int len, double prob,
+                                            double ident, ResultRec *res_pool, unsigned int res_cap,
+                                            BatchCounters *ctr) {
+  const unsigned int slot = atomicAdd(&ctr->res_used, 1u);
+  if (slot >= res_cap) {
+    atomicOr(&ctr->status, (unsigned int)ST_RES_OVERFLOW);
+    return;
+  }
+  ResultRec r;
+  r.pair = sp.pair;
+  r.strand = sp.flags & SP_REVERSE;
+  r.start_t = start_t;
+  r.start_q = start_t + shift;
+  r.len = len;
+  r.shift = shift;
+  r.prob = prob;
+  r.ident = ident;
+  res_pool[slot] = r;
+}
+
+__device__ __forceinline__ void tap_segment(int spi, int start_t, int shift, int len, SegRec *seg_tap,
+                                            unsigned int seg_tap_cap, BatchCounters *ctr) {
+  if (seg_tap == nullptr) return;
+  const unsigned int slot = atomicAdd(&ctr->seg_tap_used, 1u);
+  if (slot >= seg_tap_cap) {
+    atomicOr(&ctr->status, (unsigned int)ST_TAP_OVERFLOW);
+    return;
+  }
+  SegRec s;
+  s.sp = spi;
+  s.start_t = start_t;
+  s.shift = shift;
+  s.len = len;
+  seg_tap[slot] = s;
+}
+
+__device__ __forceinline__ uint32_t range_mask(int lo, int hi) {  // bits [lo, hi) of a 32-bit word
+  if (hi <= 0 || lo >= 32 || lo >= hi) return 0u;
+  const uint32_t upper = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
+  const uint32_t lower = lo <= 0 ? 0u : ((1u << lo) - 1u);
+  return upper & ~lower;
+}
+
+// =================================================================================================
+// K3 (fast path, both chunks pure A/C/G/T): bit-parallel diagonal scan.
+//
+// For A/C/G/T the reference's integer scores are 100 (equal) / 0 (different), so
+// "window sum > 1889" (46-wide window, CrossCorr.cc:675-716; (int)(45*0.42*100) is 1889 in IEEE
+// double, not 1890) is "at least 19 of the last 46 positions match".  Each thread owns one candidate diagonal and walks it 32 positions per step:
+// match bits come from XORing 2-bit base planes (query planes funnel-shifted by the lag), the
+// 46-wide sliding count is built bit-sliced by doubling (windows 2,4,8,16,32 then 32+8+4+2), and
+// the >= 19 test is three logic ops on the 6 count planes.  Run starts/ends give the segments.
+// =================================================================================================
+#define SX_SEGQ_CAP 3072
+
+struct FastPlanes {
+  const uint32_t *tlo, *thi, *qlo, *qhi;  // q planes are padded by one zero word in front
+};
+
+// match bits (masked to [lo,hi) of the word) + GC planes for target word w at lag `shift`
+__device__ __forceinline__ uint32_t match_word(const FastPlanes &P, int w, int shift, uint32_t vmask,
+                                               uint32_t &t_gc, uint32_t &q_gc) {
+  const int qpos = w * 32 + shift + 32;  // >= 1 by construction
+  const int wi = qpos >> 5, sh = qpos & 31;
+  const uint32_t ql = __funnelshift_r(P.qlo[wi], P.qlo[wi + 1], sh);
+  const uint32_t qh = __funnelshift_r(P.qhi[wi], P.qhi[wi + 1], sh);
+  const uint32_t tl = P.tlo[w], th = P.thi[w];
+  t_gc = (tl ^ th) & vmask;
+  q_gc = (ql ^ qh) & vmask;
+  return ~((tl ^ ql) | (th ^ qh)) & vmask;
+}
+
+__device__ __forceinline__ bool score_fast(const FastPlanes &P, int start_t, int shift, int len,
+                                           const ScoreParams &prm, double &prob, double &ident) {
+  int matches = 0, gct = 0, gcq = 0;
+  const int end = start_t + len;
+  for (int w = start_t >> 5; w <= (end - 1) >> 5; w++) {
+    const uint32_t vm = range_mask(start_t - w * 32, end - w * 32);
+    uint32_t tg, qg;
+    const uint32_t m = match_word(P, w, shift, vm, tg, qg);
+    matches += __popc(m);
+    gct += __popc(tg);
+    gcq += __popc(qg);
+  }
+  return score_counts((double)matches, (double)gct, (double)gcq, len, prm, prob, ident);
+}
+
+template <int LOG2N, int NT>
+__global__ void __launch_bounds__(NT)
+    scan_score_kernel(const SpDesc *__restrict__ sps, Slots ws, const uint16_t *__restrict__ cand_pool,
+                      const uint2 *__restrict__ cand_ref, ScoreParams prm, ResultRec *__restrict__ res_pool,
+                      unsigned int res_cap, SegRec *__restrict__ seg_tap, unsigned int seg_tap_cap,
+                      BatchCounters *ctr) {
+  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, QW = NW + 4;
+  __shared__ uint32_t s_tlo[NW], s_thi[NW], s_qlo[QW], s_qhi[QW];
+  __shared__ uint2 s_segq[SX_SEGQ_CAP];
+  __shared__ unsigned int s_nseg;
+
+  const int tid = threadIdx.x;
+  const SpDesc sp = sps[blockIdx.x];
+  const uint2 cref = cand_ref[blockIdx.x];
+  const int ncand = (int)cref.y;
+  if (ncand == 0 || cref.x == 0xffffffffu) return;
+  const SlotMeta tm = ws.meta[sp.t_slot], qm = ws.meta[sp.q_slot];
+  if ((tm.flags | qm.flags) & SLOT_NONACGT) return;  // handled by the generic kernel
+  const int tlen = tm.len, qlen = qm.len;
+
+  {
+    const uint32_t *tp = ws.planes + (size_t)sp.t_slot * 2 * NW;
+    const uint32_t *qp = ws.planes + (size_t)sp.q_slot * 2 * NW;
+    for (int i = tid; i < NW; i += NT) {
+      s_tlo[i] = tp[i];
+      s_thi[i] = tp[NW + i];
+    }
+    for (int i = tid; i < QW; i += NT) {
+      const bool in = (i >= 1 && i <= NW);
+      s_qlo[i] = in ? qp[i - 1] : 0u;
+      s_qhi[i] = in ? qp[NW + i - 1] : 0u;
+    }
+    if (tid == 0) s_nseg = 0;
+  }
+  __syncthreads();
+  FastPlanes P;
+  P.tlo = s_tlo;
+  P.thi = s_thi;
+  P.qlo = s_qlo;
+  P.qhi = s_qhi;
+
+  unsigned long long my_segments = 0;
+  for (int c0 = 0; c0 < ncand; c0 += NT) {
+    const int c = c0 + tid;
+    if (c < ncand) {
+      const int shift = (int)cand_pool[cref.x + c] - H;  // pos = idx - N/2 (CrossCorr.cc:600-602)
+      const int i0 = shift < 0 ? -shift : 0;
+      int i_end = qlen - shift;  // first i with j >= qlen
+      if (tlen - 1 < i_end) i_end = tlen - 1;  // the last target base is never scored
+      if (i_end - i0 > 46) {
+        const int eval0 = i0 + 46;  // first position whose window is evaluated (n > 45)
+        uint32_t m_prev = 0;
+        uint32_t s1p[2] = {0, 0}, s1pp[2] = {0, 0};
+        uint32_t s2p[3] = {0, 0, 0}, s2pp[3] = {0, 0, 0};
+        uint32_t s3p[4] = {0, 0, 0, 0};
+        uint32_t s4p[5] = {0, 0, 0, 0, 0};
+        int open = -1;
+        const int w_last = (i_end - 1) >> 5;
+#pragma unroll 1
+        for (int w = i0 >> 5; w <= w_last; w++) {
+          const int wb = w * 32;
+          uint32_t tg, qg;
+          const uint32_t m = match_word(P, w, shift, range_mask(i0 - wb, i_end - wb), tg, qg);
+          // window 2
+          const uint32_t m1 = __funnelshift_l(m_prev, m, 1);
+          uint32_t s1[2];
+          s1[0] = m ^ m1;
+          s1[1] = m & m1;
+          // window 4 = s1 + s1 delayed by 2
+          uint32_t a0 = __funnelshift_l(s1p[0], s1[0], 2), a1 = __funnelshift_l(s1p[1], s1[1], 2);
+          uint32_t s2[3], cy;
+          s2[0] = s1[0] ^ a0;
+          cy = s1[0] & a0;
+          s2[1] = s1[1] ^ a1 ^ cy;
+          s2[2] = (s1[1] & a1) | (cy & (s1[1] ^ a1));
+          // window 8 = s2 + s2 delayed by 4
+          uint32_t s3[4];
+          {
+            const uint32_t b0 = __funnelshift_l(s2p[0], s2[0], 4), b1 = __funnelshift_l(s2p[1], s2[1], 4),
+                           b2 = __funnelshift_l(s2p[2], s2[2], 4);
+            s3[0] = s2[0] ^ b0;
+            cy = s2[0] & b0;
+            s3[1] = s2[1] ^ b1 ^ cy;
+            cy = (s2[1] & b1) | (cy & (s2[1] ^ b1));
+            s3[2] = s2[2] ^ b2 ^ cy;
+            s3[3] = (s2[2] & b2) | (cy & (s2[2] ^ b2));
+          }
+          // window 16 = s3 + s3 delayed by 8
+          uint32_t s4[5];
+          {
+            cy = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const uint32_t b = __funnelshift_l(s3p[k], s3[k], 8);
+              s4[k] = s3[k] ^ b ^ cy;
+              cy = (s3[k] & b) | (cy & (s3[k] ^ b));
+            }
+            s4[4] = cy;
+          }
+          // window 32 = s4 + s4 delayed by 16
+          uint32_t s5[6];
+          {
+            cy = 0;
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+              const uint32_t b = __funnelshift_l(s4p[k], s4[k], 16);
+              s5[k] = s4[k] ^ b ^ cy;
+              cy = (s4[k] & b) | (cy & (s4[k] ^ b));
+            }
+            s5[5] = cy;
+          }
+          // tail of the window: positions 32..39 (s3 one word back), 40..43 (s2 delayed 40), 44..45 (s1 delayed 44)
+          const uint32_t e2_0 = __funnelshift_l(s2pp[0], s2p[0], 8), e2_1 = __funnelshift_l(s2pp[1], s2p[1], 8),
+                         e2_2 = __funnelshift_l(s2pp[2], s2p[2], 8);
+          const uint32_t e1_0 = __funnelshift_l(s1pp[0], s1p[0], 12), e1_1 = __funnelshift_l(s1pp[1], s1p[1], 12);
+          uint32_t u[3];  // e2 + e1  (<= 6)
+          u[0] = e2_0 ^ e1_0;
+          cy = e2_0 & e1_0;
+          u[1] = e2_1 ^ e1_1 ^ cy;
+          cy = (e2_1 & e1_1) | (cy & (e2_1 ^ e1_1));
+          u[2] = e2_2 ^ cy;  // cannot carry out: max 6
+          uint32_t v[4];  // s3p + u  (<= 14)
+          v[0] = s3p[0] ^ u[0];
+          cy = s3p[0] & u[0];
+          v[1] = s3p[1] ^ u[1] ^ cy;
+          cy = (s3p[1] & u[1]) | (cy & (s3p[1] ^ u[1]));
+          v[2] = s3p[2] ^ u[2] ^ cy;
+          cy = (s3p[2] & u[2]) | (cy & (s3p[2] ^ u[2]));
+          v[3] = s3p[3] ^ cy;  // max 14: no carry out
+          uint32_t cnt[6];  // s5 + v (<= 46)
+          cy = 0;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            cnt[k] = s5[k] ^ v[k] ^ cy;
+            cy = (s5[k] & v[k]) | (cy & (s5[k] ^ v[k]));
+          }
+          cnt[4] = s5[4] ^ cy;
+          cy = s5[4] & cy;
+          cnt[5] = s5[5] ^ cy;
+          // count >= 19  (19 = 0b010011)
+          uint32_t pass = cnt[5] | (cnt[4] & (cnt[3] | cnt[2] | (cnt[1] & cnt[0])));
+          pass &= range_mask(eval0 - wb, i_end - wb);
+
+          if (open >= 0 || pass != 0u) {
+            int b = 0;
+            while (b < 32) {
+              if (open < 0) {
+                const uint32_t r = pass & (0xffffffffu << b);
+                if (!r) break;
+                const int f = __ffs(r) - 1;
+                open = wb + f - 45;  // lastStart = i - m_minLen (CrossCorr.cc:709-710)
+                b = f + 1;
+              } else {
+                const uint32_t r = ~pass & (0xffffffffu << b);
+                if (!r) break;
+                const int z = __ffs(r) - 1;
+                const int seg_len = wb + z - open;
+                my_segments++;
+                tap_segment(blockIdx.x, open, shift, seg_len, seg_tap, seg_tap_cap, ctr);
+                const unsigned int slot = atomicAdd(&s_nseg, 1u);
+                if (slot < SX_SEGQ_CAP) {
+                  s_segq[slot] = make_uint2((uint32_t)open | ((uint32_t)seg_len << 16), (uint32_t)shift);
+                } else {  // queue full: score in place (rare, never dropped)
+                  double prob, ident;
+                  if (score_fast(P, open, shift, seg_len, prm, prob, ident))
+                    emit_result(sp, open, shift, seg_len, prob, ident, res_pool, res_cap, ctr);
+                }
+                open = -1;
+                b = z + 1;
+              }
+            }
+          }
+          m_prev = m;
+          s1pp[0] = s1p[0]; s1pp[1] = s1p[1];
+          s1p[0] = s1[0]; s1p[1] = s1[1];
+#pragma unroll
+          for (int k = 0; k < 3; k++) { s2pp[k] = s2p[k]; s2p[k] = s2[k]; }
+#pragma unroll
+          for (int k = 0; k < 4; k++) s3p[k] = s3[k];
+#pragma unroll
+          for (int k = 0; k < 5; k++) s4p[k] = s4[k];
+        }
+        if (open >= 0) {  // run reaches the stop position exactly at a word boundary
+          const int seg_len = i_end - open;
+          my_segments++;
+          tap_segment(blockIdx.x, open, shift, seg_len, seg_tap, seg_tap_cap, ctr);
+          const unsigned int slot = atomicAdd(&s_nseg, 1u);
+          if (slot < SX_SEGQ_CAP) {
+            s_segq[slot] = make_uint2((uint32_t)open | ((uint32_t)seg_len << 16), (uint32_t)shift);
+          } else {
+            double prob, ident;
+            if (score_fast(P, open, shift, seg_len, prm, prob, ident))
+              emit_result(sp, open, shift, seg_len, prob, ident, res_pool, res_cap, ctr);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- score the queued segments of this round, one thread each ---------------------------------
+    const int nq = min((int)s_nseg, SX_SEGQ_CAP);
+    for (int s = tid; s < nq; s += NT) {
+      const uint2 q = s_segq[s];
+      const int start_t = (int)(q.x & 0xffffu), seg_len = (int)(q.x >> 16), shift = (int)q.y;
+      double prob, ident;
+      if (score_fast(P, start_t, shift, seg_len, prm, prob, ident))
+        emit_result(sp, start_t, shift, seg_len, prob, ident, res_pool, res_cap, ctr);
+    }
+    __syncthreads();
+    if (tid == 0) s_nseg = 0;
+    __syncthreads();
+  }
+  // statistics: one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) my_segments += __shfl_xor_sync(0xffffffffu, my_segments, o);
+  if ((tid & 31) == 0 && my_segments) atomicAdd(&ctr->n_segments, my_segments);
+}
+
+// =================================================================================================
+// K3 (generic path, any IUPAC / unknown byte present): the reference's loop verbatim in spirit --
+// running integer score sum over a 46-wide window with the 128x128 score table, one diagonal per
+// thread, then FP64 scoring with sequential summation in the reference's order.
+// =================================================================================================
+__device__ __forceinline__ bool score_generic(const uint8_t *tb, const uint8_t *qb, const uint16_t *fcode,
+                                              int start_t, int shift, int len, const ScoreParams &prm,
+                                              double &prob, double &ident) {
+  double matches = 0., gct = 0., gcq = 0.;
+  for (int i = 0; i < len; i++) {
+    const uint32_t fa = fcode[tb[start_t + i]], fb = fcode[qb[start_t + shift + i]];
+    // DNA_Equal (DNAVector.cc:390-403): a + c + g + t, left to right
+    double dot = __dmul_rn(frac_of(fa, 0), frac_of(fb, 0));
+    dot = __dadd_rn(dot, __dmul_rn(frac_of(fa, 1), frac_of(fb, 1)));
+    dot = __dadd_rn(dot, __dmul_rn(frac_of(fa, 2), frac_of(fb, 2)));
+    dot = __dadd_rn(dot, __dmul_rn(frac_of(fa, 3), frac_of(fb, 3)));
+    matches = __dadd_rn(matches, dot);
+    gct = __dadd_rn(gct, __dadd_rn(frac_of(fa, 1), frac_of(fa, 2)));
+    gcq = __dadd_rn(gcq, __dadd_rn(frac_of(fb, 1), frac_of(fb, 2)));
+  }
+  return score_counts(matches, gct, gcq, len, prm, prob, ident);
+}
+
+template <int LOG2N, int NT>
+__global__ void __launch_bounds__(NT)
+    scan_score_generic_kernel(const SpDesc *__restrict__ sps, Slots ws, const uint16_t *__restrict__ cand_pool,
+                              const uint2 *__restrict__ cand_ref, ScoreParams prm,
+                              ResultRec *__restrict__ res_pool, unsigned int res_cap,
+                              SegRec *__restrict__ seg_tap, unsigned int seg_tap_cap, BatchCounters *ctr) {
+  constexpr int N = 1 << LOG2N, H = N / 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint8_t *s_t = smem_raw;              // N
+  uint8_t *s_q = s_t + N;               // N
+  uint8_t *s_score = s_q + N;           // 128*128
+  uint16_t *s_fcode = reinterpret_cast<uint16_t *>(s_score + 128 * 128);  // 128
+  uint2 *s_segq = reinterpret_cast<uint2 *>(s_fcode + 128);               // SX_SEGQ_CAP
+  __shared__ unsigned int s_nseg;
+
+  const int tid = threadIdx.x;
+  const SpDesc sp = sps[blockIdx.x];
+  const uint2 cref = cand_ref[blockIdx.x];
+  const int ncand = (int)cref.y;
+  if (ncand == 0 || cref.x == 0xffffffffu) return;
+  const SlotMeta tm = ws.meta[sp.t_slot], qm = ws.meta[sp.q_slot];
+  if (!((tm.flags | qm.flags) & SLOT_NONACGT)) return;  // handled by the bit-parallel kernel
+  const int tlen = tm.len, qlen = qm.len;
+  {
+    const uint4 *tp = reinterpret_cast<const uint4 *>(ws.bytes + (size_t)sp.t_slot * N);
+    const uint4 *qp = reinterpret_cast<const uint4 *>(ws.bytes + (size_t)sp.q_slot * N);
+    const uint4 *sc = reinterpret_cast<const uint4 *>(g_score);
+    for (int i = tid; i < N / 16; i += NT) {
+      reinterpret_cast<uint4 *>(s_t)[i] = tp[i];
+      reinterpret_cast<uint4 *>(s_q)[i] = qp[i];
+    }
+    for (int i = tid; i < 128 * 128 / 16; i += NT) reinterpret_cast<uint4 *>(s_score)[i] = sc[i];
+    if (tid < 128) s_fcode[tid] = c_fcode[tid];
+    if (tid == 0) s_nseg = 0;
+  }
+  __syncthreads();
+
+  unsigned long long my_segments = 0;
+  for (int c0 = 0; c0 < ncand; c0 += NT) {
+    const int c = c0 + tid;
+    if (c < ncand) {
+      const int shift = (int)cand_pool[cref.x + c] - H;
+      const int i0 = shift < 0 ? -shift : 0;
+      int i_end = qlen - shift;
+      if (tlen - 1 < i_end) i_end = tlen - 1;
+      int sum = 0, open = -1;
+      auto close_segment = [&](int i) {
+        const int seg_len = i - open;
+        my_segments++;
+        tap_segment(blockIdx.x, open, shift, seg_len, seg_tap, seg_tap_cap, ctr);
+        const unsigned int slot = atomicAdd(&s_nseg, 1u);
+        if (slot < SX_SEGQ_CAP) {
+          s_segq[slot] = make_uint2((uint32_t)open | ((uint32_t)seg_len << 16), (uint32_t)shift);
+        } else {
+          double prob, ident;
+          if (score_generic(s_t, s_q, s_fcode, open, shift, seg_len, prm, prob, ident))
+            emit_result(sp, open, shift, seg_len, prob, ident, res_pool, res_cap, ctr);
+        }
+        open = -1;
+      };
+      for (int i = i0; i < i_end; i++) {
+        sum += s_score[s_t[i] * 128 + s_q[i + shift]];
+        if (i - i0 > 45) {
+          sum -= s_score[s_t[i - 46] * 128 + s_q[i - 46 + shift]];
+          if (sum > 1889) {  // (int)(45 * 0.42 * 100) evaluates to 1889 in IEEE double (CrossCorr.cc:675)
+            if (open < 0) open = i - 45;
+          } else if (open >= 0) {
+            close_segment(i);
+          }
+        }
+      }
+      if (open >= 0 && i_end > i0) close_segment(i_end);
+    }
+    __syncthreads();
+    const int nq = min((int)s_nseg, SX_SEGQ_CAP);
+    for (int s = tid; s < nq; s += NT) {
+      const uint2 q = s_segq[s];
+      const int start_t = (int)(q.x & 0xffffu), seg_len = (int)(q.x >> 16), shift = (int)q.y;
+      double prob, ident;
+      if (score_generic(s_t, s_q, s_fcode, start_t, shift, seg_len, prm, prob, ident))
+        emit_result(sp, start_t, shift, seg_len, prob, ident, res_pool, res_cap, ctr);
+    }
+    __syncthreads();
+    if (tid == 0) s_nseg = 0;
+    __syncthreads();
+  }
+  for (int o = 16; o > 0; o >>= 1) my_segments += __shfl_xor_sync(0xffffffffu, my_segments, o);
+  if ((tid & 31) == 0 && my_segments) atomicAdd(&ctr->n_segments, my_segments);
+}
+
+// =================================================================================================
+// Launchers
+// =================================================================================================
+template <int LOG2N>
+struct Cfg {
+  static constexpr int NT = (LOG2N >= 14) ? 512 : 256;
+};
+
+template <int LOG2N>
+static cudaError_t encode_launch(const SigDesc *sigs, int nsig, Slots ws, float *tap, cudaStream_t st) {
+  constexpr int N = 1 << LOG2N, NT = Cfg<LOG2N>::NT;
+  const size_t smem = (size_t)N * 8 + N + 512 * 4 + 128 * 2;
+  auto k = encode_fft_kernel<LOG2N, NT>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<nsig, NT, smem, st>>>(sigs, ws, tap);
+  return cudaGetLastError();
+}
+
+template <int LOG2N>
+static cudaError_t xcorr_launch(const SpDesc *sps, int nsp, Slots ws, double cutoff, double cutoff_fast,
+                                uint16_t *cand_pool, unsigned int pool_cap, uint2 *cand_ref,
+                                BatchCounters *ctr, float *xc_tap, cudaStream_t st) {
+  constexpr int N = 1 << LOG2N, NT = Cfg<LOG2N>::NT;
+  const size_t smem = (size_t)N * 8 + (N / 32) * 4 * 2;
+  auto k = xcorr_findtop_kernel<LOG2N, NT>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<nsp, NT, smem, st>>>(sps, ws, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
+  return cudaGetLastError();
+}
+
+template <int LOG2N>
+static cudaError_t scan_launch(const SpDesc *sps, int nsp, Slots ws, const uint16_t *cand_pool,
+                               const uint2 *cand_ref, ScoreParams prm, ResultRec *res_pool, unsigned int res_cap,
+                               SegRec *seg_tap, unsigned int seg_tap_cap, BatchCounters *ctr, cudaStream_t st) {
+  constexpr int N = 1 << LOG2N, NT = 256;
+  scan_score_kernel<LOG2N, NT><<<nsp, NT, 0, st>>>(sps, ws, cand_pool, cand_ref, prm, res_pool, res_cap, seg_tap,
+                                                   seg_tap_cap, ctr);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const size_t smem = (size_t)2 * N + 128 * 128 + 128 * 2 + (size_t)SX_SEGQ_CAP * 8;
+  auto k = scan_score_generic_kernel<LOG2N, NT>;
+  e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<nsp, NT, smem, st>>>(sps, ws, cand_pool, cand_ref, prm, res_pool, res_cap, seg_tap, seg_tap_cap, ctr);
+  return cudaGetLastError();
+}
+
+#define SX_DISPATCH(log2n, CALL)       \
+  switch (log2n) {                     \
+    case 11: return CALL(11);          \
+    case 12: return CALL(12);          \
+    case 13: return CALL(13);          \
+    case 14: return CALL(14);          \
+    default: return cudaErrorInvalidValue; \
+  }
+
+cudaError_t launch_encode_fft(int log2n, const SigDesc *sigs, int nsig, Slots ws, float *tap5n,
+                              cudaStream_t stream) {
+  if (nsig <= 0) return cudaSuccess;
+#define CALL(L) encode_launch<L>(sigs, nsig, ws, tap5n, stream)
+  SX_DISPATCH(log2n, CALL)
+#undef CALL
+}
+
+cudaError_t launch_xcorr_findtop(int log2n, const SpDesc *sps, int nsp, Slots ws, double cutoff,
+                                 double cutoff_fast, uint16_t *cand_pool, unsigned int pool_cap,
+                                 uint2 *cand_ref, BatchCounters *ctr, float *xc_tap, cudaStream_t stream) {
+  if (nsp <= 0) return cudaSuccess;
+#define CALL(L) xcorr_launch<L>(sps, nsp, ws, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, xc_tap, stream)
+  SX_DISPATCH(log2n, CALL)
+#undef CALL
+}
+
+cudaError_t launch_scan_score(int log2n, const SpDesc *sps, int nsp, Slots ws, const uint16_t *cand_pool,
+                              const uint2 *cand_ref, ScoreParams prm, ResultRec *res_pool,
+                              unsigned int res_cap, SegRec *seg_tap, unsigned int seg_tap_cap,
+                              BatchCounters *ctr, cudaStream_t stream) {
+  if (nsp <= 0) return cudaSuccess;
+#define CALL(L) scan_launch<L>(sps, nsp, ws, cand_pool, cand_ref, prm, res_pool, res_cap, seg_tap, seg_tap_cap, ctr, stream)
+  SX_DISPATCH(log2n, CALL)
+#undef CALL
+}
+
+}  // namespace sx

@@ -1,0 +1,91 @@
+// Device-side data layout and kernel launchers of libsatsuma_b200 (internal header).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sx {
+
+// ---- HBM layout -------------------------------------------------------------------------------
+// A "signal slot" holds everything later kernels need about one chunk in one orientation:
+//   spec   [slot][2][N] float2 : spectra of (A + iC) and (G + iT), scrambled (DIF) bin order
+//   planes [slot][2][N/32] u32 : 2-bit base codes as two bit-planes (lo, hi); A=0 C=1 G=2 T=3
+//   bytes  [slot][N] u8        : the oriented bases (only the first len are meaningful)
+//   meta   [slot]              : length, flags, the three "quirk" spectrum values
+struct SlotMeta {
+  int32_t len;
+  int32_t flags;  // bit0: contains a byte other than A,C,G,T
+  float q_re, q_im, q_nyq;  // sum over channels of the target spectrum at bins H-1 (complex) and H (real)
+  int32_t pad[3];
+};
+enum { SLOT_NONACGT = 1 };
+
+struct Slots {
+  float2 *spec;
+  uint32_t *planes;
+  uint8_t *bytes;
+  SlotMeta *meta;
+};
+
+struct SigDesc {  // one chunk signal to encode + transform
+  const uint8_t *src;  // chunk bases, forward orientation, device memory
+  int32_t len;
+  int32_t strand;  // 1: reverse-complement while loading
+  int32_t slot;
+  int32_t pad;
+};
+
+struct SpDesc {  // one strand-pair = target slot x query slot
+  int32_t t_slot, q_slot;
+  int32_t pair;   // chunk-pair index inside the batch
+  int32_t flags;  // bit0: reverse strand, bit1: fast cutoff
+};
+enum { SP_REVERSE = 1, SP_FAST = 2 };
+
+struct ResultRec {  // one kept match, chunk-local coordinates
+  int32_t pair, strand;
+  int32_t start_t, start_q, len, shift;
+  double prob, ident;
+};
+
+struct SegRec {  // raw segment (tap only)
+  int32_t sp, start_t, shift, len;
+};
+
+struct ScoreParams {
+  double target_total, min_prob, table_value;
+  const double *table;  // 512 x 2048 or nullptr
+  int32_t min_len;
+  int32_t use_table;
+};
+
+struct BatchCounters {  // device-side, zeroed per batch
+  unsigned int cand_used;     // candidate pool entries reserved
+  unsigned int res_used;      // result records reserved
+  unsigned int seg_tap_used;  // tap records reserved
+  unsigned int status;        // bit0: candidate pool overflow, bit1: result pool overflow, bit2: tap overflow
+  unsigned long long n_candidates, n_segments, n_kept;
+};
+enum { ST_CAND_OVERFLOW = 1, ST_RES_OVERFLOW = 2, ST_TAP_OVERFLOW = 4 };
+
+// ---- launchers (sx_kernels.cu); all asynchronous on `stream`, return cudaGetLastError() --------
+cudaError_t upload_tables();  // constant/global lookup tables, once per device
+
+bool log2n_supported(int log2n);
+size_t slot_spec_elems(int log2n);  // float2 elements per slot
+
+cudaError_t launch_encode_fft(int log2n, const SigDesc *sigs, int nsig, Slots ws, float *tap5n,
+                              cudaStream_t stream);
+cudaError_t launch_xcorr_findtop(int log2n, const SpDesc *sps, int nsp, Slots ws, double cutoff,
+                                 double cutoff_fast, uint16_t *cand_pool, unsigned int pool_cap,
+                                 uint2 *cand_ref, BatchCounters *ctr, float *xc_tap, cudaStream_t stream);
+cudaError_t launch_scan_score(int log2n, const SpDesc *sps, int nsp, Slots ws, const uint16_t *cand_pool,
+                              const uint2 *cand_ref, ScoreParams prm, ResultRec *res_pool,
+                              unsigned int res_cap, SegRec *seg_tap, unsigned int seg_tap_cap,
+                              BatchCounters *ctr, cudaStream_t stream);
+
+// host copies of the lookup tables (also used by the host-side ProbTable builder)
+const double *host_frac_table();    // [128][4]
+const uint8_t *host_comp_table();   // [128]
+const uint8_t *host_score_table();  // [128][128]
+
+}  // namespace sx
