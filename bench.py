@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Benchmark of the chunk-pair cross-correlation hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path
+
+One "step" = one pass of the whole hot path (encode -> FFT -> product/inverse -> FindTop ->
+diagonal scan -> scoring -> match records) over the workload: `--pairs` independent random
+4096x4096 chunk pairs per GPU with one planted homologous segment each (BASELINE.json configs[1];
+default 1,048,576 pairs).  Under torchrun every rank owns its own shard (weak scaling, no
+collective on the data path); timing is CUDA events on the library's stream, max over ranks.
+
+`value`  : device-resident -- chunk bases already in HBM, spectra recomputed every step.
+`e2e`    : through the C ABI with HOST (pinned) buffers: sx_set_targets + sx_set_queries (H2D of all
+           bases) + sx_align_pairs (records back on the host) inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "chunk_pair_xcorrs_per_sec"
+UNIT = "chunk-pairs/s"
+CHUNK = 4096
+FFT_N = 8192
+# Algorithmic work per chunk pair (SURVEY 8d / DESIGN.md): real N-point FFT = 2.5 N log2 N flop.
+FLOP_FWD_PER_SIGNAL = 4 * 2.5 * FFT_N * 13            # 4 channels
+FLOP_XCORR_PER_STRAND = 2.5 * FFT_N * 13 + 4 * 4097 * 8  # one inverse + spectral MAC over 4 channels
+SPECTRA_BYTES_PER_SIGNAL = 2 * FFT_N * 8               # two packed complex spectra, fp32
+BASE_CMP_PER_PAIR = 1.75e6                             # diagonal-scan base comparisons (measured mean)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured", d
+        except Exception:
+            pass
+    return 6650.0, "fallback", {}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        busy = [s for s, p in zip(sm, power) if p > 250.0] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_workload(n_pairs: int, seed: int, pinned: bool):
+    """-> (T, Q) uint8 [n, 4096] ASCII arrays (numpy views of pinned torch tensors when pinned)."""
+    from satsuma2_b200 import synth
+
+    keep = None
+    if pinned:
+        import torch
+
+        tt = torch.empty((n_pairs, CHUNK), dtype=torch.uint8, pin_memory=True)
+        tq = torch.empty((n_pairs, CHUNK), dtype=torch.uint8, pin_memory=True)
+        T, Q = tt.numpy(), tq.numpy()
+        keep = (tt, tq)
+    else:
+        T = np.empty((n_pairs, CHUNK), dtype=np.uint8)
+        Q = np.empty((n_pairs, CHUNK), dtype=np.uint8)
+    synth.random_pairs(n_pairs, CHUNK, seed=seed, out_t=T, out_q=Q)
+    return T, Q, keep
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(T, Q, n_sample: int, threads: int):
+    """Times the reference's own CPU implementation (oracle/_ref, unmodified Satsuma2 compiled from
+    source) on the first n_sample pairs; falls back to the C port (oracle/) when it is not built."""
+    import oracle
+
+    n_sample = min(n_sample, T.shape[0])
+    total = float(T.shape[0]) * CHUNK
+    if oracle.have_reference():
+        R = oracle.Reference()
+        R.configure()
+        tl = [(T[i].tobytes(), 0, i, CHUNK) for i in range(n_sample)]
+        ql = [(Q[i].tobytes(), 0, i, CHUNK) for i in range(n_sample)]
+        R.set_chunks(True, tl, [CHUNK] * n_sample)
+        R.set_chunks(False, ql, [CHUNK] * n_sample)
+        R.lib.ref_set_target_total(total)
+        tp = np.array([[i, i, i, i, 0] for i in range(n_sample)], dtype=np.int32)
+        _, secs, nrec = R.align_pairs_mt(tp, threads)
+        return n_sample / secs, "reference", secs, int(nrec)
+    O = oracle.Oracle()
+    tl = [(T[i].tobytes(), 0, i, CHUNK) for i in range(n_sample)]
+    ql = [(Q[i].tobytes(), 0, i, CHUNK) for i in range(n_sample)]
+    params = O.make_params(target_total=total)
+    pairs = np.stack([np.arange(n_sample), np.arange(n_sample)], axis=1)
+    t0 = time.perf_counter()
+    rec = O.align_pairs(params, tl, ql, pairs, threads=threads)
+    secs = time.perf_counter() - t0
+    return n_sample / secs, "port", secs, len(rec)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    # each step: a bounded sample (~3 s of all-core CPU work at ~36 pairs/s/thread)
+    n_step = max(16, min(args.pairs, args.ref_pairs_per_core * cores))
+    T, Q, _ = make_workload(n_step, seed=1000 + 0, pinned=False)
+    times, kind, nrec = [], "reference", 0
+    for it in range(args.warmup + args.steps):
+        rate, kind, secs, nrec = cpu_reference_rate(T, Q, n_step, cores)
+        if it >= args.warmup:
+            times.append(secs)
+    ms = 1e3 * sum(times) / max(len(times), 1)
+    value = n_step / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: random 4096x4096 chunk pairs, one planted 60-500 bp segment at 70-95% "
+                               "identity per pair (bounded sample per step)", "pairs_per_step": n_step, "chunk": CHUNK,
+                   "fft_n": FFT_N, "cutoff": 1.8, "min_prob": 0.99},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{n_step} pairs per step through HomologyByXCorr::align_target on {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "records_per_step": nrec,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=int(os.environ.get("SX_BENCH_PAIRS", 1 << 20)),
+                    help="chunk pairs per GPU per step (configs[1] = 1M)")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("SX_BENCH_BATCH", 16384)))
+    ap.add_argument("--cpu-sample-per-core", type=int, default=400)
+    ap.add_argument("--ref-pairs-per-core", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3  # timing hygiene: at least 3 warm-up steps
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+
+    import satsuma2_b200 as sx
+    from satsuma2_b200 import build as sxbuild
+    from satsuma2_b200.dist import Group, shard_seed
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    sxbuild.build()
+    rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    grp = Group("nccl", dev)
+    n = args.pairs
+
+    T, Q, keep = make_workload(n, seed=shard_seed(1, rank), pinned=True)
+    cs_t, cs_q = sx.ChunkSet.independent(T), sx.ChunkSet.independent(Q)
+    pairs = np.ascontiguousarray(np.stack([np.arange(n), np.arange(n)], axis=1), dtype=np.int32)
+
+    # spectra are never kept across steps (cache disabled): every step redoes the whole path
+    eng = sx.XCorrEngine(device=local_rank, target_total=float(n) * CHUNK, max_batch_pairs=args.batch,
+                         spectra_cache_bytes=-1)
+    stream = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
+    t_ptr, q_ptr = T.ctypes.data, Q.ctypes.data
+    h2d_per_step = int(T.nbytes + Q.nbytes)
+
+    def step_device():
+        return eng.align_pairs(pairs, cap_hint=2 * n)
+
+    def step_e2e():
+        eng.set_targets_raw(t_ptr, cs_t)
+        eng.set_queries_raw(q_ptr, cs_q)
+        return eng.align_pairs(pairs, cap_hint=2 * n)
+
+    def timed(fn, steps, warmup, profile):
+        for _ in range(warmup):
+            rec = fn()
+        eng.reset_stats()
+        eng.set_profiling(profile)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        grp.barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0.record(stream)
+        for _ in range(steps):
+            rec = fn()
+        e1.record(stream)
+        e1.synchronize()
+        torch.cuda.synchronize()
+        grp.barrier()
+        clocks = sampler.stop()
+        ms = grp.max(e0.elapsed_time(e1))
+        st = eng.stats()
+        eng.set_profiling(False)
+        return ms, st, clocks, rec
+
+    # ---- device-resident: bases uploaded once, outside the timed region
+    eng.set_targets_raw(t_ptr, cs_t)
+    eng.set_queries_raw(q_ptr, cs_q)
+    ms_dev, st_dev, clocks, rec = timed(step_device, args.steps, args.warmup, True)
+    # ---- end to end: host buffers in, host records out, every step
+    ms_e2e, st_e2e, clocks_e2e, rec_e2e = timed(step_e2e, args.steps, max(1, args.warmup - 2), False)
+
+    total_pairs = grp.sum(float(n)) * args.steps
+    value = total_pairs / (ms_dev / 1e3)
+    e2e_value = total_pairs / (ms_e2e / 1e3)
+    d2h_per_step = int(st_e2e["d2h_bytes"] / max(args.steps, 1))
+
+    # ---- roofline of the dominant kernel (per-kernel CUDA-event time from the library, this run)
+    hbm_peak, peak_kind, peaks = load_peaks()
+    batches = max(st_dev["batches"], 1)
+    kern = {
+        "encode_fft": {"ms": st_dev["ms_encode_fft"], "launches": batches,
+                       "flop": FLOP_FWD_PER_SIGNAL * st_dev["signals"],
+                       "bytes": (SPECTRA_BYTES_PER_SIGNAL + CHUNK) * st_dev["signals"]},
+        "xcorr_findtop": {"ms": st_dev["ms_xcorr"], "launches": batches,
+                          "flop": FLOP_XCORR_PER_STRAND * st_dev["strand_pairs"],
+                          "bytes": 2 * SPECTRA_BYTES_PER_SIGNAL * st_dev["strand_pairs"]},
+        "scan_score": {"ms": st_dev["ms_scan_score"], "launches": 2 * batches, "flop": 0.0,
+                       "bytes": (4 * (FFT_N // 32) * 4) * st_dev["strand_pairs"] + 2 * st_dev["candidates"],
+                       "base_cmp": BASE_CMP_PER_PAIR * st_dev["chunk_pairs"]},
+    }
+    for k, v in kern.items():
+        secs = max(v["ms"], 1e-9) / 1e3
+        v["gbs"] = v["bytes"] / secs / 1e9
+        v["tflops"] = v["flop"] / secs / 1e12
+        v["share"] = v["ms"] / max(st_dev["ms_total"], 1e-9)
+        v["avg_launch_ms"] = v["ms"] / v["launches"]
+    dom = max(kern, key=lambda k: kern[k]["ms"])
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s at the clock seen under load
+    roofline = {
+        "kernel": dom, "bound": "hbm", "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+        "frac": kern[dom]["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_kind,
+        "avg_launch_ms": kern[dom]["avg_launch_ms"], "share_of_step": kern[dom]["share"],
+        "fp32_peak_tflops_at_clock": fp32_peak,
+        "kernels": {k: {"ms": round(v["ms"], 3), "share": round(v["share"], 4), "GB/s": round(v["gbs"], 1),
+                        "hbm_frac": round(v["gbs"] / hbm_peak, 4), "TFLOP/s": round(v["tflops"], 3),
+                        "fp32_frac": round(v["tflops"] / fp32_peak, 4)} for k, v in kern.items()},
+        "scan_base_cmp_per_s": kern["scan_score"]["base_cmp"] / max(kern["scan_score"]["ms"] / 1e3, 1e-9),
+    }
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        ns = min(n, args.cpu_sample_per_core * cores)
+        rate, kind, secs, nrec = cpu_reference_rate(T, Q, ns, cores)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                        "sample": f"first {ns} pairs of the same workload, {secs:.1f} s on {cores} threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: random 4096x4096 chunk pairs, one planted 60-500 bp segment at "
+                                   "70-95% identity per pair, half reverse strand",
+                       "pairs_per_gpu_per_step": n, "chunk": CHUNK, "fft_n": FFT_N, "cutoff": 1.8, "min_prob": 0.99,
+                       "device_batch_pairs": args.batch, "parallelism": f"pairs sharded over {world} GPU(s), no collective",
+                       "l2": f"inputs larger than L2: {h2d_per_step >> 20} MiB of bases and "
+                             f"{(3 * args.batch * SPECTRA_BYTES_PER_SIGNAL) >> 20} MiB of spectra per device batch"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_per_step,
+                    "d2h_bytes_per_step": d2h_per_step, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(st_dev["kernel_launches"]),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "records_per_step": int(len(rec)),
+            "per_pair": {"candidates": st_dev["candidates"] / max(st_dev["chunk_pairs"], 1),
+                         "segments": st_dev["segments"] / max(st_dev["chunk_pairs"], 1),
+                         "matches": st_dev["matches"] / max(st_dev["chunk_pairs"], 1)},
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    grp.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

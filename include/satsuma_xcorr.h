@@ -160,6 +160,9 @@ int sx_tap_segments(sx_ctx *ctx, int32_t target, int32_t query, int32_t strand, 
 int sx_set_profiling(sx_ctx *ctx, int32_t enabled); /* per-kernel CUDA-event timing on/off */
 int sx_get_stats(sx_ctx *ctx, sx_stats *out);
 int sx_reset_stats(sx_ctx *ctx);
+/* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so a caller
+ * can bracket calls with its own CUDA events. */
+int sx_stream(sx_ctx *ctx, void **stream_out);
 /* Host-side ProbTable::Setup (analysis/ProbTable.cc:15-56) with libm: fills 512*2048 doubles. */
 int sx_build_prob_table(double target_total, double *table);
 /* Installs the 512x2048 table used when use_prob_table != 0 (copied to the device). */

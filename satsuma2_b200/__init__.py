@@ -94,6 +94,7 @@ def load_library():
     L.sx_set_profiling.argtypes = [vp, i32]
     L.sx_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.sx_reset_stats.argtypes = [vp]
+    L.sx_stream.argtypes = [vp, C.POINTER(vp)]
     L.sx_build_prob_table.argtypes = [dbl, vp]
     L.sx_set_prob_table.argtypes = [vp, vp]
     if L.sx_abi_version() != ABI_VERSION:
@@ -288,6 +289,12 @@ class XCorrEngine:
     # ---- measurement
     def set_profiling(self, on: bool):
         _check(self._L.sx_set_profiling(self._h, int(on)))
+
+    def stream_handle(self) -> int:
+        """cudaStream_t of this context (wrap with torch.cuda.ExternalStream to record events on it)."""
+        p = C.c_void_p()
+        _check(self._L.sx_stream(self._h, C.byref(p)))
+        return int(p.value or 0)
 
     def stats(self) -> dict:
         s = Stats()

@@ -374,6 +374,11 @@ extern "C" int sx_set_profiling(sx_ctx *c, int32_t enabled) {
   c->profiling = enabled != 0;
   return SX_OK;
 }
+extern "C" int sx_stream(sx_ctx *c, void **out) {
+  if (!c || !out) return fail(SX_ERR_ARG, "null argument");
+  *out = (void *)c->stream;
+  return SX_OK;
+}
 extern "C" int sx_get_stats(sx_ctx *c, sx_stats *out) {
   if (!c || !out) return fail(SX_ERR_ARG, "null argument");
   std::lock_guard<std::mutex> lk(c->mu);
