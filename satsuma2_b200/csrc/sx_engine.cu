@@ -111,6 +111,7 @@ struct sx_ctx {
 
   ChunkStore T, Q;
   double target_total = 0;
+  double z_cut = INFINITY;
 
   // signal slots: [0, n_persist) = cached target spectra (slot == target chunk index),
   // [n_persist, n_persist + n_transient) = per-batch workspace
@@ -128,6 +129,7 @@ struct sx_ctx {
   DevBuf<uint16_t> d_cand_pool;
   DevBuf<ResultRec> d_res;
   DevBuf<SegRec> d_seg_tap;
+  DevBuf<SegRec> d_spill;
   DevBuf<BatchCounters> d_ctr;
   DevBuf<double> d_table;
   DevBuf<float> d_tap;
@@ -229,7 +231,7 @@ extern "C" void sx_destroy(sx_ctx *c) {
   if (c->Q.d_bases) cudaFree(c->Q.d_bases);
   c->spec.release(); c->planes.release(); c->sbytes.release(); c->meta.release();
   c->d_sigs.release(); c->d_sps.release(); c->d_cand_ref.release(); c->d_cand_pool.release();
-  c->d_res.release(); c->d_seg_tap.release(); c->d_ctr.release(); c->d_table.release(); c->d_tap.release();
+  c->d_res.release(); c->d_seg_tap.release(); c->d_spill.release(); c->d_ctr.release(); c->d_table.release(); c->d_tap.release();
   c->h_sigs.release(); c->h_sps.release(); c->h_res.release(); c->h_ctr.release();
   for (int i = 0; i < 5; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -419,6 +421,22 @@ struct TapRequest {
 
 }  // namespace
 
+// Largest-safe early-reject bound for the normalised deviation z (see score_counts): the smallest z
+// with 0.5*(1+erf(z))*T >= 2*(-ln min_prob), found with the host's libm.  For such z the probability
+// is <= min_prob^2, far below min_prob compared with any last-ulp difference between erf/exp
+// implementations, so rejecting without evaluating erf/exp cannot change the emitted set.
+static double compute_z_cut(double min_prob, double target_total) {
+  if (!(min_prob > 0.) || !(min_prob < 1.) || !(target_total > 0.)) return INFINITY;
+  const double need = 2. * -std::log(min_prob);
+  double lo = -40., hi = 10.;
+  if (0.5 * (1. + std::erf(hi)) * target_total < need) return INFINITY;
+  for (int it = 0; it < 200; it++) {
+    const double mid = 0.5 * (lo + hi);
+    if (0.5 * (1. + std::erf(mid)) * target_total >= need) hi = mid; else lo = mid;
+  }
+  return hi + 1e-9;
+}
+
 static ScoreParams score_params(const sx_ctx *c) {
   ScoreParams p;
   p.target_total = c->target_total;
@@ -427,6 +445,7 @@ static ScoreParams score_params(const sx_ctx *c) {
   p.table = c->d_table.p;
   p.min_len = c->cfg.min_len;
   p.use_table = (c->cfg.use_prob_table && c->have_table) ? 1 : 0;
+  p.z_cut = c->z_cut;
   return p;
 }
 
@@ -470,6 +489,7 @@ static int run_batch(sx_ctx *c, Batch &b, std::vector<sx_result> *results, TapRe
   if (c->d_res.n == 0) {
     if ((rc = c->d_res.ensure(std::max<size_t>((size_t)nsp * 8, 1 << 16))) != SX_OK) return rc;
   }
+  if (c->d_spill.n == 0 && (rc = c->d_spill.ensure((size_t)1 << 20)) != SX_OK) return rc;
   if (nsig) memcpy(c->h_sigs.p, b.sigs.data(), sizeof(SigDesc) * nsig);
   if (nsp) memcpy(c->h_sps.p, b.sps.data(), sizeof(SpDesc) * nsp);
   cudaStream_t st = c->stream;
@@ -493,6 +513,7 @@ static int run_batch(sx_ctx *c, Batch &b, std::vector<sx_result> *results, TapRe
 
   const bool prof = c->profiling;
   const Slots ws = c->slots();
+  c->z_cut = c->cfg.use_prob_table ? INFINITY : compute_z_cut(c->cfg.min_prob, c->target_total);
   const ScoreParams prm = score_params(c);
   bool need_encode = nsig > 0, need_xcorr = true;
   unsigned long long n_cand_seen = 0;
@@ -514,8 +535,8 @@ static int run_batch(sx_ctx *c, Batch &b, std::vector<sx_result> *results, TapRe
     if (nsp) {
       CU(launch_scan_score(c->log2n, c->d_sps.p, nsp, ws, c->d_cand_pool.p, c->d_cand_ref.p, prm, c->d_res.p,
                            (unsigned int)std::min<size_t>(c->d_res.n, 0xfffffff0u), d_seg_tap, seg_tap_cap,
-                           c->d_ctr.p, st));
-      c->stats.kernel_launches += 2;
+                           c->d_spill.p, (unsigned int)std::min<size_t>(c->d_spill.n, 0xfffffff0u), c->d_ctr.p, st));
+      c->stats.kernel_launches += 3;
     }
     if (prof) CU(cudaEventRecord(c->ev[3], st));
     CU(cudaMemcpyAsync(c->h_ctr.p, c->d_ctr.p, sizeof(BatchCounters), cudaMemcpyDeviceToHost, st));
@@ -546,6 +567,13 @@ static int run_batch(sx_ctx *c, Batch &b, std::vector<sx_result> *results, TapRe
       c->stats.retries++;
       need_xcorr = false;  // candidates are valid; only the scan is repeated
       // cand_ref/pool untouched, but the counter block is zeroed: K3 does not need cand_used
+      continue;
+    }
+    if (ctr.status & ST_SPILL_OVERFLOW) {
+      const size_t want = std::max<size_t>((size_t)ctr.spill_used + (ctr.spill_used >> 2), c->d_spill.n * 2);
+      if ((rc = c->d_spill.ensure(want)) != SX_OK) return rc;
+      c->stats.retries++;
+      need_xcorr = false;
       continue;
     }
     if (ctr.status & ST_TAP_OVERFLOW) return fail(SX_ERR_CAPACITY, "segment tap overflow (%u records)", ctr.seg_tap_used);

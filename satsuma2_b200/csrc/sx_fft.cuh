@@ -206,7 +206,7 @@ __device__ __forceinline__ void fft_forward(float2 *buf, int tid) {
   __syncthreads();
   fft_pass<N, L2, P::R2, false, NT>(buf, tid);
   __syncthreads();
-  if (P::R3 > 1) {
+  if constexpr (P::R3 > 1) {
     fft_pass<N, L3, (P::R3 > 1 ? P::R3 : 4), false, NT>(buf, tid);
     __syncthreads();
   }
@@ -218,7 +218,7 @@ __device__ __forceinline__ void fft_inverse(float2 *buf, int tid) {
   constexpr int N = 1 << LOG2N;
   using P = Plan<LOG2N>;
   constexpr int L1 = N / P::R0, L2 = L1 / P::R1, L3 = L2 / P::R2;
-  if (P::R3 > 1) {
+  if constexpr (P::R3 > 1) {
     fft_pass<N, L3, (P::R3 > 1 ? P::R3 : 4), true, NT>(buf, tid);
     __syncthreads();
   }

@@ -447,6 +447,12 @@ __device__ __forceinline__ bool score_counts(double matches, double gcT, double 
     const double m = __dmul_rn(p_match, dl);
     const double x = __dmul_rn(dl, ident);
     const double z = __ddiv_rn(__ddiv_rn(__dsub_rn(m, x), s), 1.414213562);
+    // exact early reject: for z > z_cut the host has verified cdf(z)*T >= 2*(-ln min_prob), i.e.
+    // prob <= min_prob^2 < min_prob whatever the last-ulp behaviour of erf/exp (NaN falls through)
+    if (z > prm.z_cut) {
+      prob = 0.;
+      return false;
+    }
     const double cdf = __dmul_rn(0.5, __dadd_rn(1., erf(z)));
     const double expect = __dmul_rn(cdf, prm.target_total);
     prob = exp(-expect);
@@ -498,265 +504,8 @@ __device__ __forceinline__ uint32_t range_mask(int lo, int hi) {  // bits [lo, h
   return upper & ~lower;
 }
 
-// =================================================================================================
-// K3 (fast path, both chunks pure A/C/G/T): bit-parallel diagonal scan.
-//
-// For A/C/G/T the reference's integer scores are 100 (equal) / 0 (different), so
-// "window sum > 1889" (46-wide window, CrossCorr.cc:675-716; (int)(45*0.42*100) is 1889 in IEEE
-// double, not 1890) is "at least 19 of the last 46 positions match".  Each thread owns one candidate diagonal and walks it 32 positions per step:
-// match bits come from XORing 2-bit base planes (query planes funnel-shifted by the lag), the
-// 46-wide sliding count is built bit-sliced by doubling (windows 2,4,8,16,32 then 32+8+4+2), and
-// the >= 19 test is three logic ops on the 6 count planes.  Run starts/ends give the segments.
-// =================================================================================================
 #define SX_SEGQ_CAP 3072
-
-struct FastPlanes {
-  const uint32_t *tlo, *thi, *qlo, *qhi;  // q planes are padded by one zero word in front
-};
-
-// match bits (masked to [lo,hi) of the word) + GC planes for target word w at lag `shift`
-__device__ __forceinline__ uint32_t match_word(const FastPlanes &P, int w, int shift, uint32_t vmask,
-                                               uint32_t &t_gc, uint32_t &q_gc) {
-  const int qpos = w * 32 + shift + 32;  // >= 1 by construction
-  const int wi = qpos >> 5, sh = qpos & 31;
-  const uint32_t ql = __funnelshift_r(P.qlo[wi], P.qlo[wi + 1], sh);
-  const uint32_t qh = __funnelshift_r(P.qhi[wi], P.qhi[wi + 1], sh);
-  const uint32_t tl = P.tlo[w], th = P.thi[w];
-  t_gc = (tl ^ th) & vmask;
-  q_gc = (ql ^ qh) & vmask;
-  return ~((tl ^ ql) | (th ^ qh)) & vmask;
-}
-
-__device__ __forceinline__ bool score_fast(const FastPlanes &P, int start_t, int shift, int len,
-                                           const ScoreParams &prm, double &prob, double &ident) {
-  int matches = 0, gct = 0, gcq = 0;
-  const int end = start_t + len;
-  for (int w = start_t >> 5; w <= (end - 1) >> 5; w++) {
-    const uint32_t vm = range_mask(start_t - w * 32, end - w * 32);
-    uint32_t tg, qg;
-    const uint32_t m = match_word(P, w, shift, vm, tg, qg);
-    matches += __popc(m);
-    gct += __popc(tg);
-    gcq += __popc(qg);
-  }
-  return score_counts((double)matches, (double)gct, (double)gcq, len, prm, prob, ident);
-}
-
-template <int LOG2N, int NT>
-__global__ void __launch_bounds__(NT)
-    scan_score_kernel(const SpDesc *__restrict__ sps, Slots ws, const uint16_t *__restrict__ cand_pool,
-                      const uint2 *__restrict__ cand_ref, ScoreParams prm, ResultRec *__restrict__ res_pool,
-                      unsigned int res_cap, SegRec *__restrict__ seg_tap, unsigned int seg_tap_cap,
-                      BatchCounters *ctr) {
-  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, QW = NW + 4;
-  __shared__ uint32_t s_tlo[NW], s_thi[NW], s_qlo[QW], s_qhi[QW];
-  __shared__ uint2 s_segq[SX_SEGQ_CAP];
-  __shared__ unsigned int s_nseg;
-
-  const int tid = threadIdx.x;
-  const SpDesc sp = sps[blockIdx.x];
-  const uint2 cref = cand_ref[blockIdx.x];
-  const int ncand = (int)cref.y;
-  if (ncand == 0 || cref.x == 0xffffffffu) return;
-  const SlotMeta tm = ws.meta[sp.t_slot], qm = ws.meta[sp.q_slot];
-  if ((tm.flags | qm.flags) & SLOT_NONACGT) return;  // handled by the generic kernel
-  const int tlen = tm.len, qlen = qm.len;
-
-  {
-    const uint32_t *tp = ws.planes + (size_t)sp.t_slot * 2 * NW;
-    const uint32_t *qp = ws.planes + (size_t)sp.q_slot * 2 * NW;
-    for (int i = tid; i < NW; i += NT) {
-      s_tlo[i] = tp[i];
-      s_thi[i] = tp[NW + i];
-    }
-    for (int i = tid; i < QW; i += NT) {
-      const bool in = (i >= 1 && i <= NW);
-      s_qlo[i] = in ? qp[i - 1] : 0u;
-      s_qhi[i] = in ? qp[NW + i - 1] : 0u;
-    }
-    if (tid == 0) s_nseg = 0;
-  }
-  __syncthreads();
-  FastPlanes P;
-  P.tlo = s_tlo;
-  P.thi = s_thi;
-  P.qlo = s_qlo;
-  P.qhi = s_qhi;
-
-  unsigned long long my_segments = 0;
-  for (int c0 = 0; c0 < ncand; c0 += NT) {
-    const int c = c0 + tid;
-    if (c < ncand) {
-      const int shift = (int)cand_pool[cref.x + c] - H;  // pos = idx - N/2 (CrossCorr.cc:600-602)
-      const int i0 = shift < 0 ? -shift : 0;
-      int i_end = qlen - shift;  // first i with j >= qlen
-      if (tlen - 1 < i_end) i_end = tlen - 1;  // the last target base is never scored
-      if (i_end - i0 > 46) {
-        const int eval0 = i0 + 46;  // first position whose window is evaluated (n > 45)
-        uint32_t m_prev = 0;
-        uint32_t s1p[2] = {0, 0}, s1pp[2] = {0, 0};
-        uint32_t s2p[3] = {0, 0, 0}, s2pp[3] = {0, 0, 0};
-        uint32_t s3p[4] = {0, 0, 0, 0};
-        uint32_t s4p[5] = {0, 0, 0, 0, 0};
-        int open = -1;
-        const int w_last = (i_end - 1) >> 5;
-#pragma unroll 1
-        for (int w = i0 >> 5; w <= w_last; w++) {
-          const int wb = w * 32;
-          uint32_t tg, qg;
-          const uint32_t m = match_word(P, w, shift, range_mask(i0 - wb, i_end - wb), tg, qg);
-          // window 2
-          const uint32_t m1 = __funnelshift_l(m_prev, m, 1);
-          uint32_t s1[2];
-          s1[0] = m ^ m1;
-          s1[1] = m & m1;
-          // window 4 = s1 + s1 delayed by 2
-          uint32_t a0 = __funnelshift_l(s1p[0], s1[0], 2), a1 = __funnelshift_l(s1p[1], s1[1], 2);
-          uint32_t s2[3], cy;
-          s2[0] = s1[0] ^ a0;
-          cy = s1[0] & a0;
-          s2[1] = s1[1] ^ a1 ^ cy;
-          s2[2] = (s1[1] & a1) | (cy & (s1[1] ^ a1));
-          // window 8 = s2 + s2 delayed by 4
-          uint32_t s3[4];
-          {
-            const uint32_t b0 = __funnelshift_l(s2p[0], s2[0], 4), b1 = __funnelshift_l(s2p[1], s2[1], 4),
-                           b2 = __funnelshift_l(s2p[2], s2[2], 4);
-            s3[0] = s2[0] ^ b0;
-            cy = s2[0] & b0;
-            s3[1] = s2[1] ^ b1 ^ cy;
-            cy = (s2[1] & b1) | (cy & (s2[1] ^ b1));
-            s3[2] = s2[2] ^ b2 ^ cy;
-            s3[3] = (s2[2] & b2) | (cy & (s2[2] ^ b2));
-          }
-          // window 16 = s3 + s3 delayed by 8
-          uint32_t s4[5];
-          {
-            cy = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              const uint32_t b = __funnelshift_l(s3p[k], s3[k], 8);
-              s4[k] = s3[k] ^ b ^ cy;
-              cy = (s3[k] & b) | (cy & (s3[k] ^ b));
-            }
-            s4[4] = cy;
-          }
-          // window 32 = s4 + s4 delayed by 16
-          uint32_t s5[6];
-          {
-            cy = 0;
-#pragma unroll
-            for (int k = 0; k < 5; k++) {
-              const uint32_t b = __funnelshift_l(s4p[k], s4[k], 16);
-              s5[k] = s4[k] ^ b ^ cy;
-              cy = (s4[k] & b) | (cy & (s4[k] ^ b));
-            }
-            s5[5] = cy;
-          }
-          // tail of the window: positions 32..39 (s3 one word back), 40..43 (s2 delayed 40), 44..45 (s1 delayed 44)
-          const uint32_t e2_0 = __funnelshift_l(s2pp[0], s2p[0], 8), e2_1 = __funnelshift_l(s2pp[1], s2p[1], 8),
-                         e2_2 = __funnelshift_l(s2pp[2], s2p[2], 8);
-          const uint32_t e1_0 = __funnelshift_l(s1pp[0], s1p[0], 12), e1_1 = __funnelshift_l(s1pp[1], s1p[1], 12);
-          uint32_t u[3];  // e2 + e1  (<= 6)
-          u[0] = e2_0 ^ e1_0;
-          cy = e2_0 & e1_0;
-          u[1] = e2_1 ^ e1_1 ^ cy;
-          cy = (e2_1 & e1_1) | (cy & (e2_1 ^ e1_1));
-          u[2] = e2_2 ^ cy;  // cannot carry out: max 6
-          uint32_t v[4];  // s3p + u  (<= 14)
-          v[0] = s3p[0] ^ u[0];
-          cy = s3p[0] & u[0];
-          v[1] = s3p[1] ^ u[1] ^ cy;
-          cy = (s3p[1] & u[1]) | (cy & (s3p[1] ^ u[1]));
-          v[2] = s3p[2] ^ u[2] ^ cy;
-          cy = (s3p[2] & u[2]) | (cy & (s3p[2] ^ u[2]));
-          v[3] = s3p[3] ^ cy;  // max 14: no carry out
-          uint32_t cnt[6];  // s5 + v (<= 46)
-          cy = 0;
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            cnt[k] = s5[k] ^ v[k] ^ cy;
-            cy = (s5[k] & v[k]) | (cy & (s5[k] ^ v[k]));
-          }
-          cnt[4] = s5[4] ^ cy;
-          cy = s5[4] & cy;
-          cnt[5] = s5[5] ^ cy;
-          // count >= 19  (19 = 0b010011)
-          uint32_t pass = cnt[5] | (cnt[4] & (cnt[3] | cnt[2] | (cnt[1] & cnt[0])));
-          pass &= range_mask(eval0 - wb, i_end - wb);
-
-          if (open >= 0 || pass != 0u) {
-            int b = 0;
-            while (b < 32) {
-              if (open < 0) {
-                const uint32_t r = pass & (0xffffffffu << b);
-                if (!r) break;
-                const int f = __ffs(r) - 1;
-                open = wb + f - 45;  // lastStart = i - m_minLen (CrossCorr.cc:709-710)
-                b = f + 1;
-              } else {
-                const uint32_t r = ~pass & (0xffffffffu << b);
-                if (!r) break;
-                const int z = __ffs(r) - 1;
-                const int seg_len = wb + z - open;
-                my_segments++;
-                tap_segment(blockIdx.x, open, shift, seg_len, seg_tap, seg_tap_cap, ctr);
-                const unsigned int slot = atomicAdd(&s_nseg, 1u);
-                if (slot < SX_SEGQ_CAP) {
-                  s_segq[slot] = make_uint2((uint32_t)open | ((uint32_t)seg_len << 16), (uint32_t)shift);
-                } else {  // queue full: score in place (rare, never dropped)
-                  double prob, ident;
-                  if (score_fast(P, open, shift, seg_len, prm, prob, ident))
-                    emit_result(sp, open, shift, seg_len, prob, ident, res_pool, res_cap, ctr);
-                }
-                open = -1;
-                b = z + 1;
-              }
-            }
-          }
-          m_prev = m;
-          s1pp[0] = s1p[0]; s1pp[1] = s1p[1];
-          s1p[0] = s1[0]; s1p[1] = s1[1];
-#pragma unroll
-          for (int k = 0; k < 3; k++) { s2pp[k] = s2p[k]; s2p[k] = s2[k]; }
-#pragma unroll
-          for (int k = 0; k < 4; k++) s3p[k] = s3[k];
-#pragma unroll
-          for (int k = 0; k < 5; k++) s4p[k] = s4[k];
-        }
-        if (open >= 0) {  // run reaches the stop position exactly at a word boundary
-          const int seg_len = i_end - open;
-          my_segments++;
-          tap_segment(blockIdx.x, open, shift, seg_len, seg_tap, seg_tap_cap, ctr);
-          const unsigned int slot = atomicAdd(&s_nseg, 1u);
-          if (slot < SX_SEGQ_CAP) {
-            s_segq[slot] = make_uint2((uint32_t)open | ((uint32_t)seg_len << 16), (uint32_t)shift);
-          } else {
-            double prob, ident;
-            if (score_fast(P, open, shift, seg_len, prm, prob, ident))
-              emit_result(sp, open, shift, seg_len, prob, ident, res_pool, res_cap, ctr);
-          }
-        }
-      }
-    }
-    __syncthreads();
-    // ---- score the queued segments of this round, one thread each ---------------------------------
-    const int nq = min((int)s_nseg, SX_SEGQ_CAP);
-    for (int s = tid; s < nq; s += NT) {
-      const uint2 q = s_segq[s];
-      const int start_t = (int)(q.x & 0xffffu), seg_len = (int)(q.x >> 16), shift = (int)q.y;
-      double prob, ident;
-      if (score_fast(P, start_t, shift, seg_len, prm, prob, ident))
-        emit_result(sp, start_t, shift, seg_len, prob, ident, res_pool, res_cap, ctr);
-    }
-    __syncthreads();
-    if (tid == 0) s_nseg = 0;
-    __syncthreads();
-  }
-  // statistics: one atomic per warp
-  for (int o = 16; o > 0; o >>= 1) my_segments += __shfl_xor_sync(0xffffffffu, my_segments, o);
-  if ((tid & 31) == 0 && my_segments) atomicAdd(&ctr->n_segments, my_segments);
-}
+#include "sx_scan.cuh"
 
 // =================================================================================================
 // K3 (generic path, any IUPAC / unknown byte present): the reference's loop verbatim in spirit --
@@ -906,11 +655,15 @@ static cudaError_t xcorr_launch(const SpDesc *sps, int nsp, Slots ws, double cut
 template <int LOG2N>
 static cudaError_t scan_launch(const SpDesc *sps, int nsp, Slots ws, const uint16_t *cand_pool,
                                const uint2 *cand_ref, ScoreParams prm, ResultRec *res_pool, unsigned int res_cap,
-                               SegRec *seg_tap, unsigned int seg_tap_cap, BatchCounters *ctr, cudaStream_t st) {
+                               SegRec *seg_tap, unsigned int seg_tap_cap, SegRec *spill, unsigned int spill_cap,
+                               BatchCounters *ctr, cudaStream_t st) {
   constexpr int N = 1 << LOG2N, NT = 256;
-  scan_score_kernel<LOG2N, NT><<<nsp, NT, 0, st>>>(sps, ws, cand_pool, cand_ref, prm, res_pool, res_cap, seg_tap,
-                                                   seg_tap_cap, ctr);
+  scan_score_kernel<LOG2N><<<nsp, SX_SCAN_NT, 0, st>>>(sps, ws, cand_pool, cand_ref, prm, res_pool, res_cap, seg_tap,
+                                                       seg_tap_cap, spill, spill_cap, ctr);
   cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  score_spill_kernel<LOG2N><<<148, 128, 0, st>>>(sps, ws, spill, prm, res_pool, res_cap, spill_cap, ctr);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const size_t smem = (size_t)2 * N + 128 * 128 + 128 * 2 + (size_t)SX_SEGQ_CAP * 8;
   auto k = scan_score_generic_kernel<LOG2N, NT>;
@@ -948,10 +701,10 @@ cudaError_t launch_xcorr_findtop(int log2n, const SpDesc *sps, int nsp, Slots ws
 
 cudaError_t launch_scan_score(int log2n, const SpDesc *sps, int nsp, Slots ws, const uint16_t *cand_pool,
                               const uint2 *cand_ref, ScoreParams prm, ResultRec *res_pool,
-                              unsigned int res_cap, SegRec *seg_tap, unsigned int seg_tap_cap,
-                              BatchCounters *ctr, cudaStream_t stream) {
+                              unsigned int res_cap, SegRec *seg_tap, unsigned int seg_tap_cap, SegRec *spill,
+                              unsigned int spill_cap, BatchCounters *ctr, cudaStream_t stream) {
   if (nsp <= 0) return cudaSuccess;
-#define CALL(L) scan_launch<L>(sps, nsp, ws, cand_pool, cand_ref, prm, res_pool, res_cap, seg_tap, seg_tap_cap, ctr, stream)
+#define CALL(L) scan_launch<L>(sps, nsp, ws, cand_pool, cand_ref, prm, res_pool, res_cap, seg_tap, seg_tap_cap, spill, spill_cap, ctr, stream)
   SX_DISPATCH(log2n, CALL)
 #undef CALL
 }
