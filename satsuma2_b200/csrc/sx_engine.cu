@@ -46,7 +46,7 @@ namespace {
 struct ChunkStore {
   int32_t n = 0;
   uint8_t *d_bases = nullptr;
-  size_t blob_bytes = 0;
+  size_t blob_bytes = 0, cap_bytes = 0;
   std::vector<int64_t> offsets;
   std::vector<int32_t> lens, starts, seq_ids, seq_sizes;
 };
@@ -253,8 +253,11 @@ static int set_store(sx_ctx *c, ChunkStore &S, const char *bases, const int64_t 
     if (seq_ids && (seq_ids[i] < 0 || seq_ids[i] >= n_seqs))
       return fail(SX_ERR_ARG, "%s: chunk %d refers to sequence %d of %d", what, i, seq_ids[i], n_seqs);
   }
-  if (S.d_bases) cudaFree(S.d_bases);
-  S.d_bases = nullptr;
+  if (S.d_bases && S.cap_bytes < blob + 16) {  // keep the device buffer across calls when it is big enough
+    cudaFree(S.d_bases);
+    S.d_bases = nullptr;
+    S.cap_bytes = 0;
+  }
   S.n = n;
   S.blob_bytes = blob;
   S.offsets.assign(offsets, offsets + n);
@@ -263,7 +266,10 @@ static int set_store(sx_ctx *c, ChunkStore &S, const char *bases, const int64_t 
   if (seq_ids) S.seq_ids.assign(seq_ids, seq_ids + n); else S.seq_ids.assign(n, 0);
   if (seq_sizes && n_seqs > 0) S.seq_sizes.assign(seq_sizes, seq_sizes + n_seqs); else S.seq_sizes.assign(1, 0);
   if (blob > 0) {
-    CU(cudaMalloc((void **)&S.d_bases, blob + 16));
+    if (!S.d_bases) {
+      CU(cudaMalloc((void **)&S.d_bases, blob + 16));
+      S.cap_bytes = blob + 16;
+    }
     CU(cudaMemcpyAsync(S.d_bases, bases, blob, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->stats.h2d_bytes += (int64_t)blob;

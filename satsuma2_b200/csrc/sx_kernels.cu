@@ -105,6 +105,12 @@ cudaError_t upload_tables() {
   if ((e = cudaMemcpyToSymbol(c_comp, h_comp, sizeof(h_comp))) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbol(c_base2, h_base2, sizeof(h_base2))) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbol(g_score, h_score, sizeof(h_score))) != cudaSuccess) return e;
+  static float2 h_tw[SX_TW_ENTRIES];
+  for (int t = 0; t < SX_TW_ENTRIES; t++) {
+    const double a = -2.0 * 3.14159265358979323846 * (double)t / (double)(1 << SX_TW_BASE_LOG2);
+    h_tw[t] = make_float2((float)cos(a), (float)sin(a));
+  }
+  if ((e = cudaMemcpyToSymbol(g_twiddle, h_tw, sizeof(h_tw))) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -128,14 +134,16 @@ __device__ __forceinline__ double warp_sum(double v) {
 // K1: encode + forward transform.  One CTA per chunk signal.
 // =================================================================================================
 template <int LOG2N, int NT>
-__global__ void __launch_bounds__(NT) encode_fft_kernel(const SigDesc *__restrict__ sigs, Slots ws,
-                                                        float *__restrict__ tap) {
+__global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
+    encode_fft_kernel(const SigDesc *__restrict__ sigs, Slots ws, float *__restrict__ tap) {
   constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, WIN = N / 512, NWARP = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2 *buf = reinterpret_cast<float2 *>(smem_raw);            // N complex
+  float2 *buf = reinterpret_cast<float2 *>(smem_raw);            // N complex (swizzled slots)
   uint8_t *sb = smem_raw + (size_t)N * sizeof(float2);            // N oriented bases
   float *went = reinterpret_cast<float *>(sb + N);                // 512 window weights
   uint16_t *s_fcode = reinterpret_cast<uint16_t *>(went + 512);   // 128 x u16
+  uint8_t *s_comp = reinterpret_cast<uint8_t *>(s_fcode + 128);   // 128
+  uint8_t *s_base2 = s_comp + 128;                                // 128
   __shared__ double s_red[4][NWARP];
   __shared__ double s_off[4];
   __shared__ int s_flags;
@@ -145,27 +153,37 @@ __global__ void __launch_bounds__(NT) encode_fft_kernel(const SigDesc *__restric
   const int len = sd.len;
   const uint8_t *__restrict__ src = sd.src;
 
-  if (tid < 128) s_fcode[tid] = c_fcode[tid];
+  if (tid < 128) {
+    s_fcode[tid] = c_fcode[tid];
+    s_comp[tid] = c_comp[tid];
+    s_base2[tid] = c_base2[tid];
+  }
   if (tid == 0) s_flags = 0;
+  // ---- 1a. stage the raw chunk in shared memory (the FFT buffer is free until step 3) -------------
+  uint8_t *raw = smem_raw;
+  if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {  // chunk stores are padded by 16 bytes
+    const uint4 *s16 = reinterpret_cast<const uint4 *>(src);
+    for (int i = tid; i < (len + 15) / 16; i += NT) reinterpret_cast<uint4 *>(raw)[i] = __ldg(s16 + i);
+  } else {
+    for (int i = tid; i < len; i += NT) raw[i] = src[i];
+  }
   __syncthreads();
 
-  // ---- 1. load (optionally reverse-complement), sanitise, bit-planes ----------------------------
+  // ---- 1b. orient (reverse-complement), sanitise, 2-bit planes ------------------------------------
   uint32_t *planes = ws.planes + (size_t)sd.slot * 2 * NW;
-  uint8_t *gbytes = ws.bytes + (size_t)sd.slot * N;
   int myflags = 0;
   for (int k0 = warp * 32; k0 < N; k0 += NT) {
     const int k = k0 + lane;
     uint32_t b = 0, code = 4;
     if (k < len) {
-      b = sd.strand ? src[len - 1 - k] : src[k];
+      b = sd.strand ? raw[len - 1 - k] : raw[k];
       if (b >= 128u) b = 0;
-      if (sd.strand) b = c_comp[b];
-      code = c_base2[b];
+      if (sd.strand) b = s_comp[b];
+      code = s_base2[b];
       if (code & 4u) myflags |= SLOT_NONACGT;
       if (code & 8u) myflags |= 2;
     }
     sb[k] = (uint8_t)b;
-    gbytes[k] = (uint8_t)b;
     const uint32_t lo = __ballot_sync(0xffffffffu, (code & 5u) == 1u);  // C or T -> bit0
     const uint32_t hi = __ballot_sync(0xffffffffu, (code & 6u) == 2u);  // G or T -> bit1
     if (lane == 0) {
@@ -176,6 +194,10 @@ __global__ void __launch_bounds__(NT) encode_fft_kernel(const SigDesc *__restric
   if (myflags) atomicOr(&s_flags, myflags);
   __syncthreads();
   const int flags = s_flags;
+  {  // oriented bases to HBM for the generic scan path and the taps, 16 bytes per thread
+    uint4 *gb = reinterpret_cast<uint4 *>(ws.bytes + (size_t)sd.slot * N);
+    for (int i = tid; i < N / 16; i += NT) gb[i] = reinterpret_cast<const uint4 *>(sb)[i];
+  }
 
   // ---- 2. window sums, entropy weights (ComputeEntropy) and channel means (SeqToPCM) ------------
   double tot[4] = {0., 0., 0., 0.};
@@ -184,10 +206,21 @@ __global__ void __launch_bounds__(NT) encode_fft_kernel(const SigDesc *__restric
     double s4[4] = {0., 0., 0., 0.};
     const int i0 = w * WIN;
     int k = 0;
-    for (int j = i0; j < i0 + WIN && j < len; j++, k++) {
-      const uint32_t fc = s_fcode[sb[j]];
+    if (!(flags & SLOT_NONACGT)) {  // pure A/C/G/T: integer counts are the exact double sums
+      int cnt[4] = {0, 0, 0, 0};
+      for (int j = i0; j < i0 + WIN && j < len; j++, k++) {
+        const uint32_t code = s_base2[sb[j]];
 #pragma unroll
-      for (int c = 0; c < 4; c++) s4[c] = __dadd_rn(s4[c], frac_of(fc, c));
+        for (int c = 0; c < 4; c++) cnt[c] += (code == (uint32_t)c);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; c++) s4[c] = (double)cnt[c];
+    } else {
+      for (int j = i0; j < i0 + WIN && j < len; j++, k++) {
+        const uint32_t fc = s_fcode[sb[j]];
+#pragma unroll
+        for (int c = 0; c < 4; c++) s4[c] = __dadd_rn(s4[c], frac_of(fc, c));
+      }
     }
 #pragma unroll
     for (int c = 0; c < 4; c++) tot[c] += s4[c];
@@ -229,20 +262,30 @@ __global__ void __launch_bounds__(NT) encode_fft_kernel(const SigDesc *__restric
 
   // ---- 3. two complex transforms: (A + iC) then (G + iT) -----------------------------------------
   float acc_re = 0.f, acc_im = 0.f, acc_ny = 0.f;
-  constexpr int PH1 = scrambled_pos<LOG2N>(H - 1), PH = scrambled_pos<LOG2N>(H),
-                PH2 = scrambled_pos<LOG2N>(H + 1);
+  constexpr int PH1 = swz(scrambled_pos<LOG2N>(H - 1)), PH = swz(scrambled_pos<LOG2N>(H)),
+                PH2 = swz(scrambled_pos<LOG2N>(H + 1));
 #pragma unroll 1
   for (int pr = 0; pr < 2; pr++) {
     const double off0 = s_off[2 * pr], off1 = s_off[2 * pr + 1];
+    // sample = (float)(weight * (fraction - mean)); for A/C/G/T the fraction is 1 or 0
+    const double hit0 = __dsub_rn(1.0, off0), miss0 = __dsub_rn(0.0, off0);
+    const double hit1 = __dsub_rn(1.0, off1), miss1 = __dsub_rn(0.0, off1);
+    const bool pure = !(flags & SLOT_NONACGT);
     for (int k = tid; k < N; k += NT) {
       float2 v = make_float2(0.f, 0.f);
       if (k < len) {
-        const uint32_t fc = s_fcode[sb[k]];
         const double e = flat ? 1.0 : (double)went[k / WIN];
-        v.x = __double2float_rn(__dmul_rn(e, __dsub_rn(frac_of(fc, 2 * pr), off0)));
-        v.y = __double2float_rn(__dmul_rn(e, __dsub_rn(frac_of(fc, 2 * pr + 1), off1)));
+        if (pure) {
+          const uint32_t code = s_base2[sb[k]];
+          v.x = __double2float_rn(__dmul_rn(e, code == (uint32_t)(2 * pr) ? hit0 : miss0));
+          v.y = __double2float_rn(__dmul_rn(e, code == (uint32_t)(2 * pr + 1) ? hit1 : miss1));
+        } else {
+          const uint32_t fc = s_fcode[sb[k]];
+          v.x = __double2float_rn(__dmul_rn(e, __dsub_rn(frac_of(fc, 2 * pr), off0)));
+          v.y = __double2float_rn(__dmul_rn(e, __dsub_rn(frac_of(fc, 2 * pr + 1), off1)));
+        }
       }
-      buf[k] = v;
+      buf[swz(k)] = v;
       if (tap != nullptr) {
         float *ts = tap + (size_t)blockIdx.x * 5 * N + (size_t)(1 + 2 * pr) * N;
         ts[k] = v.x;
@@ -251,7 +294,7 @@ __global__ void __launch_bounds__(NT) encode_fft_kernel(const SigDesc *__restric
     }
     __syncthreads();
     fft_forward<LOG2N, NT>(buf, tid);
-    // spectra out (scrambled order), 16-byte stores
+    // spectra out in shared-memory slot order (scrambled bins, swizzled slots), 16-byte stores
     float4 *dst = reinterpret_cast<float4 *>(ws.spec + ((size_t)sd.slot * 2 + pr) * N);
     const float4 *s4p = reinterpret_cast<const float4 *>(buf);
     for (int k = tid; k < N / 2; k += NT) dst[k] = s4p[k];
@@ -321,8 +364,8 @@ __global__ void __launch_bounds__(NT)
   __syncthreads();
   // ---- reference quirk (CrossCorr.cc:480-492): bins H-1 and H keep the TARGET spectrum ------------
   if (tid == 0) {
-    constexpr int PH1 = scrambled_pos<LOG2N>(H - 1), PH = scrambled_pos<LOG2N>(H),
-                  PH2 = scrambled_pos<LOG2N>(H + 1);
+    constexpr int PH1 = swz(scrambled_pos<LOG2N>(H - 1)), PH = swz(scrambled_pos<LOG2N>(H)),
+                  PH2 = swz(scrambled_pos<LOG2N>(H + 1));
     buf[PH1] = make_float2(tm.q_re, tm.q_im);
     buf[PH2] = make_float2(tm.q_re, -tm.q_im);
     buf[PH] = make_float2(tm.q_nyq, 0.f);
@@ -332,7 +375,7 @@ __global__ void __launch_bounds__(NT)
 
   // xc[i] = Re x[(i + H) mod N] / N   (rescale + half rotation, CrossCorr.cc:493-505)
   const float scale = 1.0f / (float)N;
-  auto xc_at = [&](int i) -> float { return buf[(i + H) & (N - 1)].x * scale; };
+  auto xc_at = [&](int i) -> float { return buf[swz((i + H) & (N - 1))].x * scale; };
 
   if (xc_tap != nullptr) {
     float *o = xc_tap + (size_t)blockIdx.x * N;
@@ -631,7 +674,7 @@ struct Cfg {
 template <int LOG2N>
 static cudaError_t encode_launch(const SigDesc *sigs, int nsig, Slots ws, float *tap, cudaStream_t st) {
   constexpr int N = 1 << LOG2N, NT = Cfg<LOG2N>::NT;
-  const size_t smem = (size_t)N * 8 + N + 512 * 4 + 128 * 2;
+  const size_t smem = (size_t)N * 8 + N + 512 * 4 + 128 * 2 + 256;
   auto k = encode_fft_kernel<LOG2N, NT>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
