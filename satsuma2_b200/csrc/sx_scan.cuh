@@ -19,7 +19,7 @@
 #pragma once
 
 #define SX_SCAN_NT 128
-#define SX_WQ_CAP 768  // queued segments per warp
+#define SX_LQ_CAP 40  // queued segments per lane (diagonal); more spill to a global list
 
 struct PlanePtrs {
   const uint32_t *tlo, *thi, *qlo, *qhi;  // each readable up to word NW+1 (zero padded)
@@ -48,7 +48,43 @@ __device__ __forceinline__ bool score_fast(const PlanePtrs &P, int start_t, int 
     gct += __popc((tl ^ th) & vm);
     gcq += __popc((ql ^ qh) & vm);
   }
+  // Cheap exact-by-margin reject in FP32 before the FP64 arithmetic: all inputs are small integers
+  // (exact in float), the float estimate of the normalised deviation z is within ~1e-3 of the FP64
+  // value, and z_cut already carries a factor-2 safety margin in probability, so "estimate > z_cut
+  // + 0.25" can only drop segments whose probability is far below min_prob.  NaN/inf fall through.
+  if (!prm.use_table && len >= prm.min_len) {
+    const float fl = (float)len;
+    const float num = (float)(gcq * gct + (len - gcq) * (len - gct));  // <= 2*len^2 < 2^30, exact enough
+    const float p = num / (2.f * fl * fl);
+    const float zf = (p * fl - (float)matches) * rsqrtf(p * (1.f - p) * fl) * 0.70710678f;
+    if (zf > (float)prm.z_cut + 0.25f) return false;
+  }
   return score_counts((double)matches, (double)gct, (double)gcq, len, prm, prob, ident);
+}
+
+// Appends one finished segment to the calling lane's private queue (slot-major layout: entry r of
+// lane l at [r*32 + l], so simultaneous pushes of different lanes never conflict); a full queue spills
+// to the global list.  Only start and length are stored: the lane that scanned the diagonal scores it.
+__device__ __forceinline__ void push_segment(int start_t, int shift, int seg_len, int lane, uint32_t *wq, int &cnt,
+                                             SegRec *spill, unsigned int spill_cap, SegRec *seg_tap,
+                                             unsigned int seg_tap_cap, BatchCounters *ctr) {
+  tap_segment(blockIdx.x, start_t, shift, seg_len, seg_tap, seg_tap_cap, ctr);
+  if (cnt < SX_LQ_CAP) {
+    wq[cnt * 32 + lane] = (uint32_t)start_t | ((uint32_t)seg_len << 16);
+  } else {
+    const unsigned int gs = atomicAdd(&ctr->spill_used, 1u);
+    if (gs < spill_cap) {
+      SegRec r;
+      r.sp = blockIdx.x;
+      r.start_t = start_t;
+      r.shift = shift;
+      r.len = seg_len;
+      spill[gs] = r;
+    } else {
+      atomicOr(&ctr->status, (unsigned int)ST_SPILL_OVERFLOW);
+    }
+  }
+  cnt++;
 }
 
 template <int LOG2N>
@@ -59,8 +95,7 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
                       SegRec *__restrict__ spill, unsigned int spill_cap, BatchCounters *ctr) {
   constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, PW = NW + 2, NWARP = SX_SCAN_NT / 32;
   __shared__ uint32_t s_tlo[PW], s_thi[PW], s_qlo[PW], s_qhi[PW];
-  __shared__ uint2 s_wq[NWARP][SX_WQ_CAP];
-  __shared__ unsigned int s_wqn[NWARP];
+  __shared__ uint32_t s_wq[NWARP][SX_LQ_CAP * 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SpDesc sp = sps[blockIdx.x];
@@ -80,7 +115,6 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
       s_qlo[i] = in ? qp[i] : 0u;
       s_qhi[i] = in ? qp[NW + i] : 0u;
     }
-    if (tid < NWARP) s_wqn[tid] = 0;
   }
   __syncthreads();
   PlanePtrs P;
@@ -88,8 +122,7 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
   P.thi = s_thi;
   P.qlo = s_qlo;
   P.qhi = s_qhi;
-  uint2 *wq = s_wq[warp];
-  unsigned int *wqn = &s_wqn[warp];
+  uint32_t *wq = s_wq[warp];
 
   unsigned int my_segments = 0;
   for (int g0 = warp * 32; g0 < ncand; g0 += SX_SCAN_NT) {  // warp-uniform
@@ -115,11 +148,18 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
     uint32_t s3p0 = 0, s3p1 = 0, s3p2 = 0, s3p3 = 0;
     uint32_t s4p0 = 0, s4p1 = 0, s4p2 = 0, s4p3 = 0, s4p4 = 0;
     int open = -1;  // start of the open run in diagonal coordinates, -1 = none
+    int cnt = 0;    // segments this lane has found on its diagonal
+    // raw plane words are carried from step to step: 4 shared-memory loads per step instead of 8
+    uint32_t rtl = s_tlo[min(tw0, NW)], rth = s_thi[min(tw0, NW)], rql = s_qlo[min(qw0, NW)],
+             rqh = s_qhi[min(qw0, NW)];
 
-#pragma unroll 1
+#pragma unroll 2
     for (int kw = 0; kw < nw_max; kw++) {  // warp-uniform trip count
-      uint32_t tl, th, ql, qh;
-      diag_words(P, min(tw0 + kw, NW), tsh, min(qw0 + kw, NW), qsh, tl, th, ql, qh);
+      const int tn = min(tw0 + kw + 1, NW + 1), qn = min(qw0 + kw + 1, NW + 1);
+      const uint32_t ntl = s_tlo[tn], nth = s_thi[tn], nql = s_qlo[qn], nqh = s_qhi[qn];
+      const uint32_t tl = __funnelshift_r(rtl, ntl, tsh), th = __funnelshift_r(rth, nth, tsh);
+      const uint32_t ql = __funnelshift_r(rql, nql, qsh), qh = __funnelshift_r(rqh, nqh, qsh);
+      rtl = ntl; rth = nth; rql = nql; rqh = nqh;
       const uint32_t vm = kw < nwords - 1 ? 0xffffffffu : (kw == nwords - 1 ? lastmask : 0u);
       const uint32_t m = ~((tl ^ ql) | (th ^ qh)) & vm;
       uint32_t cy;
@@ -195,82 +235,50 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
       // count >= 19 (0b010011), only where a full window has been seen (k >= 46) and inside the diagonal
       uint32_t pass = (n5 | (n4 & (n3 | n2 | (n1 & n0)))) & vm;
       if (kw < 2) pass &= (kw == 0) ? 0u : 0xffffc000u;  // warp-uniform branch
-      // run boundaries: bit b set <=> pass changes between positions b-1 and b
-      uint32_t ev = pass ^ ((pass << 1) | carry);
+      // run boundaries inside this word: rise = a run starts here, fall = first position after a run
+      const uint32_t prevp = (pass << 1) | carry;
+      const uint32_t rise = pass & ~prevp;
+      uint32_t fall = ~pass & prevp;
       carry = pass >> 31;
-      if (__any_sync(0xffffffffu, ev != 0u)) {
-        const int kb = kw * 32;
-        while (ev) {
-          const int b = __ffs(ev) - 1;
-          ev &= ev - 1;
-          if (open < 0) {
-            open = kb + b - 45;  // lastStart = i - m_minLen (CrossCorr.cc:709-710)
-          } else {
-            const int seg_len = kb + b - open;
-            const int start_t = i0 + open;
-            my_segments++;
-            tap_segment(blockIdx.x, start_t, shift, seg_len, seg_tap, seg_tap_cap, ctr);
-            const unsigned int slot = atomicAdd(wqn, 1u);
-            if (slot < SX_WQ_CAP) {
-              wq[slot] = make_uint2((uint32_t)start_t | ((uint32_t)seg_len << 16), (uint32_t)shift);
-            } else {
-              const unsigned int gs = atomicAdd(&ctr->spill_used, 1u);
-              if (gs < spill_cap) {
-                SegRec r;
-                r.sp = blockIdx.x;
-                r.start_t = start_t;
-                r.shift = shift;
-                r.len = seg_len;
-                spill[gs] = r;
-              } else {
-                atomicOr(&ctr->status, (unsigned int)ST_SPILL_OVERFLOW);
-              }
-            }
-            open = -1;
+      const int kb = kw * 32;
+      if (__any_sync(0xffffffffu, fall != 0u)) {
+        // one iteration per run that ENDS in this word (usually one); lanes work in the same instructions
+        do {
+          const int f = __ffs(fall) - 1;  // -1: nothing left for this lane
+          if (f >= 0) {
+            fall &= fall - 1u;
+            const uint32_t below = rise & ((1u << f) - 1u);
+            // the run started at the closest rise below f, or in an earlier word (carried in `open`)
+            const int start_k = below ? (kb + 31 - __clz(below) - 45) : open;  // lastStart = i - m_minLen
+            push_segment(i0 + start_k, shift, kb + f - start_k, lane, wq, cnt, spill, spill_cap, seg_tap, seg_tap_cap,
+                         ctr);
           }
-        }
-        __syncwarp();
+        } while (__any_sync(0xffffffffu, fall != 0u));
       }
+      // state at the end of the word: a run still open started at the last rise of this word, if any
+      open = carry ? (rise ? (kb + 31 - __clz(rise) - 45) : open) : -1;
       m_prev = m;
       s1q0 = s1p0; s1q1 = s1p1; s1p0 = s10; s1p1 = s11;
       s2q0 = s2p0; s2q1 = s2p1; s2q2 = s2p2; s2p0 = s20; s2p1 = s21; s2p2 = s22;
       s3p0 = s30; s3p1 = s31; s3p2 = s32; s3p3 = s33;
       s4p0 = s40; s4p1 = s41; s4p2 = s42; s4p3 = s43; s4p4 = s44;
     }
-    if (open >= 0) {  // the run reaches the stop position exactly at a word boundary
-      const int seg_len = L - open;
-      const int start_t = i0 + open;
-      my_segments++;
-      tap_segment(blockIdx.x, start_t, shift, seg_len, seg_tap, seg_tap_cap, ctr);
-      const unsigned int slot = atomicAdd(wqn, 1u);
-      if (slot < SX_WQ_CAP) {
-        wq[slot] = make_uint2((uint32_t)start_t | ((uint32_t)seg_len << 16), (uint32_t)shift);
-      } else {
-        const unsigned int gs = atomicAdd(&ctr->spill_used, 1u);
-        if (gs < spill_cap) {
-          SegRec r;
-          r.sp = blockIdx.x;
-          r.start_t = start_t;
-          r.shift = shift;
-          r.len = seg_len;
-          spill[gs] = r;
-        } else {
-          atomicOr(&ctr->status, (unsigned int)ST_SPILL_OVERFLOW);
-        }
+    // a run that reaches the stop position exactly at a word boundary closes there
+    if (open >= 0) push_segment(i0 + open, shift, L - open, lane, wq, cnt, spill, spill_cap, seg_tap, seg_tap_cap, ctr);
+    my_segments += (unsigned int)cnt;
+    __syncwarp();
+    // ---- score the segments: every lane walks its own queue ----------------------------------------
+    const int nq = min(cnt, SX_LQ_CAP);
+    const int nq_max = __reduce_max_sync(0xffffffffu, nq);
+    for (int r = 0; r < nq_max; r++) {
+      if (r < nq) {
+        const uint32_t q = wq[r * 32 + lane];
+        const int start_t = (int)(q & 0xffffu), seg_len = (int)(q >> 16);
+        double prob, ident;
+        if (score_fast(P, start_t, shift, seg_len, prm, prob, ident))
+          emit_result(sp, start_t, shift, seg_len, prob, ident, res_pool, res_cap, ctr);
       }
     }
-    __syncwarp();
-    // ---- score this group's segments, one lane each ------------------------------------------------
-    const int nq = min((int)*wqn, SX_WQ_CAP);
-    for (int s = lane; s < nq; s += 32) {
-      const uint2 q = wq[s];
-      const int start_t = (int)(q.x & 0xffffu), seg_len = (int)(q.x >> 16), sh = (int)q.y;
-      double prob, ident;
-      if (score_fast(P, start_t, sh, seg_len, prm, prob, ident))
-        emit_result(sp, start_t, sh, seg_len, prob, ident, res_pool, res_cap, ctr);
-    }
-    __syncwarp();
-    if (lane == 0) *wqn = 0;
     __syncwarp();
   }
   my_segments = __reduce_add_sync(0xffffffffu, my_segments);
