@@ -383,6 +383,16 @@ class Reference:
         self.lib.ref_prob_table(target_size, cutoff, _ptr(tab))
         return tab
 
+    def read_match_file(self, path: str):
+        """MultiMatches::Read of the reference -> (n x 10 array, n_targets, n_queries)."""
+        self.lib.ref_read_match_file.restype = C.c_long
+        self.lib.ref_read_match_file.argtypes = [C.c_char_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
+        cap = 1 << 20
+        out = np.zeros((cap, 10), dtype=np.float64)
+        nt, nq = C.c_int(), C.c_int()
+        n = self.lib.ref_read_match_file(path.encode(), _ptr(out), cap, C.byref(nt), C.byref(nq))
+        return out[: max(n, 0)].copy(), nt.value, nq.value
+
     def codec(self):
         acgt = np.zeros((128, 4))
         rc = np.zeros(128, dtype=np.uint8)

@@ -321,6 +321,26 @@ double ref_ident(const char *q, int qlen, const char *t, int tlen, int startT, i
   return PrintMatch(dq, dt, m, true);
 }
 
+// Match-file reader of the reference (MultiMatches::Read, analysis/SequenceMatch.cc:113-249): used to
+// prove that files written by the B200 host tools are consumable by MergeXCorrMatches & co.
+// out: n x 10 doubles (tID,qID,qLen,startT,startQ,len,rc,matches,prob,ident). Returns n or -1.
+long ref_read_match_file(const char *path, double *out, long cap, int *n_targets, int *n_queries) {
+  CoutSilencer s;
+  MultiMatches mm;
+  mm.Read(path);
+  if (n_targets) *n_targets = mm.GetTargetCount();
+  if (n_queries) *n_queries = mm.GetQueryCount();
+  long n = mm.GetMatchCount();
+  for (long i = 0; i < n && i < cap; i++) {
+    const SingleMatch &m = mm.GetMatch((int)i);
+    double *o = out + 10 * i;
+    o[0] = m.GetTargetID(); o[1] = m.GetQueryID(); o[2] = m.m_queryLen; o[3] = m.GetStartTarget();
+    o[4] = m.GetStartQuery(); o[5] = m.GetLength(); o[6] = m.IsRC() ? 1 : 0; o[7] = m.GetMatches();
+    o[8] = m.GetProbability(); o[9] = m.GetIdentity();
+  }
+  return n;
+}
+
 // a4: codec tables (DNAVector.cc:13-58, 351-403) for all 256 byte values (as signed char index, i.e.
 // what DNA_A(char) sees for bytes < 128; bytes >= 128 are UB in the reference and not tabulated).
 void ref_codec(double *acgt /* 128*4 */, char *rc /* 128 */, double *equal /* 128*128 */,

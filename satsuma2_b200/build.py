@@ -57,5 +57,34 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST = os.path.join(HERE, "host")
+BIN = os.path.join(HERE, "bin")
+HOST_PROGRAMS = {"HomologyByXCorr": "homology_by_xcorr_main.cc", "HomologyByXCorrSlave": "homology_slave_main.cc"}
+
+
+def build_host(force: bool = False) -> list:
+    """C++ host programs above the C ABI (drop-ins for the reference's HomologyByXCorr[Slave])."""
+    build(force=False)
+    os.makedirs(BIN, exist_ok=True)
+    outs = []
+    common = [os.path.join(HOST, "sx_host.cc")]
+    for name, main in HOST_PROGRAMS.items():
+        exe = os.path.join(BIN, name)
+        srcs = common + [os.path.join(HOST, main)]
+        deps = srcs + [os.path.join(HOST, "sx_host.h"), LIB]
+        if force or not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+            cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", exe] + srcs + [
+                "-L" + HERE, "-lsatsuma_b200", "-Wl,-rpath,$ORIGIN/..", "-lpthread"]
+            proc = subprocess.run(cmd, capture_output=True, text=True)
+            if proc.returncode != 0:
+                sys.stderr.write(proc.stdout + proc.stderr)
+                raise RuntimeError(f"g++ failed building {name}")
+        outs.append(exe)
+    return outs
+
+
 if __name__ == "__main__":
+    if "--host" in sys.argv:
+        print("\n".join(build_host(force="--force" in sys.argv)))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

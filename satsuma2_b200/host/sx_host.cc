@@ -1,0 +1,350 @@
+// Host side above the C ABI -- see sx_host.h.  Behaviour follows the reference files cited there;
+// no reference code is reused.
+#include "sx_host.h"
+
+#include <cctype>
+#include <cstdio>
+#include <cstring>
+
+namespace sxh {
+
+// ------------------------------------------------------------------------------------------------
+// FASTA.  Reference behaviour (analysis/DNAVector.cc:1190-1282, base/FileParser.cc:140-152,
+// util/mutil.cc:349-377, 1493-1526): lines end at '\n' only (a '\r' stays in the token); tokens are
+// separated by ' ' and '\t'; empty lines are skipped; a line whose first token starts with '>' opens a
+// record whose name is all tokens joined by '_' (the '>' is dropped when names are exported);
+// otherwise only the FIRST token of the line is sequence; bases seen before the first header are
+// kept and end up in front of the first record; everything is upper-cased with toupper.
+// ------------------------------------------------------------------------------------------------
+static void split_tokens(const std::string &line, std::vector<std::string> &tok) {
+  tok.clear();
+  std::string cur;
+  for (size_t i = 0; i <= line.size(); i++) {
+    const bool end = i == line.size();
+    if (end || line[i] == ' ' || line[i] == '\t') {
+      if (!cur.empty()) tok.push_back(cur);
+      cur.clear();
+    } else {
+      cur.push_back(line[i]);
+    }
+  }
+}
+
+static bool read_one_fasta(const std::string &file, std::vector<Sequence> &out, std::string *err) {
+  FILE *f = fopen(file.c_str(), "rb");
+  if (!f) {
+    if (err) *err = "cannot open " + file;
+    return false;
+  }
+  std::string line, pending;  // pending = bases collected for the current record
+  std::vector<std::string> tok;
+  bool have_record = false;
+  char buf[1 << 16];
+  bool first_line = true;
+  auto flush_line = [&](const std::string &ln) -> bool {
+    split_tokens(ln, tok);
+    if (tok.empty()) return true;
+    if (first_line && tok[0][0] == '@') {
+      if (err) *err = file + ": FASTQ input is not supported by this loader";
+      return false;
+    }
+    first_line = false;
+    if (tok[0][0] == '>') {
+      if (have_record) {
+        out.back().bases.swap(pending);
+        pending.clear();
+      }
+      std::string name = tok[0].substr(1);
+      for (size_t i = 1; i < tok.size(); i++) name += "_" + tok[i];
+      out.push_back(Sequence{name, std::string()});
+      have_record = true;
+    } else {
+      pending += tok[0];
+    }
+    return true;
+  };
+  while (fgets(buf, sizeof(buf), f)) {
+    size_t n = strlen(buf);
+    const bool eol = n > 0 && buf[n - 1] == '\n';
+    if (eol) buf[n - 1] = 0;
+    line += buf;
+    if (eol) {
+      if (!flush_line(line)) {
+        fclose(f);
+        return false;
+      }
+      line.clear();
+    }
+  }
+  if (!line.empty() && !flush_line(line)) {
+    fclose(f);
+    return false;
+  }
+  fclose(f);
+  if (have_record) out.back().bases.swap(pending);
+  return true;
+}
+
+bool read_fasta(const std::string &files, std::vector<Sequence> &out, std::string *err) {
+  out.clear();
+  size_t pos = 0;
+  while (pos <= files.size()) {
+    size_t c = files.find(',', pos);
+    if (c == std::string::npos) c = files.size();
+    const std::string one = files.substr(pos, c - pos);
+    if (!one.empty() && !read_one_fasta(one, out, err)) return false;
+    pos = c + 1;
+  }
+  for (Sequence &s : out)
+    for (char &ch : s.bases) ch = (char)toupper((unsigned char)ch);
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+void chunk_sequences(const std::vector<Sequence> &seqs, int size, int overlap, int n_blocks, int my_block,
+                     ChunkList &out) {
+  out = ChunkList();
+  const int stride = size - overlap;
+  int64_t total = 0;
+  int n = 0;
+  for (const Sequence &s : seqs) {
+    total += (int64_t)s.bases.size();
+    if ((int)s.bases.size() >= 6) n += 1 + (int)s.bases.size() / stride;
+  }
+  out.blob.reserve((size_t)total + 16);
+  out.seq_sizes.resize(seqs.size());
+  out.names.resize(seqs.size());
+  int first = 0, last = n;
+  if (n_blocks > 0) {  // SeqChunk.cc:104-116
+    const int bsize = (n + n_blocks - 1) / n_blocks;
+    first = my_block * bsize;
+    last = (my_block + 1) * bsize;
+    if (first == last) {
+      first = 0;
+      last = n;
+    }
+  }
+  int k = 0;
+  for (size_t i = 0; i < seqs.size(); i++) {
+    const std::string &b = seqs[i].bases;
+    const int64_t base_off = (int64_t)out.blob.size();
+    out.blob += b;
+    out.seq_sizes[i] = (int32_t)b.size();
+    out.names[i] = seqs[i].name;
+    const int l = (int)b.size();
+    if (l < 6) continue;
+    const int nchunks = 1 + l / stride;
+    for (int j = 0; j < nchunks; j++, k++) {
+      const int start = j * stride;
+      int end = (j + 1) * stride + overlap;
+      if (end >= l) end = l;
+      int len = end > start ? end - start : 0;
+      if (k < first || k >= last) len = 0;  // not this process's block: chunk stays empty
+      if (len > 0) {  // all N/X -> emptied (SeqChunk.cc:150-153)
+        int nn = 0;
+        for (int x = start; x < start + len; x++) nn += (b[x] == 'N' || b[x] == 'X');
+        if (nn >= len) len = 0;
+      }
+      out.offsets.push_back(base_off + start);
+      out.lens.push_back(len);
+      out.starts.push_back(start);
+      out.seq_ids.push_back((int32_t)i);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+HomologyByXCorr::HomologyByXCorr() {}
+HomologyByXCorr::~HomologyByXCorr() {
+  if (ctx_) sx_destroy(ctx_);
+}
+
+bool HomologyByXCorr::init(const Options &o, const ChunkList &target, const ChunkList &query) {
+  sx_config cfg;
+  sx_default_config(&cfg);
+  cfg.device = o.device;
+  cfg.t_chunk = o.t_chunk;
+  cfg.q_chunk = o.q_chunk;
+  cfg.cutoff = o.cutoff;
+  cfg.cutoff_fast = o.cutoff_fast;
+  cfg.min_len = o.min_len;
+  cfg.use_prob_table = o.prob_table ? 1 : 0;
+  cfg.prob_table_value = o.min_prob_flag;
+  // the slave never applies -min_prob (it keeps prob >= 0.99, Slave.cc:76); the standalone tool does
+  cfg.min_prob = o.standalone_semantics ? o.min_prob_flag : 0.99;
+  cfg.rc_coord_mode = o.standalone_semantics ? 1 : 0;
+  cfg.max_batch_pairs = o.max_batch_pairs;
+  cfg.sort_results = o.sort_results ? 1 : 0;
+  target_total_ = 0;  // Slave.cc:405-408: ALL target sequence lengths
+  for (int32_t s : target.seq_sizes) target_total_ += (double)s;
+  cfg.target_total = target_total_;
+  if (sx_create(&cfg, &ctx_) != SX_OK) {
+    err_ = sx_last_error();
+    return false;
+  }
+  if (o.prob_table) {
+    std::vector<double> tab((size_t)512 * 2048);
+    if (sx_build_prob_table(target_total_, tab.data()) != SX_OK || sx_set_prob_table(ctx_, tab.data()) != SX_OK) {
+      err_ = sx_last_error();
+      return false;
+    }
+  }
+  if (sx_set_targets(ctx_, target.blob.data(), target.offsets.data(), target.lens.data(), target.starts.data(),
+                     target.seq_ids.data(), target.n(), target.seq_sizes.data(), (int32_t)target.seq_sizes.size()) !=
+          SX_OK ||
+      sx_set_queries(ctx_, query.blob.data(), query.offsets.data(), query.lens.data(), query.starts.data(),
+                     query.seq_ids.data(), query.n(), query.seq_sizes.data(), (int32_t)query.seq_sizes.size()) != SX_OK) {
+    err_ = sx_last_error();
+    return false;
+  }
+  return true;
+}
+
+bool HomologyByXCorr::align_targets(const t_pair *p, int n, std::vector<t_result> &results) {
+  if (!ctx_) {
+    err_ = "not initialised";
+    return false;
+  }
+  const size_t base = results.size();
+  int64_t cap = 1 << 16, got = 0;
+  results.resize(base + (size_t)cap);
+  int rc = sx_align_blocks(ctx_, p, n, results.data() + base, cap, &got);
+  if (rc == SX_ERR_CAPACITY) {  // never truncated: ask again with the size the library reported
+    cap = got;
+    results.resize(base + (size_t)cap);
+    rc = sx_align_blocks(ctx_, p, n, results.data() + base, cap, &got);
+  }
+  if (rc != SX_OK) {
+    results.resize(base);
+    err_ = sx_last_error();
+    return false;
+  }
+  results.resize(base + (size_t)got);
+  return true;
+}
+
+bool HomologyByXCorr::align_target(const t_pair &p, std::vector<t_result> &results) {
+  return align_targets(&p, 1, results);
+}
+
+bool HomologyByXCorr::stats(sx_stats *s) const { return ctx_ && sx_get_stats(ctx_, s) == SX_OK; }
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Writer {
+  FILE *f;
+  bool ok = true;
+  template <typename T>
+  void put(const T &v) {
+    if (ok && fwrite(&v, sizeof(T), 1, f) != 1) ok = false;
+  }
+  void str(const std::string &s) {  // CMWriteFileStream::WriteString: long length incl. NUL, then the bytes
+    const long len = (long)s.size() + 1;
+    put(len);
+    if (ok && fwrite(s.c_str(), (size_t)len, 1, f) != 1) ok = false;
+  }
+};
+struct Reader {
+  FILE *f;
+  bool ok = true;
+  template <typename T>
+  void get(T &v) {
+    if (ok && fread(&v, sizeof(T), 1, f) != 1) ok = false;
+  }
+  void str(std::string &s) {
+    long len = 0;
+    get(len);
+    if (!ok || len < 1 || len > (1L << 24)) {
+      ok = false;
+      return;
+    }
+    std::vector<char> b((size_t)len);
+    if (fread(b.data(), (size_t)len, 1, f) != 1) ok = false;
+    s.assign(b.data(), strnlen(b.data(), (size_t)len));
+  }
+};
+}  // namespace
+
+bool MatchFile::write(const std::string &path, std::string *err) const {
+  FILE *f = fopen(path.c_str(), "wb");
+  if (!f) {
+    if (err) *err = "cannot create " + path;
+    return false;
+  }
+  Writer w{f};
+  const int32_t ver = 3;
+  w.put(ver);
+  w.put((int32_t)target_names.size());
+  for (const std::string &s : target_names) w.str(s);
+  w.put((int32_t)query_names.size());
+  for (const std::string &s : query_names) w.str(s);
+  w.put((int32_t)matches.size());
+  for (const t_result &m : matches) {
+    // SingleMatch::Write (SequenceMatch.cc:49-64): all coordinates are 32-bit ints in the file
+    w.put((int32_t)m.target_id);
+    w.put((int32_t)m.query_id);
+    w.put((int32_t)m.query_size);
+    w.put((int32_t)m.tstart);
+    w.put((int32_t)(int64_t)m.qstart);
+    w.put((int32_t)m.len);
+    w.put((int32_t)(m.reverse ? 1 : 0));
+    const double nmatch = m.ident * (double)(int32_t)m.len;  // AddMatches(ident * len)
+    w.put(nmatch);
+    w.put(m.prob);
+    w.put(m.ident);
+  }
+  for (size_t i = 0; i < target_names.size(); i++) w.put(i < target_sizes.size() ? target_sizes[i] : (int32_t)0);
+  for (size_t i = 0; i < query_names.size(); i++) w.put(i < query_sizes.size() ? query_sizes[i] : (int32_t)0);
+  const bool ok = w.ok && fclose(f) == 0;
+  if (!ok && err) *err = "write error on " + path;
+  return ok;
+}
+
+bool MatchFile::read(const std::string &path, std::string *err) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) {
+    if (err) *err = "cannot open " + path;
+    return false;
+  }
+  Reader r{f};
+  int32_t ver = 0, nt = 0, nq = 0, n = 0;
+  r.get(ver);
+  r.get(nt);
+  if (!r.ok || ver != 3 || nt < 0) {
+    fclose(f);
+    if (err) *err = path + ": not a version-3 xcorr match file";
+    return false;
+  }
+  target_names.resize((size_t)nt);
+  for (auto &s : target_names) r.str(s);
+  r.get(nq);
+  if (!r.ok || nq < 0) nq = 0;
+  query_names.resize((size_t)nq);
+  for (auto &s : query_names) r.str(s);
+  r.get(n);
+  if (!r.ok || n < 0) n = 0;
+  matches.resize((size_t)n);
+  for (t_result &m : matches) {
+    int32_t tid, qid, qlen, st, sq, len, rc;
+    double nmatch;
+    memset(&m, 0, sizeof(m));
+    r.get(tid); r.get(qid); r.get(qlen); r.get(st); r.get(sq); r.get(len); r.get(rc);
+    r.get(nmatch); r.get(m.prob); r.get(m.ident);
+    m.target_id = (uint64_t)(int64_t)tid;
+    m.query_id = (uint64_t)(int64_t)qid;
+    m.query_size = (uint64_t)(int64_t)qlen;
+    m.tstart = (uint64_t)(int64_t)st;
+    m.qstart = (uint64_t)(int64_t)sq;
+    m.len = (uint64_t)(int64_t)len;
+    m.reverse = (uint8_t)(rc != 0);
+  }
+  target_sizes.resize((size_t)nt);
+  query_sizes.resize((size_t)nq);
+  for (auto &v : target_sizes) r.get(v);
+  for (auto &v : query_sizes) r.get(v);
+  fclose(f);
+  if (!r.ok && err) *err = path + ": truncated match file";
+  return r.ok;
+}
+
+}  // namespace sxh

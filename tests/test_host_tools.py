@@ -1,0 +1,234 @@
+"""C++ host side above the C ABI (satsuma2_b200/host): FASTA loading, chunk arithmetic, the binary
+match file, and the two drop-in executables (standalone HomologyByXCorr, TCP HomologyByXCorrSlave).
+CPU tests cover parsing / chunking; GPU tests run the executables end to end."""
+import os
+import socket
+import struct
+import subprocess
+import threading
+
+import numpy as np
+import pytest
+
+from parity import rec_key
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def host_bins(sx):
+    from satsuma2_b200 import build as sxbuild
+
+    exes = sxbuild.build_host()
+    return {os.path.basename(e): e for e in exes}
+
+
+def _write_fasta(path, records, width=60, lower=False):
+    with open(path, "w") as f:
+        for name, seq in records:
+            f.write(">" + name + "\n")
+            s = seq.decode() if isinstance(seq, bytes) else seq
+            if lower:
+                s = s.lower()
+            for i in range(0, len(s), width):
+                f.write(s[i:i + width] + "\n")
+
+
+def _dump_chunks(exe, q, t, *extra):
+    out = subprocess.run([exe, "-q", q, "-t", t, "-dump_chunks", "1", *extra], capture_output=True, text=True, check=True)
+    T, Q = [], []
+    for ln in out.stdout.splitlines():
+        p = ln.split()
+        if len(p) == 5 and p[0] in ("T", "Q"):
+            rec = (int(p[1]), int(p[2][4:]), int(p[3][6:]), int(p[4][4:]))
+            (T if p[0] == "T" else Q).append(rec)
+    return T, Q
+
+
+def test_fasta_and_chunking(host_bins, tmp_path):
+    """Header tokens joined by '_', only the first token of sequence lines, soft-masking ignored,
+    all-N chunks emptied, < 6 bp sequences skipped, trailing empty chunk when l % stride == 0."""
+    rng = np.random.default_rng(1)
+    s1 = bytes(rng.choice(list(b"ACGT"), 10000).astype(np.uint8))
+    s2 = b"N" * 4096 + bytes(rng.choice(list(b"ACGT"), 4096).astype(np.uint8))
+    q = tmp_path / "q.fa"
+    t = tmp_path / "t.fa"
+    with open(q, "w") as f:
+        f.write(">chr1 some description here\n")
+        for i in range(0, len(s1), 70):
+            f.write(s1[i:i + 70].decode().lower() + "  trailing tokens are ignored\n")
+        f.write("\n>tiny\nACGT\n>chr2\n" + s2.decode() + "\n")
+    _write_fasta(t, [("t1", s1[:8192])])
+    T, Q = _dump_chunks(host_bins["HomologyByXCorr"], str(q), str(t))
+    # query: chr1 (10000 bp -> 3 chunks), tiny (< 6 bp: none), chr2 (8192 bp -> 3 chunks, first all-N, last empty)
+    assert [c[3] for c in Q] == [4096, 4096, 1808, 0, 4096, 0]
+    assert [c[1] for c in Q] == [0, 0, 0, 2, 2, 2]
+    assert [c[2] for c in Q] == [0, 4096, 8192, 0, 4096, 8192]
+    # target overlap t_chunk/2 in the standalone tool: stride 2048, 1 + 8192/2048 = 5 chunks
+    assert [(c[2], c[3]) for c in T] == [(0, 4096), (2048, 4096), (4096, 4096), (6144, 2048), (8192, 0)]
+    # -nblocks/-block: only the block's chunks keep their bases
+    T2, _ = _dump_chunks(host_bins["HomologyByXCorr"], str(q), str(t), "-nblocks", "2", "-block", "1")
+    assert [c[3] for c in T2] == [0, 0, 0, 2048, 0]
+
+
+def test_sample_chunk_counts(host_bins):
+    ref = "/root/reference/samples"
+    if not os.path.isdir(ref):
+        pytest.skip("reference samples not present")
+    T, Q = _dump_chunks(host_bins["HomologyByXCorr"], f"{ref}/human.X.part.fasta", f"{ref}/dog.X.part.fasta")
+    assert len(Q) == 245 and Q[-1][3] == 577
+    assert len(T) == 1 + 800001 // 2048 and T[-1][3] == 800001 - 390 * 2048
+
+
+def _parse_match_file(path):
+    b = open(path, "rb").read()
+    off = 0
+
+    def rd(fmt):
+        nonlocal off
+        v = struct.unpack_from("<" + fmt, b, off)
+        off += struct.calcsize("<" + fmt)
+        return v
+
+    ver, nt = rd("ii")
+    assert ver == 3
+    tn = []
+    for _ in range(nt):
+        (ln,) = rd("q")
+        tn.append(b[off:off + ln - 1].decode())
+        off += ln
+    (nq,) = rd("i")
+    qn = []
+    for _ in range(nq):
+        (ln,) = rd("q")
+        qn.append(b[off:off + ln - 1].decode())
+        off += ln
+    (n,) = rd("i")
+    recs = [rd("iiiiiiiddd") for _ in range(n)]
+    ts = rd(f"{nt}i")
+    qs = rd(f"{nq}i")
+    assert off == len(b)
+    return tn, qn, recs, ts, qs
+
+
+@pytest.mark.gpu
+def test_standalone_tool_writes_reference_compatible_match_file(host_bins, sx, oracle_lib, tmp_path):
+    """Runs the B200 HomologyByXCorr on a small FASTA pair; the v3 match file is parsed here, read
+    back by the reference's own MultiMatches::Read, and its records equal the oracle under the
+    standalone tool's semantics (target overlap size/2, -min_prob applied, RC coordinate by chunk length)."""
+    rng = np.random.default_rng(3)
+    base = rng.choice(list(b"ACGT"), 14000).astype(np.uint8)
+    tgt = base.copy()
+    qry = base.copy()
+    mut = rng.random(14000) < 0.12
+    qry[mut] = rng.choice(list(b"ACGT"), int(mut.sum()))
+    comp = np.zeros(256, np.uint8)
+    comp[list(b"ACGT")] = list(b"TGCA")
+    qry[6000:9000] = comp[qry[6000:9000][::-1]]  # an inverted block -> reverse-strand matches
+    q, t, o = tmp_path / "q.fa", tmp_path / "t.fa", tmp_path / "out.match"
+    _write_fasta(q, [("qseq extra", qry.tobytes())], lower=True)
+    _write_fasta(t, [("tseq", tgt.tobytes())])
+    r = subprocess.run([host_bins["HomologyByXCorr"], "-q", str(q), "-t", str(t), "-o", str(o)], capture_output=True,
+                       text=True)
+    assert r.returncode == 0, r.stderr
+    tn, qn, recs, ts, qs = _parse_match_file(str(o))
+    assert tn == ["tseq"] and qn == ["qseq_extra"] and ts == (14000,) and qs == (14000,)
+    assert len(recs) > 3 and any(rc[6] for rc in recs) and any(not rc[6] for rc in recs)
+    for rc in recs:
+        assert abs(rc[7] - rc[9] * rc[5]) < 1e-9 and rc[8] >= 0.9999
+    # expected set from the oracle with the same chunking and semantics
+    from satsuma2_b200 import synth
+
+    to, tl, tst = synth.chunk_sequence(tgt, 4096, 2048)
+    qo, ql, qst = synth.chunk_sequence(qry, 4096, 0)
+    T = [(tgt[a:a + n].tobytes(), int(s), 0, 14000) for a, n, s in zip(to, tl, tst)]
+    Q = [(qry[a:a + n].tobytes(), int(s), 0, 14000) for a, n, s in zip(qo, ql, qst)]
+    params = oracle_lib.make_params(min_prob=0.9999, target_total=14000.0)
+    exp = set()
+    for ti, tc in enumerate(T):
+        for qi, qc in enumerate(Q):
+            if not tc[0] or not qc[0]:
+                continue
+            for rr in oracle_lib.align_pairs(params, T, Q, [(ti, qi)]):
+                k = list(rec_key(rr))
+                if k[6]:  # standalone RC coordinate uses the real chunk length (tools/...:173,799)
+                    qstart = k[3] if k[3] < (1 << 63) else k[3] - (1 << 64)
+                    k[3] = qstart + 4096 - len(qc[0])
+                exp.add((k[1], k[0], k[2], k[4], k[3], k[5], k[6]))
+    got = set((rc[0], rc[1], rc[2], rc[3], rc[4], rc[5], rc[6]) for rc in recs)
+    assert got == exp
+    # the reference's own reader accepts the file
+    import oracle
+
+    if oracle.have_reference():
+        arr, nt, nq = oracle.Reference().read_match_file(str(o))
+        assert (nt, nq) == (1, 1) and len(arr) == len(recs)
+        assert np.allclose(arr, np.array(recs, dtype=np.float64), rtol=0, atol=0)
+
+
+@pytest.mark.gpu
+def test_slave_speaks_the_reference_wire_protocol(host_bins, sx, tmp_path):
+    """A scripted master hands t_pairs to the B200 slave over loopback TCP and
+    gets t_result records back; they equal the in-process C-ABI results."""
+    rng = np.random.default_rng(5)
+    base = rng.choice(list(b"ACGT"), 30000).astype(np.uint8)
+    qry = base.copy()
+    mut = rng.random(30000) < 0.1
+    qry[mut] = rng.choice(list(b"ACGT"), int(mut.sum()))
+    q, t = tmp_path / "q.fa", tmp_path / "t.fa"
+    _write_fasta(q, [("q", qry.tobytes())])
+    _write_fasta(t, [("t", base.tobytes())])
+    blocks = [(0, 4, 0, 3, 0), (5, 9, 4, 7, 0), (0, 9, 0, 7, 1)]
+    srv = socket.socket()
+    srv.bind(("127.0.0.1", 0))
+    srv.listen(4)
+    port = srv.getsockname()[1]
+    received, state = [], {"sent": False, "done": False}
+
+    def recv_all(c, n):
+        buf = b""
+        while len(buf) < n:
+            part = c.recv(n - len(buf))
+            if not part:
+                raise IOError("short read")
+            buf += part
+        return buf
+
+    def master():
+        while not state["done"]:
+            c, _ = srv.accept()
+            sid, n = struct.unpack("<II", recv_all(c, 8))
+            assert sid == 7
+            if n:
+                received.append(np.frombuffer(recv_all(c, 72 * n), dtype=sx.RESULT_DTYPE).copy())
+            if not state["sent"]:
+                arr = np.zeros(len(blocks), dtype=sx.PAIR_DTYPE)
+                for i, b in enumerate(blocks):
+                    arr[i]["target_from"], arr[i]["target_to"], arr[i]["query_from"], arr[i]["query_to"] = b[:4]
+                    arr[i]["fast"] = b[4]
+                c.sendall(struct.pack("<i", len(blocks)) + arr.tobytes())  # one send, like the survey's fake master
+                state["sent"] = True
+            else:
+                c.sendall(struct.pack("<i", -1))
+                state["done"] = True
+            c.close()
+
+    th = threading.Thread(target=master, daemon=True)
+    th.start()
+    r = subprocess.run([host_bins["HomologyByXCorrSlave"], "-master", "127.0.0.1", "-port", str(port), "-sid", "7", "-q",
+                        str(q), "-t", str(t)], capture_output=True, text=True, timeout=300)
+    th.join(timeout=30)
+    srv.close()
+    assert r.returncode == 0, r.stderr
+    got = np.concatenate(received) if received else np.zeros(0, dtype=sx.RESULT_DTYPE)
+    # the same blocks through the Python binding of the C ABI
+    from satsuma2_b200 import synth
+
+    to, tl, tst = synth.chunk_sequence(base, 4096, 1024)
+    qo, ql, qst = synth.chunk_sequence(qry, 4096, 0)
+    with sx.XCorrEngine(target_total=30000.0) as eng:
+        eng.set_targets(sx.ChunkSet(base, to, tl, tst, np.zeros(len(tl)), [30000]))
+        eng.set_queries(sx.ChunkSet(qry, qo, ql, qst, np.zeros(len(ql)), [30000]))
+        exp = eng.align_blocks(blocks)
+    assert len(got) == len(exp) > 0
+    assert sorted(map(rec_key, got)) == sorted(map(rec_key, exp))
