@@ -480,8 +480,56 @@ static void to_result(const sx_ctx *c, const ResultRec &r, const PairReq &pr, sx
   o->ident = r.ident;
 }
 
-static int run_batch(sx_ctx *c, Batch &b, std::vector<sx_result> *results, TapRequest *tap) {
-  const int nsig = (int)b.sigs.size(), nsp = (int)b.sps.size();
+namespace {
+struct Run {  // one batch on the device: launched asynchronously, completed by batch_finish
+  Batch *b = nullptr;
+  TapRequest *tap = nullptr;
+  int nsig = 0, nsp = 0;
+  bool need_encode = false, need_xcorr = true, active = false;
+  unsigned long long n_cand_seen = 0;
+  float *d_sig_tap = nullptr, *d_xc_tap = nullptr;
+  SegRec *d_seg_tap = nullptr;
+  unsigned int seg_tap_cap = 0;
+};
+}  // namespace
+
+// (re)launch the kernels of a batch and the asynchronous read-back of its counter block
+static int batch_kernels(sx_ctx *c, Run &r) {
+  cudaStream_t st = c->stream;
+  const bool prof = c->profiling;
+  const Slots ws = c->slots();
+  const ScoreParams prm = score_params(c);
+  CU(cudaMemsetAsync(c->d_ctr.p, 0, sizeof(BatchCounters), st));
+  if (prof) CU(cudaEventRecord(c->ev[0], st));
+  if (r.need_encode) {
+    CU(launch_encode_fft(c->log2n, c->d_sigs.p, r.nsig, ws, r.d_sig_tap, st));
+    c->stats.kernel_launches += 1;
+  }
+  if (prof) CU(cudaEventRecord(c->ev[1], st));
+  if (r.nsp && r.need_xcorr) {
+    CU(launch_xcorr_findtop(c->log2n, c->d_sps.p, r.nsp, ws, c->cfg.cutoff, c->cfg.cutoff_fast, c->d_cand_pool.p,
+                            (unsigned int)std::min<size_t>(c->d_cand_pool.n, 0xfffffff0u), c->d_cand_ref.p, c->d_ctr.p,
+                            r.d_xc_tap, st));
+    c->stats.kernel_launches += 1;
+  }
+  if (prof) CU(cudaEventRecord(c->ev[2], st));
+  if (r.nsp) {
+    CU(launch_scan_score(c->log2n, c->d_sps.p, r.nsp, ws, c->d_cand_pool.p, c->d_cand_ref.p, prm, c->d_res.p,
+                         (unsigned int)std::min<size_t>(c->d_res.n, 0xfffffff0u), r.d_seg_tap, r.seg_tap_cap,
+                         c->d_spill.p, (unsigned int)std::min<size_t>(c->d_spill.n, 0xfffffff0u), c->d_ctr.p, st));
+    c->stats.kernel_launches += 3;
+  }
+  if (prof) CU(cudaEventRecord(c->ev[3], st));
+  CU(cudaMemcpyAsync(c->h_ctr.p, c->d_ctr.p, sizeof(BatchCounters), cudaMemcpyDeviceToHost, st));
+  return SX_OK;
+}
+
+// upload the descriptors of a batch and launch it; returns without waiting for the device
+static int batch_launch(sx_ctx *c, Run &r, Batch &b, TapRequest *tap) {
+  r = Run();
+  r.b = &b;
+  r.tap = tap;
+  const int nsig = r.nsig = (int)b.sigs.size(), nsp = r.nsp = (int)b.sps.size();
   if (nsp == 0 && nsig == 0) return SX_OK;
   const size_t N = (size_t)c->N;
   int rc;
@@ -490,11 +538,10 @@ static int run_batch(sx_ctx *c, Batch &b, std::vector<sx_result> *results, TapRe
   if ((rc = c->d_sps.ensure(std::max(nsp, 1))) != SX_OK) return rc;
   if ((rc = c->h_sps.ensure(std::max(nsp, 1))) != SX_OK) return rc;
   if ((rc = c->d_cand_ref.ensure(std::max(nsp, 1))) != SX_OK) return rc;
-  if (c->d_cand_pool.n == 0 && (rc = c->d_cand_pool.ensure(std::max<size_t>((size_t)nsp * 640, 1 << 16))) != SX_OK) return rc;
-  if (c->d_cand_pool.n < (size_t)nsp * 640 && (rc = c->d_cand_pool.ensure((size_t)nsp * 640)) != SX_OK) return rc;
-  if (c->d_res.n == 0) {
-    if ((rc = c->d_res.ensure(std::max<size_t>((size_t)nsp * 8, 1 << 16))) != SX_OK) return rc;
-  }
+  if (c->d_cand_pool.n < std::max<size_t>((size_t)nsp * 640, 1 << 16) &&
+      (rc = c->d_cand_pool.ensure(std::max<size_t>((size_t)nsp * 640, 1 << 16))) != SX_OK)
+    return rc;
+  if (c->d_res.n == 0 && (rc = c->d_res.ensure(std::max<size_t>((size_t)nsp * 8, 1 << 16))) != SX_OK) return rc;
   if (c->d_spill.n == 0 && (rc = c->d_spill.ensure((size_t)1 << 20)) != SX_OK) return rc;
   if (nsig) memcpy(c->h_sigs.p, b.sigs.data(), sizeof(SigDesc) * nsig);
   if (nsp) memcpy(c->h_sps.p, b.sps.data(), sizeof(SpDesc) * nsp);
@@ -502,84 +549,69 @@ static int run_batch(sx_ctx *c, Batch &b, std::vector<sx_result> *results, TapRe
   if (nsig) CU(cudaMemcpyAsync(c->d_sigs.p, c->h_sigs.p, sizeof(SigDesc) * nsig, cudaMemcpyHostToDevice, st));
   if (nsp) CU(cudaMemcpyAsync(c->d_sps.p, c->h_sps.p, sizeof(SpDesc) * nsp, cudaMemcpyHostToDevice, st));
   c->stats.h2d_bytes += (int64_t)(sizeof(SigDesc) * nsig + sizeof(SpDesc) * nsp);
-
-  float *d_sig_tap = nullptr, *d_xc_tap = nullptr;
   if (tap && (tap->sig5n || tap->xc)) {
     if ((rc = c->d_tap.ensure((size_t)std::max(nsig, 1) * 5 * N + (size_t)std::max(nsp, 1) * N)) != SX_OK) return rc;
-    if (tap->sig5n) d_sig_tap = c->d_tap.p;
-    if (tap->xc) d_xc_tap = c->d_tap.p + (size_t)std::max(nsig, 1) * 5 * N;
+    if (tap->sig5n) r.d_sig_tap = c->d_tap.p;
+    if (tap->xc) r.d_xc_tap = c->d_tap.p + (size_t)std::max(nsig, 1) * 5 * N;
   }
-  SegRec *d_seg_tap = nullptr;
-  unsigned int seg_tap_cap = 0;
   if (tap && tap->segs) {
     if ((rc = c->d_seg_tap.ensure((size_t)1 << 20)) != SX_OK) return rc;
-    d_seg_tap = c->d_seg_tap.p;
-    seg_tap_cap = (unsigned int)c->d_seg_tap.n;
+    r.d_seg_tap = c->d_seg_tap.p;
+    r.seg_tap_cap = (unsigned int)c->d_seg_tap.n;
   }
-
-  const bool prof = c->profiling;
-  const Slots ws = c->slots();
   c->z_cut = c->cfg.use_prob_table ? INFINITY : compute_z_cut(c->cfg.min_prob, c->target_total);
-  const ScoreParams prm = score_params(c);
-  bool need_encode = nsig > 0, need_xcorr = true;
-  unsigned long long n_cand_seen = 0;
+  r.need_encode = nsig > 0;
+  r.need_xcorr = true;
+  r.active = true;
+  return batch_kernels(c, r);
+}
+
+// wait for a launched batch, grow-and-retry on pool overflow, fetch its records
+static int batch_finish(sx_ctx *c, Run &r, std::vector<sx_result> *results) {
+  if (!r.active) return SX_OK;
+  r.active = false;
+  Batch &b = *r.b;
+  TapRequest *tap = r.tap;
+  const int nsig = r.nsig, nsp = r.nsp;
+  const size_t N = (size_t)c->N;
+  cudaStream_t st = c->stream;
+  const bool prof = c->profiling;
+  int rc;
   for (int attempt = 0; attempt < 8; attempt++) {
-    CU(cudaMemsetAsync(c->d_ctr.p, 0, sizeof(BatchCounters), st));
-    if (prof) CU(cudaEventRecord(c->ev[0], st));
-    if (need_encode) {
-      CU(launch_encode_fft(c->log2n, c->d_sigs.p, nsig, ws, d_sig_tap, st));
-      c->stats.kernel_launches += 1;
-    }
-    if (prof) CU(cudaEventRecord(c->ev[1], st));
-    if (nsp && need_xcorr) {
-      CU(launch_xcorr_findtop(c->log2n, c->d_sps.p, nsp, ws, c->cfg.cutoff, c->cfg.cutoff_fast, c->d_cand_pool.p,
-                              (unsigned int)std::min<size_t>(c->d_cand_pool.n, 0xfffffff0u), c->d_cand_ref.p,
-                              c->d_ctr.p, d_xc_tap, st));
-      c->stats.kernel_launches += 1;
-    }
-    if (prof) CU(cudaEventRecord(c->ev[2], st));
-    if (nsp) {
-      CU(launch_scan_score(c->log2n, c->d_sps.p, nsp, ws, c->d_cand_pool.p, c->d_cand_ref.p, prm, c->d_res.p,
-                           (unsigned int)std::min<size_t>(c->d_res.n, 0xfffffff0u), d_seg_tap, seg_tap_cap,
-                           c->d_spill.p, (unsigned int)std::min<size_t>(c->d_spill.n, 0xfffffff0u), c->d_ctr.p, st));
-      c->stats.kernel_launches += 3;
-    }
-    if (prof) CU(cudaEventRecord(c->ev[3], st));
-    CU(cudaMemcpyAsync(c->h_ctr.p, c->d_ctr.p, sizeof(BatchCounters), cudaMemcpyDeviceToHost, st));
+    if (attempt > 0 && (rc = batch_kernels(c, r)) != SX_OK) return rc;
     CU(cudaStreamSynchronize(st));
     c->stats.d2h_bytes += (int64_t)sizeof(BatchCounters);
     if (prof) {
       float ms = 0;
-      if (need_encode) { cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->stats.ms_encode_fft += ms; }
-      if (nsp && need_xcorr) { cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->stats.ms_xcorr += ms; }
+      if (r.need_encode) { cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->stats.ms_encode_fft += ms; }
+      if (nsp && r.need_xcorr) { cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->stats.ms_xcorr += ms; }
       if (nsp) { cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->stats.ms_scan_score += ms; }
       cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]);
       c->stats.ms_total += ms;
     }
     const BatchCounters ctr = *c->h_ctr.p;
-    need_encode = false;  // spectra of this batch are in place now
-    if (need_xcorr) n_cand_seen = ctr.n_candidates;
+    r.need_encode = false;  // spectra of this batch are in place now
+    if (r.need_xcorr) r.n_cand_seen = ctr.n_candidates;
     if (ctr.status & ST_CAND_OVERFLOW) {
       // the candidate pool was too small: grow to what the kernel asked for and redo K2+K3
       const size_t want = std::max<size_t>((size_t)ctr.cand_used + (ctr.cand_used >> 2), c->d_cand_pool.n * 2);
       if ((rc = c->d_cand_pool.ensure(want)) != SX_OK) return rc;
       c->stats.retries++;
-      need_xcorr = true;
+      r.need_xcorr = true;
       continue;
     }
     if (ctr.status & ST_RES_OVERFLOW) {
       const size_t want = std::max<size_t>((size_t)ctr.res_used + (ctr.res_used >> 2), c->d_res.n * 2);
       if ((rc = c->d_res.ensure(want)) != SX_OK) return rc;
       c->stats.retries++;
-      need_xcorr = false;  // candidates are valid; only the scan is repeated
-      // cand_ref/pool untouched, but the counter block is zeroed: K3 does not need cand_used
+      r.need_xcorr = false;  // candidates are valid; only the scan is repeated
       continue;
     }
     if (ctr.status & ST_SPILL_OVERFLOW) {
       const size_t want = std::max<size_t>((size_t)ctr.spill_used + (ctr.spill_used >> 2), c->d_spill.n * 2);
       if ((rc = c->d_spill.ensure(want)) != SX_OK) return rc;
       c->stats.retries++;
-      need_xcorr = false;
+      r.need_xcorr = false;
       continue;
     }
     if (ctr.status & ST_TAP_OVERFLOW) return fail(SX_ERR_CAPACITY, "segment tap overflow (%u records)", ctr.seg_tap_used);
@@ -589,7 +621,7 @@ static int run_batch(sx_ctx *c, Batch &b, std::vector<sx_result> *results, TapRe
     c->stats.signals += nsig;
     c->stats.strand_pairs += nsp;
     c->stats.chunk_pairs += (int64_t)b.pairs.size();
-    c->stats.candidates += (int64_t)n_cand_seen;
+    c->stats.candidates += (int64_t)r.n_cand_seen;
     c->stats.segments += (int64_t)ctr.n_segments;
     c->stats.matches += (int64_t)ctr.res_used;
     if (ctr.res_used && results) {
@@ -597,10 +629,10 @@ static int run_batch(sx_ctx *c, Batch &b, std::vector<sx_result> *results, TapRe
       CU(cudaMemcpyAsync(c->h_res.p, c->d_res.p, sizeof(ResultRec) * ctr.res_used, cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
       c->stats.d2h_bytes += (int64_t)(sizeof(ResultRec) * ctr.res_used);
-      ResultRec *r = c->h_res.p;
+      ResultRec *rr = c->h_res.p;
       if (c->cfg.sort_results) {
         // reference emission order: pair, forward before reverse, candidate lag ascending, position ascending
-        std::sort(r, r + ctr.res_used, [](const ResultRec &a, const ResultRec &b2) {
+        std::sort(rr, rr + ctr.res_used, [](const ResultRec &a, const ResultRec &b2) {
           if (a.pair != b2.pair) return a.pair < b2.pair;
           if (a.strand != b2.strand) return a.strand < b2.strand;
           if (a.shift != b2.shift) return a.shift < b2.shift;
@@ -609,11 +641,11 @@ static int run_batch(sx_ctx *c, Batch &b, std::vector<sx_result> *results, TapRe
       }
       const size_t base = results->size();
       results->resize(base + ctr.res_used);
-      for (unsigned int i = 0; i < ctr.res_used; i++) to_result(c, r[i], b.pairs[r[i].pair], &(*results)[base + i]);
+      for (unsigned int i = 0; i < ctr.res_used; i++) to_result(c, rr[i], b.pairs[rr[i].pair], &(*results)[base + i]);
     }
     if (tap) {
-      if (tap->sig5n && nsig) CU(cudaMemcpy(tap->sig5n, d_sig_tap, sizeof(float) * nsig * 5 * N, cudaMemcpyDeviceToHost));
-      if (tap->xc && nsp) CU(cudaMemcpy(tap->xc, d_xc_tap, sizeof(float) * nsp * N, cudaMemcpyDeviceToHost));
+      if (tap->sig5n && nsig) CU(cudaMemcpy(tap->sig5n, r.d_sig_tap, sizeof(float) * nsig * 5 * N, cudaMemcpyDeviceToHost));
+      if (tap->xc && nsp) CU(cudaMemcpy(tap->xc, r.d_xc_tap, sizeof(float) * nsp * N, cudaMemcpyDeviceToHost));
       if (tap->cands && nsp) {
         std::vector<uint2> refs(nsp);
         CU(cudaMemcpy(refs.data(), c->d_cand_ref.p, sizeof(uint2) * nsp, cudaMemcpyDeviceToHost));
@@ -626,12 +658,19 @@ static int run_batch(sx_ctx *c, Batch &b, std::vector<sx_result> *results, TapRe
       }
       if (tap->segs) {
         tap->segs->resize(ctr.seg_tap_used);
-        if (ctr.seg_tap_used) CU(cudaMemcpy(tap->segs->data(), d_seg_tap, sizeof(SegRec) * ctr.seg_tap_used, cudaMemcpyDeviceToHost));
+        if (ctr.seg_tap_used) CU(cudaMemcpy(tap->segs->data(), r.d_seg_tap, sizeof(SegRec) * ctr.seg_tap_used, cudaMemcpyDeviceToHost));
       }
     }
     return SX_OK;
   }
   return fail(SX_ERR_CUDA, "device pools kept overflowing after 8 attempts");
+}
+
+static int run_batch(sx_ctx *c, Batch &b, std::vector<sx_result> *results, TapRequest *tap) {
+  Run r;
+  int rc = batch_launch(c, r, b, tap);
+  if (rc != SX_OK) return rc;
+  return batch_finish(c, r, results);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -688,32 +727,47 @@ static int align_list(sx_ctx *c, const PairReq *reqs, int64_t n, sx_result *out,
   if (c->Q.n == 0 && n > 0) return fail(SX_ERR_STATE, "align: no queries loaded");
   CU(cudaSetDevice(c->cfg.device));
   c->last.clear();
-  Batch b;
+  // Two batch descriptors: while the device works on one, the host assembles the next.
+  Batch bufs[2];
+  int cur = 0;
+  Run inflight;
+  auto submit = [&](Batch &nb) -> int {
+    int rc2 = batch_finish(c, inflight, &c->last);  // completes the PREVIOUS batch (no-op if none)
+    if (rc2 != SX_OK) return rc2;
+    return batch_launch(c, inflight, nb, nullptr);
+  };
   const size_t maxpairs = (size_t)c->cfg.max_batch_pairs;
   for (int64_t i = 0; i < n; i++) {
     const PairReq &r = reqs[i];
-    if (r.t < 0 || r.t >= c->T.n || r.q < 0 || r.q >= c->Q.n)
+    if (r.t < 0 || r.t >= c->T.n || r.q < 0 || r.q >= c->Q.n) {
+      batch_finish(c, inflight, &c->last);
       return fail(SX_ERR_ARG, "align: pair %lld = (target %d, query %d) out of range", (long long)i, r.t, r.q);
-    // worst case this pair needs 3 fresh transient slots
-    if (b.pairs.size() >= maxpairs || b.transient_used + 3 > c->n_transient) {
-      int rc = run_batch(c, b, &c->last, nullptr);
-      if (rc != SX_OK) return rc;
-      b.clear();
     }
-    const int32_t ts = target_slot(c, b, r.t);
-    const int32_t qs = query_slot(c, b, r.q);
-    const int32_t pidx = (int32_t)b.pairs.size();
-    b.pairs.push_back(r);
+    Batch *b = &bufs[cur];
+    // worst case this pair needs 3 fresh transient slots
+    if (b->pairs.size() >= maxpairs || b->transient_used + 3 > c->n_transient) {
+      int rc = submit(*b);
+      if (rc != SX_OK) return rc;
+      cur ^= 1;
+      b = &bufs[cur];
+      b->clear();
+    }
+    const int32_t ts = target_slot(c, *b, r.t);
+    const int32_t qs = query_slot(c, *b, r.q);
+    const int32_t pidx = (int32_t)b->pairs.size();
+    b->pairs.push_back(r);
     for (int strand = 0; strand < 2; strand++) {
       SpDesc sp;
       sp.t_slot = ts;
       sp.q_slot = qs + strand;
       sp.pair = pidx;
       sp.flags = (strand ? SP_REVERSE : 0) | (r.fast ? SP_FAST : 0);
-      b.sps.push_back(sp);
+      b->sps.push_back(sp);
     }
   }
-  int rc = run_batch(c, b, &c->last, nullptr);
+  int rc = submit(bufs[cur]);
+  if (rc != SX_OK) return rc;
+  rc = batch_finish(c, inflight, &c->last);
   if (rc != SX_OK) return rc;
   const int64_t total = (int64_t)c->last.size();
   if (n_out) *n_out = total;
