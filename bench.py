@@ -39,7 +39,7 @@ FFT_N = 8192
 FLOP_FWD_PER_SIGNAL = 4 * 2.5 * FFT_N * 13            # 4 channels
 FLOP_XCORR_PER_STRAND = 2.5 * FFT_N * 13 + 4 * 4097 * 8  # one inverse + spectral MAC over 4 channels
 SPECTRA_BYTES_PER_SIGNAL = 2 * FFT_N * 8               # two packed complex spectra, fp32
-BASE_CMP_PER_PAIR = 1.75e6                             # diagonal-scan base comparisons (measured mean)
+SCAN_ALU_OPS_PER_POSITION = 88.0 / 32.0                # bit-sliced window count: 57 LOP3 + 24 SHF + 7 match per 32 positions
 
 
 def load_peaks():
@@ -51,6 +51,15 @@ def load_peaks():
         except Exception:
             pass
     return 6650.0, "fallback", {}
+
+
+def load_traffic():
+    """dram__bytes_read+write per launch (device batch of 16384 pairs) from profiles/*_traffic.json."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(p)).get("dram_bytes_per_launch", {})
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -278,9 +287,10 @@ def main():
     e2e_value = total_pairs / (ms_e2e / 1e3)
     d2h_per_step = int(st_e2e["d2h_bytes"] / max(args.steps, 1))
 
-    # ---- roofline of the dominant kernel (per-kernel CUDA-event time from the library, this run)
+    # ---- rooflines (per-kernel CUDA-event time from the library, measured in THIS run)
     hbm_peak, peak_kind, peaks = load_peaks()
     batches = max(st_dev["batches"], 1)
+    traffic = load_traffic()  # dram bytes per launch from the committed ncu --set full captures
     kern = {
         "encode_fft": {"ms": st_dev["ms_encode_fft"], "launches": batches,
                        "flop": FLOP_FWD_PER_SIGNAL * st_dev["signals"],
@@ -288,9 +298,9 @@ def main():
         "xcorr_findtop": {"ms": st_dev["ms_xcorr"], "launches": batches,
                           "flop": FLOP_XCORR_PER_STRAND * st_dev["strand_pairs"],
                           "bytes": 2 * SPECTRA_BYTES_PER_SIGNAL * st_dev["strand_pairs"]},
-        "scan_score": {"ms": st_dev["ms_scan_score"], "launches": 2 * batches, "flop": 0.0,
+        "scan_score": {"ms": st_dev["ms_scan_score"], "launches": batches, "flop": 0.0,
                        "bytes": (4 * (FFT_N // 32) * 4) * st_dev["strand_pairs"] + 2 * st_dev["candidates"],
-                       "base_cmp": BASE_CMP_PER_PAIR * st_dev["chunk_pairs"]},
+                       "positions": float(st_dev["positions"])},
     }
     for k, v in kern.items():
         secs = max(v["ms"], 1e-9) / 1e3
@@ -301,16 +311,37 @@ def main():
     dom = max(kern, key=lambda k: kern[k]["ms"])
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s at the clock seen under load
-    roofline = {
-        "kernel": dom, "bound": "hbm", "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
-        "frac": kern[dom]["gbs"] / hbm_peak, "traffic": None, "peak_source": peak_kind,
-        "avg_launch_ms": kern[dom]["avg_launch_ms"], "share_of_step": kern[dom]["share"],
-        "fp32_peak_tflops_at_clock": fp32_peak,
-        "kernels": {k: {"ms": round(v["ms"], 3), "share": round(v["share"], 4), "GB/s": round(v["gbs"], 1),
-                        "hbm_frac": round(v["gbs"] / hbm_peak, 4), "TFLOP/s": round(v["tflops"], 3),
-                        "fp32_frac": round(v["tflops"] / fp32_peak, 4)} for k, v in kern.items()},
-        "scan_base_cmp_per_s": kern["scan_score"]["base_cmp"] / max(kern["scan_score"]["ms"] / 1e3, 1e-9),
-    }
+    # Integer roofline of the diagonal scan: LOP3/SHF issue on the ALU pipe, 64 lanes/clk/SM (half rate).
+    # Algorithmic cost = the bit-sliced 46-window count: 88 logic/shift ops per 32 positions.
+    alu_peak = 148 * 64 * sm_mhz * 1e6 / 1e12  # T lane-ops/s
+    scan_ops = kern["scan_score"]["positions"] * SCAN_ALU_OPS_PER_POSITION
+    scan_tops = scan_ops / max(kern["scan_score"]["ms"] / 1e3, 1e-9) / 1e12
+    per_kernel = {k: {"ms": round(v["ms"], 3), "share": round(v["share"], 4), "avg_launch_ms": round(v["avg_launch_ms"], 4),
+                      "GB/s": round(v["gbs"], 1), "hbm_frac": round(v["gbs"] / hbm_peak, 4),
+                      "TFLOP/s": round(v["tflops"], 3), "fp32_frac": round(v["tflops"] / fp32_peak, 4),
+                      "traffic": traffic.get(k)} for k, v in kern.items()}
+    per_kernel["scan_score"].update({"Tintop/s": round(scan_tops, 3), "alu_frac": round(scan_tops / alu_peak, 4),
+                                     "positions_per_s": kern["scan_score"]["positions"] /
+                                     max(kern["scan_score"]["ms"] / 1e3, 1e-9)})
+    if dom == "scan_score":
+        # the dominant kernel is bound by ALU-pipe instruction issue, neither by HBM (0.3 %) nor tensor cores
+        roofline = {"kernel": dom, "bound": "alu", "achieved": scan_tops, "peak": alu_peak, "unit": "Tintop/s",
+                    "frac": scan_tops / alu_peak, "traffic": traffic.get(dom), "peak_source": "148 SM x 64 lanes x clock",
+                    "hbm_frac": kern[dom]["gbs"] / hbm_peak}
+    elif dom == "xcorr_findtop":
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": kern[dom]["gbs"] / hbm_peak, "traffic": traffic.get(dom), "peak_source": peak_kind}
+    else:
+        roofline = {"kernel": dom, "bound": "fp32", "achieved": kern[dom]["tflops"], "peak": fp32_peak,
+                    "unit": "TFLOP/s", "frac": kern[dom]["tflops"] / fp32_peak, "traffic": traffic.get(dom),
+                    "peak_source": "148 SM x 128 lanes x 2 x clock", "hbm_frac": kern[dom]["gbs"] / hbm_peak}
+    roofline.update({"avg_launch_ms": kern[dom]["avg_launch_ms"], "share_of_step": kern[dom]["share"],
+                     "sm_mhz": sm_mhz, "kernels": per_kernel,
+                     # the HBM-bound kernel of the path, against the measured copy bandwidth
+                     "hbm_bound_kernel": {"kernel": "xcorr_findtop", "bound": "hbm",
+                                          "achieved": kern["xcorr_findtop"]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                                          "frac": kern["xcorr_findtop"]["gbs"] / hbm_peak,
+                                          "traffic": traffic.get("xcorr_findtop"), "peak_source": peak_kind}})
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

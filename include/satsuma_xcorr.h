@@ -106,6 +106,7 @@ typedef struct {
   double ms_xcorr;        /* kernel (c)+(d) */
   double ms_scan_score;   /* kernel (e) */
   double ms_total;        /* first launch to last kernel end, per batch, summed */
+  int64_t positions;      /* diagonal positions (base comparisons) scanned by kernel (e) */
 } sx_stats;
 
 /* ------------------------------------------------------------------ lifecycle */

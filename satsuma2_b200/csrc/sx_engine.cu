@@ -623,6 +623,7 @@ static int batch_finish(sx_ctx *c, Run &r, std::vector<sx_result> *results) {
     c->stats.chunk_pairs += (int64_t)b.pairs.size();
     c->stats.candidates += (int64_t)r.n_cand_seen;
     c->stats.segments += (int64_t)ctr.n_segments;
+    c->stats.positions += (int64_t)ctr.n_positions;
     c->stats.matches += (int64_t)ctr.res_used;
     if (ctr.res_used && results) {
       if ((rc = c->h_res.ensure(ctr.res_used)) != SX_OK) return rc;

@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(NT)
   }
   __syncthreads();
 
-  unsigned long long my_segments = 0;
+  unsigned long long my_segments = 0, my_positions = 0;
   for (int c0 = 0; c0 < ncand; c0 += NT) {
     const int c = c0 + tid;
     if (c < ncand) {
@@ -619,6 +619,7 @@ __global__ void __launch_bounds__(NT)
       int i_end = qlen - shift;
       if (tlen - 1 < i_end) i_end = tlen - 1;
       int sum = 0, open = -1;
+      if (i_end > i0) my_positions += (unsigned long long)(i_end - i0);
       auto close_segment = [&](int i) {
         const int seg_len = i - open;
         my_segments++;
@@ -661,6 +662,8 @@ __global__ void __launch_bounds__(NT)
   }
   for (int o = 16; o > 0; o >>= 1) my_segments += __shfl_xor_sync(0xffffffffu, my_segments, o);
   if ((tid & 31) == 0 && my_segments) atomicAdd(&ctr->n_segments, my_segments);
+  for (int o = 16; o > 0; o >>= 1) my_positions += __shfl_xor_sync(0xffffffffu, my_positions, o);
+  if ((tid & 31) == 0 && my_positions) atomicAdd(&ctr->n_positions, my_positions);
 }
 
 // =================================================================================================

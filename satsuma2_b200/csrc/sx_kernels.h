@@ -67,7 +67,7 @@ struct BatchCounters {  // device-side, zeroed per batch
                               // bit3: segment spill pool overflow
   unsigned int spill_used;    // segments that did not fit a warp queue
   unsigned int pad_;
-  unsigned long long n_candidates, n_segments, n_kept;
+  unsigned long long n_candidates, n_segments, n_positions;  // n_positions: diagonal positions scanned
 };
 enum { ST_CAND_OVERFLOW = 1, ST_RES_OVERFLOW = 2, ST_TAP_OVERFLOW = 4, ST_SPILL_OVERFLOW = 8 };
 

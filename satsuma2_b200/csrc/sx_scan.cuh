@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
   uint32_t *wq = s_wq[warp];
 
   unsigned int my_segments = 0;
+  unsigned long long my_positions = 0;
   for (int g0 = warp * 32; g0 < ncand; g0 += SX_SCAN_NT) {  // warp-uniform
     const int c = g0 + lane;
     int shift = 0, i0 = 0, L = 0;
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
       L = i_end - i0;
       if (L <= 46) L = 0;  // no window is ever evaluated (needs n > 45)
     }
+    my_positions += (unsigned long long)L;
     const int nwords = (L + 31) >> 5;
     const int nw_max = __reduce_max_sync(0xffffffffu, nwords);
     const int j0 = i0 + shift;
@@ -283,6 +285,8 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
   }
   my_segments = __reduce_add_sync(0xffffffffu, my_segments);
   if (lane == 0 && my_segments) atomicAdd(&ctr->n_segments, (unsigned long long)my_segments);
+  for (int o = 16; o > 0; o >>= 1) my_positions += __shfl_xor_sync(0xffffffffu, my_positions, o);
+  if (lane == 0 && my_positions) atomicAdd(&ctr->n_positions, my_positions);
 }
 
 // Segments that did not fit a warp queue: same scoring, planes read from global memory.
