@@ -265,3 +265,89 @@ def test_larger_transform_sizes(sx, oracle_lib):
             compare_pair_records(oracle_lib, got[got["query_id"] == i], exp[exp["query_id"] == i], tl[i][0], ql[i][0],
                                  0, 0, chunk, chunk, NN, 1.8, 0.99, 1e6, listed)
         _log_listed(f"transform_{NN}", listed)
+
+
+def _genome_chunks(sx, seq, size, overlap):
+    from satsuma2_b200 import synth
+
+    o, l, s = synth.chunk_sequence(seq, size, overlap)
+    cs = sx.ChunkSet(seq, o, l, s, np.zeros(len(l), np.int32), [len(seq)])
+    lst = [(seq[a:a + n].tobytes(), int(st), 0, len(seq)) for a, n, st in zip(o, l, s)]
+    return cs, lst
+
+
+def test_repeat_rich_prob_table(sx, oracle_lib):
+    """config 5: repeat-rich pair (tandem + interspersed repeats, low-complexity tracts) with
+    -prob_table 1: high candidate density, many kept records, ProbTable semantics (Q11/Q12)."""
+    from satsuma2_b200 import synth
+
+    a, b = synth.repeat_rich_pair(40000, seed=21)
+    total = float(len(a))
+    tab = sx.build_prob_table(total)
+    with sx.XCorrEngine(target_total=total, use_prob_table=1, prob_table_value=0.9999, max_batch_pairs=64) as eng:
+        eng.set_prob_table(tab)
+        tcs, T = _genome_chunks(sx, a, 4096, 1024)
+        qcs, Q = _genome_chunks(sx, b, 4096, 0)
+        eng.set_targets(tcs)
+        eng.set_queries(qcs)
+        nt, nq = len(T), len(Q)
+        got = eng.align_blocks([(0, nt - 1, 0, nq - 1, 0)])
+        st = eng.stats()
+    params = oracle_lib.make_params(target_total=total, prob_table=tab, table_value=0.9999)
+    pairs = [(t, q) for q in range(nq) for t in range(nt)]
+    exp = oracle_lib.align_pairs(params, T, Q, pairs, threads=os.cpu_count() or 1)
+    gk, ek = set(map(rec_key, got)), set(map(rec_key, exp))
+    assert len(ek) > 2000, len(ek)
+    # in table mode thousands of records hang on every candidate lag: allow only a sliver of borderline flips
+    assert len(gk ^ ek) <= 0.002 * len(ek), (len(gk), len(ek), len(gk ^ ek))
+    ge = {rec_key(r): r for r in got}
+    for r in exp:
+        k = rec_key(r)
+        if k in ge:
+            assert ge[k]["ident"] == r["ident"] and ge[k]["prob"] == r["prob"] == 0.9999
+    assert st["candidates"] / st["strand_pairs"] > 250
+
+
+def test_grid_blocks_with_cached_target_spectra(sx, oracle_lib):
+    """config 4 in miniature: a target genome and a diverged, partly inverted copy as query; t_pair
+    blocks along the syntenic diagonal (as GridSearch issues them), target spectra kept in HBM across
+    calls.  Checked against the oracle pair by pair, and cached == uncached."""
+    rng = np.random.default_rng(33)
+    n = 60000
+    tgt = rng.choice(np.frombuffer(b"ACGT", np.uint8), n)
+    qry = tgt.copy()
+    mut = rng.random(n) < 0.15
+    qry[mut] = rng.choice(np.frombuffer(b"ACGT", np.uint8), int(mut.sum()))
+    comp = np.zeros(256, np.uint8)
+    comp[list(b"ACGT")] = list(b"TGCA")
+    qry[20000:30000] = comp[qry[20000:30000][::-1]]
+    qry[41000:41500] = ord("N")
+    listed = []
+    outs = []
+    for cache in (0, -1):
+        with sx.XCorrEngine(target_total=float(n), spectra_cache_bytes=cache, max_batch_pairs=100) as eng:
+            tcs, T = _genome_chunks(sx, tgt, 4096, 1024)
+            qcs, Q = _genome_chunks(sx, qry, 4096, 0)
+            eng.set_targets(tcs)
+            eng.set_queries(qcs)
+            blocks = []
+            for qb in range(0, len(Q), 4):  # 4x6-chunk pixels along the diagonal
+                tc = int(qb * 4096 / 3072)
+                blocks.append((max(0, tc - 1), min(len(T) - 1, tc + 5), qb, min(len(Q) - 1, qb + 3), 0))
+            recs = [eng.align_blocks([b]) for b in blocks]          # one call per block: the cache is reused
+            outs.append(sorted(rec_key(r) for rr in recs for r in rr))
+            if cache == 0:
+                params = oracle_lib.make_params(target_total=float(n))
+                for b, rr in zip(blocks, recs):
+                    pairs = [(t, q) for q in range(b[2], b[3] + 1) for t in range(b[0], b[1] + 1)]
+                    exp = oracle_lib.align_pairs(params, T, Q, pairs, threads=os.cpu_count() or 1)
+                    if sorted(map(rec_key, rr)) != sorted(map(rec_key, exp)):
+                        for (t, q) in pairs:
+                            gp = eng.align_blocks([(t, t, q, q, 0)])
+                            ep = oracle_lib.align_pairs(params, T, Q, [(t, q)])
+                            compare_pair_records(oracle_lib, gp, ep, T[t][0], Q[q][0], T[t][1], Q[q][1], n, 4096, N,
+                                                 1.8, 0.99, float(n), listed)
+    assert outs[0] == outs[1] and len(outs[0]) > 20
+    assert any(k[6] for k in outs[0]) and any(not k[6] for k in outs[0])  # both strands found
+    _log_listed("grid_blocks", listed)
+    assert len(listed) <= 2, listed
