@@ -127,9 +127,13 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
   unsigned int my_segments = 0;
   unsigned long long my_positions = 0;
   for (int g0 = warp * 32; g0 < ncand; g0 += SX_SCAN_NT) {  // warp-uniform
-    const int c = g0 + lane;
+    // Candidates are sorted by lag, so diagonal lengths rise and fall like a triangle.  Pairing the
+    // k-th from the front with the k-th from the back keeps the 32 diagonals of a warp close in
+    // length (the loop runs for the longest one).
+    const int p = g0 + lane;
+    const int c = (p & 1) ? (ncand - 1 - (p >> 1)) : (p >> 1);
     int shift = 0, i0 = 0, L = 0;
-    if (c < ncand) {
+    if (p < ncand) {
       shift = (int)cand_pool[cref.x + c] - H;  // pos = idx - N/2 (CrossCorr.cc:600-602)
       i0 = shift < 0 ? -shift : 0;
       int i_end = qlen - shift;               // first i with j >= qlen
@@ -270,15 +274,34 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
     my_segments += (unsigned int)cnt;
     __syncwarp();
     // ---- score the segments: every lane walks its own queue ----------------------------------------
+    // The queues have different fill levels; spread the segments evenly over the lanes: flat index
+    // f -> (owner lane, slot) through an exclusive prefix of the counts.
     const int nq = min(cnt, SX_LQ_CAP);
-    const int nq_max = __reduce_max_sync(0xffffffffu, nq);
-    for (int r = 0; r < nq_max; r++) {
-      if (r < nq) {
-        const uint32_t q = wq[r * 32 + lane];
+    int off = nq;  // inclusive scan ...
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, off, o);
+      if (lane >= o) off += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, off, 31);
+    off -= nq;  // ... made exclusive
+    for (int f0 = 0; f0 < total; f0 += 32) {  // warp-uniform
+      const int f = f0 + lane;
+      int owner = 0;
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {  // largest lane whose offset is <= f
+        const int cand = owner + step;
+        const int v = __shfl_sync(0xffffffffu, off, cand & 31);
+        if (cand < 32 && v <= f) owner = cand;
+      }
+      const int o_off = __shfl_sync(0xffffffffu, off, owner);
+      const int o_shift = __shfl_sync(0xffffffffu, shift, owner);
+      if (f < total) {
+        const uint32_t q = wq[(f - o_off) * 32 + owner];
         const int start_t = (int)(q & 0xffffu), seg_len = (int)(q >> 16);
         double prob, ident;
-        if (score_fast(P, start_t, shift, seg_len, prm, prob, ident))
-          emit_result(sp, start_t, shift, seg_len, prob, ident, res_pool, res_cap, ctr);
+        if (score_fast(P, start_t, o_shift, seg_len, prm, prob, ident))
+          emit_result(sp, start_t, o_shift, seg_len, prob, ident, res_pool, res_cap, ctr);
       }
     }
     __syncwarp();
