@@ -614,6 +614,7 @@ static int batch_finish(sx_ctx *c, Run &r, std::vector<sx_result> *results) {
       r.need_xcorr = false;
       continue;
     }
+    if (ctr.status & ST_INTERNAL) return fail(SX_ERR_CUDA, "scan kernel: internal round limit hit");
     if (ctr.status & ST_TAP_OVERFLOW) return fail(SX_ERR_CAPACITY, "segment tap overflow (%u records)", ctr.seg_tap_used);
 
     // ---- success: account, fetch records -----------------------------------------------------------

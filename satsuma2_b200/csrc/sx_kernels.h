@@ -69,7 +69,7 @@ struct BatchCounters {  // device-side, zeroed per batch
   unsigned int pad_;
   unsigned long long n_candidates, n_segments, n_positions;  // n_positions: diagonal positions scanned
 };
-enum { ST_CAND_OVERFLOW = 1, ST_RES_OVERFLOW = 2, ST_TAP_OVERFLOW = 4, ST_SPILL_OVERFLOW = 8 };
+enum { ST_CAND_OVERFLOW = 1, ST_RES_OVERFLOW = 2, ST_TAP_OVERFLOW = 4, ST_SPILL_OVERFLOW = 8, ST_INTERNAL = 16 };
 
 // ---- launchers (sx_kernels.cu); all asynchronous on `stream`, return cudaGetLastError() --------
 cudaError_t upload_tables();  // constant/global lookup tables, once per device
