@@ -28,6 +28,10 @@
 #define SX_UNIT_CAP 512  // units queued per warp and group (more are evaluated in place)
 #define SX_SEG_CAP 448   // segments queued per warp and group (more spill to the global list)
 
+// the unit list of a warp is split in three by unit length: 1, 2, >= 3 words
+__host__ __device__ constexpr int unit_cap(int bucket) { return bucket == 0 ? 288 : bucket == 1 ? 144 : 80; }
+__host__ __device__ constexpr int unit_base(int bucket) { return bucket == 0 ? 0 : bucket == 1 ? 288 : 432; }
+
 struct PlanePtrs {
   const uint32_t *tlo, *thi, *qlo, *qhi;  // each readable up to word NW+1 (zero padded)
 };
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
   __shared__ uint32_t s_unit[NWARP][SX_UNIT_CAP];
   __shared__ uint2 s_wq[NWARP][SX_SEG_CAP];
   __shared__ int s_shift[NWARP][32];
-  __shared__ unsigned int s_nunit[NWARP], s_wqn[NWARP];
+  __shared__ unsigned int s_nunit[NWARP][4], s_wqn[NWARP];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SpDesc sp = sps[blockIdx.x];
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
       s_qhi[i] = in ? qp[NW + i] : 0u;
     }
     if (tid < NWARP) {
-      s_nunit[tid] = 0;
+      s_nunit[tid][0] = s_nunit[tid][1] = s_nunit[tid][2] = s_nunit[tid][3] = 0;
       s_wqn[tid] = 0;
     }
   }
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
   uint2 *wq = s_wq[warp];
   unsigned int *wqn = &s_wqn[warp];
   uint32_t *units = s_unit[warp];
-  unsigned int *nunit = &s_nunit[warp];
+  unsigned int *nunit = s_nunit[warp];
   const int spi = blockIdx.x;
 
   unsigned int my_segments = 0;
@@ -405,9 +409,12 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
           e_done = true;
           break;
         }
-        const unsigned int slot = atomicAdd(nunit, 1u);
-        if (slot >= SX_UNIT_CAP) break;  // list full: this unit is found again in the next round
-        units[slot] = (uint32_t)lane | ((uint32_t)ks << 5) | ((uint32_t)kk << 18);
+        // three lists by unit length (1, 2, >= 3 words) so that the 32 units evaluated together take
+        // the same number of steps
+        const int bucket = min(kk, 3) - 1;
+        const unsigned int slot = atomicAdd(&nunit[bucket], 1u);
+        if (slot >= (unsigned int)unit_cap(bucket)) break;  // list full: this unit is found again in the next round
+        units[unit_base(bucket) + slot] = (uint32_t)lane | ((uint32_t)ks << 5) | ((uint32_t)kk << 18);
         e_w = w;
         e_pos = pos;
         e_start = start;
@@ -415,13 +422,16 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
       __syncwarp();
 
       // B2. evaluate the units, one lane each, 32 at a time
-      const int nu = min((int)*nunit, SX_UNIT_CAP);
-      for (int u0 = 0; u0 < nu; u0 += 32) {  // warp-uniform
-        const int u = u0 + lane;
-        const uint32_t rec = u < nu ? units[u] : 0u;
-        const int owner = (int)(rec & 31u), ks = (int)((rec >> 5) & 0x1fffu), kk = (int)(rec >> 18);
-        const Diag od = make_diag(s_shift[warp][owner], tlen, qlen);
-        my_segments += eval_unit<NW>(P, od, ks, kk, spi, wq, wqn, spill, spill_cap, seg_tap, seg_tap_cap, ctr);
+      for (int bucket = 0; bucket < 3; bucket++) {
+        const int nu = min((int)nunit[bucket], unit_cap(bucket));
+        const uint32_t *ul = units + unit_base(bucket);
+        for (int u0 = 0; u0 < nu; u0 += 32) {  // warp-uniform
+          const int u = u0 + lane;
+          const uint32_t rec = u < nu ? ul[u] : 0u;
+          const int owner = (int)(rec & 31u), ks = (int)((rec >> 5) & 0x1fffu), kk = (int)(rec >> 18);
+          const Diag od = make_diag(s_shift[warp][owner], tlen, qlen);
+          my_segments += eval_unit<NW>(P, od, ks, kk, spi, wq, wqn, spill, spill_cap, seg_tap, seg_tap_cap, ctr);
+        }
       }
       __syncwarp();
 
@@ -437,7 +447,7 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
       __syncwarp();
       if (lane == 0) {
         *wqn = 0;
-        *nunit = 0;
+        nunit[0] = nunit[1] = nunit[2] = 0;
       }
       __syncwarp();
     } while (__any_sync(0xffffffffu, !e_done));
