@@ -135,8 +135,8 @@ struct sx_ctx {
   DevBuf<float> d_tap;
   bool have_table = false;
 
-  PinBuf<SigDesc> h_sigs;
-  PinBuf<SpDesc> h_sps;
+  PinBuf<SigDesc> h_sigs[2];  // descriptor staging, one per batch in flight / being assembled
+  PinBuf<SpDesc> h_sps[2];
   PinBuf<ResultRec> h_res;
   PinBuf<BatchCounters> h_ctr;
 
@@ -232,7 +232,7 @@ extern "C" void sx_destroy(sx_ctx *c) {
   c->spec.release(); c->planes.release(); c->sbytes.release(); c->meta.release();
   c->d_sigs.release(); c->d_sps.release(); c->d_cand_ref.release(); c->d_cand_pool.release();
   c->d_res.release(); c->d_seg_tap.release(); c->d_spill.release(); c->d_ctr.release(); c->d_table.release(); c->d_tap.release();
-  c->h_sigs.release(); c->h_sps.release(); c->h_res.release(); c->h_ctr.release();
+  c->h_sigs[0].release(); c->h_sigs[1].release(); c->h_sps[0].release(); c->h_sps[1].release(); c->h_res.release(); c->h_ctr.release();
   for (int i = 0; i < 5; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -490,6 +490,11 @@ struct Run {  // one batch on the device: launched asynchronously, completed by 
   float *d_sig_tap = nullptr, *d_xc_tap = nullptr;
   SegRec *d_seg_tap = nullptr;
   unsigned int seg_tap_cap = 0;
+  int stage = 0;             // which pinned descriptor staging buffer holds this batch
+  bool staged = false;
+  unsigned int fetch_n = 0;  // records copied to the host, waiting for conversion
+  bool fetching = false;
+  BatchCounters done_ctr;    // counters of the completed batch
 };
 }  // namespace
 
@@ -524,30 +529,40 @@ static int batch_kernels(sx_ctx *c, Run &r) {
   return SX_OK;
 }
 
-// upload the descriptors of a batch and launch it; returns without waiting for the device
-static int batch_launch(sx_ctx *c, Run &r, Batch &b, TapRequest *tap) {
+// host part of a launch: copy the descriptors of a batch into pinned staging buffer `stage`
+static int batch_stage(sx_ctx *c, Run &r, Batch &b, TapRequest *tap, int stage) {
   r = Run();
   r.b = &b;
   r.tap = tap;
+  r.stage = stage;
   const int nsig = r.nsig = (int)b.sigs.size(), nsp = r.nsp = (int)b.sps.size();
-  if (nsp == 0 && nsig == 0) return SX_OK;
+  int rc;
+  if ((rc = c->h_sigs[stage].ensure(std::max(nsig, 1))) != SX_OK) return rc;
+  if ((rc = c->h_sps[stage].ensure(std::max(nsp, 1))) != SX_OK) return rc;
+  if (nsig) memcpy(c->h_sigs[stage].p, b.sigs.data(), sizeof(SigDesc) * nsig);
+  if (nsp) memcpy(c->h_sps[stage].p, b.sps.data(), sizeof(SpDesc) * nsp);
+  r.staged = true;
+  return SX_OK;
+}
+
+// upload the staged descriptors of a batch and launch it; returns without waiting for the device
+static int batch_launch(sx_ctx *c, Run &r) {
+  const int nsig = r.nsig, nsp = r.nsp;
+  if (!r.staged || (nsp == 0 && nsig == 0)) return SX_OK;
+  TapRequest *tap = r.tap;
   const size_t N = (size_t)c->N;
   int rc;
   if ((rc = c->d_sigs.ensure(std::max(nsig, 1))) != SX_OK) return rc;
-  if ((rc = c->h_sigs.ensure(std::max(nsig, 1))) != SX_OK) return rc;
   if ((rc = c->d_sps.ensure(std::max(nsp, 1))) != SX_OK) return rc;
-  if ((rc = c->h_sps.ensure(std::max(nsp, 1))) != SX_OK) return rc;
   if ((rc = c->d_cand_ref.ensure(std::max(nsp, 1))) != SX_OK) return rc;
   if (c->d_cand_pool.n < std::max<size_t>((size_t)nsp * 640, 1 << 16) &&
       (rc = c->d_cand_pool.ensure(std::max<size_t>((size_t)nsp * 640, 1 << 16))) != SX_OK)
     return rc;
   if (c->d_res.n == 0 && (rc = c->d_res.ensure(std::max<size_t>((size_t)nsp * 8, 1 << 16))) != SX_OK) return rc;
   if (c->d_spill.n == 0 && (rc = c->d_spill.ensure((size_t)1 << 20)) != SX_OK) return rc;
-  if (nsig) memcpy(c->h_sigs.p, b.sigs.data(), sizeof(SigDesc) * nsig);
-  if (nsp) memcpy(c->h_sps.p, b.sps.data(), sizeof(SpDesc) * nsp);
   cudaStream_t st = c->stream;
-  if (nsig) CU(cudaMemcpyAsync(c->d_sigs.p, c->h_sigs.p, sizeof(SigDesc) * nsig, cudaMemcpyHostToDevice, st));
-  if (nsp) CU(cudaMemcpyAsync(c->d_sps.p, c->h_sps.p, sizeof(SpDesc) * nsp, cudaMemcpyHostToDevice, st));
+  if (nsig) CU(cudaMemcpyAsync(c->d_sigs.p, c->h_sigs[r.stage].p, sizeof(SigDesc) * nsig, cudaMemcpyHostToDevice, st));
+  if (nsp) CU(cudaMemcpyAsync(c->d_sps.p, c->h_sps[r.stage].p, sizeof(SpDesc) * nsp, cudaMemcpyHostToDevice, st));
   c->stats.h2d_bytes += (int64_t)(sizeof(SigDesc) * nsig + sizeof(SpDesc) * nsp);
   if (tap && (tap->sig5n || tap->xc)) {
     if ((rc = c->d_tap.ensure((size_t)std::max(nsig, 1) * 5 * N + (size_t)std::max(nsp, 1) * N)) != SX_OK) return rc;
@@ -566,14 +581,12 @@ static int batch_launch(sx_ctx *c, Run &r, Batch &b, TapRequest *tap) {
   return batch_kernels(c, r);
 }
 
-// wait for a launched batch, grow-and-retry on pool overflow, fetch its records
-static int batch_finish(sx_ctx *c, Run &r, std::vector<sx_result> *results) {
+// wait for a launched batch, grow-and-retry on pool overflow, then START copying its records to the
+// host (asynchronously: the next batch can be launched behind that copy)
+static int batch_wait(sx_ctx *c, Run &r) {
   if (!r.active) return SX_OK;
   r.active = false;
-  Batch &b = *r.b;
-  TapRequest *tap = r.tap;
   const int nsig = r.nsig, nsp = r.nsp;
-  const size_t N = (size_t)c->N;
   cudaStream_t st = c->stream;
   const bool prof = c->profiling;
   int rc;
@@ -617,62 +630,82 @@ static int batch_finish(sx_ctx *c, Run &r, std::vector<sx_result> *results) {
     if (ctr.status & ST_INTERNAL) return fail(SX_ERR_CUDA, "scan kernel: internal round limit hit");
     if (ctr.status & ST_TAP_OVERFLOW) return fail(SX_ERR_CAPACITY, "segment tap overflow (%u records)", ctr.seg_tap_used);
 
-    // ---- success: account, fetch records -----------------------------------------------------------
+    // ---- success: account, start fetching the records ------------------------------------------------
     c->stats.batches++;
     c->stats.signals += nsig;
     c->stats.strand_pairs += nsp;
-    c->stats.chunk_pairs += (int64_t)b.pairs.size();
+    c->stats.chunk_pairs += (int64_t)r.b->pairs.size();
     c->stats.candidates += (int64_t)r.n_cand_seen;
     c->stats.segments += (int64_t)ctr.n_segments;
     c->stats.positions += (int64_t)ctr.n_positions;
     c->stats.matches += (int64_t)ctr.res_used;
-    if (ctr.res_used && results) {
+    r.done_ctr = ctr;
+    r.fetch_n = ctr.res_used;
+    r.fetching = true;
+    if (ctr.res_used) {
       if ((rc = c->h_res.ensure(ctr.res_used)) != SX_OK) return rc;
       CU(cudaMemcpyAsync(c->h_res.p, c->d_res.p, sizeof(ResultRec) * ctr.res_used, cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
       c->stats.d2h_bytes += (int64_t)(sizeof(ResultRec) * ctr.res_used);
-      ResultRec *rr = c->h_res.p;
-      if (c->cfg.sort_results) {
-        // reference emission order: pair, forward before reverse, candidate lag ascending, position ascending
-        std::sort(rr, rr + ctr.res_used, [](const ResultRec &a, const ResultRec &b2) {
-          if (a.pair != b2.pair) return a.pair < b2.pair;
-          if (a.strand != b2.strand) return a.strand < b2.strand;
-          if (a.shift != b2.shift) return a.shift < b2.shift;
-          return a.start_t < b2.start_t;
-        });
-      }
-      const size_t base = results->size();
-      results->resize(base + ctr.res_used);
-      for (unsigned int i = 0; i < ctr.res_used; i++) to_result(c, rr[i], b.pairs[rr[i].pair], &(*results)[base + i]);
     }
-    if (tap) {
-      if (tap->sig5n && nsig) CU(cudaMemcpy(tap->sig5n, r.d_sig_tap, sizeof(float) * nsig * 5 * N, cudaMemcpyDeviceToHost));
-      if (tap->xc && nsp) CU(cudaMemcpy(tap->xc, r.d_xc_tap, sizeof(float) * nsp * N, cudaMemcpyDeviceToHost));
-      if (tap->cands && nsp) {
-        std::vector<uint2> refs(nsp);
-        CU(cudaMemcpy(refs.data(), c->d_cand_ref.p, sizeof(uint2) * nsp, cudaMemcpyDeviceToHost));
-        tap->cands->clear();
-        for (int s = 0; s < nsp; s++) {
-          std::vector<uint16_t> tmp(refs[s].y);
-          if (refs[s].y) CU(cudaMemcpy(tmp.data(), c->d_cand_pool.p + refs[s].x, sizeof(uint16_t) * refs[s].y, cudaMemcpyDeviceToHost));
-          for (uint16_t v : tmp) tap->cands->push_back((int32_t)v);
-        }
-      }
-      if (tap->segs) {
-        tap->segs->resize(ctr.seg_tap_used);
-        if (ctr.seg_tap_used) CU(cudaMemcpy(tap->segs->data(), r.d_seg_tap, sizeof(SegRec) * ctr.seg_tap_used, cudaMemcpyDeviceToHost));
-      }
-    }
+    CU(cudaEventRecord(c->ev[4], st));
     return SX_OK;
   }
   return fail(SX_ERR_CUDA, "device pools kept overflowing after 8 attempts");
 }
 
+// second half of completing a batch: wait for the record copy, convert to t_result, serve taps
+static int batch_collect(sx_ctx *c, Run &r, std::vector<sx_result> *results) {
+  if (!r.fetching) return SX_OK;
+  r.fetching = false;
+  Batch &b = *r.b;
+  TapRequest *tap = r.tap;
+  const int nsig = r.nsig, nsp = r.nsp;
+  const size_t N = (size_t)c->N;
+  const BatchCounters ctr = r.done_ctr;
+  CU(cudaEventSynchronize(c->ev[4]));
+  if (r.fetch_n && results) {
+    ResultRec *rr = c->h_res.p;
+    if (c->cfg.sort_results) {
+      // reference emission order: pair, forward before reverse, candidate lag ascending, position ascending
+      std::sort(rr, rr + r.fetch_n, [](const ResultRec &a, const ResultRec &b2) {
+        if (a.pair != b2.pair) return a.pair < b2.pair;
+        if (a.strand != b2.strand) return a.strand < b2.strand;
+        if (a.shift != b2.shift) return a.shift < b2.shift;
+        return a.start_t < b2.start_t;
+      });
+    }
+    const size_t base = results->size();
+    results->resize(base + r.fetch_n);
+    for (unsigned int i = 0; i < r.fetch_n; i++) to_result(c, rr[i], b.pairs[rr[i].pair], &(*results)[base + i]);
+  }
+  if (tap) {
+    if (tap->sig5n && nsig) CU(cudaMemcpy(tap->sig5n, r.d_sig_tap, sizeof(float) * nsig * 5 * N, cudaMemcpyDeviceToHost));
+    if (tap->xc && nsp) CU(cudaMemcpy(tap->xc, r.d_xc_tap, sizeof(float) * nsp * N, cudaMemcpyDeviceToHost));
+    if (tap->cands && nsp) {
+      std::vector<uint2> refs(nsp);
+      CU(cudaMemcpy(refs.data(), c->d_cand_ref.p, sizeof(uint2) * nsp, cudaMemcpyDeviceToHost));
+      tap->cands->clear();
+      for (int s2 = 0; s2 < nsp; s2++) {
+        std::vector<uint16_t> tmp(refs[s2].y);
+        if (refs[s2].y) CU(cudaMemcpy(tmp.data(), c->d_cand_pool.p + refs[s2].x, sizeof(uint16_t) * refs[s2].y, cudaMemcpyDeviceToHost));
+        for (uint16_t v : tmp) tap->cands->push_back((int32_t)v);
+      }
+    }
+    if (tap->segs) {
+      tap->segs->resize(ctr.seg_tap_used);
+      if (ctr.seg_tap_used) CU(cudaMemcpy(tap->segs->data(), r.d_seg_tap, sizeof(SegRec) * ctr.seg_tap_used, cudaMemcpyDeviceToHost));
+    }
+  }
+  return SX_OK;
+}
+
 static int run_batch(sx_ctx *c, Batch &b, std::vector<sx_result> *results, TapRequest *tap) {
   Run r;
-  int rc = batch_launch(c, r, b, tap);
-  if (rc != SX_OK) return rc;
-  return batch_finish(c, r, results);
+  int rc = batch_stage(c, r, b, tap, 0);
+  if (rc == SX_OK) rc = batch_launch(c, r);
+  if (rc == SX_OK) rc = batch_wait(c, r);
+  if (rc == SX_OK) rc = batch_collect(c, r, results);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -729,26 +762,40 @@ static int align_list(sx_ctx *c, const PairReq *reqs, int64_t n, sx_result *out,
   if (c->Q.n == 0 && n > 0) return fail(SX_ERR_STATE, "align: no queries loaded");
   CU(cudaSetDevice(c->cfg.device));
   c->last.clear();
-  // Two batch descriptors: while the device works on one, the host assembles the next.
+  // Two batch descriptors: while the device works on one, the host assembles AND stages the next;
+  // the next batch is launched right behind the asynchronous record copy of the previous one, and
+  // only then are those records converted on the host.
   Batch bufs[2];
+  Run runs[2];
   int cur = 0;
-  Run inflight;
-  auto submit = [&](Batch &nb) -> int {
-    int rc2 = batch_finish(c, inflight, &c->last);  // completes the PREVIOUS batch (no-op if none)
+  bool have_prev = false;
+  auto submit = [&](int idx) -> int {
+    int rc2 = batch_stage(c, runs[idx], bufs[idx], nullptr, idx);  // host only, overlaps the device
     if (rc2 != SX_OK) return rc2;
-    return batch_launch(c, inflight, nb, nullptr);
+    if (have_prev && (rc2 = batch_wait(c, runs[idx ^ 1])) != SX_OK) return rc2;
+    if ((rc2 = batch_launch(c, runs[idx])) != SX_OK) return rc2;
+    if (have_prev && (rc2 = batch_collect(c, runs[idx ^ 1], &c->last)) != SX_OK) return rc2;
+    have_prev = true;
+    return SX_OK;
+  };
+  auto drain = [&]() -> int {
+    if (!have_prev) return SX_OK;
+    int rc2 = batch_wait(c, runs[cur]);
+    if (rc2 == SX_OK) rc2 = batch_collect(c, runs[cur], &c->last);
+    have_prev = false;
+    return rc2;
   };
   const size_t maxpairs = (size_t)c->cfg.max_batch_pairs;
   for (int64_t i = 0; i < n; i++) {
     const PairReq &r = reqs[i];
     if (r.t < 0 || r.t >= c->T.n || r.q < 0 || r.q >= c->Q.n) {
-      batch_finish(c, inflight, &c->last);
+      if (have_prev) { cur ^= 1; drain(); }
       return fail(SX_ERR_ARG, "align: pair %lld = (target %d, query %d) out of range", (long long)i, r.t, r.q);
     }
     Batch *b = &bufs[cur];
     // worst case this pair needs 3 fresh transient slots
     if (b->pairs.size() >= maxpairs || b->transient_used + 3 > c->n_transient) {
-      int rc = submit(*b);
+      int rc = submit(cur);
       if (rc != SX_OK) return rc;
       cur ^= 1;
       b = &bufs[cur];
@@ -767,9 +814,9 @@ static int align_list(sx_ctx *c, const PairReq *reqs, int64_t n, sx_result *out,
       b->sps.push_back(sp);
     }
   }
-  int rc = submit(bufs[cur]);
+  int rc = submit(cur);
   if (rc != SX_OK) return rc;
-  rc = batch_finish(c, inflight, &c->last);
+  rc = drain();
   if (rc != SX_OK) return rc;
   const int64_t total = (int64_t)c->last.size();
   if (n_out) *n_out = total;
