@@ -271,6 +271,40 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
     const double hit0 = __dsub_rn(1.0, off0), miss0 = __dsub_rn(0.0, off0);
     const double hit1 = __dsub_rn(1.0, off1), miss1 = __dsub_rn(0.0, off1);
     const bool pure = !(flags & SLOT_NONACGT);
+    if (pure) {
+      // Fast path: one thread per entropy window (N/512 bases).  Inside a window the sample is one of
+      // two floats per channel -- (float)(w*(1-mean)) or (float)(w*(0-mean)) -- rounded exactly as the
+      // per-base double product of the reference; the base only selects between them.
+      const uint32_t c0 = 2 * pr, c1 = 2 * pr + 1;
+      for (int w = tid; w < 512; w += NT) {
+        const int k0 = w * WIN;
+        const double e = flat ? 1.0 : (double)went[w];
+        const float h0 = __double2float_rn(__dmul_rn(e, hit0)), m0 = __double2float_rn(__dmul_rn(e, miss0));
+        const float h1 = __double2float_rn(__dmul_rn(e, hit1)), m1 = __double2float_rn(__dmul_rn(e, miss1));
+        uint32_t packed[(WIN + 3) / 4];
+#pragma unroll
+        for (int j = 0; j < (WIN + 3) / 4; j++) packed[j] = reinterpret_cast<const uint32_t *>(sb + k0)[j];
+#pragma unroll
+        for (int j = 0; j < WIN; j++) {
+          const int k = k0 + j;
+          const uint32_t b = (packed[j >> 2] >> (8 * (j & 3))) & 0xffu;
+          const uint32_t code = ((b >> 1) & 3u) ^ ((b >> 2) & 1u);  // A,C,G,T -> 0,1,2,3
+          float2 v;
+          v.x = k < len ? (code == c0 ? h0 : m0) : 0.f;
+          v.y = k < len ? (code == c1 ? h1 : m1) : 0.f;
+          buf[swz(k)] = v;
+        }
+      }
+      if (tap != nullptr) {  // taps read back exactly what the transform is about to see
+        __syncthreads();
+        float *ts = tap + (size_t)blockIdx.x * 5 * N + (size_t)(1 + 2 * pr) * N;
+        for (int k = tid; k < N; k += NT) {
+          const float2 v = buf[swz(k)];
+          ts[k] = v.x;
+          ts[N + k] = v.y;
+        }
+      }
+    } else
     for (int k = tid; k < N; k += NT) {
       float2 v = make_float2(0.f, 0.f);
       if (k < len) {
