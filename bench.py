@@ -239,7 +239,7 @@ def main():
 
     # spectra are never kept across steps (cache disabled): every step redoes the whole path
     eng = sx.XCorrEngine(device=local_rank, target_total=float(n) * CHUNK, max_batch_pairs=args.batch,
-                         spectra_cache_bytes=-1)
+                         spectra_cache_bytes=-1, async_upload=1)
     stream = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
     t_ptr, q_ptr = T.ctypes.data, Q.ctypes.data
     h2d_per_step = int(T.nbytes + Q.nbytes)

@@ -59,7 +59,11 @@ typedef struct {
   int64_t spectra_cache_bytes; /* HBM budget for keeping target spectra resident across calls
                                   (0 = default 48 GiB, < 0 = never keep) */
   int32_t sort_results;    /* != 0: return records ordered as the reference emits them */
-  int32_t reserved[7];
+  int32_t debug_small_pools; /* test hook: start with tiny device pools so the grow-and-retry paths run */
+  int32_t async_upload;    /* != 0: sx_set_targets/queries return before the host->device copy has finished;
+                              the caller keeps `bases` alive and unmodified until the next sx_align_* call on
+                              this context returns.  Batches start as soon as the bases they need have arrived. */
+  int32_t reserved[5];
 } sx_config;
 
 /* Fills *cfg with the reference's defaults (slave semantics). */
@@ -107,6 +111,7 @@ typedef struct {
   double ms_scan_score;   /* kernel (e) */
   double ms_total;        /* first launch to last kernel end, per batch, summed */
   int64_t positions;      /* diagonal positions (base comparisons) scanned by kernel (e) */
+  int64_t spilled_segments; /* segments that overflowed a warp queue and took the global spill list */
 } sx_stats;
 
 /* ------------------------------------------------------------------ lifecycle */

@@ -40,7 +40,8 @@ class Config(C.Structure):
         ("cutoff", C.c_double), ("cutoff_fast", C.c_double), ("min_len", C.c_int32), ("use_prob_table", C.c_int32),
         ("min_prob", C.c_double), ("prob_table_value", C.c_double), ("target_total", C.c_double),
         ("rc_coord_mode", C.c_int32), ("max_batch_pairs", C.c_int32), ("spectra_cache_bytes", C.c_int64),
-        ("sort_results", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("sort_results", C.c_int32), ("debug_small_pools", C.c_int32), ("async_upload", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -50,6 +51,7 @@ class Stats(C.Structure):
         ("segments", C.c_int64), ("matches", C.c_int64), ("kernel_launches", C.c_int64), ("batches", C.c_int64),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("retries", C.c_int64), ("ms_encode_fft", C.c_double),
         ("ms_xcorr", C.c_double), ("ms_scan_score", C.c_double), ("ms_total", C.c_double), ("positions", C.c_int64),
+        ("spilled_segments", C.c_int64),
     ]
 
     def as_dict(self):

@@ -49,6 +49,10 @@ struct ChunkStore {
   size_t blob_bytes = 0, cap_bytes = 0;
   std::vector<int64_t> offsets;
   std::vector<int32_t> lens, starts, seq_ids, seq_sizes;
+  // asynchronous upload: the blob travels in pieces on the copy stream, one event per piece
+  std::vector<cudaEvent_t> piece_ev;
+  size_t piece_bytes = 0, n_pieces = 0;
+  bool async_pending = false;
 };
 
 struct PairReq {
@@ -105,6 +109,7 @@ struct sx_ctx {
   int log2n = 0, N = 0;
   std::mutex mu;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // async_upload: host->device copies of the chunk blobs
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool profiling = false;
   sx_stats stats;
@@ -206,6 +211,7 @@ extern "C" int sx_create(const sx_config *cfg, sx_ctx **out) {
   memset(&c->stats, 0, sizeof(c->stats));
   c->target_total = cfg->target_total;
   cudaError_t ce = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
   if (ce == cudaSuccess)
     for (int i = 0; i < 5 && ce == cudaSuccess; i++) ce = cudaEventCreate(&c->ev[i]);
   if (ce == cudaSuccess) ce = upload_tables();
@@ -227,6 +233,10 @@ extern "C" void sx_destroy(sx_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
   cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  for (ChunkStore *S : {&c->T, &c->Q})
+    for (cudaEvent_t e : S->piece_ev) cudaEventDestroy(e);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->T.d_bases) cudaFree(c->T.d_bases);
   if (c->Q.d_bases) cudaFree(c->Q.d_bases);
   c->spec.release(); c->planes.release(); c->sbytes.release(); c->meta.release();
@@ -270,8 +280,27 @@ static int set_store(sx_ctx *c, ChunkStore &S, const char *bases, const int64_t 
       CU(cudaMalloc((void **)&S.d_bases, blob + 16));
       S.cap_bytes = blob + 16;
     }
-    CU(cudaMemcpyAsync(S.d_bases, bases, blob, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    S.async_pending = false;
+    if (c->cfg.async_upload) {
+      // pieces on the copy stream, one event each: a batch waits only for the pieces it reads
+      CU(cudaStreamSynchronize(c->copy_stream));
+      S.piece_bytes = (size_t)32 << 20;
+      S.n_pieces = (blob + S.piece_bytes - 1) / S.piece_bytes;
+      while (S.piece_ev.size() < S.n_pieces) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        S.piece_ev.push_back(e);
+      }
+      for (size_t pi = 0; pi < S.n_pieces; pi++) {
+        const size_t off = pi * S.piece_bytes, sz = std::min(S.piece_bytes, blob - off);
+        CU(cudaMemcpyAsync(S.d_bases + off, bases + off, sz, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaEventRecord(S.piece_ev[pi], c->copy_stream));
+      }
+      S.async_pending = true;
+    } else {
+      CU(cudaMemcpyAsync(S.d_bases, bases, blob, cudaMemcpyHostToDevice, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+    }
     c->stats.h2d_bytes += (int64_t)blob;
   }
   return SX_OK;
@@ -410,11 +439,13 @@ struct Batch {
   std::vector<SpDesc> sps;
   std::vector<PairReq> pairs;  // batch-local pair index -> chunk indices
   size_t transient_used = 0;
+  size_t t_need = 0, q_need = 0;  // highest byte of the target / query blob this batch reads (+1)
   std::unordered_map<int32_t, int32_t> tslot;  // target chunk -> slot (transient mode)
   std::unordered_map<int32_t, int32_t> qslot;  // query chunk  -> forward slot (rc slot = +1)
   void clear() {
     sigs.clear(); sps.clear(); pairs.clear(); tslot.clear(); qslot.clear();
     transient_used = 0;
+    t_need = q_need = 0;
   }
 };
 
@@ -555,12 +586,26 @@ static int batch_launch(sx_ctx *c, Run &r) {
   if ((rc = c->d_sigs.ensure(std::max(nsig, 1))) != SX_OK) return rc;
   if ((rc = c->d_sps.ensure(std::max(nsp, 1))) != SX_OK) return rc;
   if ((rc = c->d_cand_ref.ensure(std::max(nsp, 1))) != SX_OK) return rc;
-  if (c->d_cand_pool.n < std::max<size_t>((size_t)nsp * 640, 1 << 16) &&
-      (rc = c->d_cand_pool.ensure(std::max<size_t>((size_t)nsp * 640, 1 << 16))) != SX_OK)
-    return rc;
-  if (c->d_res.n == 0 && (rc = c->d_res.ensure(std::max<size_t>((size_t)nsp * 8, 1 << 16))) != SX_OK) return rc;
-  if (c->d_spill.n == 0 && (rc = c->d_spill.ensure((size_t)1 << 20)) != SX_OK) return rc;
+  if (c->cfg.debug_small_pools) {  // test hook: start with pools that must overflow, so the grow-and-retry paths run
+    if (c->d_cand_pool.n == 0 && (rc = c->d_cand_pool.ensure(64)) != SX_OK) return rc;
+    if (c->d_res.n == 0 && (rc = c->d_res.ensure(4)) != SX_OK) return rc;
+    if (c->d_spill.n == 0 && (rc = c->d_spill.ensure(2)) != SX_OK) return rc;
+  } else {
+    if (c->d_cand_pool.n < std::max<size_t>((size_t)nsp * 640, 1 << 16) &&
+        (rc = c->d_cand_pool.ensure(std::max<size_t>((size_t)nsp * 640, 1 << 16))) != SX_OK)
+      return rc;
+    if (c->d_res.n == 0 && (rc = c->d_res.ensure(std::max<size_t>((size_t)nsp * 8, 1 << 16))) != SX_OK) return rc;
+    if (c->d_spill.n == 0 && (rc = c->d_spill.ensure((size_t)1 << 20)) != SX_OK) return rc;
+  }
   cudaStream_t st = c->stream;
+  for (int which = 0; which < 2; which++) {  // async_upload: wait for the last blob piece this batch reads
+    const ChunkStore &S = which ? c->Q : c->T;
+    const size_t need = which ? r.b->q_need : r.b->t_need;
+    if (S.async_pending && need > 0 && S.n_pieces > 0) {
+      const size_t piece = std::min((need - 1) / S.piece_bytes, S.n_pieces - 1);
+      CU(cudaStreamWaitEvent(st, S.piece_ev[piece], 0));
+    }
+  }
   if (nsig) CU(cudaMemcpyAsync(c->d_sigs.p, c->h_sigs[r.stage].p, sizeof(SigDesc) * nsig, cudaMemcpyHostToDevice, st));
   if (nsp) CU(cudaMemcpyAsync(c->d_sps.p, c->h_sps[r.stage].p, sizeof(SpDesc) * nsp, cudaMemcpyHostToDevice, st));
   c->stats.h2d_bytes += (int64_t)(sizeof(SigDesc) * nsig + sizeof(SpDesc) * nsp);
@@ -639,6 +684,7 @@ static int batch_wait(sx_ctx *c, Run &r) {
     c->stats.segments += (int64_t)ctr.n_segments;
     c->stats.positions += (int64_t)ctr.n_positions;
     c->stats.matches += (int64_t)ctr.res_used;
+    c->stats.spilled_segments += (int64_t)ctr.spill_used;
     r.done_ctr = ctr;
     r.fetch_n = ctr.res_used;
     r.fetching = true;
@@ -717,6 +763,7 @@ static int32_t target_slot(sx_ctx *c, Batch &b, int32_t t) {
       SigDesc s;
       s.src = c->T.d_bases + c->T.offsets[t];
       s.len = c->T.lens[t];
+      b.t_need = std::max(b.t_need, (size_t)c->T.offsets[t] + (size_t)c->T.lens[t]);
       s.strand = 0;
       s.slot = t;
       s.pad = 0;
@@ -731,6 +778,7 @@ static int32_t target_slot(sx_ctx *c, Batch &b, int32_t t) {
   SigDesc s;
   s.src = c->T.d_bases + c->T.offsets[t];
   s.len = c->T.lens[t];
+  b.t_need = std::max(b.t_need, (size_t)c->T.offsets[t] + (size_t)c->T.lens[t]);
   s.strand = 0;
   s.slot = slot;
   s.pad = 0;
@@ -748,6 +796,7 @@ static int32_t query_slot(sx_ctx *c, Batch &b, int32_t q) {
     SigDesc s;
     s.src = c->Q.d_bases + c->Q.offsets[q];
     s.len = c->Q.lens[q];
+    b.q_need = std::max(b.q_need, (size_t)c->Q.offsets[q] + (size_t)c->Q.lens[q]);
     s.strand = strand;
     s.slot = slot + strand;
     s.pad = 0;
@@ -870,6 +919,8 @@ static int tap_prepare(sx_ctx *c, int32_t target, int32_t query, int32_t strand,
     return fail(SX_ERR_ARG, "tap: (target %d, query %d, strand %d) out of range", target, query, strand);
   if (c->n_transient < 3) return fail(SX_ERR_STATE, "tap: no workspace (call sx_set_targets first)");
   CU(cudaSetDevice(c->cfg.device));
+  b.t_need = c->T.blob_bytes;
+  b.q_need = c->Q.blob_bytes;
   const int32_t base = (int32_t)c->n_persist;
   SigDesc s;
   s.src = c->T.d_bases + c->T.offsets[target];
@@ -905,6 +956,8 @@ extern "C" int sx_tap_signal(sx_ctx *c, int32_t is_target, int32_t chunk, int32_
   if (c->n_transient < 1) return fail(SX_ERR_STATE, "tap: no workspace (call sx_set_targets first)");
   CU(cudaSetDevice(c->cfg.device));
   Batch b;
+  b.t_need = c->T.blob_bytes;
+  b.q_need = c->Q.blob_bytes;
   SigDesc s;
   s.src = S.d_bases + S.offsets[chunk];
   s.len = S.lens[chunk];
