@@ -49,9 +49,12 @@ struct ChunkStore {
   size_t blob_bytes = 0, cap_bytes = 0;
   std::vector<int64_t> offsets;
   std::vector<int32_t> lens, starts, seq_ids, seq_sizes;
-  // asynchronous upload: the blob travels in pieces on the copy stream, one event per piece
+  // asynchronous upload: the blob travels in pieces on the copy stream, one event per piece; pieces are
+  // enqueued when a batch needs them (plus a look-ahead), so target and query pieces interleave in the
+  // order the batches consume them
   std::vector<cudaEvent_t> piece_ev;
-  size_t piece_bytes = 0, n_pieces = 0;
+  size_t piece_bytes = 0, n_pieces = 0, enq_pieces = 0;
+  const char *h_src = nullptr;
   bool async_pending = false;
 };
 
@@ -125,12 +128,14 @@ struct sx_ctx {
   DevBuf<uint32_t> planes;
   DevBuf<uint8_t> sbytes;
   DevBuf<SlotMeta> meta;
+  DevBuf<float2> wn;  // e^{-2 pi i n / N}, n < N/2
   std::vector<uint8_t> t_valid;  // persistent target slot holds a spectrum
 
   // per-batch device buffers
   DevBuf<SigDesc> d_sigs;
   DevBuf<SpDesc> d_sps;
   DevBuf<uint2> d_cand_ref;
+  DevBuf<uint32_t> d_lists;  // [pair list | direct list] of strand-pair indices (launch_xcorr_findtop)
   DevBuf<uint16_t> d_cand_pool;
   DevBuf<ResultRec> d_res;
   DevBuf<SegRec> d_seg_tap;
@@ -142,6 +147,7 @@ struct sx_ctx {
 
   PinBuf<SigDesc> h_sigs[2];  // descriptor staging, one per batch in flight / being assembled
   PinBuf<SpDesc> h_sps[2];
+  PinBuf<uint32_t> h_lists[2];
   PinBuf<ResultRec> h_res;
   PinBuf<BatchCounters> h_ctr;
 
@@ -153,6 +159,7 @@ struct sx_ctx {
     s.planes = planes.p;
     s.bytes = sbytes.p;
     s.meta = meta.p;
+    s.wn = wn.p;
     return s;
   }
 };
@@ -221,6 +228,13 @@ extern "C" int sx_create(const sx_config *cfg, sx_ctx **out) {
   }
   int rc = c->d_ctr.ensure(1);
   if (rc == SX_OK) rc = c->h_ctr.ensure(1);
+  if (rc == SX_OK) rc = c->wn.ensure((size_t)c->N / 2);
+  if (rc == SX_OK) {
+    std::vector<float2> w((size_t)c->N / 2);
+    fill_wn_table(c->log2n, w.data());
+    if (cudaMemcpy(c->wn.p, w.data(), sizeof(float2) * w.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+      rc = fail(SX_ERR_CUDA, "sx_create: twiddle table upload failed");
+  }
   if (rc != SX_OK) {
     delete c;
     return rc;
@@ -239,7 +253,8 @@ extern "C" void sx_destroy(sx_ctx *c) {
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->T.d_bases) cudaFree(c->T.d_bases);
   if (c->Q.d_bases) cudaFree(c->Q.d_bases);
-  c->spec.release(); c->planes.release(); c->sbytes.release(); c->meta.release();
+  c->spec.release(); c->planes.release(); c->sbytes.release(); c->meta.release(); c->wn.release();
+  c->d_lists.release(); c->h_lists[0].release(); c->h_lists[1].release();
   c->d_sigs.release(); c->d_sps.release(); c->d_cand_ref.release(); c->d_cand_pool.release();
   c->d_res.release(); c->d_seg_tap.release(); c->d_spill.release(); c->d_ctr.release(); c->d_table.release(); c->d_tap.release();
   c->h_sigs[0].release(); c->h_sigs[1].release(); c->h_sps[0].release(); c->h_sps[1].release(); c->h_res.release(); c->h_ctr.release();
@@ -282,19 +297,16 @@ static int set_store(sx_ctx *c, ChunkStore &S, const char *bases, const int64_t 
     }
     S.async_pending = false;
     if (c->cfg.async_upload) {
-      // pieces on the copy stream, one event each: a batch waits only for the pieces it reads
+      // nothing travels yet: upload_pieces() enqueues the pieces as the batches ask for them
       CU(cudaStreamSynchronize(c->copy_stream));
-      S.piece_bytes = (size_t)32 << 20;
+      S.piece_bytes = (size_t)16 << 20;
       S.n_pieces = (blob + S.piece_bytes - 1) / S.piece_bytes;
+      S.enq_pieces = 0;
+      S.h_src = bases;
       while (S.piece_ev.size() < S.n_pieces) {
         cudaEvent_t e;
         CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         S.piece_ev.push_back(e);
-      }
-      for (size_t pi = 0; pi < S.n_pieces; pi++) {
-        const size_t off = pi * S.piece_bytes, sz = std::min(S.piece_bytes, blob - off);
-        CU(cudaMemcpyAsync(S.d_bases + off, bases + off, sz, cudaMemcpyHostToDevice, c->copy_stream));
-        CU(cudaEventRecord(S.piece_ev[pi], c->copy_stream));
       }
       S.async_pending = true;
     } else {
@@ -303,6 +315,33 @@ static int set_store(sx_ctx *c, ChunkStore &S, const char *bases, const int64_t 
     }
     c->stats.h2d_bytes += (int64_t)blob;
   }
+  return SX_OK;
+}
+
+// async_upload: enqueue blob pieces [enq_pieces, upto) on the copy stream
+static int upload_pieces(sx_ctx *c, ChunkStore &S, size_t upto) {
+  upto = std::min(upto, S.n_pieces);
+  for (size_t pi = S.enq_pieces; pi < upto; pi++) {
+    const size_t off = pi * S.piece_bytes, sz = std::min(S.piece_bytes, S.blob_bytes - off);
+    CU(cudaMemcpyAsync(S.d_bases + off, S.h_src + off, sz, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaEventRecord(S.piece_ev[pi], c->copy_stream));
+  }
+  S.enq_pieces = std::max(S.enq_pieces, upto);
+  return SX_OK;
+}
+
+// async_upload: everything not yet sent goes now and the host waits for it -- after this the caller's
+// buffers are no longer referenced (the contract of sx_config::async_upload)
+static int finish_uploads(sx_ctx *c) {
+  bool any = false;
+  for (ChunkStore *S : {&c->T, &c->Q}) {
+    if (!S->async_pending) continue;
+    int rc = upload_pieces(c, *S, S->n_pieces);
+    if (rc != SX_OK) return rc;
+    any = true;
+  }
+  if (any) CU(cudaStreamSynchronize(c->copy_stream));
+  c->T.async_pending = c->Q.async_pending = false;
   return SX_OK;
 }
 
@@ -438,12 +477,13 @@ struct Batch {
   std::vector<SigDesc> sigs;
   std::vector<SpDesc> sps;
   std::vector<PairReq> pairs;  // batch-local pair index -> chunk indices
+  std::vector<uint32_t> pair_list, direct_list;  // strand-pair indices for the two correlation kernels
   size_t transient_used = 0;
   size_t t_need = 0, q_need = 0;  // highest byte of the target / query blob this batch reads (+1)
   std::unordered_map<int32_t, int32_t> tslot;  // target chunk -> slot (transient mode)
   std::unordered_map<int32_t, int32_t> qslot;  // query chunk  -> forward slot (rc slot = +1)
   void clear() {
-    sigs.clear(); sps.clear(); pairs.clear(); tslot.clear(); qslot.clear();
+    sigs.clear(); sps.clear(); pairs.clear(); tslot.clear(); qslot.clear(); pair_list.clear(); direct_list.clear();
     transient_used = 0;
     t_need = q_need = 0;
   }
@@ -454,6 +494,7 @@ struct TapRequest {
   float *xc = nullptr;      // host, N per strand-pair
   std::vector<int32_t> *cands = nullptr;
   std::vector<SegRec> *segs = nullptr;
+  int sp_select = -1;  // >= 0: xc / cands / segs of this strand-pair only
 };
 
 }  // namespace
@@ -515,7 +556,7 @@ namespace {
 struct Run {  // one batch on the device: launched asynchronously, completed by batch_finish
   Batch *b = nullptr;
   TapRequest *tap = nullptr;
-  int nsig = 0, nsp = 0;
+  int nsig = 0, nsp = 0, n_pairlist = 0, n_direct = 0;
   bool need_encode = false, need_xcorr = true, active = false;
   unsigned long long n_cand_seen = 0;
   float *d_sig_tap = nullptr, *d_xc_tap = nullptr;
@@ -543,10 +584,11 @@ static int batch_kernels(sx_ctx *c, Run &r) {
   }
   if (prof) CU(cudaEventRecord(c->ev[1], st));
   if (r.nsp && r.need_xcorr) {
-    CU(launch_xcorr_findtop(c->log2n, c->d_sps.p, r.nsp, ws, c->cfg.cutoff, c->cfg.cutoff_fast, c->d_cand_pool.p,
+    CU(launch_xcorr_findtop(c->log2n, c->d_sps.p, c->d_lists.p, r.n_pairlist, c->d_lists.p + r.n_pairlist, r.n_direct, ws,
+                            c->cfg.cutoff, c->cfg.cutoff_fast, c->d_cand_pool.p,
                             (unsigned int)std::min<size_t>(c->d_cand_pool.n, 0xfffffff0u), c->d_cand_ref.p, c->d_ctr.p,
                             r.d_xc_tap, st));
-    c->stats.kernel_launches += 1;
+    c->stats.kernel_launches += (r.n_pairlist > 0) + (r.n_direct > 0);
   }
   if (prof) CU(cudaEventRecord(c->ev[2], st));
   if (r.nsp) {
@@ -572,6 +614,11 @@ static int batch_stage(sx_ctx *c, Run &r, Batch &b, TapRequest *tap, int stage) 
   if ((rc = c->h_sps[stage].ensure(std::max(nsp, 1))) != SX_OK) return rc;
   if (nsig) memcpy(c->h_sigs[stage].p, b.sigs.data(), sizeof(SigDesc) * nsig);
   if (nsp) memcpy(c->h_sps[stage].p, b.sps.data(), sizeof(SpDesc) * nsp);
+  r.n_pairlist = (int)b.pair_list.size();
+  r.n_direct = (int)b.direct_list.size();
+  if ((rc = c->h_lists[stage].ensure(std::max(r.n_pairlist + r.n_direct, 1))) != SX_OK) return rc;
+  if (r.n_pairlist) memcpy(c->h_lists[stage].p, b.pair_list.data(), sizeof(uint32_t) * r.n_pairlist);
+  if (r.n_direct) memcpy(c->h_lists[stage].p + r.n_pairlist, b.direct_list.data(), sizeof(uint32_t) * r.n_direct);
   r.staged = true;
   return SX_OK;
 }
@@ -586,6 +633,7 @@ static int batch_launch(sx_ctx *c, Run &r) {
   if ((rc = c->d_sigs.ensure(std::max(nsig, 1))) != SX_OK) return rc;
   if ((rc = c->d_sps.ensure(std::max(nsp, 1))) != SX_OK) return rc;
   if ((rc = c->d_cand_ref.ensure(std::max(nsp, 1))) != SX_OK) return rc;
+  if ((rc = c->d_lists.ensure(std::max(r.n_pairlist + r.n_direct, 1))) != SX_OK) return rc;
   if (c->cfg.debug_small_pools) {  // test hook: start with pools that must overflow, so the grow-and-retry paths run
     if (c->d_cand_pool.n == 0 && (rc = c->d_cand_pool.ensure(64)) != SX_OK) return rc;
     if (c->d_res.n == 0 && (rc = c->d_res.ensure(4)) != SX_OK) return rc;
@@ -598,17 +646,22 @@ static int batch_launch(sx_ctx *c, Run &r) {
     if (c->d_spill.n == 0 && (rc = c->d_spill.ensure((size_t)1 << 20)) != SX_OK) return rc;
   }
   cudaStream_t st = c->stream;
-  for (int which = 0; which < 2; which++) {  // async_upload: wait for the last blob piece this batch reads
-    const ChunkStore &S = which ? c->Q : c->T;
+  // async_upload: send the blob pieces this batch reads (normally already sent as look-ahead) and make
+  // the compute stream wait for the last of them
+  for (int which = 0; which < 2; which++) {
+    ChunkStore &S = which ? c->Q : c->T;
     const size_t need = which ? r.b->q_need : r.b->t_need;
-    if (S.async_pending && need > 0 && S.n_pieces > 0) {
-      const size_t piece = std::min((need - 1) / S.piece_bytes, S.n_pieces - 1);
-      CU(cudaStreamWaitEvent(st, S.piece_ev[piece], 0));
-    }
+    if (!S.async_pending || S.n_pieces == 0 || need == 0) continue;
+    const size_t upto = std::min((need - 1) / S.piece_bytes + 1, S.n_pieces);
+    if ((rc = upload_pieces(c, S, upto)) != SX_OK) return rc;
+    CU(cudaStreamWaitEvent(st, S.piece_ev[upto - 1], 0));
   }
   if (nsig) CU(cudaMemcpyAsync(c->d_sigs.p, c->h_sigs[r.stage].p, sizeof(SigDesc) * nsig, cudaMemcpyHostToDevice, st));
   if (nsp) CU(cudaMemcpyAsync(c->d_sps.p, c->h_sps[r.stage].p, sizeof(SpDesc) * nsp, cudaMemcpyHostToDevice, st));
-  c->stats.h2d_bytes += (int64_t)(sizeof(SigDesc) * nsig + sizeof(SpDesc) * nsp);
+  if (r.n_pairlist + r.n_direct)
+    CU(cudaMemcpyAsync(c->d_lists.p, c->h_lists[r.stage].p, sizeof(uint32_t) * (r.n_pairlist + r.n_direct),
+                       cudaMemcpyHostToDevice, st));
+  c->stats.h2d_bytes += (int64_t)(sizeof(SigDesc) * nsig + sizeof(SpDesc) * nsp + sizeof(uint32_t) * (r.n_pairlist + r.n_direct));
   if (tap && (tap->sig5n || tap->xc)) {
     if ((rc = c->d_tap.ensure((size_t)std::max(nsig, 1) * 5 * N + (size_t)std::max(nsp, 1) * N)) != SX_OK) return rc;
     if (tap->sig5n) r.d_sig_tap = c->d_tap.p;
@@ -623,7 +676,19 @@ static int batch_launch(sx_ctx *c, Run &r) {
   r.need_encode = nsig > 0;
   r.need_xcorr = true;
   r.active = true;
-  return batch_kernels(c, r);
+  if ((rc = batch_kernels(c, r)) != SX_OK) return rc;
+  // async_upload look-ahead: the next batches' bases travel while this one computes.  Queued AFTER this
+  // batch's descriptor copies: the host->device copy engine works in order, bulk pieces ahead of the
+  // descriptors would delay the kernels by their transfer time.
+  for (int which = 0; which < 2; which++) {
+    ChunkStore &S = which ? c->Q : c->T;
+    const size_t need = which ? r.b->q_need : r.b->t_need;
+    if (!S.async_pending || S.n_pieces == 0) continue;
+    const size_t upto = need > 0 ? std::min((need - 1) / S.piece_bytes + 1, S.n_pieces) : 0;
+    const size_t ahead = (2 * (size_t)c->cfg.max_batch_pairs * (size_t)c->cfg.t_chunk) / S.piece_bytes + 2;
+    if ((rc = upload_pieces(c, S, upto + ahead)) != SX_OK) return rc;
+  }
+  return SX_OK;
 }
 
 // wait for a launched batch, grow-and-retry on pool overflow, then START copying its records to the
@@ -726,20 +791,30 @@ static int batch_collect(sx_ctx *c, Run &r, std::vector<sx_result> *results) {
   }
   if (tap) {
     if (tap->sig5n && nsig) CU(cudaMemcpy(tap->sig5n, r.d_sig_tap, sizeof(float) * nsig * 5 * N, cudaMemcpyDeviceToHost));
-    if (tap->xc && nsp) CU(cudaMemcpy(tap->xc, r.d_xc_tap, sizeof(float) * nsp * N, cudaMemcpyDeviceToHost));
+    const int sel = tap->sp_select;
+    if (tap->xc && nsp) {
+      if (sel >= 0)
+        CU(cudaMemcpy(tap->xc, r.d_xc_tap + (size_t)sel * N, sizeof(float) * N, cudaMemcpyDeviceToHost));
+      else
+        CU(cudaMemcpy(tap->xc, r.d_xc_tap, sizeof(float) * nsp * N, cudaMemcpyDeviceToHost));
+    }
     if (tap->cands && nsp) {
       std::vector<uint2> refs(nsp);
       CU(cudaMemcpy(refs.data(), c->d_cand_ref.p, sizeof(uint2) * nsp, cudaMemcpyDeviceToHost));
       tap->cands->clear();
       for (int s2 = 0; s2 < nsp; s2++) {
+        if (sel >= 0 && s2 != sel) continue;
         std::vector<uint16_t> tmp(refs[s2].y);
         if (refs[s2].y) CU(cudaMemcpy(tmp.data(), c->d_cand_pool.p + refs[s2].x, sizeof(uint16_t) * refs[s2].y, cudaMemcpyDeviceToHost));
         for (uint16_t v : tmp) tap->cands->push_back((int32_t)v);
       }
     }
     if (tap->segs) {
-      tap->segs->resize(ctr.seg_tap_used);
-      if (ctr.seg_tap_used) CU(cudaMemcpy(tap->segs->data(), r.d_seg_tap, sizeof(SegRec) * ctr.seg_tap_used, cudaMemcpyDeviceToHost));
+      std::vector<SegRec> all(ctr.seg_tap_used);
+      if (ctr.seg_tap_used) CU(cudaMemcpy(all.data(), r.d_seg_tap, sizeof(SegRec) * ctr.seg_tap_used, cudaMemcpyDeviceToHost));
+      tap->segs->clear();
+      for (const SegRec &sr : all)
+        if (sel < 0 || sr.sp == sel) tap->segs->push_back(sr);
     }
   }
   return SX_OK;
@@ -751,7 +826,8 @@ static int run_batch(sx_ctx *c, Batch &b, std::vector<sx_result> *results, TapRe
   if (rc == SX_OK) rc = batch_launch(c, r);
   if (rc == SX_OK) rc = batch_wait(c, r);
   if (rc == SX_OK) rc = batch_collect(c, r, results);
-  return rc;
+  const int rc2 = finish_uploads(c);
+  return rc != SX_OK ? rc : rc2;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -766,7 +842,7 @@ static int32_t target_slot(sx_ctx *c, Batch &b, int32_t t) {
       b.t_need = std::max(b.t_need, (size_t)c->T.offsets[t] + (size_t)c->T.lens[t]);
       s.strand = 0;
       s.slot = t;
-      s.pad = 0;
+      s.rc_slot1 = 0;
       b.sigs.push_back(s);
       c->t_valid[t] = 1;
     }
@@ -781,10 +857,19 @@ static int32_t target_slot(sx_ctx *c, Batch &b, int32_t t) {
   b.t_need = std::max(b.t_need, (size_t)c->T.offsets[t] + (size_t)c->T.lens[t]);
   s.strand = 0;
   s.slot = slot;
-  s.pad = 0;
+  s.rc_slot1 = 0;
   b.sigs.push_back(s);
   b.tslot.emplace(t, slot);
   return slot;
+}
+
+// The reverse-strand signal of a chunk is the forward signal reversed with the channels swapped
+// (A<->T, C<->G) whenever the entropy windows of both orientations cover the same bases: the chunk
+// length is a multiple of the window (N/512), or below 1024 where every weight is 1.  Then
+// no reverse spectrum is computed at all: xcorr_pair_kernel derives both strands from the forward one.
+static bool rc_derivable(const sx_ctx *c, int32_t len) {
+  const int win = c->N / 512;
+  return len >= 1 && (len % win == 0 || len < 1024);
 }
 
 static int32_t query_slot(sx_ctx *c, Batch &b, int32_t q) {
@@ -792,21 +877,41 @@ static int32_t query_slot(sx_ctx *c, Batch &b, int32_t q) {
   if (it != b.qslot.end()) return it->second;
   const int32_t slot = (int32_t)(c->n_persist + b.transient_used);
   b.transient_used += 2;
-  for (int strand = 0; strand < 2; strand++) {
+  const bool derive = rc_derivable(c, c->Q.lens[q]);
+  for (int strand = 0; strand < (derive ? 1 : 2); strand++) {
     SigDesc s;
     s.src = c->Q.d_bases + c->Q.offsets[q];
     s.len = c->Q.lens[q];
     b.q_need = std::max(b.q_need, (size_t)c->Q.offsets[q] + (size_t)c->Q.lens[q]);
     s.strand = strand;
     s.slot = slot + strand;
-    s.pad = 0;
+    s.rc_slot1 = derive ? slot + 2 : 0;  // planes / bytes / meta of the other orientation go to slot + 1
     b.sigs.push_back(s);
   }
   b.qslot.emplace(q, slot);
   return slot;
 }
 
-static int align_list(sx_ctx *c, const PairReq *reqs, int64_t n, sx_result *out, int64_t cap, int64_t *n_out) {
+// the two strand-pairs of a chunk pair: consecutive entries of sps, forward first
+static void push_pair(sx_ctx *c, Batch &b, int32_t ts, int32_t qs, int32_t qlen, int32_t pidx, int fast) {
+  const uint32_t first = (uint32_t)b.sps.size();
+  for (int strand = 0; strand < 2; strand++) {
+    SpDesc sp;
+    sp.t_slot = ts;
+    sp.q_slot = qs + strand;
+    sp.pair = pidx;
+    sp.flags = (strand ? SP_REVERSE : 0) | (fast ? SP_FAST : 0);
+    b.sps.push_back(sp);
+  }
+  if (rc_derivable(c, qlen)) {
+    b.pair_list.push_back(first);
+  } else {
+    b.direct_list.push_back(first);
+    b.direct_list.push_back(first + 1);
+  }
+}
+
+static int align_list_inner(sx_ctx *c, const PairReq *reqs, int64_t n, sx_result *out, int64_t cap, int64_t *n_out) {
   if (c->T.n == 0 && n > 0) return fail(SX_ERR_STATE, "align: no targets loaded");
   if (c->Q.n == 0 && n > 0) return fail(SX_ERR_STATE, "align: no queries loaded");
   CU(cudaSetDevice(c->cfg.device));
@@ -854,14 +959,7 @@ static int align_list(sx_ctx *c, const PairReq *reqs, int64_t n, sx_result *out,
     const int32_t qs = query_slot(c, *b, r.q);
     const int32_t pidx = (int32_t)b->pairs.size();
     b->pairs.push_back(r);
-    for (int strand = 0; strand < 2; strand++) {
-      SpDesc sp;
-      sp.t_slot = ts;
-      sp.q_slot = qs + strand;
-      sp.pair = pidx;
-      sp.flags = (strand ? SP_REVERSE : 0) | (r.fast ? SP_FAST : 0);
-      b->sps.push_back(sp);
-    }
+    push_pair(c, *b, ts, qs, c->Q.lens[r.q], pidx, r.fast);
   }
   int rc = submit(cur);
   if (rc != SX_OK) return rc;
@@ -872,6 +970,12 @@ static int align_list(sx_ctx *c, const PairReq *reqs, int64_t n, sx_result *out,
   if (total > cap) return fail(SX_ERR_CAPACITY, "align: %lld records, buffer holds %lld", (long long)total, (long long)cap);
   if (total && out) memcpy(out, c->last.data(), sizeof(sx_result) * (size_t)total);
   return SX_OK;
+}
+
+static int align_list(sx_ctx *c, const PairReq *reqs, int64_t n, sx_result *out, int64_t cap, int64_t *n_out) {
+  const int rc = align_list_inner(c, reqs, n, out, cap, n_out);
+  const int rc2 = finish_uploads(c);  // bases no batch asked for still leave the caller's buffers now
+  return rc != SX_OK ? rc : rc2;
 }
 
 extern "C" int sx_align_pairs(sx_ctx *c, const int32_t *pairs, int64_t n, int32_t fast, sx_result *out, int64_t cap,
@@ -921,30 +1025,24 @@ static int tap_prepare(sx_ctx *c, int32_t target, int32_t query, int32_t strand,
   CU(cudaSetDevice(c->cfg.device));
   b.t_need = c->T.blob_bytes;
   b.q_need = c->Q.blob_bytes;
+  // the chunk pair exactly as align_list builds it (both strands, production kernels); the tap then
+  // picks the strand-pair it was asked for
   const int32_t base = (int32_t)c->n_persist;
   SigDesc s;
   s.src = c->T.d_bases + c->T.offsets[target];
   s.len = c->T.lens[target];
   s.strand = 0;
   s.slot = base;
-  s.pad = 0;
+  s.rc_slot1 = 0;
   b.sigs.push_back(s);
-  s.src = c->Q.d_bases + c->Q.offsets[query];
-  s.len = c->Q.lens[query];
-  s.strand = strand;
-  s.slot = base + 1;
-  b.sigs.push_back(s);
-  SpDesc sp;
-  sp.t_slot = base;
-  sp.q_slot = base + 1;
-  sp.pair = 0;
-  sp.flags = (strand ? SP_REVERSE : 0) | (fast ? SP_FAST : 0);
-  b.sps.push_back(sp);
+  b.transient_used = 1;
+  const int32_t qs = query_slot(c, b, query);
   PairReq pr;
   pr.t = target;
   pr.q = query;
   pr.fast = fast;
   b.pairs.push_back(pr);
+  push_pair(c, b, base, qs, c->Q.lens[query], 0, fast);
   return SX_OK;
 }
 
@@ -963,7 +1061,7 @@ extern "C" int sx_tap_signal(sx_ctx *c, int32_t is_target, int32_t chunk, int32_
   s.len = S.lens[chunk];
   s.strand = strand;
   s.slot = (int32_t)c->n_persist;
-  s.pad = 0;
+  s.rc_slot1 = 0;
   b.sigs.push_back(s);
   TapRequest t;
   t.sig5n = out5;
@@ -978,6 +1076,7 @@ extern "C" int sx_tap_xcorr(sx_ctx *c, int32_t target, int32_t query, int32_t st
   if (rc != SX_OK) return rc;
   TapRequest t;
   t.xc = out;
+  t.sp_select = strand;
   return run_batch(c, b, nullptr, &t);
 }
 
@@ -991,6 +1090,7 @@ extern "C" int sx_tap_candidates(sx_ctx *c, int32_t target, int32_t query, int32
   std::vector<int32_t> cands;
   TapRequest t;
   t.cands = &cands;
+  t.sp_select = strand;
   if ((rc = run_batch(c, b, nullptr, &t)) != SX_OK) return rc;
   *n_out = (int32_t)cands.size();
   if ((int32_t)cands.size() > cap) return fail(SX_ERR_CAPACITY, "sx_tap_candidates: %zu candidates", cands.size());
@@ -1008,6 +1108,7 @@ extern "C" int sx_tap_segments(sx_ctx *c, int32_t target, int32_t query, int32_t
   std::vector<SegRec> segs;
   TapRequest t;
   t.segs = &segs;
+  t.sp_select = strand;
   if ((rc = run_batch(c, b, nullptr, &t)) != SX_OK) return rc;
   std::sort(segs.begin(), segs.end(), [](const SegRec &a, const SegRec &b2) {
     if (a.shift != b2.shift) return a.shift < b2.shift;

@@ -1,20 +1,24 @@
 // In-shared-memory complex FFTs for the cross-correlation kernels (sm_100a).
 //
 // Replaces extern/RealFFT (FFTReal<float>::do_fft / do_ifft, FFTReal.hpp:145-245): the
-// reference runs 12 radix-2 real transforms of N points per strand-pair; here two real
-// channels ride one complex N-point transform (A + iC, G + iT), the forward transform is
-// an in-place decimation-in-frequency network that leaves the spectrum in mixed-radix
-// digit-reversed order, and the inverse is its exact adjoint (decimation-in-time) that
-// consumes that order and returns natural order -- so no bit-reversal pass exists at all:
-// the spectral product in between is element-wise and order-agnostic.
+// reference runs 12 radix-2 real transforms of N points per strand-pair.  Here
+//   * two real channels ride one complex transform (A + iC, G + iT);
+//   * the N-point transform is split once by decimation in frequency into two INDEPENDENT
+//     H = N/2 point transforms: even bins = FFT_H(z[n] + z[n+H]), odd bins = FFT_H((z[n] - z[n+H]) w_N^n).
+//     A chunk never exceeds H bases in the default configuration, so z[n+H] = 0 and the split costs
+//     nothing: the encoder writes z and z*w_N^n side by side.  The spectrum is stored as
+//     [even half | odd half]; the inverse runs the two H-point inverses and one radix-2 combine;
+//   * each H-point transform is an in-place decimation-in-frequency network that leaves its bins in
+//     mixed-radix digit-reversed order, the inverse is its exact adjoint (decimation in time) that
+//     consumes that order -- no reordering pass exists: the spectral product in between is
+//     element-wise (plus a bin <-> N - bin pairing that stays inside each half, see scrambled_neg).
 //
 // One pass = every thread pulls R points (stride S) from shared memory into registers,
 // does an R-point DFT, applies the inter-stage twiddles and writes back in place.
 //
 // Shared-memory layout: logical element l lives at physical slot swz(l) = l ^ f(l), where f is an
 // XOR-linear function of address bits 4..7 that only changes the low 4 bits.  With 8-byte elements
-// (16 banks per half-warp) this makes EVERY pass conflict-free, including the last two whose
-// natural strides (8 and 1 butterflies apart = 64 and 8 elements) would be 2- and 8-way conflicted.
+// (16 banks per half-warp) this makes EVERY pass of every plan conflict-free (tools/fft_bank_check.py).
 // Because f is linear and base / m*S never share bits, swz(base + m*S) = (base + m*S) ^ f(base) ^ f(m*S)
 // with f(m*S) a compile-time constant: one extra XOR per element.
 #pragma once
@@ -124,22 +128,23 @@ struct Dft<16, INV> {
   }
 };
 
-// Inter-stage twiddle table: tw[t] = e^{-2 pi i t / 16384}, t < 2048 (filled by upload_tables()).
-// A transform of length N uses entries t * (16384 / N); every pass needs indices < N/8 only.
-#define SX_TW_BASE_LOG2 14
-#define SX_TW_ENTRIES 2048
+// Inter-stage twiddle table: tw[t] = e^{-2 pi i t / 32768}, t < 4096 (filled by upload_tables()).
+// A transform of length L uses entries j * (32768 / L); every pass needs angles below 2 pi / 8 only.
+#define SX_TW_BASE_LOG2 15
+#define SX_TW_ENTRIES 4096
 static __device__ float2 g_twiddle[SX_TW_ENTRIES];  // this header is compiled into one translation unit only
 
-// ---- one in-place pass over a (swizzled) shared-memory buffer of N complex points ----------
+// ---- one in-place pass over a (swizzled) shared-memory buffer of NPTS complex points --------
 // L = current sub-transform length, R = radix, S = L/R.  Butterfly b: j = b mod S,
-// block = b div S, points at block*L + j + m*S.
+// block = b div S, points at block*L + j + m*S.  NPTS is a multiple of L (N for the two halves in
+// one CTA, H when a CTA of a cluster holds one half).
 // Forward (DIF): DFT_R then multiply output p by W_L^{j p};  inverse (DIT): conj-twiddle then DFT_R^*.
-template <int LOG2N, int L, int R, bool INV, int NT>
+template <int NPTS, int L, int R, bool INV, int NT>
 __device__ __forceinline__ void fft_pass(float2 *buf, int tid) {
-  constexpr int N = 1 << LOG2N;
   constexpr int S = L / R;
+  constexpr int LOG2L = __builtin_ctz(L);
 #pragma unroll 1
-  for (int b = tid; b < N / R; b += NT) {
+  for (int b = tid; b < NPTS / R; b += NT) {
     const int j = b & (S - 1);
     const int base = (b / S) * L + j;
     const int fb = swz_f(base);
@@ -148,7 +153,7 @@ __device__ __forceinline__ void fft_pass(float2 *buf, int tid) {
     for (int m = 0; m < R; m++) x[m] = buf[(base + m * S) ^ (fb ^ swz_f(m * S))];
     float2 w[R];  // W_L^{j p}: W_L^{j} from the table, the powers by binary powering (<= 4 roundings)
     if (S > 1) {
-      w[1] = __ldg(&g_twiddle[j * ((N / L) << (SX_TW_BASE_LOG2 - LOG2N))]);
+      w[1] = __ldg(&g_twiddle[j << (SX_TW_BASE_LOG2 - LOG2L)]);
 #pragma unroll
       for (int p = 2; p < R; p++) w[p] = (p & 1) ? cmul(w[p - 1], w[1]) : cmul(w[p / 2], w[p / 2]);
     }
@@ -166,67 +171,96 @@ __device__ __forceinline__ void fft_pass(float2 *buf, int tid) {
   }
 }
 
-// ---- plans: radices per transform length (product = N) -------------------------------------
+// ---- plans: radices of the H = N/2 point transforms (product = H) ---------------------------
 template <int LOG2N>
 struct Plan;
 template <>
-struct Plan<11> { static constexpr int R0 = 16, R1 = 16, R2 = 8, R3 = 1; };
+struct Plan<11> { static constexpr int R0 = 16, R1 = 8, R2 = 8, R3 = 1; };
 template <>
-struct Plan<12> { static constexpr int R0 = 16, R1 = 16, R2 = 16, R3 = 1; };
+struct Plan<12> { static constexpr int R0 = 16, R1 = 16, R2 = 8, R3 = 1; };
 template <>
-struct Plan<13> { static constexpr int R0 = 16, R1 = 8, R2 = 8, R3 = 8; };
+struct Plan<13> { static constexpr int R0 = 16, R1 = 16, R2 = 16, R3 = 1; };
 template <>
-struct Plan<14> { static constexpr int R0 = 16, R1 = 16, R2 = 8, R3 = 8; };
+struct Plan<14> { static constexpr int R0 = 16, R1 = 8, R2 = 8, R3 = 8; };
+template <>
+struct Plan<15> { static constexpr int R0 = 16, R1 = 16, R2 = 8, R3 = 8; };
 
-// LOGICAL position of natural-order bin k in the scrambled (DIF output) order; its shared-memory
-// slot is swz() of this.
+// LOGICAL position (inside its half) of bin m of an H-point transform in the scrambled (DIF output)
+// order; the shared-memory slot is swz() of it.  Natural bin k of the N-point transform lives in
+// half (k & 1) at scrambled_pos(k >> 1).
 template <int LOG2N>
-__host__ __device__ constexpr int scrambled_pos(int k) {
-  int L = 1 << LOG2N, r = 0;
+__host__ __device__ constexpr int scrambled_pos(int m) {
+  int L = 1 << (LOG2N - 1), r = 0;
   const int rad[4] = {Plan<LOG2N>::R0, Plan<LOG2N>::R1, Plan<LOG2N>::R2, Plan<LOG2N>::R3};
   for (int i = 0; i < 4; i++) {
     if (rad[i] == 1) break;
     int S = L / rad[i];
-    r += (k % rad[i]) * S;
-    k /= rad[i];
+    r += (m % rad[i]) * S;
+    m /= rad[i];
     L = S;
   }
   return r;
 }
+// inverse of scrambled_pos
+template <int LOG2N>
+__host__ __device__ constexpr int natural_bin(int r) {
+  int L = 1 << (LOG2N - 1), m = 0, mul = 1;
+  const int rad[4] = {Plan<LOG2N>::R0, Plan<LOG2N>::R1, Plan<LOG2N>::R2, Plan<LOG2N>::R3};
+  for (int i = 0; i < 4; i++) {
+    if (rad[i] == 1) break;
+    int S = L / rad[i];
+    m += (r / S) * mul;
+    r %= S;
+    mul *= rad[i];
+    L = S;
+  }
+  return m;
+}
+// physical slot (index into a [even half | odd half] spectrum or FFT buffer) of natural bin k, 0 <= k < N
+template <int LOG2N>
+__host__ __device__ constexpr int bin_slot(int k) {
+  return (k & 1) * (1 << (LOG2N - 1)) + swz(scrambled_pos<LOG2N>(k >> 1));
+}
+// radix of the last pass = number of consecutive scrambled positions that differ only in the top digit of m
+template <int LOG2N>
+__host__ __device__ constexpr int last_radix() {
+  return Plan<LOG2N>::R3 > 1 ? Plan<LOG2N>::R3 : Plan<LOG2N>::R2;
+}
 
-// Forward transform, natural order in -> scrambled order out.  Ends with a barrier.
-template <int LOG2N, int NT>
-__device__ __forceinline__ void fft_forward(float2 *buf, int tid) {
-  constexpr int N = 1 << LOG2N;
+// The H-point transforms of a buffer of NPTS points (NPTS = N: both halves; NPTS = H: one half),
+// natural order in -> scrambled order out.  Ends with a barrier.
+template <int LOG2N, int NPTS, int NT>
+__device__ __forceinline__ void fft_forward_halves(float2 *buf, int tid) {
+  constexpr int H = 1 << (LOG2N - 1);
   using P = Plan<LOG2N>;
-  constexpr int L1 = N / P::R0, L2 = L1 / P::R1, L3 = L2 / P::R2;
-  fft_pass<LOG2N, N, P::R0, false, NT>(buf, tid);
+  constexpr int L1 = H / P::R0, L2 = L1 / P::R1, L3 = L2 / P::R2;
+  fft_pass<NPTS, H, P::R0, false, NT>(buf, tid);
   __syncthreads();
-  fft_pass<LOG2N, L1, P::R1, false, NT>(buf, tid);
+  fft_pass<NPTS, L1, P::R1, false, NT>(buf, tid);
   __syncthreads();
-  fft_pass<LOG2N, L2, P::R2, false, NT>(buf, tid);
+  fft_pass<NPTS, L2, P::R2, false, NT>(buf, tid);
   __syncthreads();
   if constexpr (P::R3 > 1) {
-    fft_pass<LOG2N, L3, P::R3, false, NT>(buf, tid);
+    fft_pass<NPTS, L3, P::R3, false, NT>(buf, tid);
     __syncthreads();
   }
 }
 
-// Inverse (unscaled) transform, scrambled order in -> natural order out.  Ends with a barrier.
-template <int LOG2N, int NT>
-__device__ __forceinline__ void fft_inverse(float2 *buf, int tid) {
-  constexpr int N = 1 << LOG2N;
+// Inverse (unscaled) H-point transforms, scrambled order in -> natural order out.  Ends with a barrier.
+template <int LOG2N, int NPTS, int NT>
+__device__ __forceinline__ void fft_inverse_halves(float2 *buf, int tid) {
+  constexpr int H = 1 << (LOG2N - 1);
   using P = Plan<LOG2N>;
-  constexpr int L1 = N / P::R0, L2 = L1 / P::R1, L3 = L2 / P::R2;
+  constexpr int L1 = H / P::R0, L2 = L1 / P::R1, L3 = L2 / P::R2;
   if constexpr (P::R3 > 1) {
-    fft_pass<LOG2N, L3, P::R3, true, NT>(buf, tid);
+    fft_pass<NPTS, L3, P::R3, true, NT>(buf, tid);
     __syncthreads();
   }
-  fft_pass<LOG2N, L2, P::R2, true, NT>(buf, tid);
+  fft_pass<NPTS, L2, P::R2, true, NT>(buf, tid);
   __syncthreads();
-  fft_pass<LOG2N, L1, P::R1, true, NT>(buf, tid);
+  fft_pass<NPTS, L1, P::R1, true, NT>(buf, tid);
   __syncthreads();
-  fft_pass<LOG2N, N, P::R0, true, NT>(buf, tid);
+  fft_pass<NPTS, H, P::R0, true, NT>(buf, tid);
   __syncthreads();
 }
 

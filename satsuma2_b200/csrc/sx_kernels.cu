@@ -115,6 +115,14 @@ cudaError_t upload_tables() {
 }
 
 bool log2n_supported(int log2n) { return log2n >= 11 && log2n <= 14; }
+
+void fill_wn_table(int log2n, float2 *out) {
+  const int N = 1 << log2n;
+  for (int n = 0; n < N / 2; n++) {
+    const double a = -2.0 * 3.14159265358979323846 * (double)n / (double)N;
+    out[n] = make_float2((float)cos(a), (float)sin(a));
+  }
+}
 size_t slot_spec_elems(int log2n) { return (size_t)2 << log2n; }
 
 // fraction of channel c (0..3) for a table entry; exact doubles {0,1,1/2,1/3,1/4}
@@ -133,6 +141,17 @@ __device__ __forceinline__ double warp_sum(double v) {
 // =================================================================================================
 // K1: encode + forward transform.  One CTA per chunk signal.
 // =================================================================================================
+// e^{-2 pi i j / N} for small j as a compile-time constant (Taylor series in double: the angle is
+// below 2 pi * 64 / 2048, six terms are exact to double rounding)
+__host__ __device__ constexpr double cx_cos_small(double a) {
+  const double a2 = a * a;
+  return 1. - a2 / 2. * (1. - a2 / 12. * (1. - a2 / 30. * (1. - a2 / 56. * (1. - a2 / 90. * (1. - a2 / 132.)))));
+}
+__host__ __device__ constexpr double cx_sin_small(double a) {
+  const double a2 = a * a;
+  return a * (1. - a2 / 6. * (1. - a2 / 20. * (1. - a2 / 42. * (1. - a2 / 72. * (1. - a2 / 110. * (1. - a2 / 156.))))));
+}
+
 template <int LOG2N, int NT>
 __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
     encode_fft_kernel(const SigDesc *__restrict__ sigs, Slots ws, float *__restrict__ tap) {
@@ -152,6 +171,7 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
   const SigDesc sd = sigs[blockIdx.x];
   const int len = sd.len;
   const uint8_t *__restrict__ src = sd.src;
+  const float2 *__restrict__ wn = ws.wn;
 
   if (tid < 128) {
     s_fcode[tid] = c_fcode[tid];
@@ -170,34 +190,50 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
   __syncthreads();
 
   // ---- 1b. orient (reverse-complement), sanitise, 2-bit planes ------------------------------------
-  uint32_t *planes = ws.planes + (size_t)sd.slot * 2 * NW;
+  // A second round writes the OTHER orientation's planes / bytes / meta to slot rc_slot1 - 1 when the
+  // host derives that strand's correlation from this signal's spectrum (no transform of its own).
   int myflags = 0;
-  for (int k0 = warp * 32; k0 < N; k0 += NT) {
-    const int k = k0 + lane;
-    uint32_t b = 0, code = 4;
-    if (k < len) {
-      b = sd.strand ? raw[len - 1 - k] : raw[k];
-      if (b >= 128u) b = 0;
-      if (sd.strand) b = s_comp[b];
-      code = s_base2[b];
-      if (code & 4u) myflags |= SLOT_NONACGT;
-      if (code & 8u) myflags |= 2;
+  const int rounds = sd.rc_slot1 ? 2 : 1;
+  for (int round = rounds - 1; round >= 0; round--) {  // the signal's own orientation last: it stays in sb
+    const int strand = round ? (sd.strand ^ 1) : sd.strand;
+    const int slot = round ? (sd.rc_slot1 - 1) : sd.slot;
+    uint32_t *planes = ws.planes + (size_t)slot * 2 * NW;
+    if (round != rounds - 1) __syncthreads();  // the previous round's bytes have left sb
+    for (int k0 = warp * 32; k0 < N; k0 += NT) {
+      const int k = k0 + lane;
+      uint32_t b = 0, code = 4;
+      if (k < len) {
+        b = strand ? raw[len - 1 - k] : raw[k];
+        if (b >= 128u) b = 0;
+        if (strand) b = s_comp[b];
+        code = s_base2[b];
+        if (code & 4u) myflags |= SLOT_NONACGT;
+        if (code & 8u) myflags |= 2;
+      }
+      sb[k] = (uint8_t)b;
+      const uint32_t lo = __ballot_sync(0xffffffffu, (code & 5u) == 1u);  // C or T -> bit0
+      const uint32_t hi = __ballot_sync(0xffffffffu, (code & 6u) == 2u);  // G or T -> bit1
+      if (lane == 0) {
+        planes[k0 >> 5] = lo;
+        planes[NW + (k0 >> 5)] = hi;
+      }
     }
-    sb[k] = (uint8_t)b;
-    const uint32_t lo = __ballot_sync(0xffffffffu, (code & 5u) == 1u);  // C or T -> bit0
-    const uint32_t hi = __ballot_sync(0xffffffffu, (code & 6u) == 2u);  // G or T -> bit1
-    if (lane == 0) {
-      planes[k0 >> 5] = lo;
-      planes[NW + (k0 >> 5)] = hi;
+    if (myflags) atomicOr(&s_flags, myflags);
+    __syncthreads();
+    {  // oriented bases to HBM for the generic scan path and the taps, 16 bytes per thread
+      uint4 *gb = reinterpret_cast<uint4 *>(ws.bytes + (size_t)slot * N);
+      for (int i = tid; i < N / 16; i += NT) gb[i] = reinterpret_cast<const uint4 *>(sb)[i];
+    }
+    if (round && tid == 0) {
+      SlotMeta m;
+      m.len = len;
+      m.flags = s_flags & SLOT_NONACGT;  // same letters in both orientations (complement keeps the class)
+      m.q_re = m.q_im = m.q_nyq = 0.f;
+      m.pad[0] = m.pad[1] = m.pad[2] = 0;
+      ws.meta[slot] = m;
     }
   }
-  if (myflags) atomicOr(&s_flags, myflags);
-  __syncthreads();
   const int flags = s_flags;
-  {  // oriented bases to HBM for the generic scan path and the taps, 16 bytes per thread
-    uint4 *gb = reinterpret_cast<uint4 *>(ws.bytes + (size_t)sd.slot * N);
-    for (int i = tid; i < N / 16; i += NT) gb[i] = reinterpret_cast<const uint4 *>(sb)[i];
-  }
 
   // ---- 2. window sums, entropy weights (ComputeEntropy) and channel means (SeqToPCM) ------------
   double tot[4] = {0., 0., 0., 0.};
@@ -261,26 +297,29 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
   }
 
   // ---- 3. two complex transforms: (A + iC) then (G + iT) -----------------------------------------
+  // The N-point transform is split once (sx_fft.cuh): half 0 of the buffer gets e[n] = z[n] + z[n+H],
+  // half 1 gets o[n] = (z[n] - z[n+H]) w_N^n; a chunk of at most H bases has z[n+H] = 0.
   float acc_re = 0.f, acc_im = 0.f, acc_ny = 0.f;
-  constexpr int PH1 = swz(scrambled_pos<LOG2N>(H - 1)), PH = swz(scrambled_pos<LOG2N>(H)),
-                PH2 = swz(scrambled_pos<LOG2N>(H + 1));
+  constexpr int PH1 = bin_slot<LOG2N>(H - 1), PH = bin_slot<LOG2N>(H), PH2 = bin_slot<LOG2N>(H + 1);
+  const bool pure = !(flags & SLOT_NONACGT);
+  const bool fastgen = pure && len <= H;
 #pragma unroll 1
   for (int pr = 0; pr < 2; pr++) {
     const double off0 = s_off[2 * pr], off1 = s_off[2 * pr + 1];
     // sample = (float)(weight * (fraction - mean)); for A/C/G/T the fraction is 1 or 0
     const double hit0 = __dsub_rn(1.0, off0), miss0 = __dsub_rn(0.0, off0);
     const double hit1 = __dsub_rn(1.0, off1), miss1 = __dsub_rn(0.0, off1);
-    const bool pure = !(flags & SLOT_NONACGT);
-    if (pure) {
+    if (fastgen) {
       // Fast path: one thread per entropy window (N/512 bases).  Inside a window the sample is one of
       // two floats per channel -- (float)(w*(1-mean)) or (float)(w*(0-mean)) -- rounded exactly as the
       // per-base double product of the reference; the base only selects between them.
       const uint32_t c0 = 2 * pr, c1 = 2 * pr + 1;
-      for (int w = tid; w < 512; w += NT) {
+      for (int w = tid; w < H / WIN; w += NT) {
         const int k0 = w * WIN;
         const double e = flat ? 1.0 : (double)went[w];
         const float h0 = __double2float_rn(__dmul_rn(e, hit0)), m0 = __double2float_rn(__dmul_rn(e, miss0));
         const float h1 = __double2float_rn(__dmul_rn(e, hit1)), m1 = __double2float_rn(__dmul_rn(e, miss1));
+        const float2 wb = __ldg(wn + k0);  // w_N^{k0}; w_N^{k0 + j} = wb * (compile-time) w_N^j
         uint32_t packed[(WIN + 3) / 4];
 #pragma unroll
         for (int j = 0; j < (WIN + 3) / 4; j++) packed[j] = reinterpret_cast<const uint32_t *>(sb + k0)[j];
@@ -292,43 +331,56 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
           float2 v;
           v.x = k < len ? (code == c0 ? h0 : m0) : 0.f;
           v.y = k < len ? (code == c1 ? h1 : m1) : 0.f;
+          constexpr double ang = -2.0 * 3.14159265358979323846 / (double)N;
+          const float2 st = make_float2((float)cx_cos_small(ang * j), (float)cx_sin_small(ang * j));
+          const float2 wk = j == 0 ? wb : cmul(wb, st);
           buf[swz(k)] = v;
+          buf[H + swz(k)] = cmul(v, wk);
         }
       }
       if (tap != nullptr) {  // taps read back exactly what the transform is about to see
         __syncthreads();
         float *ts = tap + (size_t)blockIdx.x * 5 * N + (size_t)(1 + 2 * pr) * N;
         for (int k = tid; k < N; k += NT) {
-          const float2 v = buf[swz(k)];
+          const float2 v = k < H ? buf[swz(k)] : make_float2(0.f, 0.f);
           ts[k] = v.x;
           ts[N + k] = v.y;
         }
       }
-    } else
-    for (int k = tid; k < N; k += NT) {
-      float2 v = make_float2(0.f, 0.f);
-      if (k < len) {
-        const double e = flat ? 1.0 : (double)went[k / WIN];
-        if (pure) {
-          const uint32_t code = s_base2[sb[k]];
-          v.x = __double2float_rn(__dmul_rn(e, code == (uint32_t)(2 * pr) ? hit0 : miss0));
-          v.y = __double2float_rn(__dmul_rn(e, code == (uint32_t)(2 * pr + 1) ? hit1 : miss1));
-        } else {
-          const uint32_t fc = s_fcode[sb[k]];
-          v.x = __double2float_rn(__dmul_rn(e, __dsub_rn(frac_of(fc, 2 * pr), off0)));
-          v.y = __double2float_rn(__dmul_rn(e, __dsub_rn(frac_of(fc, 2 * pr + 1), off1)));
+    } else {
+      // general path (IUPAC letters, or a query chunk longer than H): the whole signal in natural
+      // order first, then the radix-2 split in place
+      for (int k = tid; k < N; k += NT) {
+        float2 v = make_float2(0.f, 0.f);
+        if (k < len) {
+          const double e = flat ? 1.0 : (double)went[k / WIN];
+          if (pure) {
+            const uint32_t code = s_base2[sb[k]];
+            v.x = __double2float_rn(__dmul_rn(e, code == (uint32_t)(2 * pr) ? hit0 : miss0));
+            v.y = __double2float_rn(__dmul_rn(e, code == (uint32_t)(2 * pr + 1) ? hit1 : miss1));
+          } else {
+            const uint32_t fc = s_fcode[sb[k]];
+            v.x = __double2float_rn(__dmul_rn(e, __dsub_rn(frac_of(fc, 2 * pr), off0)));
+            v.y = __double2float_rn(__dmul_rn(e, __dsub_rn(frac_of(fc, 2 * pr + 1), off1)));
+          }
+        }
+        buf[swz(k)] = v;
+        if (tap != nullptr) {
+          float *ts = tap + (size_t)blockIdx.x * 5 * N + (size_t)(1 + 2 * pr) * N;
+          ts[k] = v.x;
+          ts[N + k] = v.y;
         }
       }
-      buf[swz(k)] = v;
-      if (tap != nullptr) {
-        float *ts = tap + (size_t)blockIdx.x * 5 * N + (size_t)(1 + 2 * pr) * N;
-        ts[k] = v.x;
-        ts[N + k] = v.y;
+      __syncthreads();
+      for (int n = tid; n < H; n += NT) {
+        const float2 a = buf[swz(n)], b = buf[H + swz(n)];
+        buf[swz(n)] = cadd(a, b);
+        buf[H + swz(n)] = cmul(csub(a, b), __ldg(wn + n));
       }
     }
     __syncthreads();
-    fft_forward<LOG2N, NT>(buf, tid);
-    // spectra out in shared-memory slot order (scrambled bins, swizzled slots), 16-byte stores
+    fft_forward_halves<LOG2N, N, NT>(buf, tid);
+    // spectra out in shared-memory slot order ([even | odd] halves, scrambled bins, swizzled slots)
     float4 *dst = reinterpret_cast<float4 *>(ws.spec + ((size_t)sd.slot * 2 + pr) * N);
     const float4 *s4p = reinterpret_cast<const float4 *>(buf);
     for (int k = tid; k < N / 2; k += NT) dst[k] = s4p[k];
@@ -357,67 +409,29 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
 }
 
 // =================================================================================================
-// K2: spectral product + inverse transform + FindTop.  One CTA per strand-pair.
+// K2: spectral product + inverse transform + FindTop.
+//   xcorr_pair_kernel   one CTA per CHUNK PAIR: both strands from the forward query spectrum, one
+//                       inverse transform (forward strand in the real part, reverse in the imaginary)
+//   xcorr_findtop_kernel one CTA per strand-pair (reverse-strand signal with its own spectrum)
 // =================================================================================================
-template <int LOG2N, int NT>
-__global__ void __launch_bounds__(NT)
-    xcorr_findtop_kernel(const SpDesc *__restrict__ sps, Slots ws, double cutoff, double cutoff_fast,
-                         uint16_t *__restrict__ cand_pool, unsigned int pool_cap, uint2 *__restrict__ cand_ref,
-                         BatchCounters *ctr, float *__restrict__ xc_tap) {
-  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, NB = N / 256, NWARP = NT / 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2 *buf = reinterpret_cast<float2 *>(smem_raw);
-  uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw + (size_t)N * sizeof(float2));  // NW words
-  uint32_t *wpre = mask + NW;                                                            // NW prefix counts
-  __shared__ double s_thr[NB];
-  __shared__ unsigned int s_wtot[NWARP];
-  __shared__ unsigned int s_base;
-
+// FindTop (SeqAnalyzer::FindTop, CrossCorr.cc:878-944) over xc[i] = COMP(buf[(i + off) mod N]) * scale:
+// RMS envelope per 256 lags (float square, double accumulate), threshold env*cutoff + 1, ballot
+// mask, block scan, ordered compaction into the candidate pool (one atomic per strand-pair).
+template <int LOG2N, int NT, int COMP>
+__device__ __forceinline__ void findtop(const float2 *buf, int off, float scale, double co, uint32_t *mask,
+                                        double *s_thr, unsigned int *s_wtot, unsigned int *s_base, int spi,
+                                        uint16_t *__restrict__ cand_pool, unsigned int pool_cap,
+                                        uint2 *__restrict__ cand_ref, BatchCounters *ctr, float *__restrict__ xc_tap) {
+  constexpr int N = 1 << LOG2N, NW = N / 32, NB = N / 256, NWARP = NT / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const SpDesc sp = sps[blockIdx.x];
-  const SlotMeta tm = ws.meta[sp.t_slot];
-
-  // ---- product: P = conj(U1) V1 + conj(U2) V2 (bin order is irrelevant here) ----------------------
-  {
-    const float4 *U1 = reinterpret_cast<const float4 *>(ws.spec + ((size_t)sp.t_slot * 2) * N);
-    const float4 *U2 = U1 + N / 2;
-    const float4 *V1 = reinterpret_cast<const float4 *>(ws.spec + ((size_t)sp.q_slot * 2) * N);
-    const float4 *V2 = V1 + N / 2;
-    float4 *dst = reinterpret_cast<float4 *>(buf);
-#pragma unroll 2
-    for (int k = tid; k < N / 2; k += NT) {
-      const float4 u1 = __ldg(U1 + k), u2 = __ldg(U2 + k), v1 = __ldg(V1 + k), v2 = __ldg(V2 + k);
-      float4 p;
-      p.x = (v1.x * u1.x + v1.y * u1.y) + (v2.x * u2.x + v2.y * u2.y);
-      p.y = (v1.y * u1.x - v1.x * u1.y) + (v2.y * u2.x - v2.x * u2.y);
-      p.z = (v1.z * u1.z + v1.w * u1.w) + (v2.z * u2.z + v2.w * u2.w);
-      p.w = (v1.w * u1.z - v1.z * u1.w) + (v2.w * u2.z - v2.z * u2.w);
-      dst[k] = p;
-    }
-  }
-  __syncthreads();
-  // ---- reference quirk (CrossCorr.cc:480-492): bins H-1 and H keep the TARGET spectrum ------------
-  if (tid == 0) {
-    constexpr int PH1 = swz(scrambled_pos<LOG2N>(H - 1)), PH = swz(scrambled_pos<LOG2N>(H)),
-                  PH2 = swz(scrambled_pos<LOG2N>(H + 1));
-    buf[PH1] = make_float2(tm.q_re, tm.q_im);
-    buf[PH2] = make_float2(tm.q_re, -tm.q_im);
-    buf[PH] = make_float2(tm.q_nyq, 0.f);
-  }
-  __syncthreads();
-  fft_inverse<LOG2N, NT>(buf, tid);
-
-  // xc[i] = Re x[(i + H) mod N] / N   (rescale + half rotation, CrossCorr.cc:493-505)
-  const float scale = 1.0f / (float)N;
-  auto xc_at = [&](int i) -> float { return buf[swz((i + H) & (N - 1))].x * scale; };
-
+  auto xc_at = [&](int i) -> float {
+    const float2 v = buf[swz((i + off) & (N - 1))];
+    return (COMP ? v.y : v.x) * scale;
+  };
   if (xc_tap != nullptr) {
-    float *o = xc_tap + (size_t)blockIdx.x * N;
+    float *o = xc_tap + (size_t)spi * N;
     for (int i = tid; i < N; i += NT) o[i] = xc_at(i);
   }
-
-  // ---- FindTop: RMS envelope per 256 lags (float square, double accumulate), threshold ------------
-  const double co = (sp.flags & SP_FAST) ? cutoff_fast : cutoff;
   for (int b = warp; b < NB; b += NWARP) {
     double acc = 0.;
     if (NB > 8) {
@@ -472,12 +486,12 @@ __global__ void __launch_bounds__(NT)
     } else {
       base = 0;
     }
-    s_base = base;
-    cand_ref[blockIdx.x] = make_uint2(base, total);
+    *s_base = base;
+    cand_ref[spi] = make_uint2(base, total);
     atomicAdd(&ctr->n_candidates, (unsigned long long)total);
   }
   __syncthreads();
-  const unsigned int base = s_base;
+  const unsigned int base = *s_base;
   if (base != 0xffffffffu && total > 0) {
     unsigned int o = base + wbase + (incl - mine);
 #pragma unroll
@@ -493,7 +507,156 @@ __global__ void __launch_bounds__(NT)
       }
     }
   }
-  (void)wpre;
+  __syncthreads();  // mask / s_thr / s_base are reused by the next strand
+}
+
+// the two H-point inverses, then the radix-2 combine x[n] = e[n] + w_N^{-n} o[n], x[n+H] = e[n] - w_N^{-n} o[n]
+// in place (natural order, swizzled slots).  Ends with a barrier.
+template <int LOG2N, int NT>
+__device__ __forceinline__ void inverse_full(float2 *buf, const float2 *__restrict__ wn, int tid) {
+  constexpr int N = 1 << LOG2N, H = N / 2;
+  fft_inverse_halves<LOG2N, N, NT>(buf, tid);
+  for (int n = tid; n < H; n += NT) {
+    const float2 e = buf[swz(n)], o = buf[H + swz(n)];
+    const float2 t = cmulc(o, __ldg(wn + n));
+    buf[swz(n)] = cadd(e, t);
+    buf[H + swz(n)] = csub(e, t);
+  }
+  __syncthreads();
+}
+
+template <int LOG2N, int NT>
+__global__ void __launch_bounds__(NT)
+    xcorr_pair_kernel(const uint32_t *__restrict__ pair_list, const SpDesc *__restrict__ sps, Slots ws, double cutoff,
+                      double cutoff_fast, uint16_t *__restrict__ cand_pool, unsigned int pool_cap,
+                      uint2 *__restrict__ cand_ref, BatchCounters *ctr, float *__restrict__ xc_tap) {
+  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, NB = N / 256, NWARP = NT / 32;
+  constexpr int LR = last_radix<LOG2N>();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *buf = reinterpret_cast<float2 *>(smem_raw);
+  uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw + (size_t)N * sizeof(float2));  // NW words
+  __shared__ double s_thr[NB];
+  __shared__ unsigned int s_wtot[NWARP];
+  __shared__ unsigned int s_base;
+
+  const int tid = threadIdx.x;
+  const int spi = (int)pair_list[blockIdx.x];  // forward strand-pair; the reverse one is spi + 1
+  const SpDesc sp = sps[spi];
+  const SlotMeta tm = ws.meta[sp.t_slot];
+  const int qlen = ws.meta[sp.q_slot].len;
+
+  // ---- products of both strands, Hermitian-symmetrised and packed: buf = 2 (Pf_h + i Pr_h) ---------
+  //   forward   Pf[k] = conj(U1) V1 + conj(U2) V2
+  //   reverse   the reverse-complement signal is the forward one reversed with channels swapped A<->T,
+  //             C<->G (exact when the entropy windows line up, which the host checks); reversed about
+  //             index 0 its packed spectra are i conj(V2), i conj(V1), so
+  //             Pr'[k] = i conj(U1 V2 + U2 V1), and its correlation is the true one rotated by qlen - 1 lags.
+  //   X_h[k] = (X[k] + conj X[N-k]) / 2 keeps exactly the real part of the inverse transform.
+  {
+    const float2 *U1 = ws.spec + ((size_t)sp.t_slot * 2) * N, *U2 = U1 + N;
+    const float2 *V1 = ws.spec + ((size_t)sp.q_slot * 2) * N, *V2 = V1 + N;
+#pragma unroll 2
+    for (int it = tid; it < H; it += NT) {
+      int pa, pb;
+      if (it < H / 2) {  // even bins: m <-> (H - m) mod H; m < H/2 <=> top digit (last in scrambled order) < LR/2
+        const int r = (it / (LR / 2)) * LR + (it % (LR / 2));
+        const int m2 = (H - natural_bin<LOG2N>(r)) & (H - 1);
+        pa = swz(r);
+        pb = swz(scrambled_pos<LOG2N>(m2));
+      } else {  // odd bins: m <-> H - 1 - m, i.e. scrambled position r <-> H - 1 - r
+        const int r = it - H / 2;
+        pa = H + swz(r);
+        pb = H + swz(H - 1 - r);
+      }
+      const float2 u1a = __ldg(U1 + pa), u2a = __ldg(U2 + pa), v1a = __ldg(V1 + pa), v2a = __ldg(V2 + pa);
+      const float2 u1b = __ldg(U1 + pb), u2b = __ldg(U2 + pb), v1b = __ldg(V1 + pb), v2b = __ldg(V2 + pb);
+      const float2 a = cadd(cmulc(v1a, u1a), cmulc(v2a, u2a));
+      const float2 b = cadd(cmulc(v1b, u1b), cmulc(v2b, u2b));
+      const float2 g = cadd(cmul(u1a, v2a), cmul(u2a, v1a));
+      const float2 h = cadd(cmul(u1b, v2b), cmul(u2b, v1b));
+      const float sx_ = a.x + b.x, dx = g.x - h.x, sy = g.y + h.y, dy = a.y - b.y;
+      buf[pa] = make_float2(sx_ - dx, sy + dy);
+      buf[pb] = make_float2(sx_ + dx, sy - dy);
+    }
+  }
+  __syncthreads();
+  // ---- reference quirk (CrossCorr.cc:480-492): bins H-1 and H keep the TARGET spectrum, on both strands;
+  //      the reverse strand's copy carries the rotation phase e^{+2 pi i k (qlen-1) / N}
+  if (tid == 0) {
+    constexpr int PH1 = bin_slot<LOG2N>(H - 1), PH = bin_slot<LOG2N>(H), PH2 = bin_slot<LOG2N>(H + 1);
+    const int rot = qlen - 1;
+    auto put = [&](int slot, int k, float2 t) {
+      float sn, cs;
+      sincospif(2.0f * (float)(((long long)k * rot) & (N - 1)) / (float)N, &sn, &cs);
+      const float2 tr = cmul(t, make_float2(cs, sn));
+      buf[slot] = make_float2(2.f * (t.x - tr.y), 2.f * (t.y + tr.x));  // 2 (t + i tr)
+    };
+    put(PH1, H - 1, make_float2(tm.q_re, tm.q_im));
+    put(PH2, H + 1, make_float2(tm.q_re, -tm.q_im));
+    put(PH, H, make_float2(tm.q_nyq, 0.f));
+  }
+  __syncthreads();
+  inverse_full<LOG2N, NT>(buf, ws.wn, tid);
+
+  // xc[i] = x[(i + H) mod N] / N (rescale + half rotation, CrossCorr.cc:493-505); the factor 2 above
+  const float scale = 0.5f / (float)N;
+  const double co = (sp.flags & SP_FAST) ? cutoff_fast : cutoff;
+  findtop<LOG2N, NT, 0>(buf, H, scale, co, mask, s_thr, s_wtot, &s_base, spi, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
+  findtop<LOG2N, NT, 1>(buf, (H - (qlen - 1)) & (N - 1), scale, co, mask, s_thr, s_wtot, &s_base, spi + 1, cand_pool,
+                        pool_cap, cand_ref, ctr, xc_tap);
+}
+
+template <int LOG2N, int NT>
+__global__ void __launch_bounds__(NT)
+    xcorr_findtop_kernel(const uint32_t *__restrict__ direct_list, const SpDesc *__restrict__ sps, Slots ws,
+                         double cutoff, double cutoff_fast, uint16_t *__restrict__ cand_pool, unsigned int pool_cap,
+                         uint2 *__restrict__ cand_ref, BatchCounters *ctr, float *__restrict__ xc_tap) {
+  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, NB = N / 256, NWARP = NT / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *buf = reinterpret_cast<float2 *>(smem_raw);
+  uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw + (size_t)N * sizeof(float2));  // NW words
+  __shared__ double s_thr[NB];
+  __shared__ unsigned int s_wtot[NWARP];
+  __shared__ unsigned int s_base;
+
+  const int tid = threadIdx.x;
+  const int spi = (int)direct_list[blockIdx.x];
+  const SpDesc sp = sps[spi];
+  const SlotMeta tm = ws.meta[sp.t_slot];
+
+  // ---- product: P = conj(U1) V1 + conj(U2) V2 (bin order is irrelevant here) ----------------------
+  {
+    const float4 *U1 = reinterpret_cast<const float4 *>(ws.spec + ((size_t)sp.t_slot * 2) * N);
+    const float4 *U2 = U1 + N / 2;
+    const float4 *V1 = reinterpret_cast<const float4 *>(ws.spec + ((size_t)sp.q_slot * 2) * N);
+    const float4 *V2 = V1 + N / 2;
+    float4 *dst = reinterpret_cast<float4 *>(buf);
+#pragma unroll 2
+    for (int k = tid; k < N / 2; k += NT) {
+      const float4 u1 = __ldg(U1 + k), u2 = __ldg(U2 + k), v1 = __ldg(V1 + k), v2 = __ldg(V2 + k);
+      float4 p;
+      p.x = (v1.x * u1.x + v1.y * u1.y) + (v2.x * u2.x + v2.y * u2.y);
+      p.y = (v1.y * u1.x - v1.x * u1.y) + (v2.y * u2.x - v2.x * u2.y);
+      p.z = (v1.z * u1.z + v1.w * u1.w) + (v2.z * u2.z + v2.w * u2.w);
+      p.w = (v1.w * u1.z - v1.z * u1.w) + (v2.w * u2.z - v2.z * u2.w);
+      dst[k] = p;
+    }
+  }
+  __syncthreads();
+  // ---- reference quirk (CrossCorr.cc:480-492): bins H-1 and H keep the TARGET spectrum ------------
+  if (tid == 0) {
+    constexpr int PH1 = bin_slot<LOG2N>(H - 1), PH = bin_slot<LOG2N>(H), PH2 = bin_slot<LOG2N>(H + 1);
+    buf[PH1] = make_float2(tm.q_re, tm.q_im);
+    buf[PH2] = make_float2(tm.q_re, -tm.q_im);
+    buf[PH] = make_float2(tm.q_nyq, 0.f);
+  }
+  __syncthreads();
+  inverse_full<LOG2N, NT>(buf, ws.wn, tid);
+
+  // xc[i] = Re x[(i + H) mod N] / N   (rescale + half rotation, CrossCorr.cc:493-505)
+  const float scale = 1.0f / (float)N;
+  const double co = (sp.flags & SP_FAST) ? cutoff_fast : cutoff;
+  findtop<LOG2N, NT, 0>(buf, H, scale, co, mask, s_thr, s_wtot, &s_base, spi, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
 }
 
 // =================================================================================================
@@ -720,16 +883,27 @@ static cudaError_t encode_launch(const SigDesc *sigs, int nsig, Slots ws, float 
 }
 
 template <int LOG2N>
-static cudaError_t xcorr_launch(const SpDesc *sps, int nsp, Slots ws, double cutoff, double cutoff_fast,
-                                uint16_t *cand_pool, unsigned int pool_cap, uint2 *cand_ref,
-                                BatchCounters *ctr, float *xc_tap, cudaStream_t st) {
+static cudaError_t xcorr_launch(const SpDesc *sps, const uint32_t *pair_list, int n_pairs, const uint32_t *direct_list,
+                                int n_direct, Slots ws, double cutoff, double cutoff_fast, uint16_t *cand_pool,
+                                unsigned int pool_cap, uint2 *cand_ref, BatchCounters *ctr, float *xc_tap,
+                                cudaStream_t st) {
   constexpr int N = 1 << LOG2N, NT = Cfg<LOG2N>::NT;
-  const size_t smem = (size_t)N * 8 + (N / 32) * 4 * 2;
-  auto k = xcorr_findtop_kernel<LOG2N, NT>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  k<<<nsp, NT, smem, st>>>(sps, ws, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
-  return cudaGetLastError();
+  const size_t smem = (size_t)N * 8 + (N / 32) * 4;
+  if (n_pairs > 0) {
+    auto k = xcorr_pair_kernel<LOG2N, NT>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<n_pairs, NT, smem, st>>>(pair_list, sps, ws, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  if (n_direct > 0) {
+    auto k = xcorr_findtop_kernel<LOG2N, NT>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<n_direct, NT, smem, st>>>(direct_list, sps, ws, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 template <int LOG2N>
@@ -770,11 +944,12 @@ cudaError_t launch_encode_fft(int log2n, const SigDesc *sigs, int nsig, Slots ws
 #undef CALL
 }
 
-cudaError_t launch_xcorr_findtop(int log2n, const SpDesc *sps, int nsp, Slots ws, double cutoff,
+cudaError_t launch_xcorr_findtop(int log2n, const SpDesc *sps, const uint32_t *pair_list, int n_pairs,
+                                 const uint32_t *direct_list, int n_direct, Slots ws, double cutoff,
                                  double cutoff_fast, uint16_t *cand_pool, unsigned int pool_cap,
                                  uint2 *cand_ref, BatchCounters *ctr, float *xc_tap, cudaStream_t stream) {
-  if (nsp <= 0) return cudaSuccess;
-#define CALL(L) xcorr_launch<L>(sps, nsp, ws, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, xc_tap, stream)
+  if (n_pairs <= 0 && n_direct <= 0) return cudaSuccess;
+#define CALL(L) xcorr_launch<L>(sps, pair_list, n_pairs, direct_list, n_direct, ws, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, xc_tap, stream)
   SX_DISPATCH(log2n, CALL)
 #undef CALL
 }

@@ -7,7 +7,8 @@ namespace sx {
 
 // ---- HBM layout -------------------------------------------------------------------------------
 // A "signal slot" holds everything later kernels need about one chunk in one orientation:
-//   spec   [slot][2][N] float2 : spectra of (A + iC) and (G + iT), scrambled (DIF) bin order
+//   spec   [slot][2][N] float2 : spectra of (A + iC) and (G + iT); each as [even bins | odd bins], every
+//                                half in the scrambled (DIF) order of the H-point transform (sx_fft.cuh)
 //   planes [slot][2][N/32] u32 : 2-bit base codes as two bit-planes (lo, hi); A=0 C=1 G=2 T=3
 //   bytes  [slot][N] u8        : the oriented bases (only the first len are meaningful)
 //   meta   [slot]              : length, flags, the three "quirk" spectrum values
@@ -24,6 +25,7 @@ struct Slots {
   uint32_t *planes;
   uint8_t *bytes;
   SlotMeta *meta;
+  const float2 *wn;  // e^{-2 pi i n / N}, n < N/2 (per context: the radix-2 split / combine twiddles)
 };
 
 struct SigDesc {  // one chunk signal to encode + transform
@@ -31,7 +33,8 @@ struct SigDesc {  // one chunk signal to encode + transform
   int32_t len;
   int32_t strand;  // 1: reverse-complement while loading
   int32_t slot;
-  int32_t pad;
+  int32_t rc_slot1;  // != 0: also write the reverse-complement planes / bytes / meta (no spectrum) to slot
+                     // rc_slot1 - 1; its correlation is derived from the forward spectrum (xcorr_pair_kernel)
 };
 
 struct SpDesc {  // one strand-pair = target slot x query slot
@@ -79,9 +82,13 @@ size_t slot_spec_elems(int log2n);  // float2 elements per slot
 
 cudaError_t launch_encode_fft(int log2n, const SigDesc *sigs, int nsig, Slots ws, float *tap5n,
                               cudaStream_t stream);
-cudaError_t launch_xcorr_findtop(int log2n, const SpDesc *sps, int nsp, Slots ws, double cutoff,
+// pair_list: index of the forward strand-pair of every chunk pair whose reverse strand is derived from the
+// forward query spectrum (one CTA does both strands); direct_list: strand-pairs correlated one by one
+cudaError_t launch_xcorr_findtop(int log2n, const SpDesc *sps, const uint32_t *pair_list, int n_pairs,
+                                 const uint32_t *direct_list, int n_direct, Slots ws, double cutoff,
                                  double cutoff_fast, uint16_t *cand_pool, unsigned int pool_cap,
                                  uint2 *cand_ref, BatchCounters *ctr, float *xc_tap, cudaStream_t stream);
+void fill_wn_table(int log2n, float2 *host_out);  // N/2 entries
 cudaError_t launch_scan_score(int log2n, const SpDesc *sps, int nsp, Slots ws, const uint16_t *cand_pool,
                               const uint2 *cand_ref, ScoreParams prm, ResultRec *res_pool,
                               unsigned int res_cap, SegRec *seg_tap, unsigned int seg_tap_cap, SegRec *spill,
