@@ -143,6 +143,7 @@ struct sx_ctx {
   DevBuf<BatchCounters> d_ctr;
   DevBuf<double> d_table;
   DevBuf<float> d_tap;
+  DevBuf<float2> d_scratch;  // split transforms (N = 32768): e[n] / o[n] of every correlation job between the two kernels
   bool have_table = false;
 
   PinBuf<SigDesc> h_sigs[2];  // descriptor staging, one per batch in flight / being assembled
@@ -199,7 +200,7 @@ extern "C" int sx_create(const sx_config *cfg, sx_ctx **out) {
   if (cfg->abi_version != SX_ABI_VERSION) return fail(SX_ERR_ARG, "sx_create: ABI version %d != %d", cfg->abi_version, SX_ABI_VERSION);
   const int l = pick_log2n(cfg->t_chunk);
   if (l < 0 || !log2n_supported(l))
-    return fail(SX_ERR_ARG, "sx_create: t_chunk=%d unsupported (2*t_chunk must be a power of two in [2048,16384])", cfg->t_chunk);
+    return fail(SX_ERR_ARG, "sx_create: t_chunk=%d unsupported (2*t_chunk must be a power of two in [2048,32768])", cfg->t_chunk);
   if (cfg->q_chunk < 1 || cfg->q_chunk > 2 * cfg->t_chunk)
     return fail(SX_ERR_ARG, "sx_create: q_chunk=%d must be in [1, 2*t_chunk]", cfg->q_chunk);
   int ndev = 0;
@@ -213,7 +214,7 @@ extern "C" int sx_create(const sx_config *cfg, sx_ctx **out) {
   c->cfg = *cfg;
   c->log2n = l;
   c->N = 1 << l;
-  if (c->cfg.max_batch_pairs <= 0) c->cfg.max_batch_pairs = 16384;
+  if (c->cfg.max_batch_pairs <= 0) c->cfg.max_batch_pairs = log2n_split(l) ? 4096 : 16384;
   if (c->cfg.spectra_cache_bytes == 0) c->cfg.spectra_cache_bytes = (int64_t)48 << 30;
   memset(&c->stats, 0, sizeof(c->stats));
   c->target_total = cfg->target_total;
@@ -256,7 +257,7 @@ extern "C" void sx_destroy(sx_ctx *c) {
   c->spec.release(); c->planes.release(); c->sbytes.release(); c->meta.release(); c->wn.release();
   c->d_lists.release(); c->h_lists[0].release(); c->h_lists[1].release();
   c->d_sigs.release(); c->d_sps.release(); c->d_cand_ref.release(); c->d_cand_pool.release();
-  c->d_res.release(); c->d_seg_tap.release(); c->d_spill.release(); c->d_ctr.release(); c->d_table.release(); c->d_tap.release();
+  c->d_scratch.release(); c->d_res.release(); c->d_seg_tap.release(); c->d_spill.release(); c->d_ctr.release(); c->d_table.release(); c->d_tap.release();
   c->h_sigs[0].release(); c->h_sigs[1].release(); c->h_sps[0].release(); c->h_sps[1].release(); c->h_res.release(); c->h_ctr.release();
   for (int i = 0; i < 5; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -587,8 +588,8 @@ static int batch_kernels(sx_ctx *c, Run &r) {
     CU(launch_xcorr_findtop(c->log2n, c->d_sps.p, c->d_lists.p, r.n_pairlist, c->d_lists.p + r.n_pairlist, r.n_direct, ws,
                             c->cfg.cutoff, c->cfg.cutoff_fast, c->d_cand_pool.p,
                             (unsigned int)std::min<size_t>(c->d_cand_pool.n, 0xfffffff0u), c->d_cand_ref.p, c->d_ctr.p,
-                            r.d_xc_tap, st));
-    c->stats.kernel_launches += (r.n_pairlist > 0) + (r.n_direct > 0);
+                            r.d_xc_tap, c->d_scratch.p, st));
+    c->stats.kernel_launches += log2n_split(c->log2n) ? 2 : (r.n_pairlist > 0) + (r.n_direct > 0);
   }
   if (prof) CU(cudaEventRecord(c->ev[2], st));
   if (r.nsp) {
@@ -634,6 +635,8 @@ static int batch_launch(sx_ctx *c, Run &r) {
   if ((rc = c->d_sps.ensure(std::max(nsp, 1))) != SX_OK) return rc;
   if ((rc = c->d_cand_ref.ensure(std::max(nsp, 1))) != SX_OK) return rc;
   if ((rc = c->d_lists.ensure(std::max(r.n_pairlist + r.n_direct, 1))) != SX_OK) return rc;
+  if (log2n_split(c->log2n) && (rc = c->d_scratch.ensure((size_t)std::max(r.n_pairlist + r.n_direct, 1) * N)) != SX_OK)
+    return rc;
   if (c->cfg.debug_small_pools) {  // test hook: start with pools that must overflow, so the grow-and-retry paths run
     if (c->d_cand_pool.n == 0 && (rc = c->d_cand_pool.ensure(64)) != SX_OK) return rc;
     if (c->d_res.n == 0 && (rc = c->d_res.ensure(4)) != SX_OK) return rc;

@@ -114,7 +114,8 @@ cudaError_t upload_tables() {
   return cudaSuccess;
 }
 
-bool log2n_supported(int log2n) { return log2n >= 11 && log2n <= 14; }
+bool log2n_supported(int log2n) { return log2n >= 11 && log2n <= 15; }
+bool log2n_split(int log2n) { return log2n >= 15; }
 
 void fill_wn_table(int log2n, float2 *out) {
   const int N = 1 << log2n;
@@ -152,27 +153,20 @@ __host__ __device__ constexpr double cx_sin_small(double a) {
   return a * (1. - a2 / 6. * (1. - a2 / 20. * (1. - a2 / 42. * (1. - a2 / 72. * (1. - a2 / 110. * (1. - a2 / 156.))))));
 }
 
+// Steps 1-2 of the encoder, shared by the whole-signal and the half-signal kernels: stage the raw chunk,
+// orient (reverse-complement) and sanitise it into sb[], write the 2-bit planes / oriented bytes (and the
+// other orientation's, see SigDesc::rc_slot1) when `side` is set, entropy weights per window into went[],
+// channel means into s_off[].  Returns the slot flags.  `raw` may alias any buffer that is free until the
+// signal is generated.  Ends with a barrier.
 template <int LOG2N, int NT>
-__global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
-    encode_fft_kernel(const SigDesc *__restrict__ sigs, Slots ws, float *__restrict__ tap) {
-  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, WIN = N / 512, NWARP = NT / 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2 *buf = reinterpret_cast<float2 *>(smem_raw);            // N complex (swizzled slots)
-  uint8_t *sb = smem_raw + (size_t)N * sizeof(float2);            // N oriented bases
-  float *went = reinterpret_cast<float *>(sb + N);                // 512 window weights
-  uint16_t *s_fcode = reinterpret_cast<uint16_t *>(went + 512);   // 128 x u16
-  uint8_t *s_comp = reinterpret_cast<uint8_t *>(s_fcode + 128);   // 128
-  uint8_t *s_base2 = s_comp + 128;                                // 128
-  __shared__ double s_red[4][NWARP];
-  __shared__ double s_off[4];
-  __shared__ int s_flags;
-
+__device__ __forceinline__ int encode_prepare(const SigDesc &sd, const Slots &ws, uint8_t *raw, uint8_t *sb, float *went,
+                                              uint16_t *s_fcode, uint8_t *s_comp, uint8_t *s_base2,
+                                              double (*s_red)[NT / 32], double *s_off, int *s_flags_p, bool side) {
+  constexpr int N = 1 << LOG2N, NW = N / 32, WIN = N / 512, NWARP = NT / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const SigDesc sd = sigs[blockIdx.x];
   const int len = sd.len;
   const uint8_t *__restrict__ src = sd.src;
-  const float2 *__restrict__ wn = ws.wn;
-
+  int &s_flags = *s_flags_p;
   if (tid < 128) {
     s_fcode[tid] = c_fcode[tid];
     s_comp[tid] = c_comp[tid];
@@ -180,7 +174,6 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
   }
   if (tid == 0) s_flags = 0;
   // ---- 1a. stage the raw chunk in shared memory (the FFT buffer is free until step 3) -------------
-  uint8_t *raw = smem_raw;
   if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {  // chunk stores are padded by 16 bytes
     const uint4 *s16 = reinterpret_cast<const uint4 *>(src);
     for (int i = tid; i < (len + 15) / 16; i += NT) reinterpret_cast<uint4 *>(raw)[i] = __ldg(s16 + i);
@@ -213,18 +206,18 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
       sb[k] = (uint8_t)b;
       const uint32_t lo = __ballot_sync(0xffffffffu, (code & 5u) == 1u);  // C or T -> bit0
       const uint32_t hi = __ballot_sync(0xffffffffu, (code & 6u) == 2u);  // G or T -> bit1
-      if (lane == 0) {
+      if (lane == 0 && side) {
         planes[k0 >> 5] = lo;
         planes[NW + (k0 >> 5)] = hi;
       }
     }
     if (myflags) atomicOr(&s_flags, myflags);
     __syncthreads();
-    {  // oriented bases to HBM for the generic scan path and the taps, 16 bytes per thread
+    if (side) {  // oriented bases to HBM for the generic scan path and the taps, 16 bytes per thread
       uint4 *gb = reinterpret_cast<uint4 *>(ws.bytes + (size_t)slot * N);
       for (int i = tid; i < N / 16; i += NT) gb[i] = reinterpret_cast<const uint4 *>(sb)[i];
     }
-    if (round && tid == 0) {
+    if (round && tid == 0 && side) {
       SlotMeta m;
       m.len = len;
       m.flags = s_flags & SLOT_NONACGT;  // same letters in both orientations (complement keeps the class)
@@ -289,6 +282,30 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
     s_off[tid] = __ddiv_rn(sum, (double)len);
   }
   __syncthreads();
+  return flags;
+}
+
+template <int LOG2N, int NT>
+__global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
+    encode_fft_kernel(const SigDesc *__restrict__ sigs, Slots ws, float *__restrict__ tap) {
+  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, WIN = N / 512, NWARP = NT / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *buf = reinterpret_cast<float2 *>(smem_raw);            // N complex (swizzled slots)
+  uint8_t *sb = smem_raw + (size_t)N * sizeof(float2);            // N oriented bases
+  float *went = reinterpret_cast<float *>(sb + N);                // 512 window weights
+  uint16_t *s_fcode = reinterpret_cast<uint16_t *>(went + 512);   // 128 x u16
+  uint8_t *s_comp = reinterpret_cast<uint8_t *>(s_fcode + 128);   // 128
+  uint8_t *s_base2 = s_comp + 128;                                // 128
+  __shared__ double s_red[4][NWARP];
+  __shared__ double s_off[4];
+  __shared__ int s_flags;
+
+  const int tid = threadIdx.x;
+  const SigDesc sd = sigs[blockIdx.x];
+  const int len = sd.len;
+  const float2 *__restrict__ wn = ws.wn;
+
+  const int flags = encode_prepare<LOG2N, NT>(sd, ws, smem_raw, sb, went, s_fcode, s_comp, s_base2, s_red, s_off, &s_flags, true);
   const bool flat = len < 1024;  // "Skip entropy": weight 1 everywhere (CrossCorr.cc:39-44)
 
   if (tap != nullptr) {
@@ -408,6 +425,112 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
   }
 }
 
+// K1 for transforms that do not fit one CTA's shared memory (N = 32768: 256 KiB of complex points): the
+// two H-point transforms of the split (sx_fft.cuh) are independent, so a signal is handled by TWO CTAs,
+// blockIdx.y = half: 0 builds e[n] = z[n] + z[n+H] (even bins), 1 builds o[n] = (z[n] - z[n+H]) w_N^n (odd
+// bins).  Both repeat the cheap encoding steps; only half 0 writes planes / bytes / taps.  The quirk bins
+// H-1 and H+1 are odd (half 1), bin H is even (half 0): the meta fields are written field by field.
+template <int LOG2N, int NT>
+__global__ void __launch_bounds__(NT, 1)
+    encode_fft_half_kernel(const SigDesc *__restrict__ sigs, Slots ws, float *__restrict__ tap) {
+  constexpr int N = 1 << LOG2N, H = N / 2, WIN = N / 512, NWARP = NT / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *buf = reinterpret_cast<float2 *>(smem_raw);            // H complex (swizzled slots)
+  uint8_t *sb = smem_raw + (size_t)H * sizeof(float2);            // N oriented bases
+  float *went = reinterpret_cast<float *>(sb + N);                // 512 window weights
+  uint16_t *s_fcode = reinterpret_cast<uint16_t *>(went + 512);   // 128 x u16
+  uint8_t *s_comp = reinterpret_cast<uint8_t *>(s_fcode + 128);   // 128
+  uint8_t *s_base2 = s_comp + 128;                                // 128
+  __shared__ double s_red[4][NWARP];
+  __shared__ double s_off[4];
+  __shared__ int s_flags;
+
+  const int tid = threadIdx.x;
+  const int half = blockIdx.y;
+  const SigDesc sd = sigs[blockIdx.x];
+  const int len = sd.len;
+  const float2 *__restrict__ wn = ws.wn;
+
+  const int flags = encode_prepare<LOG2N, NT>(sd, ws, smem_raw, sb, went, s_fcode, s_comp, s_base2, s_red, s_off, &s_flags,
+                                              half == 0);
+  const bool flat = len < 1024;  // "Skip entropy": weight 1 everywhere (CrossCorr.cc:39-44)
+  const bool pure = !(flags & SLOT_NONACGT);
+  if (tap != nullptr && half == 0) {
+    float *te = tap + (size_t)blockIdx.x * 5 * N;
+    for (int k = tid; k < N; k += NT) te[k] = flat ? 1.f : (k < len ? went[k / WIN] : 0.f);
+  }
+
+  float acc_re = 0.f, acc_im = 0.f, acc_ny = 0.f;
+  // slots inside this CTA's half
+  constexpr int PH1 = bin_slot<LOG2N>(H - 1) - H, PH2 = bin_slot<LOG2N>(H + 1) - H, PH = bin_slot<LOG2N>(H);
+#pragma unroll 1
+  for (int pr = 0; pr < 2; pr++) {
+    const double off0 = s_off[2 * pr], off1 = s_off[2 * pr + 1];
+    // sample k of the packed signal: (float)(weight * (fraction - mean)) per channel (SeqToPCM), 0 past the end
+    auto sample = [&](int k) -> float2 {
+      float2 v = make_float2(0.f, 0.f);
+      if (k < len) {
+        const double e = flat ? 1.0 : (double)went[k / WIN];
+        double f0, f1;
+        if (pure) {
+          const uint32_t code = s_base2[sb[k]];
+          f0 = code == (uint32_t)(2 * pr) ? 1.0 : 0.0;
+          f1 = code == (uint32_t)(2 * pr + 1) ? 1.0 : 0.0;
+        } else {
+          const uint32_t fc = s_fcode[sb[k]];
+          f0 = frac_of(fc, 2 * pr);
+          f1 = frac_of(fc, 2 * pr + 1);
+        }
+        v.x = __double2float_rn(__dmul_rn(e, __dsub_rn(f0, off0)));
+        v.y = __double2float_rn(__dmul_rn(e, __dsub_rn(f1, off1)));
+      }
+      return v;
+    };
+    if (tap != nullptr && half == 0) {
+      float *ts = tap + (size_t)blockIdx.x * 5 * N + (size_t)(1 + 2 * pr) * N;
+      for (int k = tid; k < N; k += NT) {
+        const float2 v = sample(k);
+        ts[k] = v.x;
+        ts[N + k] = v.y;
+      }
+    }
+    for (int n = tid; n < H; n += NT) {
+      const float2 a = sample(n), b = sample(n + H);
+      buf[swz(n)] = half == 0 ? cadd(a, b) : cmul(csub(a, b), __ldg(wn + n));
+    }
+    __syncthreads();
+    fft_forward_halves<LOG2N, H, NT>(buf, tid);
+    float4 *dst = reinterpret_cast<float4 *>(ws.spec + ((size_t)sd.slot * 2 + pr) * N + (size_t)half * H);
+    const float4 *s4p = reinterpret_cast<const float4 *>(buf);
+    for (int k = tid; k < H / 2; k += NT) dst[k] = s4p[k];
+    if (tid == 0) {
+      if (half == 1) {  // per-channel bins from the packed transform, see encode_fft_kernel
+        const float2 a = buf[PH1], z2 = buf[PH2];
+        const float2 b = make_float2(z2.x, -z2.y);
+        const float2 s = cadd(a, b), d = csub(a, b);
+        acc_re += 0.5f * s.x + 0.5f * d.y;
+        acc_im += 0.5f * s.y - 0.5f * d.x;
+      } else {
+        const float2 zn = buf[PH];
+        acc_ny += zn.x + zn.y;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    SlotMeta *m = ws.meta + sd.slot;
+    if (half == 0) {
+      m->len = len;
+      m->flags = flags & SLOT_NONACGT;
+      m->q_nyq = acc_ny;
+      m->pad[0] = m->pad[1] = m->pad[2] = 0;
+    } else {
+      m->q_re = acc_re;
+      m->q_im = acc_im;
+    }
+  }
+}
+
 // =================================================================================================
 // K2: spectral product + inverse transform + FindTop.
 //   xcorr_pair_kernel   one CTA per CHUNK PAIR: both strands from the forward query spectrum, one
@@ -417,17 +540,14 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
 // FindTop (SeqAnalyzer::FindTop, CrossCorr.cc:878-944) over xc[i] = COMP(buf[(i + off) mod N]) * scale:
 // RMS envelope per 256 lags (float square, double accumulate), threshold env*cutoff + 1, ballot
 // mask, block scan, ordered compaction into the candidate pool (one atomic per strand-pair).
-template <int LOG2N, int NT, int COMP>
-__device__ __forceinline__ void findtop(const float2 *buf, int off, float scale, double co, uint32_t *mask,
-                                        double *s_thr, unsigned int *s_wtot, unsigned int *s_base, int spi,
-                                        uint16_t *__restrict__ cand_pool, unsigned int pool_cap,
-                                        uint2 *__restrict__ cand_ref, BatchCounters *ctr, float *__restrict__ xc_tap) {
+template <int LOG2N, int NT, class XcAt>
+__device__ __forceinline__ void findtop_impl(XcAt xc_at, double co, uint32_t *mask, double *s_thr,
+                                             unsigned int *s_wtot, unsigned int *s_base, int spi,
+                                             uint16_t *__restrict__ cand_pool, unsigned int pool_cap,
+                                             uint2 *__restrict__ cand_ref, BatchCounters *ctr,
+                                             float *__restrict__ xc_tap) {
   constexpr int N = 1 << LOG2N, NW = N / 32, NB = N / 256, NWARP = NT / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  auto xc_at = [&](int i) -> float {
-    const float2 v = buf[swz((i + off) & (N - 1))];
-    return (COMP ? v.y : v.x) * scale;
-  };
   if (xc_tap != nullptr) {
     float *o = xc_tap + (size_t)spi * N;
     for (int i = tid; i < N; i += NT) o[i] = xc_at(i);
@@ -508,6 +628,20 @@ __device__ __forceinline__ void findtop(const float2 *buf, int off, float scale,
     }
   }
   __syncthreads();  // mask / s_thr / s_base are reused by the next strand
+}
+
+// FindTop over component COMP of a swizzled complex buffer holding the unscaled inverse transform
+template <int LOG2N, int NT, int COMP>
+__device__ __forceinline__ void findtop(const float2 *buf, int off, float scale, double co, uint32_t *mask,
+                                        double *s_thr, unsigned int *s_wtot, unsigned int *s_base, int spi,
+                                        uint16_t *__restrict__ cand_pool, unsigned int pool_cap,
+                                        uint2 *__restrict__ cand_ref, BatchCounters *ctr, float *__restrict__ xc_tap) {
+  constexpr int N = 1 << LOG2N;
+  auto xc_at = [&](int i) -> float {
+    const float2 v = buf[swz((i + off) & (N - 1))];
+    return (COMP ? v.y : v.x) * scale;
+  };
+  findtop_impl<LOG2N, NT>(xc_at, co, mask, s_thr, s_wtot, s_base, spi, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
 }
 
 // the two H-point inverses, then the radix-2 combine x[n] = e[n] + w_N^{-n} o[n], x[n+H] = e[n] - w_N^{-n} o[n]
@@ -657,6 +791,145 @@ __global__ void __launch_bounds__(NT)
   const float scale = 1.0f / (float)N;
   const double co = (sp.flags & SP_FAST) ? cutoff_fast : cutoff;
   findtop<LOG2N, NT, 0>(buf, H, scale, co, mask, s_thr, s_wtot, &s_base, spi, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
+}
+
+// ---- K2 for transforms that do not fit one CTA (N = 32768) ------------------------------------------
+// xcorr_half_kernel: grid (jobs, 2); job < n_pairs is a chunk pair handled like xcorr_pair_kernel, the
+// rest are single strand-pairs handled like xcorr_findtop_kernel; blockIdx.y = half (even / odd bins).
+// Product, quirk bins and the H-point inverse of one half in shared memory; the natural-order result
+// e[n] (half 0) / o[n] (half 1) goes to a scratch buffer in HBM (L2-resident for the next kernel).
+// combine_findtop_kernel: one CTA per strand-pair: x[n] = e[n] + w_N^{-n} o[n], x[n+H] = e[n] - w_N^{-n} o[n],
+// the component of its strand, rescale + rotation, then FindTop on the real vector in shared memory.
+template <int LOG2N, int NT>
+__global__ void __launch_bounds__(NT, 1)
+    xcorr_half_kernel(const uint32_t *__restrict__ pair_list, int n_pairs, const uint32_t *__restrict__ direct_list,
+                      const SpDesc *__restrict__ sps, Slots ws, float2 *__restrict__ scratch) {
+  constexpr int N = 1 << LOG2N, H = N / 2;
+  constexpr int LR = last_radix<LOG2N>();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *buf = reinterpret_cast<float2 *>(smem_raw);  // H complex: this CTA's half
+  const int tid = threadIdx.x, half = blockIdx.y, job = blockIdx.x;
+  const bool is_pair = job < n_pairs;
+  const int spi = (int)(is_pair ? pair_list[job] : direct_list[job - n_pairs]);
+  const SpDesc sp = sps[spi];
+  const SlotMeta tm = ws.meta[sp.t_slot];
+  const int qlen = ws.meta[sp.q_slot].len;
+  const float2 *U1 = ws.spec + ((size_t)sp.t_slot * 2) * N + (size_t)half * H, *U2 = U1 + N;
+  const float2 *V1 = ws.spec + ((size_t)sp.q_slot * 2) * N + (size_t)half * H, *V2 = V1 + N;
+  constexpr int PH1 = bin_slot<LOG2N>(H - 1) - H, PH2 = bin_slot<LOG2N>(H + 1) - H, PH = bin_slot<LOG2N>(H);
+  if (is_pair) {
+    // both strands, Hermitian-symmetrised and packed (see xcorr_pair_kernel)
+#pragma unroll 2
+    for (int it = tid; it < H / 2; it += NT) {
+      int pa, pb;
+      if (half == 0) {  // even bins: m <-> (H - m) mod H
+        const int r = (it / (LR / 2)) * LR + (it % (LR / 2));
+        const int m2 = (H - natural_bin<LOG2N>(r)) & (H - 1);
+        pa = swz(r);
+        pb = swz(scrambled_pos<LOG2N>(m2));
+      } else {  // odd bins: scrambled position r <-> H - 1 - r
+        pa = swz(it);
+        pb = swz(H - 1 - it);
+      }
+      const float2 u1a = __ldg(U1 + pa), u2a = __ldg(U2 + pa), v1a = __ldg(V1 + pa), v2a = __ldg(V2 + pa);
+      const float2 u1b = __ldg(U1 + pb), u2b = __ldg(U2 + pb), v1b = __ldg(V1 + pb), v2b = __ldg(V2 + pb);
+      const float2 a = cadd(cmulc(v1a, u1a), cmulc(v2a, u2a));
+      const float2 b = cadd(cmulc(v1b, u1b), cmulc(v2b, u2b));
+      const float2 g = cadd(cmul(u1a, v2a), cmul(u2a, v1a));
+      const float2 h = cadd(cmul(u1b, v2b), cmul(u2b, v1b));
+      const float sx_ = a.x + b.x, dx = g.x - h.x, sy = g.y + h.y, dy = a.y - b.y;
+      buf[pa] = make_float2(sx_ - dx, sy + dy);
+      buf[pb] = make_float2(sx_ + dx, sy - dy);
+    }
+    __syncthreads();
+    if (tid == 0) {  // quirk bins with the reverse strand's rotation phase (see xcorr_pair_kernel)
+      const int rot = qlen - 1;
+      auto put = [&](int slot, int k, float2 t) {
+        float sn, cs;
+        sincospif(2.0f * (float)(((long long)k * rot) & (N - 1)) / (float)N, &sn, &cs);
+        const float2 tr = cmul(t, make_float2(cs, sn));
+        buf[slot] = make_float2(2.f * (t.x - tr.y), 2.f * (t.y + tr.x));
+      };
+      if (half == 1) {
+        put(PH1, H - 1, make_float2(tm.q_re, tm.q_im));
+        put(PH2, H + 1, make_float2(tm.q_re, -tm.q_im));
+      } else {
+        put(PH, H, make_float2(tm.q_nyq, 0.f));
+      }
+    }
+  } else {
+    const float4 *u1 = reinterpret_cast<const float4 *>(U1), *u2 = reinterpret_cast<const float4 *>(U2);
+    const float4 *v1 = reinterpret_cast<const float4 *>(V1), *v2 = reinterpret_cast<const float4 *>(V2);
+    float4 *dst = reinterpret_cast<float4 *>(buf);
+#pragma unroll 2
+    for (int k = tid; k < H / 2; k += NT) {
+      const float4 a1 = __ldg(u1 + k), a2 = __ldg(u2 + k), b1 = __ldg(v1 + k), b2 = __ldg(v2 + k);
+      float4 p;
+      p.x = (b1.x * a1.x + b1.y * a1.y) + (b2.x * a2.x + b2.y * a2.y);
+      p.y = (b1.y * a1.x - b1.x * a1.y) + (b2.y * a2.x - b2.x * a2.y);
+      p.z = (b1.z * a1.z + b1.w * a1.w) + (b2.z * a2.z + b2.w * a2.w);
+      p.w = (b1.w * a1.z - b1.z * a1.w) + (b2.w * a2.z - b2.z * a2.w);
+      dst[k] = p;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (half == 1) {
+        buf[PH1] = make_float2(tm.q_re, tm.q_im);
+        buf[PH2] = make_float2(tm.q_re, -tm.q_im);
+      } else {
+        buf[PH] = make_float2(tm.q_nyq, 0.f);
+      }
+    }
+  }
+  __syncthreads();
+  fft_inverse_halves<LOG2N, H, NT>(buf, tid);
+  float2 *out = scratch + ((size_t)job * 2 + half) * H;
+  for (int n = tid; n < H; n += NT) out[n] = buf[swz(n)];
+}
+
+template <int LOG2N, int NT>
+__global__ void __launch_bounds__(NT, 1)
+    combine_findtop_kernel(const uint32_t *__restrict__ pair_list, int n_pairs, const uint32_t *__restrict__ direct_list,
+                           const SpDesc *__restrict__ sps, Slots ws, const float2 *__restrict__ scratch, double cutoff,
+                           double cutoff_fast, uint16_t *__restrict__ cand_pool, unsigned int pool_cap,
+                           uint2 *__restrict__ cand_ref, BatchCounters *ctr, float *__restrict__ xc_tap) {
+  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, NB = N / 256, NWARP = NT / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float *xs = reinterpret_cast<float *>(smem_raw);                                       // N lags
+  uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw + (size_t)N * sizeof(float));  // NW words
+  __shared__ double s_thr[NB];
+  __shared__ unsigned int s_wtot[NWARP];
+  __shared__ unsigned int s_base;
+  const int tid = threadIdx.x, sj = blockIdx.x;
+  int job, comp, spi;
+  if (sj < 2 * n_pairs) {
+    job = sj >> 1;
+    comp = sj & 1;
+    spi = (int)pair_list[job] + comp;
+  } else {
+    job = n_pairs + (sj - 2 * n_pairs);
+    comp = 0;
+    spi = (int)direct_list[sj - 2 * n_pairs];
+  }
+  const SpDesc sp = sps[spi];
+  const int qlen = ws.meta[sp.q_slot].len;
+  // xc[i] = x[(i + off) mod N] * scale: rescale + half rotation (CrossCorr.cc:493-505); the derived reverse
+  // strand is additionally rotated by qlen - 1 lags and the pair product carries a factor 2
+  const float scale = (sj < 2 * n_pairs ? 0.5f : 1.0f) / (float)N;
+  const int off = comp ? ((H - (qlen - 1)) & (N - 1)) : H;
+  const float2 *e = scratch + (size_t)job * 2 * H, *o = e + H;
+  const float2 *__restrict__ wn = ws.wn;
+  for (int n = tid; n < H; n += NT) {
+    const float2 ev = __ldg(e + n), ov = __ldg(o + n);
+    const float2 t = cmulc(ov, __ldg(wn + n));
+    const float2 lo = cadd(ev, t), hi = csub(ev, t);
+    xs[(n - off) & (N - 1)] = (comp ? lo.y : lo.x) * scale;
+    xs[(n + H - off) & (N - 1)] = (comp ? hi.y : hi.x) * scale;
+  }
+  __syncthreads();
+  const double co = (sp.flags & SP_FAST) ? cutoff_fast : cutoff;
+  auto xc_at = [&](int i) -> float { return xs[i]; };
+  findtop_impl<LOG2N, NT>(xc_at, co, mask, s_thr, s_wtot, &s_base, spi, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
 }
 
 // =================================================================================================
@@ -869,25 +1142,54 @@ __global__ void __launch_bounds__(NT)
 template <int LOG2N>
 struct Cfg {
   static constexpr int NT = (LOG2N >= 14) ? 512 : 256;
+  // N = 32768: the complex buffer (256 KiB) exceeds one CTA's shared memory; every transform is handled
+  // by two CTAs, one per half of the radix-2 split, with the combine step going through HBM/L2
+  static constexpr bool SPLIT = LOG2N >= 15;
 };
 
 template <int LOG2N>
 static cudaError_t encode_launch(const SigDesc *sigs, int nsig, Slots ws, float *tap, cudaStream_t st) {
   constexpr int N = 1 << LOG2N, NT = Cfg<LOG2N>::NT;
+  if constexpr (Cfg<LOG2N>::SPLIT) {  // one CTA per half signal
+    const size_t smem = (size_t)(N / 2) * 8 + N + 512 * 4 + 128 * 2 + 256;
+    auto k = encode_fft_half_kernel<LOG2N, NT>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<dim3(nsig, 2), NT, smem, st>>>(sigs, ws, tap);
+    return cudaGetLastError();
+  } else {
   const size_t smem = (size_t)N * 8 + N + 512 * 4 + 128 * 2 + 256;
   auto k = encode_fft_kernel<LOG2N, NT>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<nsig, NT, smem, st>>>(sigs, ws, tap);
   return cudaGetLastError();
+  }
 }
 
 template <int LOG2N>
 static cudaError_t xcorr_launch(const SpDesc *sps, const uint32_t *pair_list, int n_pairs, const uint32_t *direct_list,
                                 int n_direct, Slots ws, double cutoff, double cutoff_fast, uint16_t *cand_pool,
                                 unsigned int pool_cap, uint2 *cand_ref, BatchCounters *ctr, float *xc_tap,
-                                cudaStream_t st) {
+                                float2 *scratch, cudaStream_t st) {
   constexpr int N = 1 << LOG2N, NT = Cfg<LOG2N>::NT;
+  if constexpr (Cfg<LOG2N>::SPLIT) {
+    if (scratch == nullptr) return cudaErrorInvalidValue;
+    const int jobs = n_pairs + n_direct;
+    auto k1 = xcorr_half_kernel<LOG2N, NT>;
+    const size_t smem1 = (size_t)(N / 2) * 8;
+    cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    if (e != cudaSuccess) return e;
+    k1<<<dim3(jobs, 2), NT, smem1, st>>>(pair_list, n_pairs, direct_list, sps, ws, scratch);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    auto k2 = combine_findtop_kernel<LOG2N, NT>;
+    const size_t smem2 = (size_t)N * 4 + (N / 32) * 4;
+    e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e != cudaSuccess) return e;
+    k2<<<2 * n_pairs + n_direct, NT, smem2, st>>>(pair_list, n_pairs, direct_list, sps, ws, scratch, cutoff, cutoff_fast,
+                                                 cand_pool, pool_cap, cand_ref, ctr, xc_tap);
+    return cudaGetLastError();
+  } else {
   const size_t smem = (size_t)N * 8 + (N / 32) * 4;
   if (n_pairs > 0) {
     auto k = xcorr_pair_kernel<LOG2N, NT>;
@@ -904,6 +1206,7 @@ static cudaError_t xcorr_launch(const SpDesc *sps, const uint32_t *pair_list, in
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   return cudaSuccess;
+  }
 }
 
 template <int LOG2N>
@@ -912,9 +1215,15 @@ static cudaError_t scan_launch(const SpDesc *sps, int nsp, Slots ws, const uint1
                                SegRec *seg_tap, unsigned int seg_tap_cap, SegRec *spill, unsigned int spill_cap,
                                BatchCounters *ctr, cudaStream_t st) {
   constexpr int N = 1 << LOG2N, NT = 256;
-  scan_score_kernel<LOG2N><<<nsp, SX_SCAN_NT, 0, st>>>(sps, ws, cand_pool, cand_ref, prm, res_pool, res_cap, seg_tap,
-                                                       seg_tap_cap, spill, spill_cap, ctr);
-  cudaError_t e = cudaGetLastError();
+  constexpr size_t scan_smem = scan_smem_bytes<LOG2N>();
+  cudaError_t e = cudaSuccess;
+  if (scan_smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(scan_score_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
+    if (e != cudaSuccess) return e;
+  }
+  scan_score_kernel<LOG2N><<<nsp, SX_SCAN_NT, scan_smem, st>>>(sps, ws, cand_pool, cand_ref, prm, res_pool, res_cap,
+                                                               seg_tap, seg_tap_cap, spill, spill_cap, ctr);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   score_spill_kernel<LOG2N><<<148, 128, 0, st>>>(sps, ws, spill, prm, res_pool, res_cap, spill_cap, ctr);
   e = cudaGetLastError();
@@ -933,6 +1242,7 @@ static cudaError_t scan_launch(const SpDesc *sps, int nsp, Slots ws, const uint1
     case 12: return CALL(12);          \
     case 13: return CALL(13);          \
     case 14: return CALL(14);          \
+    case 15: return CALL(15);          \
     default: return cudaErrorInvalidValue; \
   }
 
@@ -947,9 +1257,10 @@ cudaError_t launch_encode_fft(int log2n, const SigDesc *sigs, int nsig, Slots ws
 cudaError_t launch_xcorr_findtop(int log2n, const SpDesc *sps, const uint32_t *pair_list, int n_pairs,
                                  const uint32_t *direct_list, int n_direct, Slots ws, double cutoff,
                                  double cutoff_fast, uint16_t *cand_pool, unsigned int pool_cap,
-                                 uint2 *cand_ref, BatchCounters *ctr, float *xc_tap, cudaStream_t stream) {
+                                 uint2 *cand_ref, BatchCounters *ctr, float *xc_tap, float2 *scratch,
+                                 cudaStream_t stream) {
   if (n_pairs <= 0 && n_direct <= 0) return cudaSuccess;
-#define CALL(L) xcorr_launch<L>(sps, pair_list, n_pairs, direct_list, n_direct, ws, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, xc_tap, stream)
+#define CALL(L) xcorr_launch<L>(sps, pair_list, n_pairs, direct_list, n_direct, ws, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, xc_tap, scratch, stream)
   SX_DISPATCH(log2n, CALL)
 #undef CALL
 }

@@ -78,6 +78,8 @@ enum { ST_CAND_OVERFLOW = 1, ST_RES_OVERFLOW = 2, ST_TAP_OVERFLOW = 4, ST_SPILL_
 cudaError_t upload_tables();  // constant/global lookup tables, once per device
 
 bool log2n_supported(int log2n);
+bool log2n_split(int log2n);  // transforms handled by two CTAs (N = 32768): launch_xcorr_findtop needs `scratch`,
+                              // N float2 per chunk-pair job / single strand-pair job
 size_t slot_spec_elems(int log2n);  // float2 elements per slot
 
 cudaError_t launch_encode_fft(int log2n, const SigDesc *sigs, int nsig, Slots ws, float *tap5n,
@@ -87,7 +89,8 @@ cudaError_t launch_encode_fft(int log2n, const SigDesc *sigs, int nsig, Slots ws
 cudaError_t launch_xcorr_findtop(int log2n, const SpDesc *sps, const uint32_t *pair_list, int n_pairs,
                                  const uint32_t *direct_list, int n_direct, Slots ws, double cutoff,
                                  double cutoff_fast, uint16_t *cand_pool, unsigned int pool_cap,
-                                 uint2 *cand_ref, BatchCounters *ctr, float *xc_tap, cudaStream_t stream);
+                                 uint2 *cand_ref, BatchCounters *ctr, float *xc_tap, float2 *scratch,
+                                 cudaStream_t stream);
 void fill_wn_table(int log2n, float2 *host_out);  // N/2 entries
 cudaError_t launch_scan_score(int log2n, const SpDesc *sps, int nsp, Slots ws, const uint16_t *cand_pool,
                               const uint2 *cand_ref, ScoreParams prm, ResultRec *res_pool,

@@ -264,6 +264,12 @@ __device__ __forceinline__ int eval_unit(const PlanePtrs &P, const Diag &d, int 
 }
 
 template <int LOG2N>
+constexpr size_t scan_smem_bytes() {
+  constexpr size_t N = (size_t)1 << LOG2N, NW = N / 32, PW = NW + 2, NWARP = SX_SCAN_NT / 32, NBW = (NW + 31) / 32;
+  return NWARP * SX_SEG_CAP * 8 + 4 * PW * 4 + NWARP * NBW * 32 * 4 + NWARP * SX_UNIT_CAP * 4 + NWARP * 32 * 4;
+}
+
+template <int LOG2N>
 __global__ void __launch_bounds__(SX_SCAN_NT)
     scan_score_kernel(const SpDesc *__restrict__ sps, Slots ws, const uint16_t *__restrict__ cand_pool,
                       const uint2 *__restrict__ cand_ref, ScoreParams prm, ResultRec *__restrict__ res_pool,
@@ -271,11 +277,14 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
                       SegRec *__restrict__ spill, unsigned int spill_cap, BatchCounters *ctr) {
   constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, PW = NW + 2, NWARP = SX_SCAN_NT / 32;
   constexpr int NBW = (NW + 31) / 32;  // 32-bit words of the per-diagonal "word survives the filter" bitset
-  __shared__ uint32_t s_tlo[PW], s_thi[PW], s_qlo[PW], s_qhi[PW];
-  __shared__ uint32_t s_need[NWARP][NBW][32];
-  __shared__ uint32_t s_unit[NWARP][SX_UNIT_CAP];
-  __shared__ uint2 s_wq[NWARP][SX_SEG_CAP];
-  __shared__ int s_shift[NWARP][32];
+  // dynamic shared memory (scan_smem_bytes<LOG2N>(): above the 48 KiB static limit for N = 32768)
+  extern __shared__ __align__(16) unsigned char scan_smem[];
+  uint2(*s_wq)[SX_SEG_CAP] = reinterpret_cast<uint2(*)[SX_SEG_CAP]>(scan_smem);
+  uint32_t *s_tlo = reinterpret_cast<uint32_t *>(s_wq + NWARP), *s_thi = s_tlo + PW, *s_qlo = s_thi + PW,
+           *s_qhi = s_qlo + PW;
+  uint32_t(*s_need)[NBW][32] = reinterpret_cast<uint32_t(*)[NBW][32]>(s_qhi + PW);
+  uint32_t(*s_unit)[SX_UNIT_CAP] = reinterpret_cast<uint32_t(*)[SX_UNIT_CAP]>(s_need + NWARP);
+  int(*s_shift)[32] = reinterpret_cast<int(*)[32]>(s_unit + NWARP);
   __shared__ unsigned int s_nunit[NWARP][4], s_wqn[NWARP];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -238,12 +238,13 @@ def test_capacity_error_reports_required_size(sx, golden_samples):
 
 
 def test_larger_transform_sizes(sx, oracle_lib):
-    """config 3 (first half): 8192-bp chunks, N = 16384; and small N = 2048/4096."""
+    """config 3: 8192-bp chunks (N = 16384, one CTA per transform) and 16384-bp chunks (N = 32768, two CTAs
+    per transform with the combine step through HBM); and small N = 2048/4096."""
     from satsuma2_b200 import synth
 
-    for chunk in (8192, 2048, 1024):
+    for chunk in (16384, 8192, 2048, 1024):
         NN = 2 * chunk
-        n = 6
+        n = 4 if chunk == 16384 else 6
         T, Q, _ = synth.random_pairs(n, chunk, seed=chunk)
         listed = []
         with sx.XCorrEngine(t_chunk=chunk, q_chunk=chunk, target_total=1e6) as eng:
@@ -265,6 +266,74 @@ def test_larger_transform_sizes(sx, oracle_lib):
             compare_pair_records(oracle_lib, got[got["query_id"] == i], exp[exp["query_id"] == i], tl[i][0], ql[i][0],
                                  0, 0, chunk, chunk, NN, 1.8, 0.99, 1e6, listed)
         _log_listed(f"transform_{NN}", listed)
+
+
+@pytest.mark.parametrize("NN", [16384, 32768])
+def test_large_transforms_against_reference_vectors(sx, oracle_lib, golden_large, NN):
+    """config 3 against the reference's OWN outputs (tests/golden/large_n.npz).  The reference's float FFT
+    drifts from the exact transform at these sizes; REF_XC_TOL documents the allowance."""
+    from conftest import REF_XC_TOL
+
+    g = golden_large
+    chunk = NN // 2
+    t, q = g[f"t_{NN}"], g[f"q_{NN}"]
+    with sx.XCorrEngine(t_chunk=chunk, q_chunk=chunk, target_total=1e6) as eng:
+        eng.set_targets(sx.ChunkSet.independent(t[None, :]))
+        eng.set_queries(sx.ChunkSet.independent(q[None, :]))
+        for strand in (0, 1):
+            ref_xc = g[f"xc_{NN}_{strand}"]
+            assert xc_rel_err(eng.tap_xcorr(0, 0, strand), ref_xc) < REF_XC_TOL[NN]
+            compare_candidates(oracle_lib, eng.tap_candidates(0, 0, strand), ref_xc, 1.8)
+        got = eng.align_pairs([(0, 0)])
+    exp = g[f"records_{NN}"]
+    assert sorted(rec_key(r) for r in got) == sorted(rec_key(r) for r in exp)
+    ge = {rec_key(r): r for r in exp}
+    for r in got:
+        assert r["ident"] == ge[rec_key(r)]["ident"]
+        assert abs(float(r["prob"]) - float(ge[rec_key(r)]["prob"])) <= 1e-6 * abs(float(ge[rec_key(r)]["prob"]))
+
+
+def test_split_transform_edge_cases(sx, oracle_lib):
+    """N = 32768: ragged chunk lengths (reverse strand not derivable from the forward spectrum -> single
+    strand-pair jobs), short chunks with flat weights, query longer than half the transform, IUPAC / N runs
+    (generic scan path) and an empty chunk -- the same parity contract as at N = 8192."""
+    chunk, NN = 16384, 32768
+    rng = np.random.default_rng(77)
+
+    def rnd(n):
+        return rng.choice(np.frombuffer(b"ACGT", np.uint8), size=n)
+
+    base = rnd(chunk)
+    mut = base.copy()
+    idx = rng.choice(chunk, size=chunk // 8, replace=False)
+    mut[idx] = rnd(len(idx))
+    T = [base, base[:16001], rnd(900), base, base[:5000], rnd(0)]
+    Q = [mut, mut[:16001], rnd(700), np.concatenate([mut, rnd(9000)])[:25000], mut[:5000].copy(), rnd(2000)]
+    Q[4][100:140] = ord("N")
+    Q[4][700:710] = np.frombuffer(b"RYKMSWBDHV", np.uint8)
+    n = len(T)
+
+    tl = [(T[i].tobytes(), 0, i, len(T[i])) for i in range(n)]
+    ql = [(Q[i].tobytes(), 0, i, len(Q[i])) for i in range(n)]
+    listed = []
+    with sx.XCorrEngine(t_chunk=chunk, q_chunk=2 * chunk, target_total=1e6) as eng:
+        eng.set_targets(sx.ChunkSet.from_list(tl))
+        eng.set_queries(sx.ChunkSet.from_list(ql))
+        for i in range(n - 1):
+            for strand in (0, 1):
+                qs = oracle_lib.revcomp(Q[i].tobytes()) if strand else Q[i].tobytes()
+                ref_xc = oracle_lib.xcorr(T[i].tobytes(), qs, NN)
+                assert np.array_equal(eng.tap_signal(False, i, strand), oracle_lib.encode(qs, NN))
+                assert xc_rel_err(eng.tap_xcorr(i, i, strand), ref_xc) < XC_TOL
+                compare_candidates(oracle_lib, eng.tap_candidates(i, i, strand), ref_xc, 1.8)
+        got = eng.align_pairs([(i, i) for i in range(n)])
+    params = oracle_lib.make_params(t_chunk=chunk, q_chunk=2 * chunk, target_total=1e6)
+    exp = oracle_lib.align_pairs(params, tl, ql, [(i, i) for i in range(n)], threads=4)
+    assert len(exp) > 0
+    for i in range(n):
+        compare_pair_records(oracle_lib, got[got["query_id"] == i], exp[exp["query_id"] == i], tl[i][0], ql[i][0],
+                             0, 0, len(Q[i]), 2 * chunk, NN, 1.8, 0.99, 1e6, listed)
+    _log_listed("split_transform_edge_cases", listed)
 
 
 def _genome_chunks(sx, seq, size, overlap):

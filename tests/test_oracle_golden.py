@@ -112,3 +112,27 @@ def test_oracle_threshold_constant(oracle_lib):
     assert oracle_lib.score(ord("A"), ord("A")) == 100 and oracle_lib.score(ord("A"), ord("C")) == 0
     assert oracle_lib.score(ord("N"), ord("N")) == 25 and oracle_lib.score(ord("N"), ord("A")) == 25
     assert oracle_lib.score(ord("X"), ord("X")) == 100 and oracle_lib.score(0, 0) == 100
+
+
+@pytest.mark.parametrize("NN", [16384, 32768])
+def test_large_transforms_against_reference(oracle_lib, golden_large, NN):
+    """config 3: the float64 oracle vs the reference's own vectors at N = 16384 / 32768."""
+    from conftest import REF_XC_TOL
+
+    g = golden_large
+    t, q = g[f"t_{NN}"].tobytes(), g[f"q_{NN}"].tobytes()
+    chunk = NN // 2
+    for strand in (0, 1):
+        qs = oracle_lib.revcomp(q) if strand else q
+        ref_xc = g[f"xc_{NN}_{strand}"]
+        assert xc_rel_err(oracle_lib.xcorr(t, qs, NN), ref_xc) < REF_XC_TOL[NN]
+        assert np.array_equal(oracle_lib.findtop(ref_xc, 1.8), g[f"cands_{NN}_{strand}"])
+        # the oracle's own vector gives the same candidate list up to lags AT the threshold (listed by the helper)
+        compare_candidates(oracle_lib, oracle_lib.findtop(oracle_lib.xcorr(t, qs, NN), 1.8), ref_xc, 1.8)
+    params = oracle_lib.make_params(t_chunk=chunk, q_chunk=chunk, target_total=1e6)
+    got = oracle_lib.align_pairs(params, [(t, 0, 0, chunk)], [(q, 0, 0, chunk)], [(0, 0)])
+    exp = g[f"records_{NN}"]
+    assert sorted(rec_key(r) for r in got) == sorted(rec_key(r) for r in exp)
+    ge = {rec_key(r): r for r in exp}
+    for r in got:
+        assert r["prob"] == ge[rec_key(r)]["prob"] and r["ident"] == ge[rec_key(r)]["ident"]
