@@ -1215,14 +1215,15 @@ static cudaError_t scan_launch(const SpDesc *sps, int nsp, Slots ws, const uint1
                                SegRec *seg_tap, unsigned int seg_tap_cap, SegRec *spill, unsigned int spill_cap,
                                BatchCounters *ctr, cudaStream_t st) {
   constexpr int N = 1 << LOG2N, NT = 256;
-  constexpr size_t scan_smem = scan_smem_bytes<LOG2N>();
+  constexpr size_t scan_smem = ScanCfg<LOG2N>::SMEM;
+  constexpr int SPC = ScanCfg<LOG2N>::SPC;
   cudaError_t e = cudaSuccess;
   if (scan_smem > 48 * 1024) {
     e = cudaFuncSetAttribute(scan_score_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
     if (e != cudaSuccess) return e;
   }
-  scan_score_kernel<LOG2N><<<nsp, SX_SCAN_NT, scan_smem, st>>>(sps, ws, cand_pool, cand_ref, prm, res_pool, res_cap,
-                                                               seg_tap, seg_tap_cap, spill, spill_cap, ctr);
+  scan_score_kernel<LOG2N><<<(nsp + SPC - 1) / SPC, SX_SCAN_NT, scan_smem, st>>>(
+      sps, nsp, ws, cand_pool, cand_ref, prm, res_pool, res_cap, seg_tap, seg_tap_cap, spill, spill_cap, ctr);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   score_spill_kernel<LOG2N><<<148, 128, 0, st>>>(sps, ws, spill, prm, res_pool, res_cap, spill_cap, ctr);

@@ -5,35 +5,48 @@
 // reference's integer scores are 100 (equal) / 0 (different), so "window sum > 1889" (46-wide
 // window; (int)(45*0.42*100) is 1889 in IEEE double) is "at least 19 of the last 46 positions match".
 //
-// One CTA per strand-pair, the 2-bit base planes of both chunks in shared memory; each WARP takes
-// groups of 32 candidate lags.  Everything is done in DIAGONAL coordinates k = i - i0, 32 positions
-// (one word of match bits) at a time.  Three phases per group:
+// One CTA (4 warps) per chunk pair = two consecutive strand-pairs; the 2-bit base planes of the chunks
+// sit in shared memory.  The candidate lags are cut into groups of 32 which the warps take from a
+// shared counter, so no warp idles while a sibling still has groups.  A warp works on its group alone,
+// one diagonal per lane, in DIAGONAL coordinates k = i - i0, 32 positions (one word of match bits) at a
+// time:
 //
-//  A. filter (one diagonal per lane, warp-uniform loop): match word m = XOR of the planes, then an
-//     exact NECESSARY condition for any window ending in this word to reach 19: for each quarter of
-//     the word, the popcount of the 53 positions that cover all windows ending in that quarter.  On
-//     random DNA ~88 % of the words fail it and need nothing more.  Survivors are recorded as bits.
-//  B. units: maximal runs of surviving words.  The word before and after a unit has no passing
-//     position, so units are independent.  They are spread over the lanes; a lane evaluates a unit
-//     with the exact bit-sliced 46-window count (doubling: windows 2,4,8,16,32, then 32+8+4+2; ">= 19"
-//     is three logic ops on the six count planes), starting two words early with empty history --
-//     every window ending inside the unit lies within those words, so the result is exact.  Run
-//     starts/ends inside the unit give the segments, exactly as the reference's sequential loop.
-//  C. scoring: segments are spread over the lanes; popcounts over the planes, an FP32 pre-reject, the
-//     exact early reject and the reference's FP64 formula (score_counts).
-// A full queue spills to a global list scored by score_spill_kernel -- nothing is dropped.
+//  A. filter (warp-uniform loop over the words): match word m = XOR of the planes, then an exact
+//     NECESSARY condition for any window ending in this word to reach 19: for each quarter of the word,
+//     the popcount of the 53 positions that cover all windows ending in that quarter.  On random DNA
+//     ~89 % of the words fail it and need nothing more.  Survivors are recorded as bits.
+//  B. every surviving word becomes one work item (lane:5 | word:10); a warp scan gives each lane its
+//     slots in the item list, and the list is evaluated 32 items at a time, one per lane: the exact
+//     bit-sliced 46-window count (doubling: windows 2,4,8,16,32, then 32+8+4+2; ">= 19" is three logic
+//     ops on the six count planes) from the word and its two predecessors -- every window ending in the
+//     word lies within those three, so the result is exact -- as straight-line code that computes only
+//     the planes that can influence it.  The pass words go to shared memory.
+//  C. runs of passing positions are the segments, exactly as the reference's sequential loop emits
+//     them.  Every run start (item, bit) is queued (slots from a warp scan); the queue is then worked
+//     off one run per lane: follow the run through the next items of the same diagonal (a word that
+//     is not an item has no passing position), then score the segment: popcounts over the planes, an
+//     FP32 pre-reject, the exact early reject and the reference's FP64 formula (score_counts).
 #pragma once
 
 #define SX_SCAN_NT 128
-#define SX_UNIT_CAP 512  // units queued per warp and group (more are evaluated in place)
-#define SX_SEG_CAP 448   // segments queued per warp and group (more spill to the global list)
+#define SX_SCAN_WARPS (SX_SCAN_NT / 32)
+#define SX_RUN_CAP 512  // runs (= segments) queued per warp and round: a batch of 32 items has at most 32 x 16
 
-// the unit list of a warp is split in three by unit length: 1, 2, >= 3 words
-__host__ __device__ constexpr int unit_cap(int bucket) { return bucket == 0 ? 288 : bucket == 1 ? 144 : 80; }
-__host__ __device__ constexpr int unit_base(int bucket) { return bucket == 0 ? 0 : bucket == 1 ? 288 : 432; }
+template <int LOG2N>
+struct ScanCfg {
+  static constexpr int NW = (1 << LOG2N) / 32;                // words per plane
+  static constexpr int PAD = 2;                               // zero words in front of every plane
+  static constexpr int PW = NW + PAD + 2;                     // padded plane length (word NW + 1 is still readable)
+  static constexpr int NBW = (NW + 31) / 32;                  // words of a lane's survivor bitset
+  static constexpr int SPC = LOG2N <= 14 ? 2 : 1;             // strand-pairs per CTA
+  static constexpr int ITEM_CAP = NW > 512 ? NW : 512;        // items listed per round (>= the most one lane can have)
+  static constexpr size_t WARP_BYTES = (size_t)SX_RUN_CAP * 4 + (size_t)NBW * 32 * 4 + (size_t)ITEM_CAP * 4 +
+                                       (size_t)ITEM_CAP * 2 + 32 * 4;
+  static constexpr size_t SMEM = (size_t)SPC * 4 * PW * 4 + SX_SCAN_WARPS * WARP_BYTES;
+};
 
 struct PlanePtrs {
-  const uint32_t *tlo, *thi, *qlo, *qhi;  // each readable up to word NW+1 (zero padded)
+  const uint32_t *tlo, *thi, *qlo, *qhi;  // each readable from word -2 to word NW+1 (zero padded)
 };
 
 // 32 positions of both sequences starting at target bit tw*32+tsh / query bit qw*32+qsh
@@ -97,247 +110,303 @@ __device__ __forceinline__ Diag make_diag(int shift, int tlen, int qlen) {
   return d;
 }
 
-// match bits of diagonal word kw (positions 32kw..32kw+31 of the diagonal), zero outside [0, L)
-template <int NW>
-__device__ __forceinline__ uint32_t match_bits(const PlanePtrs &P, const Diag &d, int kw) {
-  uint32_t tl, th, ql, qh;
-  diag_words(P, min(d.tw0 + kw, NW), d.tsh, min(d.qw0 + kw, NW), d.qsh, tl, th, ql, qh);
-  const uint32_t vm = kw < d.nwords - 1 ? 0xffffffffu : (kw == d.nwords - 1 ? d.lastmask : 0u);
-  return ~((tl ^ ql) | (th ^ qh)) & vm;
+// ---- bit-sliced sliding counts -------------------------------------------------------------------
+// Plane j of a struct holds bit j of the count of matches in the window ENDING at each of the 32
+// positions of a word.  "prev" = the same quantity one word earlier on the diagonal.
+struct W2 { uint32_t p0, p1; };              // window 2,  count <= 2
+struct W4 { uint32_t p0, p1, p2; };          // window 4,  count <= 4
+struct W8 { uint32_t p0, p1, p2, p3; };      // window 8,  count <= 8
+struct W16 { uint32_t p0, p1, p2, p3, p4; };  // window 16, count <= 16
+
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a ^ b)); }
+
+__device__ __forceinline__ W2 win2(uint32_t m_prev, uint32_t m) {
+  const uint32_t m1 = __funnelshift_l(m_prev, m, 1);
+  W2 r;
+  r.p0 = m ^ m1;
+  r.p1 = m & m1;
+  return r;
+}
+__device__ __forceinline__ W4 win4(const W2 &pv, const W2 &c) {  // c + (c delayed by 2)
+  const uint32_t a0 = __funnelshift_l(pv.p0, c.p0, 2), a1 = __funnelshift_l(pv.p1, c.p1, 2);
+  W4 r;
+  r.p0 = c.p0 ^ a0;
+  const uint32_t cy = c.p0 & a0;
+  r.p1 = c.p1 ^ a1 ^ cy;
+  r.p2 = maj3(c.p1, a1, cy);
+  return r;
+}
+__device__ __forceinline__ W8 win8(const W4 &pv, const W4 &c) {  // c + (c delayed by 4)
+  const uint32_t b0 = __funnelshift_l(pv.p0, c.p0, 4), b1 = __funnelshift_l(pv.p1, c.p1, 4),
+                 b2 = __funnelshift_l(pv.p2, c.p2, 4);
+  W8 r;
+  r.p0 = c.p0 ^ b0;
+  uint32_t cy = c.p0 & b0;
+  r.p1 = c.p1 ^ b1 ^ cy;
+  cy = maj3(c.p1, b1, cy);
+  r.p2 = c.p2 ^ b2 ^ cy;
+  r.p3 = maj3(c.p2, b2, cy);
+  return r;
+}
+__device__ __forceinline__ W16 win16(const W8 &pv, const W8 &c) {  // c + (c delayed by 8)
+  const uint32_t c0 = __funnelshift_l(pv.p0, c.p0, 8), c1 = __funnelshift_l(pv.p1, c.p1, 8),
+                 c2 = __funnelshift_l(pv.p2, c.p2, 8), c3 = __funnelshift_l(pv.p3, c.p3, 8);
+  W16 r;
+  r.p0 = c.p0 ^ c0;
+  uint32_t cy = c.p0 & c0;
+  r.p1 = c.p1 ^ c1 ^ cy;
+  cy = maj3(c.p1, c1, cy);
+  r.p2 = c.p2 ^ c2 ^ cy;
+  cy = maj3(c.p2, c2, cy);
+  r.p3 = c.p3 ^ c3 ^ cy;
+  r.p4 = maj3(c.p3, c3, cy);
+  return r;
+}
+// Positions of the word whose 46-window holds >= 19 matches.  s4 / s4p: window-16 counts of this word and
+// the previous one; s3p, s2p, s1p: window-8/4/2 counts of the previous word; s2q, s1q: two words back.
+// 46 = 32 (s4 + s4 delayed 16) + 8 (s3 one word back) + 4 (s2 delayed 40) + 2 (s1 delayed 44).
+__device__ __forceinline__ uint32_t pass_word(const W16 &s4p, const W16 &s4, const W8 &s3p, const W4 &s2q,
+                                              const W4 &s2p, const W2 &s1q, const W2 &s1p) {
+  const uint32_t d0 = __funnelshift_l(s4p.p0, s4.p0, 16), d1 = __funnelshift_l(s4p.p1, s4.p1, 16),
+                 d2 = __funnelshift_l(s4p.p2, s4.p2, 16), d3 = __funnelshift_l(s4p.p3, s4.p3, 16),
+                 d4 = __funnelshift_l(s4p.p4, s4.p4, 16);
+  const uint32_t s50 = s4.p0 ^ d0;
+  uint32_t cy = s4.p0 & d0;
+  const uint32_t s51 = s4.p1 ^ d1 ^ cy;
+  cy = maj3(s4.p1, d1, cy);
+  const uint32_t s52 = s4.p2 ^ d2 ^ cy;
+  cy = maj3(s4.p2, d2, cy);
+  const uint32_t s53 = s4.p3 ^ d3 ^ cy;
+  cy = maj3(s4.p3, d3, cy);
+  const uint32_t s54 = s4.p4 ^ d4 ^ cy;
+  const uint32_t s55 = maj3(s4.p4, d4, cy);
+  const uint32_t e20 = __funnelshift_l(s2q.p0, s2p.p0, 8), e21 = __funnelshift_l(s2q.p1, s2p.p1, 8),
+                 e22 = __funnelshift_l(s2q.p2, s2p.p2, 8);
+  const uint32_t e10 = __funnelshift_l(s1q.p0, s1p.p0, 12), e11 = __funnelshift_l(s1q.p1, s1p.p1, 12);
+  const uint32_t u0 = e20 ^ e10;  // u = e2 + e1 <= 6
+  cy = e20 & e10;
+  const uint32_t u1 = e21 ^ e11 ^ cy;
+  cy = maj3(e21, e11, cy);
+  const uint32_t u2 = e22 ^ cy;
+  const uint32_t v0 = s3p.p0 ^ u0;  // v = s3(prev word) + u <= 14
+  cy = s3p.p0 & u0;
+  const uint32_t v1 = s3p.p1 ^ u1 ^ cy;
+  cy = maj3(s3p.p1, u1, cy);
+  const uint32_t v2 = s3p.p2 ^ u2 ^ cy;
+  cy = maj3(s3p.p2, u2, cy);
+  const uint32_t v3 = s3p.p3 ^ cy;
+  const uint32_t n0 = s50 ^ v0;  // count = s5 + v <= 46
+  cy = s50 & v0;
+  const uint32_t n1 = s51 ^ v1 ^ cy;
+  cy = maj3(s51, v1, cy);
+  const uint32_t n2 = s52 ^ v2 ^ cy;
+  cy = maj3(s52, v2, cy);
+  const uint32_t n3 = s53 ^ v3 ^ cy;
+  cy = maj3(s53, v3, cy);
+  const uint32_t n4 = s54 ^ cy;
+  const uint32_t n5 = s55 ^ (s54 & cy);
+  return n5 | (n4 & (n3 | n2 | (n1 & n0)));  // count >= 19 (0b010011)
+}
+// exclusive prefix sum over the warp; *total = sum over all lanes
+__device__ __forceinline__ unsigned int warp_excl_scan(unsigned int v, unsigned int *total) {
+  const int lane = threadIdx.x & 31;
+  unsigned int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  *total = __shfl_sync(0xffffffffu, incl, 31);
+  return incl - v;
 }
 
-// one finished segment -> warp queue (shared-memory atomic), spill list when full
-__device__ __forceinline__ void push_segment(int spi, int start_t, int shift, int seg_len, uint2 *wq, unsigned int *wqn,
-                                             SegRec *spill, unsigned int spill_cap, SegRec *seg_tap,
-                                             unsigned int seg_tap_cap, BatchCounters *ctr) {
-  tap_segment(spi, start_t, shift, seg_len, seg_tap, seg_tap_cap, ctr);
-  const unsigned int slot = atomicAdd(wqn, 1u);
-  if (slot < SX_SEG_CAP) {
-    wq[slot] = make_uint2((uint32_t)start_t | ((uint32_t)seg_len << 16), (uint32_t)shift);
-  } else {
-    const unsigned int gs = atomicAdd(&ctr->spill_used, 1u);
-    if (gs < spill_cap) {
-      SegRec r;
-      r.sp = spi;
-      r.start_t = start_t;
-      r.shift = shift;
-      r.len = seg_len;
-      spill[gs] = r;
-    } else {
-      atomicOr(&ctr->status, (unsigned int)ST_SPILL_OVERFLOW);
-    }
-  }
-}
-
-// Exact evaluation of one unit = diagonal words [ks, ks+k) of diagonal d: bit-sliced 46-window count,
-// run extraction, segments pushed.  Starts two words early with empty history (see file header).
-// WARP-COLLECTIVE: all 32 lanes call it together (k = 0 for a lane without a unit); the step loop
-// runs for the longest unit of the warp and re-converges every step.
-template <int NW>
-__device__ __forceinline__ int eval_unit(const PlanePtrs &P, const Diag &d, int ks, int k, int spi, uint2 *wq,
-                                         unsigned int *wqn, SegRec *spill, unsigned int spill_cap, SegRec *seg_tap,
-                                         unsigned int seg_tap_cap, BatchCounters *ctr) {
-  uint32_t m_prev = 0, carry = 0;
-  uint32_t s1p0 = 0, s1p1 = 0, s1q0 = 0, s1q1 = 0;
-  uint32_t s2p0 = 0, s2p1 = 0, s2p2 = 0, s2q0 = 0, s2q1 = 0, s2q2 = 0;
-  uint32_t s3p0 = 0, s3p1 = 0, s3p2 = 0, s3p3 = 0;
-  uint32_t s4p0 = 0, s4p1 = 0, s4p2 = 0, s4p3 = 0, s4p4 = 0;
-  int open = -1;  // start of the open run (diagonal coordinates), -1 = none
-  int nseg = 0;
-  const int k_end = ks + k;
-  const int kw0 = max(ks - 2, 0);
-  const int max_steps = __reduce_max_sync(0xffffffffu, k > 0 ? k_end - kw0 : 0);
-#pragma unroll 1
-  for (int step = 0; step < max_steps; step++) {  // warp-uniform
-   const int kw = kw0 + step;
-   if (kw < k_end && k > 0) {
-    const uint32_t m = match_bits<NW>(P, d, kw);
-    uint32_t cy;
-    // window 2
-    const uint32_t m1 = __funnelshift_l(m_prev, m, 1);
-    const uint32_t s10 = m ^ m1, s11 = m & m1;
-    // window 4 = s1 + (s1 delayed by 2)
-    const uint32_t a0 = __funnelshift_l(s1p0, s10, 2), a1 = __funnelshift_l(s1p1, s11, 2);
-    const uint32_t s20 = s10 ^ a0;
-    cy = s10 & a0;
-    const uint32_t s21 = s11 ^ a1 ^ cy;
-    const uint32_t s22 = (s11 & a1) | (cy & (s11 ^ a1));
-    // window 8 = s2 + (s2 delayed by 4)
-    const uint32_t b0 = __funnelshift_l(s2p0, s20, 4), b1 = __funnelshift_l(s2p1, s21, 4),
-                   b2 = __funnelshift_l(s2p2, s22, 4);
-    const uint32_t s30 = s20 ^ b0;
-    cy = s20 & b0;
-    const uint32_t s31 = s21 ^ b1 ^ cy;
-    cy = (s21 & b1) | (cy & (s21 ^ b1));
-    const uint32_t s32 = s22 ^ b2 ^ cy;
-    const uint32_t s33 = (s22 & b2) | (cy & (s22 ^ b2));
-    // window 16 = s3 + (s3 delayed by 8)
-    const uint32_t c0 = __funnelshift_l(s3p0, s30, 8), c1 = __funnelshift_l(s3p1, s31, 8),
-                   c2 = __funnelshift_l(s3p2, s32, 8), c3 = __funnelshift_l(s3p3, s33, 8);
-    const uint32_t s40 = s30 ^ c0;
-    cy = s30 & c0;
-    const uint32_t s41 = s31 ^ c1 ^ cy;
-    cy = (s31 & c1) | (cy & (s31 ^ c1));
-    const uint32_t s42 = s32 ^ c2 ^ cy;
-    cy = (s32 & c2) | (cy & (s32 ^ c2));
-    const uint32_t s43 = s33 ^ c3 ^ cy;
-    const uint32_t s44 = (s33 & c3) | (cy & (s33 ^ c3));
-    if (kw >= ks) {  // warm-up words only feed the history
-      // window 32 = s4 + (s4 delayed by 16)
-      const uint32_t d0 = __funnelshift_l(s4p0, s40, 16), d1 = __funnelshift_l(s4p1, s41, 16),
-                     d2 = __funnelshift_l(s4p2, s42, 16), d3 = __funnelshift_l(s4p3, s43, 16),
-                     d4 = __funnelshift_l(s4p4, s44, 16);
-      const uint32_t s50 = s40 ^ d0;
-      cy = s40 & d0;
-      const uint32_t s51 = s41 ^ d1 ^ cy;
-      cy = (s41 & d1) | (cy & (s41 ^ d1));
-      const uint32_t s52 = s42 ^ d2 ^ cy;
-      cy = (s42 & d2) | (cy & (s42 ^ d2));
-      const uint32_t s53 = s43 ^ d3 ^ cy;
-      cy = (s43 & d3) | (cy & (s43 ^ d3));
-      const uint32_t s54 = s44 ^ d4 ^ cy;
-      const uint32_t s55 = (s44 & d4) | (cy & (s44 ^ d4));
-      // tail of the 46-window: positions 32..39 = s3 one word back, 40..43 = s2 delayed 40, 44..45 = s1 delayed 44
-      const uint32_t e20 = __funnelshift_l(s2q0, s2p0, 8), e21 = __funnelshift_l(s2q1, s2p1, 8),
-                     e22 = __funnelshift_l(s2q2, s2p2, 8);
-      const uint32_t e10 = __funnelshift_l(s1q0, s1p0, 12), e11 = __funnelshift_l(s1q1, s1p1, 12);
-      const uint32_t u0 = e20 ^ e10;  // u = e2 + e1 <= 6
-      cy = e20 & e10;
-      const uint32_t u1 = e21 ^ e11 ^ cy;
-      cy = (e21 & e11) | (cy & (e21 ^ e11));
-      const uint32_t u2 = e22 ^ cy;
-      const uint32_t v0 = s3p0 ^ u0;  // v = s3(prev word) + u <= 14
-      cy = s3p0 & u0;
-      const uint32_t v1 = s3p1 ^ u1 ^ cy;
-      cy = (s3p1 & u1) | (cy & (s3p1 ^ u1));
-      const uint32_t v2 = s3p2 ^ u2 ^ cy;
-      cy = (s3p2 & u2) | (cy & (s3p2 ^ u2));
-      const uint32_t v3 = s3p3 ^ cy;
-      const uint32_t n0 = s50 ^ v0;  // count = s5 + v <= 46
-      cy = s50 & v0;
-      const uint32_t n1 = s51 ^ v1 ^ cy;
-      cy = (s51 & v1) | (cy & (s51 ^ v1));
-      const uint32_t n2 = s52 ^ v2 ^ cy;
-      cy = (s52 & v2) | (cy & (s52 ^ v2));
-      const uint32_t n3 = s53 ^ v3 ^ cy;
-      cy = (s53 & v3) | (cy & (s53 ^ v3));
-      const uint32_t n4 = s54 ^ cy;
-      const uint32_t n5 = s55 ^ (s54 & cy);
-      // count >= 19 (0b010011), only where a full window has been seen (k >= 46) and inside the diagonal
-      const uint32_t vm = kw < d.nwords - 1 ? 0xffffffffu : (kw == d.nwords - 1 ? d.lastmask : 0u);
-      uint32_t pass = (n5 | (n4 & (n3 | n2 | (n1 & n0)))) & vm;
-      if (kw < 2) pass &= (kw == 0) ? 0u : 0xffffc000u;
-      // run boundaries inside this word: rise = a run starts here, fall = first position after a run
-      const uint32_t prevp = (pass << 1) | carry;
-      const uint32_t rise = pass & ~prevp;
-      uint32_t fall = ~pass & prevp;
-      carry = pass >> 31;
-      const int kb = kw * 32;
-      while (fall) {
-        const int f = __ffs(fall) - 1;
-        fall &= fall - 1u;
-        const uint32_t below = rise & ((1u << f) - 1u);
-        // the run started at the closest rise below f, or in an earlier word (carried in `open`)
-        const int start_k = below ? (kb + 31 - __clz(below) - 45) : open;  // lastStart = i - m_minLen
-        push_segment(spi, d.i0 + start_k, d.shift, kb + f - start_k, wq, wqn, spill, spill_cap, seg_tap, seg_tap_cap,
-                     ctr);
-        nseg++;
-      }
-      open = carry ? (rise ? (kb + 31 - __clz(rise) - 45) : open) : -1;
-    }
-    m_prev = m;
-    s1q0 = s1p0; s1q1 = s1p1; s1p0 = s10; s1p1 = s11;
-    s2q0 = s2p0; s2q1 = s2p1; s2q2 = s2p2; s2p0 = s20; s2p1 = s21; s2p2 = s22;
-    s3p0 = s30; s3p1 = s31; s3p2 = s32; s3p3 = s33;
-    s4p0 = s40; s4p1 = s41; s4p2 = s42; s4p3 = s43; s4p4 = s44;
-   }
-   __syncwarp();
-  }
-  // The word after a unit has no passing position (or the diagonal ends): an open run closes at the
-  // word boundary / at the stop position L.
-  if (open >= 0) {
-    const int close = min(k_end * 32, d.L);
-    push_segment(spi, d.i0 + open, d.shift, close - open, wq, wqn, spill, spill_cap, seg_tap, seg_tap_cap, ctr);
-    nseg++;
-  }
-  return nseg;
-}
-
-template <int LOG2N>
-constexpr size_t scan_smem_bytes() {
-  constexpr size_t N = (size_t)1 << LOG2N, NW = N / 32, PW = NW + 2, NWARP = SX_SCAN_NT / 32, NBW = (NW + 31) / 32;
-  return NWARP * SX_SEG_CAP * 8 + 4 * PW * 4 + NWARP * NBW * 32 * 4 + NWARP * SX_UNIT_CAP * 4 + NWARP * 32 * 4;
+// Exact pass word of diagonal word kw (kw < d.nwords): the three match words kw-2 .. kw from four consecutive
+// words of every plane, then only the count planes that can reach the result: word kw-2 feeds windows 2 / 4
+// (their top bits), word kw-1 windows 2 .. 16.
+__device__ __forceinline__ uint32_t eval_word(const PlanePtrs &P, const Diag &d, int kw) {
+  const uint32_t *tl = P.tlo + d.tw0 + kw - 2, *th = P.thi + d.tw0 + kw - 2;
+  const uint32_t *ql = P.qlo + d.qw0 + kw - 2, *qh = P.qhi + d.qw0 + kw - 2;
+  const uint32_t a0 = tl[0], a1 = tl[1], a2 = tl[2], a3 = tl[3];
+  const uint32_t b0 = th[0], b1 = th[1], b2 = th[2], b3 = th[3];
+  const uint32_t c0 = ql[0], c1 = ql[1], c2 = ql[2], c3 = ql[3];
+  const uint32_t e0 = qh[0], e1 = qh[1], e2 = qh[2], e3 = qh[3];
+  const int ts = d.tsh, qs = d.qsh;
+  uint32_t mA = ~((__funnelshift_r(a0, a1, ts) ^ __funnelshift_r(c0, c1, qs)) |
+                  (__funnelshift_r(b0, b1, ts) ^ __funnelshift_r(e0, e1, qs)));
+  uint32_t mB = ~((__funnelshift_r(a1, a2, ts) ^ __funnelshift_r(c1, c2, qs)) |
+                  (__funnelshift_r(b1, b2, ts) ^ __funnelshift_r(e1, e2, qs)));
+  uint32_t mC = ~((__funnelshift_r(a2, a3, ts) ^ __funnelshift_r(c2, c3, qs)) |
+                  (__funnelshift_r(b2, b3, ts) ^ __funnelshift_r(e2, e3, qs)));
+  if (kw < 2) mA = 0u;  // before the diagonal starts
+  if (kw < 1) mB = 0u;
+  if (kw == d.nwords - 1) mC &= d.lastmask;
+  const W2 zero2 = {0u, 0u};
+  const W8 zero8 = {0u, 0u, 0u, 0u};
+  // only the top bits of word A's planes are ever read: empty history below them is exact
+  const W2 s1A = win2(0u, mA);
+  const W4 s2A = win4(zero2, s1A);
+  const W2 s1B = win2(mA, mB);
+  const W4 s2B = win4(s1A, s1B);
+  const W8 s3B = win8(s2A, s2B);
+  const W16 s4B = win16(zero8, s3B);  // only its top 16 bits are read: they depend on s3B alone
+  const W2 s1C = win2(mB, mC);
+  const W4 s2C = win4(s1B, s1C);
+  const W8 s3C = win8(s2B, s2C);
+  const W16 s4C = win16(s3B, s3C);
+  uint32_t pass = pass_word(s4B, s4C, s3B, s2A, s2B, s1A, s1B);
+  // a window is only evaluated once 46 positions have been seen (k >= 46) and inside the diagonal
+  if (kw == d.nwords - 1) pass &= d.lastmask;
+  if (kw < 2) pass &= (kw == 0) ? 0u : 0xffffc000u;
+  return pass;
 }
 
 template <int LOG2N>
 __global__ void __launch_bounds__(SX_SCAN_NT)
-    scan_score_kernel(const SpDesc *__restrict__ sps, Slots ws, const uint16_t *__restrict__ cand_pool,
+    scan_score_kernel(const SpDesc *__restrict__ sps, int nsp, Slots ws, const uint16_t *__restrict__ cand_pool,
                       const uint2 *__restrict__ cand_ref, ScoreParams prm, ResultRec *__restrict__ res_pool,
                       unsigned int res_cap, SegRec *__restrict__ seg_tap, unsigned int seg_tap_cap,
                       SegRec *__restrict__ spill, unsigned int spill_cap, BatchCounters *ctr) {
-  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, PW = NW + 2, NWARP = SX_SCAN_NT / 32;
-  constexpr int NBW = (NW + 31) / 32;  // 32-bit words of the per-diagonal "word survives the filter" bitset
-  // dynamic shared memory (scan_smem_bytes<LOG2N>(): above the 48 KiB static limit for N = 32768)
+  using C = ScanCfg<LOG2N>;
+  constexpr int N = 1 << LOG2N, H = N / 2, NW = C::NW, PW = C::PW, NBW = C::NBW, SPC = C::SPC, PAD = C::PAD;
+  constexpr int ITEM_CAP = C::ITEM_CAP;
   extern __shared__ __align__(16) unsigned char scan_smem[];
-  uint2(*s_wq)[SX_SEG_CAP] = reinterpret_cast<uint2(*)[SX_SEG_CAP]>(scan_smem);
-  uint32_t *s_tlo = reinterpret_cast<uint32_t *>(s_wq + NWARP), *s_thi = s_tlo + PW, *s_qlo = s_thi + PW,
-           *s_qhi = s_qlo + PW;
-  uint32_t(*s_need)[NBW][32] = reinterpret_cast<uint32_t(*)[NBW][32]>(s_qhi + PW);
-  uint32_t(*s_unit)[SX_UNIT_CAP] = reinterpret_cast<uint32_t(*)[SX_UNIT_CAP]>(s_need + NWARP);
-  int(*s_shift)[32] = reinterpret_cast<int(*)[32]>(s_unit + NWARP);
-  __shared__ unsigned int s_nunit[NWARP][4], s_wqn[NWARP];
+  uint32_t *s_planes = reinterpret_cast<uint32_t *>(scan_smem);  // [SPC][tlo, thi, qlo, qhi][PW]
+  __shared__ unsigned int s_next;
+  __shared__ int s_ncand[SPC];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const SpDesc sp = sps[blockIdx.x];
-  const uint2 cref = cand_ref[blockIdx.x];
-  const int ncand = (int)cref.y;
-  if (ncand == 0 || cref.x == 0xffffffffu) return;
-  const SlotMeta tm = ws.meta[sp.t_slot], qm = ws.meta[sp.q_slot];
-  if ((tm.flags | qm.flags) & SLOT_NONACGT) return;  // handled by the generic kernel
-  const int tlen = tm.len, qlen = qm.len;
-  {
+  unsigned char *wbase = scan_smem + (size_t)SPC * 4 * PW * 4 + (size_t)warp * C::WARP_BYTES;
+  uint32_t *wq = reinterpret_cast<uint32_t *>(wbase);                         // SX_RUN_CAP run starts: item | bit << 16
+  uint32_t(*s_need)[32] = reinterpret_cast<uint32_t(*)[32]>(wq + SX_RUN_CAP);  // [NBW][32]
+  uint32_t *passw = reinterpret_cast<uint32_t *>(s_need + NBW);               // ITEM_CAP
+  uint16_t *items = reinterpret_cast<uint16_t *>(passw + ITEM_CAP);           // ITEM_CAP
+  int *s_shift = reinterpret_cast<int *>(items + ITEM_CAP);                   // 32
+
+  const int sp0 = blockIdx.x * SPC;
+  if (tid < SPC) {
+    int nc = 0;
+    const int spi = sp0 + tid;
+    if (spi < nsp) {
+      const uint2 cref = cand_ref[spi];
+      const SpDesc sp = sps[spi];
+      const bool generic = ((ws.meta[sp.t_slot].flags | ws.meta[sp.q_slot].flags) & SLOT_NONACGT) != 0;  // other kernel
+      if (cref.x != 0xffffffffu && !generic) nc = (int)cref.y;
+    }
+    s_ncand[tid] = nc;
+  }
+  if (tid == 0) s_next = 0;
+  __syncthreads();
+  int ncand[SPC], gstart[SPC + 1];
+  gstart[0] = 0;
+#pragma unroll
+  for (int j = 0; j < SPC; j++) {
+    ncand[j] = s_ncand[j];
+    gstart[j + 1] = gstart[j] + ((ncand[j] + 31) >> 5);
+  }
+  if (gstart[SPC] == 0) return;
+#pragma unroll
+  for (int j = 0; j < SPC; j++) {
+    if (ncand[j] == 0) continue;
+    const SpDesc sp = sps[sp0 + j];
     const uint32_t *tp = ws.planes + (size_t)sp.t_slot * 2 * NW;
     const uint32_t *qp = ws.planes + (size_t)sp.q_slot * 2 * NW;
+    uint32_t *pl = s_planes + (size_t)j * 4 * PW;
     for (int i = tid; i < PW; i += SX_SCAN_NT) {
-      const bool in = i < NW;
-      s_tlo[i] = in ? tp[i] : 0u;
-      s_thi[i] = in ? tp[NW + i] : 0u;
-      s_qlo[i] = in ? qp[i] : 0u;
-      s_qhi[i] = in ? qp[NW + i] : 0u;
-    }
-    if (tid < NWARP) {
-      s_nunit[tid][0] = s_nunit[tid][1] = s_nunit[tid][2] = s_nunit[tid][3] = 0;
-      s_wqn[tid] = 0;
+      const int w = i - PAD;
+      const bool in = w >= 0 && w < NW;
+      pl[i] = in ? __ldg(tp + w) : 0u;
+      pl[PW + i] = in ? __ldg(tp + NW + w) : 0u;
+      pl[2 * PW + i] = in ? __ldg(qp + w) : 0u;
+      pl[3 * PW + i] = in ? __ldg(qp + NW + w) : 0u;
     }
   }
   __syncthreads();
-  PlanePtrs P;
-  P.tlo = s_tlo;
-  P.thi = s_thi;
-  P.qlo = s_qlo;
-  P.qhi = s_qhi;
-  uint2 *wq = s_wq[warp];
-  unsigned int *wqn = &s_wqn[warp];
-  uint32_t *units = s_unit[warp];
-  unsigned int *nunit = s_nunit[warp];
-  const int spi = blockIdx.x;
 
   unsigned int my_segments = 0;
   unsigned long long my_positions = 0;
-  for (int g0 = warp * 32; g0 < ncand; g0 += SX_SCAN_NT) {  // warp-uniform
+  unsigned int qn = 0;  // segments in this warp's queue (warp-uniform)
+  for (;;) {  // groups of 32 candidate lags, handed out dynamically
+    unsigned int g = 0;
+    if (lane == 0) g = atomicAdd(&s_next, 1u);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= (unsigned int)gstart[SPC]) break;
+    int j = 0, nc = ncand[0], gbase = 0;
+#pragma unroll
+    for (int jj = 1; jj < SPC; jj++)
+      if ((int)g >= gstart[jj]) {
+        j = jj;
+        nc = ncand[jj];
+        gbase = gstart[jj];
+      }
+    const int spi = sp0 + j;
+    const SpDesc sp = sps[spi];
+    const uint2 cref = cand_ref[spi];
+    const int tlen = ws.meta[sp.t_slot].len, qlen = ws.meta[sp.q_slot].len;
+    PlanePtrs P;
+    P.tlo = s_planes + (size_t)j * 4 * PW + PAD;
+    P.thi = P.tlo + PW;
+    P.qlo = P.thi + PW;
+    P.qhi = P.qlo + PW;
+
     // Candidates are sorted by lag, so diagonal lengths rise and fall like a triangle.  Pairing the
     // k-th from the front with the k-th from the back keeps the 32 diagonals of a warp close in length.
-    const int p = g0 + lane;
-    const int c = (p & 1) ? (ncand - 1 - (p >> 1)) : (p >> 1);
+    // One queued run start (item i, bit s) -> its segment -> probability filter.  A run starts at the first
+    // passing position minus 45 ("lastStart = i - m_minLen", CrossCorr.cc:700) and ends at the first failing
+    // position or where the diagonal stops; it goes on through the next items of the same diagonal (a word
+    // that is no item has no passing position).
+    int n_round = 0;
+    auto do_run = [&](int i, int s_) {
+      const uint32_t it = items[i], pass = passw[i];
+      const Diag od = make_diag(s_shift[it & 31u], tlen, qlen);
+      const int kb = (int)(it >> 5) * 32;
+      const uint32_t z = ~(pass >> s_);  // zeros shifted in at the top read as failing
+      const int run = z ? (__ffs(z) - 1) : 32;
+      int e = kb + s_ + run;
+      if (s_ + run == 32) {
+        int ni = i + 1;
+        uint32_t nit = it + 32u;
+        while (ni < n_round && items[ni] == nit) {
+          const uint32_t p2 = passw[ni];
+          if (p2 != 0xffffffffu) {
+            e += __ffs(~p2) - 1;
+            break;
+          }
+          e += 32;
+          ni++;
+          nit += 32u;
+        }
+      }
+      e = min(e, od.L);
+      const int start_k = kb + s_ - 45;
+      const int start_t = od.i0 + start_k, seg_len = e - start_k;
+      tap_segment(spi, start_t, od.shift, seg_len, seg_tap, seg_tap_cap, ctr);
+      double prob, ident;
+      if (score_fast(P, start_t, od.shift, seg_len, prm, prob, ident))
+        emit_result(sp, start_t, od.shift, seg_len, prob, ident, res_pool, res_cap, ctr);
+    };
+    // work off the queued run starts, one per lane (warp-collective)
+    auto flush_queue = [&]() {
+      __syncwarp();
+      for (int r = lane; r < (int)qn; r += 32) {
+        const uint32_t rec = wq[r];
+        do_run((int)(rec & 0xffffu), (int)(rec >> 16));
+      }
+      __syncwarp();
+      qn = 0;
+    };
+
+    const int p = ((int)g - gbase) * 32 + lane;
+    const int c = (p & 1) ? (nc - 1 - (p >> 1)) : (p >> 1);
     int shift = 0;
     Diag d = make_diag(0, 0, 0);
-    if (p < ncand) {
+    if (p < nc) {
       shift = (int)cand_pool[cref.x + c] - H;  // pos = idx - N/2 (CrossCorr.cc:600-602)
       d = make_diag(shift, tlen, qlen);
     }
-    s_shift[warp][lane] = shift;
+    s_shift[lane] = shift;
     my_positions += (unsigned long long)d.L;
     const int nw_max = __reduce_max_sync(0xffffffffu, d.nwords);
+    const int nbw = (nw_max + 31) >> 5;
 
     // ---- A. filter -------------------------------------------------------------------------------
     // Quarter q of word kw (positions 32kw+8q .. +7): every window ending there lies inside the 53
@@ -346,120 +415,119 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
     //   q1: m[kw-2] bits 27..31 + m[kw-1]            + m[kw] bits 0..15
     //   q2:                       m[kw-1] bits 3..31  + m[kw] bits 0..23
     //   q3:                       m[kw-1] bits 11..31 + m[kw]
-    int pp_all = 0, pp_ge3 = 0, pp_ge11 = 0;  // of m[kw-1]
-    int p2_ge19 = 0, p2_ge27 = 0;             // of m[kw-2]
-    int q_ge19 = 0, q_ge27 = 0;               // of m[kw-1], become p2_* next step
-    uint32_t acc = 0;
-    uint32_t rtl = s_tlo[min(d.tw0, NW)], rth = s_thi[min(d.tw0, NW)], rql = s_qlo[min(d.qw0, NW)],
-             rqh = s_qhi[min(d.qw0, NW)];
+    unsigned int n_items = 0;
+    {
+      int pp_all = 0, pp_ge3 = 0, pp_ge11 = 0;  // of m[kw-1]
+      int p2_ge19 = 0, p2_ge27 = 0;             // of m[kw-2]
+      int q_ge19 = 0, q_ge27 = 0;               // of m[kw-1], become p2_* next step
+      const uint32_t *ptl = P.tlo + d.tw0, *pth = P.thi + d.tw0, *pql = P.qlo + d.qw0, *pqh = P.qhi + d.qw0;
+      uint32_t rtl = ptl[0], rth = pth[0], rql = pql[0], rqh = pqh[0];
+      int rem = d.L;  // positions of the diagonal at and after word kw
+      for (int w = 0; w < nbw; w++) {  // warp-uniform
+        uint32_t acc = 0, bit = 1u;
+        const int kw_end = min(nw_max, w * 32 + 32);
 #pragma unroll 2
-    for (int kw = 0; kw < nw_max; kw++) {  // warp-uniform trip count
-      const int tn = min(d.tw0 + kw + 1, NW + 1), qn = min(d.qw0 + kw + 1, NW + 1);
-      const uint32_t ntl = s_tlo[tn], nth = s_thi[tn], nql = s_qlo[qn], nqh = s_qhi[qn];
-      const uint32_t tl = __funnelshift_r(rtl, ntl, d.tsh), th = __funnelshift_r(rth, nth, d.tsh);
-      const uint32_t ql = __funnelshift_r(rql, nql, d.qsh), qh = __funnelshift_r(rqh, nqh, d.qsh);
-      rtl = ntl; rth = nth; rql = nql; rqh = nqh;
-      const uint32_t vm = kw < d.nwords - 1 ? 0xffffffffu : (kw == d.nwords - 1 ? d.lastmask : 0u);
-      const uint32_t m = ~((tl ^ ql) | (th ^ qh)) & vm;
-      const int c_all = __popc(m), c_lo8 = __popc(m & 0xffu), c_lo16 = __popc(m & 0xffffu),
-                c_lo24 = __popc(m & 0xffffffu);
-      const int u0 = p2_ge19 + pp_all + c_lo8;
-      const int u1 = p2_ge27 + pp_all + c_lo16;
-      const int u2 = pp_ge3 + c_lo24;
-      const int u3 = pp_ge11 + c_all;
-      const bool need = max(max(u0, u1), max(u2, u3)) >= 19;
-      acc |= (need ? 1u : 0u) << (kw & 31);
-      if ((kw & 31) == 31) {  // warp-uniform
-        s_need[warp][kw >> 5][lane] = acc;
-        acc = 0;
+        for (int kw = w * 32; kw < kw_end; kw++) {  // warp-uniform trip count
+          const int kn = min(kw + 1, d.nwords);  // a shorter diagonal idles and must not read past its planes
+          const uint32_t ntl = ptl[kn], nth = pth[kn], nql = pql[kn], nqh = pqh[kn];
+          const uint32_t tl = __funnelshift_r(rtl, ntl, d.tsh), th = __funnelshift_r(rth, nth, d.tsh);
+          const uint32_t ql = __funnelshift_r(rql, nql, d.qsh), qh = __funnelshift_r(rqh, nqh, d.qsh);
+          rtl = ntl; rth = nth; rql = nql; rqh = nqh;
+          // the diagonal's last word is partial, words after it are empty
+          const uint32_t vm = rem >= 32 ? 0xffffffffu : (rem > 0 ? d.lastmask : 0u);
+          const uint32_t m = ~((tl ^ ql) | (th ^ qh)) & vm;
+          const int c_all = __popc(m), c_lo8 = __popc(m & 0xffu), c_lo16 = __popc(m & 0xffffu),
+                    c_lo24 = __popc(m & 0xffffffu);
+          const int u0 = p2_ge19 + pp_all + c_lo8;
+          const int u1 = p2_ge27 + pp_all + c_lo16;
+          const int u2 = pp_ge3 + c_lo24;
+          const int u3 = pp_ge11 + c_all;
+          if (rem > 0 && max(max(u0, u1), max(u2, u3)) >= 19) acc |= bit;
+          bit <<= 1;
+          rem -= 32;
+          p2_ge19 = q_ge19;
+          p2_ge27 = q_ge27;
+          pp_all = c_all;
+          pp_ge3 = __popc(m >> 3);
+          pp_ge11 = __popc(m >> 11);
+          q_ge19 = __popc(m >> 19);
+          q_ge27 = __popc(m >> 27);
+        }
+        s_need[w][lane] = acc;
+        n_items += __popc(acc);
       }
-      p2_ge19 = q_ge19;
-      p2_ge27 = q_ge27;
-      pp_all = c_all;
-      pp_ge3 = __popc(m >> 3);
-      pp_ge11 = __popc(m >> 11);
-      q_ge19 = __popc(m >> 19);
-      q_ge27 = __popc(m >> 27);
     }
-    if (nw_max & 31) s_need[warp][nw_max >> 5][lane] = acc;
     __syncwarp();
 
-    // ---- B/C in rounds: enumerate units until the list is full, evaluate them, score the segments --
-    const int nbw = (nw_max + 31) >> 5;
-    int e_w = 0, e_pos = 0, e_start = -1;  // enumeration state: bitset word, bit position, open run start
-    bool e_done = (d.nwords == 0);
-    do {
-      // B1. units = maximal runs of surviving words, (lane:5 | first word:13 | words:14)
-      while (!e_done) {
-        // find the next run end from (e_w, e_pos, e_start) without committing the state yet
-        int w = e_w, pos = e_pos, start = e_start, ks = -1, kk = 0;
-        while (w < nbw) {
-          const uint32_t bits = s_need[warp][w][lane];
-          if (start < 0) {
-            const uint32_t r = pos < 32 ? (bits >> pos) : 0u;
-            if (!r) { w++; pos = 0; continue; }
-            pos += __ffs(r) - 1;
-            start = w * 32 + pos;
+    // ---- B. one item per surviving word; rounds of as many lanes as fit the item list (normally one round)
+    unsigned int total_items;
+    const unsigned int off_all = warp_excl_scan(n_items, &total_items);
+    unsigned int done_upto = 0;  // items of lanes whose offset is below this have been handled
+    while (done_upto < total_items) {  // warp-uniform
+      // lanes [first, last): the longest run of lanes from the first unhandled one whose items fit the list
+      const bool fits = off_all >= done_upto && off_all + n_items <= done_upto + ITEM_CAP;
+      const unsigned int fit_mask = __ballot_sync(0xffffffffu, fits);
+      const unsigned int started = __ballot_sync(0xffffffffu, off_all >= done_upto);
+      const int first = __ffs(started) - 1;
+      // first lane at or after `first` that does not fit ends the round
+      const unsigned int nofit_after = ~fit_mask & (0xffffffffu << first);
+      const int last = nofit_after ? (__ffs(nofit_after) - 1) : 32;
+      const bool mine = lane >= first && lane < last;
+      const unsigned int round_base = __shfl_sync(0xffffffffu, off_all, first);
+      const unsigned int round_end =
+          last < 32 ? __shfl_sync(0xffffffffu, off_all, last & 31) : total_items;
+      n_round = (int)(round_end - round_base);
+      if (mine) {
+        unsigned int o = off_all - round_base;
+        for (int w = 0; w < nbw; w++) {
+          uint32_t b = s_need[w][lane];
+          while (b) {
+            const int pos = __ffs(b) - 1;
+            b &= b - 1u;
+            items[o++] = (uint16_t)(lane | ((w * 32 + pos) << 5));
           }
-          // length of the run of ones at pos (zeros shifted in from the top end it at bit 32)
-          const uint32_t z = pos < 32 ? ~(bits >> pos) : 1u;
-          const int run = (pos == 0 && bits == 0xffffffffu) ? 32 : __ffs(z) - 1;
-          pos += run;
-          if (pos < 32 || w == nbw - 1) {  // the run ends here (or the diagonal does)
-            ks = start;
-            kk = w * 32 + pos - start;
-            start = -1;
-            break;
+        }
+      }
+      __syncwarp();
+      // B2. exact pass words, one item per lane
+      for (int i0 = 0; i0 < n_round; i0 += 32) {  // warp-uniform
+        const int i = i0 + lane;
+        if (i < n_round) {
+          const uint32_t it = items[i];
+          const Diag od = make_diag(s_shift[it & 31u], tlen, qlen);
+          passw[i] = eval_word(P, od, (int)(it >> 5));
+        }
+      }
+      __syncwarp();
+      // C1. queue every run start of every item (slots from a warp scan); a full queue is worked off first
+      for (int i0 = 0; i0 < n_round; i0 += 32) {  // warp-uniform
+        const int i = i0 + lane;
+        uint32_t pass = 0, carry_in = 0;
+        if (i < n_round) {
+          const uint32_t it = items[i];
+          pass = passw[i];
+          if (i > 0 && items[i - 1] == it - 32u) carry_in = passw[i - 1] >> 31;  // same diagonal, previous word
+        }
+        uint32_t rise = pass & ~((pass << 1) | carry_in);
+        const unsigned int mine_n = (unsigned int)__popc(rise);
+        unsigned int tot;
+        unsigned int slot = warp_excl_scan(mine_n, &tot);
+        if (tot != 0) {
+          if (qn + tot > SX_RUN_CAP) flush_queue();
+          slot += qn;
+          qn += tot;
+          my_segments += mine_n;
+          while (rise) {
+            const int s_ = __ffs(rise) - 1;
+            rise &= rise - 1u;
+            wq[slot++] = (uint32_t)i | ((uint32_t)s_ << 16);
           }
-          w++;  // the run continues in the next stretch
-          pos = 0;
         }
-        if (ks < 0) {
-          e_done = true;
-          break;
-        }
-        // three lists by unit length (1, 2, >= 3 words) so that the 32 units evaluated together take
-        // the same number of steps
-        const int bucket = min(kk, 3) - 1;
-        const unsigned int slot = atomicAdd(&nunit[bucket], 1u);
-        if (slot >= (unsigned int)unit_cap(bucket)) break;  // list full: this unit is found again in the next round
-        units[unit_base(bucket) + slot] = (uint32_t)lane | ((uint32_t)ks << 5) | ((uint32_t)kk << 18);
-        e_w = w;
-        e_pos = pos;
-        e_start = start;
+        __syncwarp();
       }
-      __syncwarp();
-
-      // B2. evaluate the units, one lane each, 32 at a time
-      for (int bucket = 0; bucket < 3; bucket++) {
-        const int nu = min((int)nunit[bucket], unit_cap(bucket));
-        const uint32_t *ul = units + unit_base(bucket);
-        for (int u0 = 0; u0 < nu; u0 += 32) {  // warp-uniform
-          const int u = u0 + lane;
-          const uint32_t rec = u < nu ? ul[u] : 0u;
-          const int owner = (int)(rec & 31u), ks = (int)((rec >> 5) & 0x1fffu), kk = (int)(rec >> 18);
-          const Diag od = make_diag(s_shift[warp][owner], tlen, qlen);
-          my_segments += eval_unit<NW>(P, od, ks, kk, spi, wq, wqn, spill, spill_cap, seg_tap, seg_tap_cap, ctr);
-        }
-      }
-      __syncwarp();
-
-      // C. score the segments found so far, spread over the lanes
-      const int nq = min((int)*wqn, SX_SEG_CAP);
-      for (int sidx = lane; sidx < nq; sidx += 32) {
-        const uint2 q = wq[sidx];
-        const int start_t = (int)(q.x & 0xffffu), seg_len = (int)(q.x >> 16), sh = (int)q.y;
-        double prob, ident;
-        if (score_fast(P, start_t, sh, seg_len, prm, prob, ident))
-          emit_result(sp, start_t, sh, seg_len, prob, ident, res_pool, res_cap, ctr);
-      }
-      __syncwarp();
-      if (lane == 0) {
-        *wqn = 0;
-        nunit[0] = nunit[1] = nunit[2] = 0;
-      }
-      __syncwarp();
-    } while (__any_sync(0xffffffffu, !e_done));
+      flush_queue();  // C2. before the item list is reused
+      done_upto = round_end;
+    }
   }
   my_segments = __reduce_add_sync(0xffffffffu, my_segments);
   if (lane == 0 && my_segments) atomicAdd(&ctr->n_segments, (unsigned long long)my_segments);

@@ -336,6 +336,42 @@ def test_split_transform_edge_cases(sx, oracle_lib):
     _log_listed("split_transform_edge_cases", listed)
 
 
+@pytest.mark.parametrize("chunk", [4096, 8192])
+def test_periodic_sequences_overflow_unit_list(sx, oracle_lib, chunk):
+    """A 32-mer repeated every 128 bases (spacer C in the target, G in the query): every lag that is a
+    multiple of 128 is a candidate and its diagonal alternates matching and non-matching words, so a group
+    of 32 diagonals holds far more evaluation units than the scan kernel lists per round, and thousands of
+    segments per strand-pair (queue flushes).  Same parity contract as everywhere."""
+    NN = 2 * chunk
+    rng = np.random.default_rng(5)
+    motif = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=32)
+    period_t = np.concatenate([motif, np.full(96, ord("C"), np.uint8)])
+    period_q = np.concatenate([motif, np.full(96, ord("G"), np.uint8)])
+    t = np.tile(period_t, chunk // 128)
+    q = np.tile(period_q, chunk // 128)
+    tl, ql = [(t.tobytes(), 0, 0, chunk)], [(q.tobytes(), 0, 0, chunk)]
+    listed = []
+    with sx.XCorrEngine(t_chunk=chunk, q_chunk=chunk, target_total=1e6) as eng:
+        eng.set_targets(sx.ChunkSet.from_list(tl))
+        eng.set_queries(sx.ChunkSet.from_list(ql))
+        ref_xc = oracle_lib.xcorr(tl[0][0], ql[0][0], NN)
+        cands = eng.tap_candidates(0, 0, 0)
+        compare_candidates(oracle_lib, cands, ref_xc, 1.8)
+        assert len(cands) >= 48
+        segs = eng.tap_segments(0, 0, 0)
+        exp_segs = oracle_lib.matchup(ql[0][0], tl[0][0], ref_xc, 1.8)
+        common = set(cands.tolist()) & set(oracle_lib.findtop(ref_xc, 1.8).tolist())
+        lag = lambda s_: int(s_["start_query"]) - int(s_["start_target"]) + NN // 2  # noqa: E731
+        got = [tuple(int(x) for x in s_) for s_ in segs if lag(s_) in common]
+        exp = [tuple(int(x) for x in s_) for s_ in exp_segs if lag(s_) in common]
+        assert got == exp and len(exp) > 1000
+        got = eng.align_pairs([(0, 0)])
+    params = oracle_lib.make_params(t_chunk=chunk, q_chunk=chunk, target_total=1e6)
+    exp = oracle_lib.align_pairs(params, tl, ql, [(0, 0)])
+    compare_pair_records(oracle_lib, got, exp, tl[0][0], ql[0][0], 0, 0, chunk, chunk, NN, 1.8, 0.99, 1e6, listed)
+    _log_listed(f"periodic_{chunk}", listed)
+
+
 def _genome_chunks(sx, seq, size, overlap):
     from satsuma2_b200 import synth
 
