@@ -183,16 +183,14 @@ __device__ __forceinline__ int encode_prepare(const SigDesc &sd, const Slots &ws
   __syncthreads();
 
   // ---- 1b. orient (reverse-complement), sanitise, 2-bit planes ------------------------------------
-  // A second round writes the OTHER orientation's planes / bytes / meta to slot rc_slot1 - 1 when the
-  // host derives that strand's correlation from this signal's spectrum (no transform of its own).
-  int myflags = 0;
-  const int rounds = sd.rc_slot1 ? 2 : 1;
-  for (int round = rounds - 1; round >= 0; round--) {  // the signal's own orientation last: it stays in sb
-    const int strand = round ? (sd.strand ^ 1) : sd.strand;
-    const int slot = round ? (sd.rc_slot1 - 1) : sd.slot;
+  // Only the first len32 positions are visited; the rest of the planes is zero-filled with plain stores.
+  // The plane words are kept in shared memory (behind the staged chunk) for the derivation below.
+  const int len32 = (len + 31) & ~31, nwords = len32 >> 5;
+  uint32_t *s_pl = reinterpret_cast<uint32_t *>(raw + N);  // [2][NW], inside the (still unused) FFT buffer
+  auto orient_round = [&](int strand, int slot, bool to_hbm) {
+    int myflags = 0;
     uint32_t *planes = ws.planes + (size_t)slot * 2 * NW;
-    if (round != rounds - 1) __syncthreads();  // the previous round's bytes have left sb
-    for (int k0 = warp * 32; k0 < N; k0 += NT) {
+    for (int k0 = warp * 32; k0 < len32; k0 += NT) {
       const int k = k0 + lane;
       uint32_t b = 0, code = 4;
       if (k < len) {
@@ -206,27 +204,75 @@ __device__ __forceinline__ int encode_prepare(const SigDesc &sd, const Slots &ws
       sb[k] = (uint8_t)b;
       const uint32_t lo = __ballot_sync(0xffffffffu, (code & 5u) == 1u);  // C or T -> bit0
       const uint32_t hi = __ballot_sync(0xffffffffu, (code & 6u) == 2u);  // G or T -> bit1
-      if (lane == 0 && side) {
-        planes[k0 >> 5] = lo;
-        planes[NW + (k0 >> 5)] = hi;
+      if (lane == 0) {
+        s_pl[k0 >> 5] = lo;
+        s_pl[NW + (k0 >> 5)] = hi;
       }
     }
     if (myflags) atomicOr(&s_flags, myflags);
     __syncthreads();
-    if (side) {  // oriented bases to HBM for the generic scan path and the taps, 16 bytes per thread
-      uint4 *gb = reinterpret_cast<uint4 *>(ws.bytes + (size_t)slot * N);
-      for (int i = tid; i < N / 16; i += NT) gb[i] = reinterpret_cast<const uint4 *>(sb)[i];
+    if (to_hbm) {
+      for (int w = tid; w < NW; w += NT) {
+        planes[w] = w < nwords ? s_pl[w] : 0u;
+        planes[NW + w] = w < nwords ? s_pl[NW + w] : 0u;
+      }
+      // The oriented bases go to HBM only when the chunk holds a letter other than A/C/G/T: the byte-wise scan
+      // kernel rebuilds pure chunks from their planes (SlotMeta::flags tells which).  16 bytes per thread.
+      if (s_flags & SLOT_NONACGT) {
+        uint4 *gb = reinterpret_cast<uint4 *>(ws.bytes + (size_t)slot * N);
+        for (int i = tid; i < len32 / 16; i += NT) gb[i] = reinterpret_cast<const uint4 *>(sb)[i];
+      }
     }
-    if (round && tid == 0 && side) {
+  };
+  orient_round(sd.strand, sd.slot, side);
+  const int flags = s_flags;
+  if (sd.rc_slot1) {
+    // The OTHER orientation's planes / bytes / meta go to slot rc_slot1 - 1: the host derives that strand's
+    // correlation from this signal's spectrum, it gets no transform of its own.
+    const int oslot = sd.rc_slot1 - 1;
+    if (!(flags & SLOT_NONACGT)) {
+      // pure A/C/G/T: reverse complement = complemented codes in reverse order, i.e. bit-reversed inverted
+      // plane words: position k of the other strand is position len-1-k of this one.  With len-1 = 32 q + r
+      // word j is (R[q-j] >> (31-r)) | (R[q-j-1] << (r+1)), R[x] = brev(~plane[x]); bits past the end fall
+      // out at the bottom of R[q] and are cut at the top of word q.  The bit-parallel scan kernel needs no bytes.
+      if (side) {
+        uint32_t *planes = ws.planes + (size_t)oslot * 2 * NW;
+        const int q = (len - 1) >> 5, r = (len - 1) & 31;
+        for (int j = tid; j < NW; j += NT) {
+          uint32_t lo = 0u, hi = 0u;
+          if (j <= q && len > 0) {
+            const uint32_t l0 = __brev(~s_pl[q - j]), h0 = __brev(~s_pl[NW + q - j]);
+            const uint32_t l1 = j < q ? __brev(~s_pl[q - j - 1]) : 0u, h1 = j < q ? __brev(~s_pl[NW + q - j - 1]) : 0u;
+            lo = __funnelshift_r(l0, l1, 31 - r);
+            hi = __funnelshift_r(h0, h1, 31 - r);
+            if (j == q) {
+              const uint32_t vm = r == 31 ? 0xffffffffu : ((2u << r) - 1u);
+              lo &= vm;
+              hi &= vm;
+            }
+          }
+          planes[j] = lo;
+          planes[NW + j] = hi;
+        }
+      }
+    } else {
+      // IUPAC / unknown letters: the byte-wise scan kernel needs the other strand's bytes; orient it in full,
+      // then restore this signal's own orientation in sb
+      __syncthreads();
+      orient_round(sd.strand ^ 1, oslot, side);
+      __syncthreads();
+      orient_round(sd.strand, sd.slot, false);
+    }
+    if (tid == 0 && side) {
       SlotMeta m;
       m.len = len;
-      m.flags = s_flags & SLOT_NONACGT;  // same letters in both orientations (complement keeps the class)
+      m.flags = flags & SLOT_NONACGT;  // same letters in both orientations (complement keeps the class)
       m.q_re = m.q_im = m.q_nyq = 0.f;
       m.pad[0] = m.pad[1] = m.pad[2] = 0;
-      ws.meta[slot] = m;
+      ws.meta[oslot] = m;
     }
   }
-  const int flags = s_flags;
+  __syncthreads();  // s_pl (inside the FFT buffer) is dead from here on
 
   // ---- 2. window sums, entropy weights (ComputeEntropy) and channel means (SeqToPCM) ------------
   double tot[4] = {0., 0., 0., 0.};
@@ -1067,13 +1113,30 @@ __global__ void __launch_bounds__(NT)
   if (!((tm.flags | qm.flags) & SLOT_NONACGT)) return;  // handled by the bit-parallel kernel
   const int tlen = tm.len, qlen = qm.len;
   {
-    const uint4 *tp = reinterpret_cast<const uint4 *>(ws.bytes + (size_t)sp.t_slot * N);
-    const uint4 *qp = reinterpret_cast<const uint4 *>(ws.bytes + (size_t)sp.q_slot * N);
+    // bases of both chunks: from the oriented bytes when the chunk holds IUPAC / unknown letters, rebuilt from
+    // the 2-bit planes when it is pure A/C/G/T (the encoder stores bytes only for the former)
+    constexpr int NWp = N / 32;
+    auto load_bases = [&](uint8_t *dst, int slot, const SlotMeta &m) {
+      if (m.flags & SLOT_NONACGT) {
+        const uint4 *src16 = reinterpret_cast<const uint4 *>(ws.bytes + (size_t)slot * N);
+        for (int i = tid; i < (m.len + 15) / 16; i += NT) reinterpret_cast<uint4 *>(dst)[i] = src16[i];
+      } else {
+        const uint32_t *pl = ws.planes + (size_t)slot * 2 * NWp;
+        for (int i = tid; i < (m.len + 3) / 4; i += NT) {  // 4 bases per thread
+          const uint32_t lo = (pl[i >> 3] >> ((i & 7) * 4)) & 15u, hi = (pl[NWp + (i >> 3)] >> ((i & 7) * 4)) & 15u;
+          uint32_t w = 0;
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            const uint32_t code = ((lo >> b) & 1u) | (((hi >> b) & 1u) << 1);
+            w |= ((0x54474341u >> (8 * code)) & 0xffu) << (8 * b);  // "ACGT"[code]
+          }
+          reinterpret_cast<uint32_t *>(dst)[i] = w;
+        }
+      }
+    };
+    load_bases(s_t, sp.t_slot, tm);
+    load_bases(s_q, sp.q_slot, qm);
     const uint4 *sc = reinterpret_cast<const uint4 *>(g_score);
-    for (int i = tid; i < N / 16; i += NT) {
-      reinterpret_cast<uint4 *>(s_t)[i] = tp[i];
-      reinterpret_cast<uint4 *>(s_q)[i] = qp[i];
-    }
     for (int i = tid; i < 128 * 128 / 16; i += NT) reinterpret_cast<uint4 *>(s_score)[i] = sc[i];
     if (tid < 128) s_fcode[tid] = c_fcode[tid];
     if (tid == 0) s_nseg = 0;
