@@ -129,6 +129,7 @@ struct sx_ctx {
   DevBuf<uint8_t> sbytes;
   DevBuf<SlotMeta> meta;
   DevBuf<float2> wn;  // e^{-2 pi i n / N}, n < N/2
+  DevBuf<double> ent_table;  // fill_ent_table()
   std::vector<uint8_t> t_valid;  // persistent target slot holds a spectrum
 
   // per-batch device buffers
@@ -161,6 +162,7 @@ struct sx_ctx {
     s.bytes = sbytes.p;
     s.meta = meta.p;
     s.wn = wn.p;
+    s.ent_table = ent_table.p;
     return s;
   }
 };
@@ -236,6 +238,13 @@ extern "C" int sx_create(const sx_config *cfg, sx_ctx **out) {
     if (cudaMemcpy(c->wn.p, w.data(), sizeof(float2) * w.size(), cudaMemcpyHostToDevice) != cudaSuccess)
       rc = fail(SX_ERR_CUDA, "sx_create: twiddle table upload failed");
   }
+  if (rc == SX_OK) rc = c->ent_table.ensure(ent_table_elems(c->log2n));
+  if (rc == SX_OK) {
+    std::vector<double> et(ent_table_elems(c->log2n));
+    fill_ent_table(c->log2n, et.data());
+    if (cudaMemcpy(c->ent_table.p, et.data(), sizeof(double) * et.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+      rc = fail(SX_ERR_CUDA, "sx_create: entropy table upload failed");
+  }
   if (rc != SX_OK) {
     delete c;
     return rc;
@@ -254,7 +263,7 @@ extern "C" void sx_destroy(sx_ctx *c) {
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->T.d_bases) cudaFree(c->T.d_bases);
   if (c->Q.d_bases) cudaFree(c->Q.d_bases);
-  c->spec.release(); c->planes.release(); c->sbytes.release(); c->meta.release(); c->wn.release();
+  c->spec.release(); c->planes.release(); c->sbytes.release(); c->meta.release(); c->wn.release(); c->ent_table.release();
   c->d_lists.release(); c->h_lists[0].release(); c->h_lists[1].release();
   c->d_sigs.release(); c->d_sps.release(); c->d_cand_ref.release(); c->d_cand_pool.release();
   c->d_scratch.release(); c->d_res.release(); c->d_seg_tap.release(); c->d_spill.release(); c->d_ctr.release(); c->d_table.release(); c->d_tap.release();

@@ -126,6 +126,26 @@ void fill_wn_table(int log2n, float2 *out) {
 }
 size_t slot_spec_elems(int log2n) { return (size_t)2 << log2n; }
 
+// Entropy terms of CCSignal::ComputeEntropy (analysis/CrossCorr.cc:28-33, 70-88) for integer base counts:
+// out[k * (WIN + 1) + c] = p < 0.001 ? 0 : p * log(p) / 0.69314718056 with p = c / k, for window lengths
+// k = 1 .. WIN (WIN = N / 512) and counts c = 0 .. k.  Built with the host's libm, like the reference.
+size_t ent_table_elems(int log2n) {
+  const size_t win = ((size_t)1 << log2n) / 512;
+  return (win + 1) * (win + 1);
+}
+void fill_ent_table(int log2n, double *out) {
+  const int win = (1 << log2n) / 512;
+  for (int k = 0; k <= win; k++)
+    for (int c = 0; c <= win; c++) {
+      double e = 0.;
+      if (k > 0 && c <= k) {
+        const double p = (double)c / (double)k;
+        e = (p < 0.001) ? 0.0 : p * log(p) / 0.69314718056;
+      }
+      out[(size_t)k * (win + 1) + c] = e;
+    }
+}
+
 // fraction of channel c (0..3) for a table entry; exact doubles {0,1,1/2,1/3,1/4}
 __device__ __forceinline__ double frac_of(uint32_t fcode, int c) {
   const uint32_t v = (fcode >> (4 * c)) & 15u;
@@ -173,20 +193,77 @@ __device__ __forceinline__ int encode_prepare(const SigDesc &sd, const Slots &ws
     s_base2[tid] = c_base2[tid];
   }
   if (tid == 0) s_flags = 0;
-  // ---- 1a. stage the raw chunk in shared memory (the FFT buffer is free until step 3) -------------
-  if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {  // chunk stores are padded by 16 bytes
-    const uint4 *s16 = reinterpret_cast<const uint4 *>(src);
-    for (int i = tid; i < (len + 15) / 16; i += NT) reinterpret_cast<uint4 *>(raw)[i] = __ldg(s16 + i);
-  } else {
-    for (int i = tid; i < len; i += NT) raw[i] = src[i];
-  }
   __syncthreads();
-
-  // ---- 1b. orient (reverse-complement), sanitise, 2-bit planes ------------------------------------
-  // Only the first len32 positions are visited; the rest of the planes is zero-filled with plain stores.
-  // The plane words are kept in shared memory (behind the staged chunk) for the derivation below.
   const int len32 = (len + 31) & ~31, nwords = len32 >> 5;
-  uint32_t *s_pl = reinterpret_cast<uint32_t *>(raw + N);  // [2][NW], inside the (still unused) FFT buffer
+  // plane words of this signal, [2][NW], kept in shared memory inside the (still unused) FFT buffer behind the
+  // staged chunk: the reverse-complement derivation and the window counts below read them
+  uint32_t *s_pl = reinterpret_cast<uint32_t *>(raw + N);
+
+  // ---- 1 (fast). forward strand, pure A/C/G/T: 16 bases per thread straight from HBM, no per-base work.
+  // Four bases per 32-bit word: code = ((b >> 1) & 3) ^ ((b >> 2) & 1) maps A,C,G,T -> 0,1,2,3; the word is
+  // valid iff rebuilding the letters from the codes gives it back; the code bits of four bytes are gathered
+  // into a nibble by one multiplication.  Anything else (a letter outside A/C/G/T, a reverse-strand signal)
+  // takes the byte-wise path below, which is the general statement of the same thing.
+  bool fast_done = false;
+  if (sd.strand == 0) {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src - mis);  // chunk stores are padded by 16 bytes
+    const bool al16 = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+    uint32_t bad = 0;
+    for (int t = tid; t < (len32 >> 4); t += NT) {
+      uint32_t w4[4] = {0u, 0u, 0u, 0u};
+      if (t * 16 < len) {
+        if (al16) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src) + t);
+          w4[0] = v.x; w4[1] = v.y; w4[2] = v.z; w4[3] = v.w;
+        } else {
+          uint32_t x[5];
+#pragma unroll
+          for (int i = 0; i < 5; i++) x[i] = __ldg(s32 + t * 4 + i);
+#pragma unroll
+          for (int i = 0; i < 4; i++) w4[i] = __funnelshift_r(x[i], x[i + 1], 8 * mis);
+        }
+      }
+      uint32_t lo16 = 0, hi16 = 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int nv = min(max(len - (t * 16 + i * 4), 0), 4);  // bases of this word inside the chunk
+        const uint32_t bm = nv == 0 ? 0u : (0xffffffffu >> (8 * (4 - nv)));
+        const uint32_t w = w4[i] & bm;
+        w4[i] = w;
+        const uint32_t c = ((w >> 1) & 0x03030303u) ^ ((w >> 2) & 0x01010101u);
+        const uint32_t c0 = c & 0x01010101u & bm, c1 = (c >> 1) & 0x01010101u & bm, c01 = c0 & c1;
+        const uint32_t letters = (0x41414141u & bm) + 2u * c0 + 6u * c1 + 11u * c01;  // A, C = A+2, G = A+6, T = A+19
+        bad |= letters ^ w;
+        lo16 |= ((c0 * 0x01020408u) >> 24) << (4 * i);
+        hi16 |= ((c1 * 0x01020408u) >> 24) << (4 * i);
+      }
+      reinterpret_cast<uint4 *>(sb)[t] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      reinterpret_cast<uint16_t *>(s_pl)[t] = (uint16_t)lo16;
+      reinterpret_cast<uint16_t *>(s_pl + NW)[t] = (uint16_t)hi16;
+    }
+    fast_done = __syncthreads_or(bad != 0u) == 0;
+    if (fast_done && side) {
+      uint32_t *planes = ws.planes + (size_t)sd.slot * 2 * NW;
+      for (int w = tid; w < NW; w += NT) {
+        planes[w] = w < nwords ? s_pl[w] : 0u;
+        planes[NW + w] = w < nwords ? s_pl[NW + w] : 0u;
+      }
+    }
+  }
+  if (!fast_done) {
+    // ---- 1a. stage the raw chunk in shared memory (the FFT buffer is free until step 3) -----------
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+      const uint4 *s16 = reinterpret_cast<const uint4 *>(src);
+      for (int i = tid; i < (len + 15) / 16; i += NT) reinterpret_cast<uint4 *>(raw)[i] = __ldg(s16 + i);
+    } else {
+      for (int i = tid; i < len; i += NT) raw[i] = src[i];
+    }
+    __syncthreads();
+  }
+
+  // ---- 1b. orient (reverse-complement), sanitise, 2-bit planes, byte by byte --------------------------
+  // Only the first len32 positions are visited; the rest of the planes is zero-filled with plain stores.
   auto orient_round = [&](int strand, int slot, bool to_hbm) {
     int myflags = 0;
     uint32_t *planes = ws.planes + (size_t)slot * 2 * NW;
@@ -224,7 +301,7 @@ __device__ __forceinline__ int encode_prepare(const SigDesc &sd, const Slots &ws
       }
     }
   };
-  orient_round(sd.strand, sd.slot, side);
+  if (!fast_done) orient_round(sd.strand, sd.slot, side);
   const int flags = s_flags;
   if (sd.rc_slot1) {
     // The OTHER orientation's planes / bytes / meta go to slot rc_slot1 - 1: the host derives that strand's
@@ -272,7 +349,7 @@ __device__ __forceinline__ int encode_prepare(const SigDesc &sd, const Slots &ws
       ws.meta[oslot] = m;
     }
   }
-  __syncthreads();  // s_pl (inside the FFT buffer) is dead from here on
+  __syncthreads();
 
   // ---- 2. window sums, entropy weights (ComputeEntropy) and channel means (SeqToPCM) ------------
   double tot[4] = {0., 0., 0., 0.};
@@ -281,30 +358,56 @@ __device__ __forceinline__ int encode_prepare(const SigDesc &sd, const Slots &ws
     double s4[4] = {0., 0., 0., 0.};
     const int i0 = w * WIN;
     int k = 0;
-    if (!(flags & SLOT_NONACGT)) {  // pure A/C/G/T: integer counts are the exact double sums
-      int cnt[4] = {0, 0, 0, 0};
-      for (int j = i0; j < i0 + WIN && j < len; j++, k++) {
-        const uint32_t code = s_base2[sb[j]];
+    double s = 0.;
+    if (!(flags & SLOT_NONACGT)) {
+      // pure A/C/G/T: the counts come from the plane bits of the window (integer counts are the exact double
+      // sums), the terms p*log(p)/ln2 from a table the host built with its libm: [k][count], k = window length
+      k = min(WIN, len - i0);
+      uint32_t lo, hi;
+      int cntT, cntC, cntG;
+      if (WIN <= 32) {
+        const uint32_t wm = k >= 32 ? 0xffffffffu : ((1u << k) - 1u);
+        lo = (s_pl[i0 >> 5] >> (i0 & 31)) & wm;
+        hi = (s_pl[NW + (i0 >> 5)] >> (i0 & 31)) & wm;
+        cntT = __popc(lo & hi);
+        cntC = __popc(lo & ~hi);
+        cntG = __popc(hi & ~lo);
+      } else {  // windows of 64 bases = two plane words (bits past the end of the chunk are zero)
+        cntT = cntC = cntG = 0;
 #pragma unroll
-        for (int c = 0; c < 4; c++) cnt[c] += (code == (uint32_t)c);
+        for (int h = 0; h < WIN / 32; h++) {
+          const bool in = (i0 >> 5) + h < nwords;  // plane words are only written up to the chunk's last word
+          lo = in ? s_pl[(i0 >> 5) + h] : 0u;
+          hi = in ? s_pl[NW + (i0 >> 5) + h] : 0u;
+          cntT += __popc(lo & hi);
+          cntC += __popc(lo & ~hi);
+          cntG += __popc(hi & ~lo);
+        }
+      }
+      const int cnt[4] = {k - cntT - cntC - cntG, cntC, cntG, cntT};
+      const double *et = ws.ent_table + (size_t)k * (WIN + 1);
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        s4[c] = (double)cnt[c];
+        const double e = __ldg(et + cnt[c]);
+        s = (c == 0) ? e : __dadd_rn(s, e);
       }
 #pragma unroll
-      for (int c = 0; c < 4; c++) s4[c] = (double)cnt[c];
+      for (int c = 0; c < 4; c++) tot[c] += s4[c];
     } else {
       for (int j = i0; j < i0 + WIN && j < len; j++, k++) {
         const uint32_t fc = s_fcode[sb[j]];
 #pragma unroll
         for (int c = 0; c < 4; c++) s4[c] = __dadd_rn(s4[c], frac_of(fc, c));
       }
-    }
 #pragma unroll
-    for (int c = 0; c < 4; c++) tot[c] += s4[c];
-    double s = 0.;
+      for (int c = 0; c < 4; c++) tot[c] += s4[c];
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-      const double p = __ddiv_rn(s4[c], (double)k);
-      const double e = (p < 0.001) ? 0.0 : __ddiv_rn(__dmul_rn(p, log(p)), 0.69314718056);
-      s = (c == 0) ? e : __dadd_rn(s, e);
+      for (int c = 0; c < 4; c++) {
+        const double p = __ddiv_rn(s4[c], (double)k);
+        const double e = (p < 0.001) ? 0.0 : __ddiv_rn(__dmul_rn(p, log(p)), 0.69314718056);
+        s = (c == 0) ? e : __dadd_rn(s, e);
+      }
     }
     float v = __double2float_rn(-s);
     if (v < 0.f) v = 0.f;

@@ -26,6 +26,7 @@ struct Slots {
   uint8_t *bytes;
   SlotMeta *meta;
   const float2 *wn;  // e^{-2 pi i n / N}, n < N/2 (per context: the radix-2 split / combine twiddles)
+  const double *ent_table;  // entropy terms for integer base counts, fill_ent_table()
 };
 
 struct SigDesc {  // one chunk signal to encode + transform
@@ -92,6 +93,8 @@ cudaError_t launch_xcorr_findtop(int log2n, const SpDesc *sps, const uint32_t *p
                                  uint2 *cand_ref, BatchCounters *ctr, float *xc_tap, float2 *scratch,
                                  cudaStream_t stream);
 void fill_wn_table(int log2n, float2 *host_out);  // N/2 entries
+size_t ent_table_elems(int log2n);
+void fill_ent_table(int log2n, double *host_out);  // ent_table_elems() entries
 cudaError_t launch_scan_score(int log2n, const SpDesc *sps, int nsp, Slots ws, const uint16_t *cand_pool,
                               const uint2 *cand_ref, ScoreParams prm, ResultRec *res_pool,
                               unsigned int res_cap, SegRec *seg_tap, unsigned int seg_tap_cap, SegRec *spill,
