@@ -235,9 +235,15 @@ class XCorrEngine:
         _check(self._L.sx_set_prob_table(self._h, t.ctypes.data))
 
     # ---- hot path
-    def _collect(self, call, guess: int) -> np.ndarray:
-        cap = max(guess, 1024)
-        out = np.zeros(cap, dtype=RESULT_DTYPE)
+    def _collect(self, call, guess: int, out: np.ndarray = None) -> np.ndarray:
+        """Runs an align call into `out` (a caller-owned RESULT_DTYPE array that is reused across calls) or into
+        a fresh array of `guess` records; returns the filled prefix (a view)."""
+        if out is not None:
+            assert out.dtype == RESULT_DTYPE and out.flags["C_CONTIGUOUS"]
+            cap = len(out)
+        else:
+            cap = max(guess, 1024)
+            out = np.zeros(cap, dtype=RESULT_DTYPE)
         n = C.c_int64(0)
         rc = call(out, cap, n)
         if rc == SX_ERR_CAPACITY:  # never truncated: redo with the size the library asked for
@@ -257,11 +263,11 @@ class XCorrEngine:
             lambda out, cap, n: self._L.sx_align_blocks(self._h, arr.ctypes.data, len(arr), out.ctypes.data, cap,
                                                         C.byref(n)), cap_hint or 1 << 16)
 
-    def align_pairs(self, pairs, fast: bool = False, cap_hint: int = 0) -> np.ndarray:
+    def align_pairs(self, pairs, fast: bool = False, cap_hint: int = 0, out: np.ndarray = None) -> np.ndarray:
         p = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
         return self._collect(
-            lambda out, cap, n: self._L.sx_align_pairs(self._h, p.ctypes.data, len(p), int(fast), out.ctypes.data,
-                                                       cap, C.byref(n)), cap_hint or max(1 << 16, 4 * len(p)))
+            lambda o, cap, n: self._L.sx_align_pairs(self._h, p.ctypes.data, len(p), int(fast), o.ctypes.data,
+                                                     cap, C.byref(n)), cap_hint or max(1 << 16, 4 * len(p)), out)
 
     # ---- taps
     def tap_signal(self, is_target: bool, chunk: int, strand: int = 0) -> np.ndarray:

@@ -113,7 +113,7 @@ struct sx_ctx {
   std::mutex mu;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // async_upload: host->device copies of the chunk blobs
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[2][5] = {{nullptr, nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr, nullptr}};  // per batch in flight
   bool profiling = false;
   sx_stats stats;
 
@@ -122,7 +122,8 @@ struct sx_ctx {
   double z_cut = INFINITY;
 
   // signal slots: [0, n_persist) = cached target spectra (slot == target chunk index),
-  // [n_persist, n_persist + n_transient) = per-batch workspace
+  // then two per-batch workspaces of n_transient slots each: while the device still works on batch k, batch
+  // k+1 is already being encoded into the other one
   size_t n_persist = 0, n_transient = 0;
   DevBuf<float2> spec;
   DevBuf<uint32_t> planes;
@@ -133,7 +134,7 @@ struct sx_ctx {
   std::vector<uint8_t> t_valid;  // persistent target slot holds a spectrum
 
   // per-batch device buffers
-  DevBuf<SigDesc> d_sigs;
+  DevBuf<SigDesc> d_sigs[2];  // one per batch in flight (the next batch's encode is queued behind the current scan)
   DevBuf<SpDesc> d_sps;
   DevBuf<uint2> d_cand_ref;
   DevBuf<uint32_t> d_lists;  // [pair list | direct list] of strand-pair indices (launch_xcorr_findtop)
@@ -153,7 +154,6 @@ struct sx_ctx {
   PinBuf<ResultRec> h_res;
   PinBuf<BatchCounters> h_ctr;
 
-  std::vector<sx_result> last;  // records of the last align call
 
   Slots slots() const {
     Slots s;
@@ -223,7 +223,7 @@ extern "C" int sx_create(const sx_config *cfg, sx_ctx **out) {
   cudaError_t ce = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
   if (ce == cudaSuccess)
-    for (int i = 0; i < 5 && ce == cudaSuccess; i++) ce = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 10 && ce == cudaSuccess; i++) ce = cudaEventCreate(&c->ev[i / 5][i % 5]);
   if (ce == cudaSuccess) ce = upload_tables();
   if (ce != cudaSuccess) {
     delete c;
@@ -265,11 +265,11 @@ extern "C" void sx_destroy(sx_ctx *c) {
   if (c->Q.d_bases) cudaFree(c->Q.d_bases);
   c->spec.release(); c->planes.release(); c->sbytes.release(); c->meta.release(); c->wn.release(); c->ent_table.release();
   c->d_lists.release(); c->h_lists[0].release(); c->h_lists[1].release();
-  c->d_sigs.release(); c->d_sps.release(); c->d_cand_ref.release(); c->d_cand_pool.release();
+  c->d_sigs[0].release(); c->d_sigs[1].release(); c->d_sps.release(); c->d_cand_ref.release(); c->d_cand_pool.release();
   c->d_scratch.release(); c->d_res.release(); c->d_seg_tap.release(); c->d_spill.release(); c->d_ctr.release(); c->d_table.release(); c->d_tap.release();
   c->h_sigs[0].release(); c->h_sigs[1].release(); c->h_sps[0].release(); c->h_sps[1].release(); c->h_res.release(); c->h_ctr.release();
-  for (int i = 0; i < 5; i++)
-    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 10; i++)
+    if (c->ev[i / 5][i % 5]) cudaEventDestroy(c->ev[i / 5][i % 5]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -366,7 +366,7 @@ static int alloc_slots(sx_ctx *c) {
   size_t persist = 0;
   if (c->cfg.spectra_cache_bytes > 0 && (size_t)c->T.n * sb <= (size_t)c->cfg.spectra_cache_bytes) persist = (size_t)c->T.n;
   const size_t transient = (size_t)3 * (size_t)c->cfg.max_batch_pairs;
-  const size_t total = persist + transient;
+  const size_t total = persist + 2 * transient;
   const size_t N = (size_t)c->N;
   int rc;
   if ((rc = c->spec.ensure(total * 2 * N)) != SX_OK) return rc;
@@ -488,6 +488,7 @@ struct Batch {
   std::vector<SpDesc> sps;
   std::vector<PairReq> pairs;  // batch-local pair index -> chunk indices
   std::vector<uint32_t> pair_list, direct_list;  // strand-pair indices for the two correlation kernels
+  size_t slot_base = 0;  // first slot of this batch's workspace
   size_t transient_used = 0;
   size_t t_need = 0, q_need = 0;  // highest byte of the target / query blob this batch reads (+1)
   std::unordered_map<int32_t, int32_t> tslot;  // target chunk -> slot (transient mode)
@@ -497,6 +498,13 @@ struct Batch {
     transient_used = 0;
     t_need = q_need = 0;
   }
+};
+
+// where the records of an align call go: straight into the caller's buffer while they fit; beyond its
+// capacity they are only counted, so that the call can report the size it needs (nothing is truncated silently)
+struct ResultSink {
+  sx_result *out = nullptr;
+  int64_t cap = 0, n = 0;
 };
 
 struct TapRequest {
@@ -568,6 +576,7 @@ struct Run {  // one batch on the device: launched asynchronously, completed by 
   TapRequest *tap = nullptr;
   int nsig = 0, nsp = 0, n_pairlist = 0, n_direct = 0;
   bool need_encode = false, need_xcorr = true, active = false;
+  bool early_done = false;  // descriptors of the signals uploaded and the encode kernel queued
   unsigned long long n_cand_seen = 0;
   float *d_sig_tap = nullptr, *d_xc_tap = nullptr;
   SegRec *d_seg_tap = nullptr;
@@ -580,19 +589,16 @@ struct Run {  // one batch on the device: launched asynchronously, completed by 
 };
 }  // namespace
 
-// (re)launch the kernels of a batch and the asynchronous read-back of its counter block
+// (re)launch the correlation and scan kernels of a batch and the asynchronous read-back of its counter block
+// (the encode kernel has been queued by batch_launch_early)
 static int batch_kernels(sx_ctx *c, Run &r) {
   cudaStream_t st = c->stream;
   const bool prof = c->profiling;
   const Slots ws = c->slots();
   const ScoreParams prm = score_params(c);
+  cudaEvent_t *ev = c->ev[r.stage];
   CU(cudaMemsetAsync(c->d_ctr.p, 0, sizeof(BatchCounters), st));
-  if (prof) CU(cudaEventRecord(c->ev[0], st));
-  if (r.need_encode) {
-    CU(launch_encode_fft(c->log2n, c->d_sigs.p, r.nsig, ws, r.d_sig_tap, st));
-    c->stats.kernel_launches += 1;
-  }
-  if (prof) CU(cudaEventRecord(c->ev[1], st));
+  if (prof) CU(cudaEventRecord(ev[1], st));
   if (r.nsp && r.need_xcorr) {
     CU(launch_xcorr_findtop(c->log2n, c->d_sps.p, c->d_lists.p, r.n_pairlist, c->d_lists.p + r.n_pairlist, r.n_direct, ws,
                             c->cfg.cutoff, c->cfg.cutoff_fast, c->d_cand_pool.p,
@@ -600,14 +606,14 @@ static int batch_kernels(sx_ctx *c, Run &r) {
                             r.d_xc_tap, c->d_scratch.p, st));
     c->stats.kernel_launches += log2n_split(c->log2n) ? 2 : (r.n_pairlist > 0) + (r.n_direct > 0);
   }
-  if (prof) CU(cudaEventRecord(c->ev[2], st));
+  if (prof) CU(cudaEventRecord(ev[2], st));
   if (r.nsp) {
     CU(launch_scan_score(c->log2n, c->d_sps.p, r.nsp, ws, c->d_cand_pool.p, c->d_cand_ref.p, prm, c->d_res.p,
                          (unsigned int)std::min<size_t>(c->d_res.n, 0xfffffff0u), r.d_seg_tap, r.seg_tap_cap,
                          c->d_spill.p, (unsigned int)std::min<size_t>(c->d_spill.n, 0xfffffff0u), c->d_ctr.p, st));
-    c->stats.kernel_launches += 3;
+    c->stats.kernel_launches += 2;
   }
-  if (prof) CU(cudaEventRecord(c->ev[3], st));
+  if (prof) CU(cudaEventRecord(ev[3], st));
   CU(cudaMemcpyAsync(c->h_ctr.p, c->d_ctr.p, sizeof(BatchCounters), cudaMemcpyDeviceToHost, st));
   return SX_OK;
 }
@@ -633,29 +639,21 @@ static int batch_stage(sx_ctx *c, Run &r, Batch &b, TapRequest *tap, int stage) 
   return SX_OK;
 }
 
-// upload the staged descriptors of a batch and launch it; returns without waiting for the device
-static int batch_launch(sx_ctx *c, Run &r) {
+// First half of launching a batch: upload the signal descriptors and queue the encode kernel.  It only
+// writes this batch's own workspace slots (and not yet valid cached target slots), so it may be queued
+// while the previous batch is still running -- the device then goes from that batch's scan straight into
+// this one's encode while the host reads the previous counters.
+static int batch_launch_early(sx_ctx *c, Run &r) {
   const int nsig = r.nsig, nsp = r.nsp;
-  if (!r.staged || (nsp == 0 && nsig == 0)) return SX_OK;
+  if (!r.staged || r.early_done || (nsp == 0 && nsig == 0)) return SX_OK;
   TapRequest *tap = r.tap;
   const size_t N = (size_t)c->N;
   int rc;
-  if ((rc = c->d_sigs.ensure(std::max(nsig, 1))) != SX_OK) return rc;
-  if ((rc = c->d_sps.ensure(std::max(nsp, 1))) != SX_OK) return rc;
-  if ((rc = c->d_cand_ref.ensure(std::max(nsp, 1))) != SX_OK) return rc;
-  if ((rc = c->d_lists.ensure(std::max(r.n_pairlist + r.n_direct, 1))) != SX_OK) return rc;
-  if (log2n_split(c->log2n) && (rc = c->d_scratch.ensure((size_t)std::max(r.n_pairlist + r.n_direct, 1) * N)) != SX_OK)
-    return rc;
-  if (c->cfg.debug_small_pools) {  // test hook: start with pools that must overflow, so the grow-and-retry paths run
-    if (c->d_cand_pool.n == 0 && (rc = c->d_cand_pool.ensure(64)) != SX_OK) return rc;
-    if (c->d_res.n == 0 && (rc = c->d_res.ensure(4)) != SX_OK) return rc;
-    if (c->d_spill.n == 0 && (rc = c->d_spill.ensure(2)) != SX_OK) return rc;
-  } else {
-    if (c->d_cand_pool.n < std::max<size_t>((size_t)nsp * 640, 1 << 16) &&
-        (rc = c->d_cand_pool.ensure(std::max<size_t>((size_t)nsp * 640, 1 << 16))) != SX_OK)
-      return rc;
-    if (c->d_res.n == 0 && (rc = c->d_res.ensure(std::max<size_t>((size_t)nsp * 8, 1 << 16))) != SX_OK) return rc;
-    if (c->d_spill.n == 0 && (rc = c->d_spill.ensure((size_t)1 << 20)) != SX_OK) return rc;
+  if ((rc = c->d_sigs[r.stage].ensure(std::max(nsig, 1))) != SX_OK) return rc;
+  if (tap && (tap->sig5n || tap->xc)) {
+    if ((rc = c->d_tap.ensure((size_t)std::max(nsig, 1) * 5 * N + (size_t)std::max(nsp, 1) * N)) != SX_OK) return rc;
+    if (tap->sig5n) r.d_sig_tap = c->d_tap.p;
+    if (tap->xc) r.d_xc_tap = c->d_tap.p + (size_t)std::max(nsig, 1) * 5 * N;
   }
   cudaStream_t st = c->stream;
   // async_upload: send the blob pieces this batch reads (normally already sent as look-ahead) and make
@@ -668,24 +666,56 @@ static int batch_launch(sx_ctx *c, Run &r) {
     if ((rc = upload_pieces(c, S, upto)) != SX_OK) return rc;
     CU(cudaStreamWaitEvent(st, S.piece_ev[upto - 1], 0));
   }
-  if (nsig) CU(cudaMemcpyAsync(c->d_sigs.p, c->h_sigs[r.stage].p, sizeof(SigDesc) * nsig, cudaMemcpyHostToDevice, st));
+  if (nsig) {
+    CU(cudaMemcpyAsync(c->d_sigs[r.stage].p, c->h_sigs[r.stage].p, sizeof(SigDesc) * nsig, cudaMemcpyHostToDevice, st));
+    c->stats.h2d_bytes += (int64_t)(sizeof(SigDesc) * nsig);
+  }
+  if (c->profiling) CU(cudaEventRecord(c->ev[r.stage][0], st));
+  if (nsig) {
+    CU(launch_encode_fft(c->log2n, c->d_sigs[r.stage].p, nsig, c->slots(), r.d_sig_tap, st));
+    c->stats.kernel_launches += 1;
+  }
+  r.need_encode = nsig > 0;  // only tells batch_wait that this batch had an encode kernel to account for
+  r.early_done = true;
+  return SX_OK;
+}
+
+// Second half: upload the strand-pair descriptors, launch the correlation and scan kernels; returns without
+// waiting for the device.  The previous batch must have finished with the shared device pools.
+static int batch_launch(sx_ctx *c, Run &r) {
+  const int nsig = r.nsig, nsp = r.nsp;
+  if (!r.staged || (nsp == 0 && nsig == 0)) return SX_OK;
+  TapRequest *tap = r.tap;
+  const size_t N = (size_t)c->N;
+  int rc;
+  if ((rc = batch_launch_early(c, r)) != SX_OK) return rc;
+  if ((rc = c->d_sps.ensure(std::max(nsp, 1))) != SX_OK) return rc;
+  if ((rc = c->d_cand_ref.ensure(std::max(nsp, 1))) != SX_OK) return rc;
+  if ((rc = c->d_lists.ensure(std::max(r.n_pairlist + r.n_direct, 1))) != SX_OK) return rc;
+  if (log2n_split(c->log2n) && (rc = c->d_scratch.ensure((size_t)std::max(r.n_pairlist + r.n_direct, 1) * N)) != SX_OK)
+    return rc;
+  if (c->cfg.debug_small_pools) {  // test hook: start with pools that must overflow, so the grow-and-retry paths run
+    if (c->d_cand_pool.n == 0 && (rc = c->d_cand_pool.ensure(64)) != SX_OK) return rc;
+    if (c->d_res.n == 0 && (rc = c->d_res.ensure(4)) != SX_OK) return rc;
+  } else {
+    if (c->d_cand_pool.n < std::max<size_t>((size_t)nsp * 640, 1 << 16) &&
+        (rc = c->d_cand_pool.ensure(std::max<size_t>((size_t)nsp * 640, 1 << 16))) != SX_OK)
+      return rc;
+    if (c->d_res.n == 0 && (rc = c->d_res.ensure(std::max<size_t>((size_t)nsp * 8, 1 << 16))) != SX_OK) return rc;
+  }
+  if (c->d_spill.n == 0 && (rc = c->d_spill.ensure(16)) != SX_OK) return rc;
+  cudaStream_t st = c->stream;
   if (nsp) CU(cudaMemcpyAsync(c->d_sps.p, c->h_sps[r.stage].p, sizeof(SpDesc) * nsp, cudaMemcpyHostToDevice, st));
   if (r.n_pairlist + r.n_direct)
     CU(cudaMemcpyAsync(c->d_lists.p, c->h_lists[r.stage].p, sizeof(uint32_t) * (r.n_pairlist + r.n_direct),
                        cudaMemcpyHostToDevice, st));
-  c->stats.h2d_bytes += (int64_t)(sizeof(SigDesc) * nsig + sizeof(SpDesc) * nsp + sizeof(uint32_t) * (r.n_pairlist + r.n_direct));
-  if (tap && (tap->sig5n || tap->xc)) {
-    if ((rc = c->d_tap.ensure((size_t)std::max(nsig, 1) * 5 * N + (size_t)std::max(nsp, 1) * N)) != SX_OK) return rc;
-    if (tap->sig5n) r.d_sig_tap = c->d_tap.p;
-    if (tap->xc) r.d_xc_tap = c->d_tap.p + (size_t)std::max(nsig, 1) * 5 * N;
-  }
+  c->stats.h2d_bytes += (int64_t)(sizeof(SpDesc) * nsp + sizeof(uint32_t) * (r.n_pairlist + r.n_direct));
   if (tap && tap->segs) {
     if ((rc = c->d_seg_tap.ensure((size_t)1 << 20)) != SX_OK) return rc;
     r.d_seg_tap = c->d_seg_tap.p;
     r.seg_tap_cap = (unsigned int)c->d_seg_tap.n;
   }
   c->z_cut = c->cfg.use_prob_table ? INFINITY : compute_z_cut(c->cfg.min_prob, c->target_total);
-  r.need_encode = nsig > 0;
   r.need_xcorr = true;
   r.active = true;
   if ((rc = batch_kernels(c, r)) != SX_OK) return rc;
@@ -718,10 +748,13 @@ static int batch_wait(sx_ctx *c, Run &r) {
     c->stats.d2h_bytes += (int64_t)sizeof(BatchCounters);
     if (prof) {
       float ms = 0;
-      if (r.need_encode) { cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->stats.ms_encode_fft += ms; }
-      if (nsp && r.need_xcorr) { cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->stats.ms_xcorr += ms; }
-      if (nsp) { cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->stats.ms_scan_score += ms; }
-      cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]);
+      cudaEvent_t *ev = c->ev[r.stage];
+      // ev[0] .. ev[1] spans the encode kernel plus whatever the stream did before the rest of this batch was
+      // queued (nothing when the host keeps up: the encode kernel hides the host's turnaround)
+      if (r.need_encode) { cudaEventElapsedTime(&ms, ev[0], ev[1]); c->stats.ms_encode_fft += ms; }
+      if (nsp && r.need_xcorr) { cudaEventElapsedTime(&ms, ev[1], ev[2]); c->stats.ms_xcorr += ms; }
+      if (nsp) { cudaEventElapsedTime(&ms, ev[2], ev[3]); c->stats.ms_scan_score += ms; }
+      cudaEventElapsedTime(&ms, r.need_encode ? ev[0] : ev[1], ev[3]);
       c->stats.ms_total += ms;
     }
     const BatchCounters ctr = *c->h_ctr.p;
@@ -770,14 +803,14 @@ static int batch_wait(sx_ctx *c, Run &r) {
       CU(cudaMemcpyAsync(c->h_res.p, c->d_res.p, sizeof(ResultRec) * ctr.res_used, cudaMemcpyDeviceToHost, st));
       c->stats.d2h_bytes += (int64_t)(sizeof(ResultRec) * ctr.res_used);
     }
-    CU(cudaEventRecord(c->ev[4], st));
+    CU(cudaEventRecord(c->ev[r.stage][4], st));
     return SX_OK;
   }
   return fail(SX_ERR_CUDA, "device pools kept overflowing after 8 attempts");
 }
 
 // second half of completing a batch: wait for the record copy, convert to t_result, serve taps
-static int batch_collect(sx_ctx *c, Run &r, std::vector<sx_result> *results) {
+static int batch_collect(sx_ctx *c, Run &r, ResultSink *results) {
   if (!r.fetching) return SX_OK;
   r.fetching = false;
   Batch &b = *r.b;
@@ -785,7 +818,7 @@ static int batch_collect(sx_ctx *c, Run &r, std::vector<sx_result> *results) {
   const int nsig = r.nsig, nsp = r.nsp;
   const size_t N = (size_t)c->N;
   const BatchCounters ctr = r.done_ctr;
-  CU(cudaEventSynchronize(c->ev[4]));
+  CU(cudaEventSynchronize(c->ev[r.stage][4]));
   if (r.fetch_n && results) {
     ResultRec *rr = c->h_res.p;
     if (c->cfg.sort_results) {
@@ -797,9 +830,9 @@ static int batch_collect(sx_ctx *c, Run &r, std::vector<sx_result> *results) {
         return a.start_t < b2.start_t;
       });
     }
-    const size_t base = results->size();
-    results->resize(base + r.fetch_n);
-    for (unsigned int i = 0; i < r.fetch_n; i++) to_result(c, rr[i], b.pairs[rr[i].pair], &(*results)[base + i]);
+    if (results->out && results->n + (int64_t)r.fetch_n <= results->cap)
+      for (unsigned int i = 0; i < r.fetch_n; i++) to_result(c, rr[i], b.pairs[rr[i].pair], results->out + results->n + i);
+    results->n += (int64_t)r.fetch_n;
   }
   if (tap) {
     if (tap->sig5n && nsig) CU(cudaMemcpy(tap->sig5n, r.d_sig_tap, sizeof(float) * nsig * 5 * N, cudaMemcpyDeviceToHost));
@@ -832,7 +865,7 @@ static int batch_collect(sx_ctx *c, Run &r, std::vector<sx_result> *results) {
   return SX_OK;
 }
 
-static int run_batch(sx_ctx *c, Batch &b, std::vector<sx_result> *results, TapRequest *tap) {
+static int run_batch(sx_ctx *c, Batch &b, ResultSink *results, TapRequest *tap) {
   Run r;
   int rc = batch_stage(c, r, b, tap, 0);
   if (rc == SX_OK) rc = batch_launch(c, r);
@@ -862,7 +895,7 @@ static int32_t target_slot(sx_ctx *c, Batch &b, int32_t t) {
   }
   auto it = b.tslot.find(t);
   if (it != b.tslot.end()) return it->second;
-  const int32_t slot = (int32_t)(c->n_persist + b.transient_used++);
+  const int32_t slot = (int32_t)(b.slot_base + b.transient_used++);
   SigDesc s;
   s.src = c->T.d_bases + c->T.offsets[t];
   s.len = c->T.lens[t];
@@ -887,7 +920,7 @@ static bool rc_derivable(const sx_ctx *c, int32_t len) {
 static int32_t query_slot(sx_ctx *c, Batch &b, int32_t q) {
   auto it = b.qslot.find(q);
   if (it != b.qslot.end()) return it->second;
-  const int32_t slot = (int32_t)(c->n_persist + b.transient_used);
+  const int32_t slot = (int32_t)(b.slot_base + b.transient_used);
   b.transient_used += 2;
   const bool derive = rc_derivable(c, c->Q.lens[q]);
   for (int strand = 0; strand < (derive ? 1 : 2); strand++) {
@@ -927,27 +960,32 @@ static int align_list_inner(sx_ctx *c, const PairReq *reqs, int64_t n, sx_result
   if (c->T.n == 0 && n > 0) return fail(SX_ERR_STATE, "align: no targets loaded");
   if (c->Q.n == 0 && n > 0) return fail(SX_ERR_STATE, "align: no queries loaded");
   CU(cudaSetDevice(c->cfg.device));
-  c->last.clear();
+  ResultSink sink;
+  sink.out = out;
+  sink.cap = cap;
   // Two batch descriptors: while the device works on one, the host assembles AND stages the next;
   // the next batch is launched right behind the asynchronous record copy of the previous one, and
   // only then are those records converted on the host.
   Batch bufs[2];
   Run runs[2];
+  bufs[0].slot_base = c->n_persist;
+  bufs[1].slot_base = c->n_persist + c->n_transient;
   int cur = 0;
   bool have_prev = false;
   auto submit = [&](int idx) -> int {
     int rc2 = batch_stage(c, runs[idx], bufs[idx], nullptr, idx);  // host only, overlaps the device
     if (rc2 != SX_OK) return rc2;
+    if ((rc2 = batch_launch_early(c, runs[idx])) != SX_OK) return rc2;  // encode queued behind the previous scan
     if (have_prev && (rc2 = batch_wait(c, runs[idx ^ 1])) != SX_OK) return rc2;
     if ((rc2 = batch_launch(c, runs[idx])) != SX_OK) return rc2;
-    if (have_prev && (rc2 = batch_collect(c, runs[idx ^ 1], &c->last)) != SX_OK) return rc2;
+    if (have_prev && (rc2 = batch_collect(c, runs[idx ^ 1], &sink)) != SX_OK) return rc2;
     have_prev = true;
     return SX_OK;
   };
   auto drain = [&]() -> int {
     if (!have_prev) return SX_OK;
     int rc2 = batch_wait(c, runs[cur]);
-    if (rc2 == SX_OK) rc2 = batch_collect(c, runs[cur], &c->last);
+    if (rc2 == SX_OK) rc2 = batch_collect(c, runs[cur], &sink);
     have_prev = false;
     return rc2;
   };
@@ -977,10 +1015,10 @@ static int align_list_inner(sx_ctx *c, const PairReq *reqs, int64_t n, sx_result
   if (rc != SX_OK) return rc;
   rc = drain();
   if (rc != SX_OK) return rc;
-  const int64_t total = (int64_t)c->last.size();
+  const int64_t total = sink.n;
   if (n_out) *n_out = total;
-  if (total > cap) return fail(SX_ERR_CAPACITY, "align: %lld records, buffer holds %lld", (long long)total, (long long)cap);
-  if (total && out) memcpy(out, c->last.data(), sizeof(sx_result) * (size_t)total);
+  if (total > cap || (total > 0 && !out))
+    return fail(SX_ERR_CAPACITY, "align: %lld records, buffer holds %lld", (long long)total, (long long)cap);
   return SX_OK;
 }
 
@@ -1035,6 +1073,7 @@ static int tap_prepare(sx_ctx *c, int32_t target, int32_t query, int32_t strand,
     return fail(SX_ERR_ARG, "tap: (target %d, query %d, strand %d) out of range", target, query, strand);
   if (c->n_transient < 3) return fail(SX_ERR_STATE, "tap: no workspace (call sx_set_targets first)");
   CU(cudaSetDevice(c->cfg.device));
+  b.slot_base = c->n_persist;
   b.t_need = c->T.blob_bytes;
   b.q_need = c->Q.blob_bytes;
   // the chunk pair exactly as align_list builds it (both strands, production kernels); the tap then
