@@ -111,7 +111,7 @@ typedef struct {
   double ms_scan_score;   /* kernel (e) */
   double ms_total;        /* first launch to last kernel end, per batch, summed */
   int64_t positions;      /* diagonal positions (base comparisons) scanned by kernel (e) */
-  int64_t spilled_segments; /* segments that overflowed a warp queue and took the global spill list */
+  int64_t spilled_segments; /* reserved (always 0: the scan kernel works its segment queue off before it fills) */
 } sx_stats;
 
 /* ------------------------------------------------------------------ lifecycle */

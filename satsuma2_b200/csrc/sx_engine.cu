@@ -141,7 +141,6 @@ struct sx_ctx {
   DevBuf<uint16_t> d_cand_pool;
   DevBuf<ResultRec> d_res;
   DevBuf<SegRec> d_seg_tap;
-  DevBuf<SegRec> d_spill;
   DevBuf<BatchCounters> d_ctr;
   DevBuf<double> d_table;
   DevBuf<float> d_tap;
@@ -266,7 +265,7 @@ extern "C" void sx_destroy(sx_ctx *c) {
   c->spec.release(); c->planes.release(); c->sbytes.release(); c->meta.release(); c->wn.release(); c->ent_table.release();
   c->d_lists.release(); c->h_lists[0].release(); c->h_lists[1].release();
   c->d_sigs[0].release(); c->d_sigs[1].release(); c->d_sps.release(); c->d_cand_ref.release(); c->d_cand_pool.release();
-  c->d_scratch.release(); c->d_res.release(); c->d_seg_tap.release(); c->d_spill.release(); c->d_ctr.release(); c->d_table.release(); c->d_tap.release();
+  c->d_scratch.release(); c->d_res.release(); c->d_seg_tap.release(); c->d_ctr.release(); c->d_table.release(); c->d_tap.release();
   c->h_sigs[0].release(); c->h_sigs[1].release(); c->h_sps[0].release(); c->h_sps[1].release(); c->h_res.release(); c->h_ctr.release();
   for (int i = 0; i < 10; i++)
     if (c->ev[i / 5][i % 5]) cudaEventDestroy(c->ev[i / 5][i % 5]);
@@ -609,8 +608,7 @@ static int batch_kernels(sx_ctx *c, Run &r) {
   if (prof) CU(cudaEventRecord(ev[2], st));
   if (r.nsp) {
     CU(launch_scan_score(c->log2n, c->d_sps.p, r.nsp, ws, c->d_cand_pool.p, c->d_cand_ref.p, prm, c->d_res.p,
-                         (unsigned int)std::min<size_t>(c->d_res.n, 0xfffffff0u), r.d_seg_tap, r.seg_tap_cap,
-                         c->d_spill.p, (unsigned int)std::min<size_t>(c->d_spill.n, 0xfffffff0u), c->d_ctr.p, st));
+                         (unsigned int)std::min<size_t>(c->d_res.n, 0xfffffff0u), r.d_seg_tap, r.seg_tap_cap, c->d_ctr.p, st));
     c->stats.kernel_launches += 2;
   }
   if (prof) CU(cudaEventRecord(ev[3], st));
@@ -703,7 +701,6 @@ static int batch_launch(sx_ctx *c, Run &r) {
       return rc;
     if (c->d_res.n == 0 && (rc = c->d_res.ensure(std::max<size_t>((size_t)nsp * 8, 1 << 16))) != SX_OK) return rc;
   }
-  if (c->d_spill.n == 0 && (rc = c->d_spill.ensure(16)) != SX_OK) return rc;
   cudaStream_t st = c->stream;
   if (nsp) CU(cudaMemcpyAsync(c->d_sps.p, c->h_sps[r.stage].p, sizeof(SpDesc) * nsp, cudaMemcpyHostToDevice, st));
   if (r.n_pairlist + r.n_direct)
@@ -775,13 +772,6 @@ static int batch_wait(sx_ctx *c, Run &r) {
       r.need_xcorr = false;  // candidates are valid; only the scan is repeated
       continue;
     }
-    if (ctr.status & ST_SPILL_OVERFLOW) {
-      const size_t want = std::max<size_t>((size_t)ctr.spill_used + (ctr.spill_used >> 2), c->d_spill.n * 2);
-      if ((rc = c->d_spill.ensure(want)) != SX_OK) return rc;
-      c->stats.retries++;
-      r.need_xcorr = false;
-      continue;
-    }
     if (ctr.status & ST_INTERNAL) return fail(SX_ERR_CUDA, "scan kernel: internal round limit hit");
     if (ctr.status & ST_TAP_OVERFLOW) return fail(SX_ERR_CAPACITY, "segment tap overflow (%u records)", ctr.seg_tap_used);
 
@@ -794,7 +784,6 @@ static int batch_wait(sx_ctx *c, Run &r) {
     c->stats.segments += (int64_t)ctr.n_segments;
     c->stats.positions += (int64_t)ctr.n_positions;
     c->stats.matches += (int64_t)ctr.res_used;
-    c->stats.spilled_segments += (int64_t)ctr.spill_used;
     r.done_ctr = ctr;
     r.fetch_n = ctr.res_used;
     r.fetching = true;

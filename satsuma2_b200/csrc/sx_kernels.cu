@@ -1194,7 +1194,7 @@ __device__ __forceinline__ bool score_generic(const uint8_t *tb, const uint8_t *
 
 template <int LOG2N, int NT>
 __global__ void __launch_bounds__(NT)
-    scan_score_generic_kernel(const SpDesc *__restrict__ sps, Slots ws, const uint16_t *__restrict__ cand_pool,
+    scan_score_generic_kernel(const SpDesc *__restrict__ sps, int nsp, Slots ws, const uint16_t *__restrict__ cand_pool,
                               const uint2 *__restrict__ cand_ref, ScoreParams prm,
                               ResultRec *__restrict__ res_pool, unsigned int res_cap,
                               SegRec *__restrict__ seg_tap, unsigned int seg_tap_cap, BatchCounters *ctr) {
@@ -1208,12 +1208,17 @@ __global__ void __launch_bounds__(NT)
   __shared__ unsigned int s_nseg;
 
   const int tid = threadIdx.x;
-  const SpDesc sp = sps[blockIdx.x];
-  const uint2 cref = cand_ref[blockIdx.x];
+  if (ctr->n_generic == 0) return;  // the bit-parallel kernel saw nothing for this one (the usual case)
+  unsigned long long my_segments = 0, my_positions = 0;
+  // a fixed grid strides over the strand-pairs
+  for (int spi = blockIdx.x; spi < nsp; spi += gridDim.x) {
+  __syncthreads();  // the previous strand-pair's shared-memory contents are dead
+  const SpDesc sp = sps[spi];
+  const uint2 cref = cand_ref[spi];
   const int ncand = (int)cref.y;
-  if (ncand == 0 || cref.x == 0xffffffffu) return;
+  if (ncand == 0 || cref.x == 0xffffffffu) continue;
   const SlotMeta tm = ws.meta[sp.t_slot], qm = ws.meta[sp.q_slot];
-  if (!((tm.flags | qm.flags) & SLOT_NONACGT)) return;  // handled by the bit-parallel kernel
+  if (!((tm.flags | qm.flags) & SLOT_NONACGT)) continue;  // handled by the bit-parallel kernel
   const int tlen = tm.len, qlen = qm.len;
   {
     // bases of both chunks: from the oriented bytes when the chunk holds IUPAC / unknown letters, rebuilt from
@@ -1246,7 +1251,6 @@ __global__ void __launch_bounds__(NT)
   }
   __syncthreads();
 
-  unsigned long long my_segments = 0, my_positions = 0;
   for (int c0 = 0; c0 < ncand; c0 += NT) {
     const int c = c0 + tid;
     if (c < ncand) {
@@ -1259,7 +1263,7 @@ __global__ void __launch_bounds__(NT)
       auto close_segment = [&](int i) {
         const int seg_len = i - open;
         my_segments++;
-        tap_segment(blockIdx.x, open, shift, seg_len, seg_tap, seg_tap_cap, ctr);
+        tap_segment(spi, open, shift, seg_len, seg_tap, seg_tap_cap, ctr);
         const unsigned int slot = atomicAdd(&s_nseg, 1u);
         if (slot < SX_SEGQ_CAP) {
           s_segq[slot] = make_uint2((uint32_t)open | ((uint32_t)seg_len << 16), (uint32_t)shift);
@@ -1296,6 +1300,7 @@ __global__ void __launch_bounds__(NT)
     if (tid == 0) s_nseg = 0;
     __syncthreads();
   }
+  }  // strand-pairs
   for (int o = 16; o > 0; o >>= 1) my_segments += __shfl_xor_sync(0xffffffffu, my_segments, o);
   if ((tid & 31) == 0 && my_segments) atomicAdd(&ctr->n_segments, my_segments);
   for (int o = 16; o > 0; o >>= 1) my_positions += __shfl_xor_sync(0xffffffffu, my_positions, o);
@@ -1378,7 +1383,7 @@ static cudaError_t xcorr_launch(const SpDesc *sps, const uint32_t *pair_list, in
 template <int LOG2N>
 static cudaError_t scan_launch(const SpDesc *sps, int nsp, Slots ws, const uint16_t *cand_pool,
                                const uint2 *cand_ref, ScoreParams prm, ResultRec *res_pool, unsigned int res_cap,
-                               SegRec *seg_tap, unsigned int seg_tap_cap, SegRec *spill, unsigned int spill_cap,
+                               SegRec *seg_tap, unsigned int seg_tap_cap,
                                BatchCounters *ctr, cudaStream_t st) {
   constexpr int N = 1 << LOG2N, NT = 256;
   constexpr size_t scan_smem = ScanCfg<LOG2N>::SMEM;
@@ -1389,17 +1394,15 @@ static cudaError_t scan_launch(const SpDesc *sps, int nsp, Slots ws, const uint1
     if (e != cudaSuccess) return e;
   }
   scan_score_kernel<LOG2N><<<(nsp + SPC - 1) / SPC, SX_SCAN_NT, scan_smem, st>>>(
-      sps, nsp, ws, cand_pool, cand_ref, prm, res_pool, res_cap, seg_tap, seg_tap_cap, spill, spill_cap, ctr);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  score_spill_kernel<LOG2N><<<148, 128, 0, st>>>(sps, ws, spill, prm, res_pool, res_cap, spill_cap, ctr);
+      sps, nsp, ws, cand_pool, cand_ref, prm, res_pool, res_cap, seg_tap, seg_tap_cap, ctr);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const size_t smem = (size_t)2 * N + 128 * 128 + 128 * 2 + (size_t)SX_SEGQ_CAP * 8;
   auto k = scan_score_generic_kernel<LOG2N, NT>;
   e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<nsp, NT, smem, st>>>(sps, ws, cand_pool, cand_ref, prm, res_pool, res_cap, seg_tap, seg_tap_cap, ctr);
+  k<<<nsp < 592 ? nsp : 592, NT, smem, st>>>(sps, nsp, ws, cand_pool, cand_ref, prm, res_pool, res_cap, seg_tap, seg_tap_cap,
+                                           ctr);  // 148 SMs x 4
   return cudaGetLastError();
 }
 
@@ -1434,10 +1437,10 @@ cudaError_t launch_xcorr_findtop(int log2n, const SpDesc *sps, const uint32_t *p
 
 cudaError_t launch_scan_score(int log2n, const SpDesc *sps, int nsp, Slots ws, const uint16_t *cand_pool,
                               const uint2 *cand_ref, ScoreParams prm, ResultRec *res_pool,
-                              unsigned int res_cap, SegRec *seg_tap, unsigned int seg_tap_cap, SegRec *spill,
-                              unsigned int spill_cap, BatchCounters *ctr, cudaStream_t stream) {
+                              unsigned int res_cap, SegRec *seg_tap, unsigned int seg_tap_cap, BatchCounters *ctr,
+                              cudaStream_t stream) {
   if (nsp <= 0) return cudaSuccess;
-#define CALL(L) scan_launch<L>(sps, nsp, ws, cand_pool, cand_ref, prm, res_pool, res_cap, seg_tap, seg_tap_cap, spill, spill_cap, ctr, stream)
+#define CALL(L) scan_launch<L>(sps, nsp, ws, cand_pool, cand_ref, prm, res_pool, res_cap, seg_tap, seg_tap_cap, ctr, stream)
   SX_DISPATCH(log2n, CALL)
 #undef CALL
 }

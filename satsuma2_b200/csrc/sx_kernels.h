@@ -67,13 +67,13 @@ struct BatchCounters {  // device-side, zeroed per batch
   unsigned int cand_used;     // candidate pool entries reserved
   unsigned int res_used;      // result records reserved
   unsigned int seg_tap_used;  // tap records reserved
-  unsigned int status;        // bit0: candidate pool overflow, bit1: result pool overflow, bit2: tap overflow,
-                              // bit3: segment spill pool overflow
-  unsigned int spill_used;    // segments that did not fit a warp queue
+  unsigned int status;        // bit0: candidate pool overflow, bit1: result pool overflow, bit2: tap overflow
+  unsigned int n_generic;     // strand-pairs with candidates that the byte-wise scan kernel has to do (set by the
+                              // bit-parallel one; 0 lets the byte-wise kernel leave at once)
   unsigned int pad_;
   unsigned long long n_candidates, n_segments, n_positions;  // n_positions: diagonal positions scanned
 };
-enum { ST_CAND_OVERFLOW = 1, ST_RES_OVERFLOW = 2, ST_TAP_OVERFLOW = 4, ST_SPILL_OVERFLOW = 8, ST_INTERNAL = 16 };
+enum { ST_CAND_OVERFLOW = 1, ST_RES_OVERFLOW = 2, ST_TAP_OVERFLOW = 4, ST_INTERNAL = 16 };
 
 // ---- launchers (sx_kernels.cu); all asynchronous on `stream`, return cudaGetLastError() --------
 cudaError_t upload_tables();  // constant/global lookup tables, once per device
@@ -97,8 +97,8 @@ size_t ent_table_elems(int log2n);
 void fill_ent_table(int log2n, double *host_out);  // ent_table_elems() entries
 cudaError_t launch_scan_score(int log2n, const SpDesc *sps, int nsp, Slots ws, const uint16_t *cand_pool,
                               const uint2 *cand_ref, ScoreParams prm, ResultRec *res_pool,
-                              unsigned int res_cap, SegRec *seg_tap, unsigned int seg_tap_cap, SegRec *spill,
-                              unsigned int spill_cap, BatchCounters *ctr, cudaStream_t stream);
+                              unsigned int res_cap, SegRec *seg_tap, unsigned int seg_tap_cap, BatchCounters *ctr,
+                              cudaStream_t stream);
 
 // host copies of the lookup tables (also used by the host-side ProbTable builder)
 const double *host_frac_table();    // [128][4]

@@ -264,8 +264,7 @@ template <int LOG2N>
 __global__ void __launch_bounds__(SX_SCAN_NT)
     scan_score_kernel(const SpDesc *__restrict__ sps, int nsp, Slots ws, const uint16_t *__restrict__ cand_pool,
                       const uint2 *__restrict__ cand_ref, ScoreParams prm, ResultRec *__restrict__ res_pool,
-                      unsigned int res_cap, SegRec *__restrict__ seg_tap, unsigned int seg_tap_cap,
-                      SegRec *__restrict__ spill, unsigned int spill_cap, BatchCounters *ctr) {
+                      unsigned int res_cap, SegRec *__restrict__ seg_tap, unsigned int seg_tap_cap, BatchCounters *ctr) {
   using C = ScanCfg<LOG2N>;
   constexpr int N = 1 << LOG2N, H = N / 2, NW = C::NW, PW = C::PW, NBW = C::NBW, SPC = C::SPC, PAD = C::PAD;
   constexpr int ITEM_CAP = C::ITEM_CAP;
@@ -291,6 +290,7 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
       const SpDesc sp = sps[spi];
       const bool generic = ((ws.meta[sp.t_slot].flags | ws.meta[sp.q_slot].flags) & SLOT_NONACGT) != 0;  // other kernel
       if (cref.x != 0xffffffffu && !generic) nc = (int)cref.y;
+      if (cref.x != 0xffffffffu && generic && cref.y > 0) atomicAdd(&ctr->n_generic, 1u);
     }
     s_ncand[tid] = nc;
   }
@@ -533,38 +533,4 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
   if (lane == 0 && my_segments) atomicAdd(&ctr->n_segments, (unsigned long long)my_segments);
   for (int o = 16; o > 0; o >>= 1) my_positions += __shfl_xor_sync(0xffffffffu, my_positions, o);
   if (lane == 0 && my_positions) atomicAdd(&ctr->n_positions, my_positions);
-}
-
-// Segments that did not fit a warp queue: same scoring, planes read from global memory.
-template <int LOG2N>
-__global__ void __launch_bounds__(128)
-    score_spill_kernel(const SpDesc *__restrict__ sps, Slots ws, const SegRec *__restrict__ spill, ScoreParams prm,
-                       ResultRec *__restrict__ res_pool, unsigned int res_cap, unsigned int spill_cap,
-                       BatchCounters *ctr) {
-  constexpr int N = 1 << LOG2N, NW = N / 32;
-  const unsigned int n = min(ctr->spill_used, spill_cap);
-  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const SegRec r = spill[i];
-    const SpDesc sp = sps[r.sp];
-    const uint32_t *tp = ws.planes + (size_t)sp.t_slot * 2 * NW;
-    const uint32_t *qp = ws.planes + (size_t)sp.q_slot * 2 * NW;
-    int matches = 0, gct = 0, gcq = 0;
-    const int qoff = r.start_t + r.shift;
-    for (int k = 0; k < r.len; k += 32) {
-      const int tw = (r.start_t + k) >> 5, tsh = (r.start_t + k) & 31, qw = (qoff + k) >> 5, qsh = (qoff + k) & 31;
-      auto ld = [&](const uint32_t *p, int w) -> uint32_t { return w < NW ? p[w] : 0u; };
-      const uint32_t tl = __funnelshift_r(ld(tp, tw), ld(tp, tw + 1), tsh);
-      const uint32_t th = __funnelshift_r(ld(tp + NW, tw), ld(tp + NW, tw + 1), tsh);
-      const uint32_t ql = __funnelshift_r(ld(qp, qw), ld(qp, qw + 1), qsh);
-      const uint32_t qh = __funnelshift_r(ld(qp + NW, qw), ld(qp + NW, qw + 1), qsh);
-      const int rem = r.len - k;
-      const uint32_t vm = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
-      matches += __popc(~((tl ^ ql) | (th ^ qh)) & vm);
-      gct += __popc((tl ^ th) & vm);
-      gcq += __popc((ql ^ qh) & vm);
-    }
-    double prob, ident;
-    if (score_counts((double)matches, (double)gct, (double)gcq, r.len, prm, prob, ident))
-      emit_result(sp, r.start_t, r.shift, r.len, prob, ident, res_pool, res_cap, ctr);
-  }
 }

@@ -459,7 +459,7 @@ def test_grid_blocks_with_cached_target_spectra(sx, oracle_lib):
 
 
 def test_pool_overflow_grows_and_retries(sx):
-    """Device pools (candidates, records, spill list) that are too small are grown and the affected
+    """Device pools (candidates, records) that are too small are grown and the affected
     kernels re-run: nothing is truncated, the result set is the one a roomy engine returns."""
     from satsuma2_b200 import synth
 
