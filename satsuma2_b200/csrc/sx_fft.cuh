@@ -139,8 +139,11 @@ static __device__ float2 g_twiddle[SX_TW_ENTRIES];  // this header is compiled i
 // block = b div S, points at block*L + j + m*S.  NPTS is a multiple of L (N for the two halves in
 // one CTA, H when a CTA of a cluster holds one half).
 // Forward (DIF): DFT_R then multiply output p by W_L^{j p};  inverse (DIT): conj-twiddle then DFT_R^*.
-template <int NPTS, int L, int R, bool INV, int NT>
-__device__ __forceinline__ void fft_pass(float2 *buf, int tid) {
+// tw: table of this pass in shared memory, tw[j] = W_L^j for j < S (see TwTables), or nullptr = read the global
+// table.  The inverse applies the twiddles BEFORE the butterfly, so the latency of that load is exposed: its
+// kernels stage the few hundred entries they need in shared memory; the forward side hides it behind the math.
+template <int NPTS, int L, int R, bool INV, int NT, bool SMEM_TW = false>
+__device__ __forceinline__ void fft_pass(float2 *buf, int tid, const float2 *tw = nullptr) {
   constexpr int S = L / R;
   constexpr int LOG2L = __builtin_ctz(L);
 #pragma unroll 1
@@ -153,7 +156,7 @@ __device__ __forceinline__ void fft_pass(float2 *buf, int tid) {
     for (int m = 0; m < R; m++) x[m] = buf[(base + m * S) ^ (fb ^ swz_f(m * S))];
     float2 w[R];  // W_L^{j p}: W_L^{j} from the table, the powers by binary powering (<= 4 roundings)
     if (S > 1) {
-      w[1] = __ldg(&g_twiddle[j << (SX_TW_BASE_LOG2 - LOG2L)]);
+      w[1] = SMEM_TW ? tw[j] : __ldg(&g_twiddle[j << (SX_TW_BASE_LOG2 - LOG2L)]);
 #pragma unroll
       for (int p = 2; p < R; p++) w[p] = (p & 1) ? cmul(w[p - 1], w[1]) : cmul(w[p / 2], w[p / 2]);
     }
@@ -246,21 +249,42 @@ __device__ __forceinline__ void fft_forward_halves(float2 *buf, int tid) {
   }
 }
 
-// Inverse (unscaled) H-point transforms, scrambled order in -> natural order out.  Ends with a barrier.
+// Shared-memory twiddle tables of the passes of an H-point transform: pass i (sub-transform length L_i, stride
+// S_i = L_i / R_i) owns S_i entries W_{L_i}^j at offset OFF_i; passes with S = 1 need none.
+template <int LOG2N>
+struct TwTables {
+  using P = Plan<LOG2N>;
+  static constexpr int H = 1 << (LOG2N - 1);
+  static constexpr int L0 = H, L1 = L0 / P::R0, L2 = L1 / P::R1, L3 = L2 / P::R2;
+  static constexpr int S0 = L0 / P::R0, S1 = L1 / P::R1, S2 = L2 / P::R2, S3 = P::R3 > 1 ? L3 / P::R3 : 1;
+  static constexpr int OFF0 = 0, OFF1 = OFF0 + (S0 > 1 ? S0 : 0), OFF2 = OFF1 + (S1 > 1 ? S1 : 0),
+                       OFF3 = OFF2 + (S2 > 1 ? S2 : 0), TOTAL = OFF3 + (S3 > 1 ? S3 : 0);
+  template <int NT>
+  static __device__ __forceinline__ void load(float2 *tw, int tid) {  // the caller synchronises before use
+    if (S0 > 1) for (int j = tid; j < S0; j += NT) tw[OFF0 + j] = __ldg(&g_twiddle[j << (SX_TW_BASE_LOG2 - __builtin_ctz(L0))]);
+    if (S1 > 1) for (int j = tid; j < S1; j += NT) tw[OFF1 + j] = __ldg(&g_twiddle[j << (SX_TW_BASE_LOG2 - __builtin_ctz(L1))]);
+    if (S2 > 1) for (int j = tid; j < S2; j += NT) tw[OFF2 + j] = __ldg(&g_twiddle[j << (SX_TW_BASE_LOG2 - __builtin_ctz(L2))]);
+    if (S3 > 1) for (int j = tid; j < S3; j += NT) tw[OFF3 + j] = __ldg(&g_twiddle[j << (SX_TW_BASE_LOG2 - __builtin_ctz(L3))]);
+  }
+};
+
+// Inverse (unscaled) H-point transforms, scrambled order in -> natural order out.  tw: TwTables<LOG2N> in shared
+// memory.  Ends with a barrier.
 template <int LOG2N, int NPTS, int NT>
-__device__ __forceinline__ void fft_inverse_halves(float2 *buf, int tid) {
+__device__ __forceinline__ void fft_inverse_halves(float2 *buf, int tid, const float2 *tw) {
   constexpr int H = 1 << (LOG2N - 1);
   using P = Plan<LOG2N>;
+  using T = TwTables<LOG2N>;
   constexpr int L1 = H / P::R0, L2 = L1 / P::R1, L3 = L2 / P::R2;
   if constexpr (P::R3 > 1) {
-    fft_pass<NPTS, L3, P::R3, true, NT>(buf, tid);
+    fft_pass<NPTS, L3, P::R3, true, NT, true>(buf, tid, tw + T::OFF3);
     __syncthreads();
   }
-  fft_pass<NPTS, L2, P::R2, true, NT>(buf, tid);
+  fft_pass<NPTS, L2, P::R2, true, NT, true>(buf, tid, tw + T::OFF2);
   __syncthreads();
-  fft_pass<NPTS, L1, P::R1, true, NT>(buf, tid);
+  fft_pass<NPTS, L1, P::R1, true, NT, true>(buf, tid, tw + T::OFF1);
   __syncthreads();
-  fft_pass<NPTS, H, P::R0, true, NT>(buf, tid);
+  fft_pass<NPTS, H, P::R0, true, NT, true>(buf, tid, tw + T::OFF0);
   __syncthreads();
 }
 

@@ -796,9 +796,9 @@ __device__ __forceinline__ void findtop(const float2 *buf, int off, float scale,
 // the two H-point inverses, then the radix-2 combine x[n] = e[n] + w_N^{-n} o[n], x[n+H] = e[n] - w_N^{-n} o[n]
 // in place (natural order, swizzled slots).  Ends with a barrier.
 template <int LOG2N, int NT>
-__device__ __forceinline__ void inverse_full(float2 *buf, const float2 *__restrict__ wn, int tid) {
+__device__ __forceinline__ void inverse_full(float2 *buf, const float2 *__restrict__ wn, int tid, const float2 *tw) {
   constexpr int N = 1 << LOG2N, H = N / 2;
-  fft_inverse_halves<LOG2N, N, NT>(buf, tid);
+  fft_inverse_halves<LOG2N, N, NT>(buf, tid, tw);
   for (int n = tid; n < H; n += NT) {
     const float2 e = buf[swz(n)], o = buf[H + swz(n)];
     const float2 t = cmulc(o, __ldg(wn + n));
@@ -809,7 +809,7 @@ __device__ __forceinline__ void inverse_full(float2 *buf, const float2 *__restri
 }
 
 template <int LOG2N, int NT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
     xcorr_pair_kernel(const uint32_t *__restrict__ pair_list, const SpDesc *__restrict__ sps, Slots ws, double cutoff,
                       double cutoff_fast, uint16_t *__restrict__ cand_pool, unsigned int pool_cap,
                       uint2 *__restrict__ cand_ref, BatchCounters *ctr, float *__restrict__ xc_tap) {
@@ -818,11 +818,13 @@ __global__ void __launch_bounds__(NT)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *buf = reinterpret_cast<float2 *>(smem_raw);
   uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw + (size_t)N * sizeof(float2));  // NW words
+  float2 *s_tw = reinterpret_cast<float2 *>(mask + NW);  // TwTables<LOG2N>::TOTAL inverse-pass twiddles
   __shared__ double s_thr[NB];
   __shared__ unsigned int s_wtot[NWARP];
   __shared__ unsigned int s_base;
 
   const int tid = threadIdx.x;
+  TwTables<LOG2N>::template load<NT>(s_tw, tid);  // used after the barriers below
   const int spi = (int)pair_list[blockIdx.x];  // forward strand-pair; the reverse one is spi + 1
   const SpDesc sp = sps[spi];
   const SlotMeta tm = ws.meta[sp.t_slot];
@@ -838,28 +840,62 @@ __global__ void __launch_bounds__(NT)
   {
     const float2 *U1 = ws.spec + ((size_t)sp.t_slot * 2) * N, *U2 = U1 + N;
     const float2 *V1 = ws.spec + ((size_t)sp.q_slot * 2) * N, *V2 = V1 + N;
-#pragma unroll 2
-    for (int it = tid; it < H; it += NT) {
-      int pa, pb;
-      if (it < H / 2) {  // even bins: m <-> (H - m) mod H; m < H/2 <=> top digit (last in scrambled order) < LR/2
-        const int r = (it / (LR / 2)) * LR + (it % (LR / 2));
-        const int m2 = (H - natural_bin<LOG2N>(r)) & (H - 1);
-        pa = swz(r);
-        pb = swz(scrambled_pos<LOG2N>(m2));
-      } else {  // odd bins: m <-> H - 1 - m, i.e. scrambled position r <-> H - 1 - r
-        const int r = it - H / 2;
-        pa = H + swz(r);
-        pb = H + swz(H - 1 - r);
-      }
-      const float2 u1a = __ldg(U1 + pa), u2a = __ldg(U2 + pa), v1a = __ldg(V1 + pa), v2a = __ldg(V2 + pa);
-      const float2 u1b = __ldg(U1 + pb), u2b = __ldg(U2 + pb), v1b = __ldg(V1 + pb), v2b = __ldg(V2 + pb);
+    // one bin pair (slot a, its mirror slot b) -> the two packed values
+    auto product = [](float2 u1a, float2 u2a, float2 v1a, float2 v2a, float2 u1b, float2 u2b, float2 v1b, float2 v2b,
+                      float2 &oa, float2 &ob) {
       const float2 a = cadd(cmulc(v1a, u1a), cmulc(v2a, u2a));
       const float2 b = cadd(cmulc(v1b, u1b), cmulc(v2b, u2b));
       const float2 g = cadd(cmul(u1a, v2a), cmul(u2a, v1a));
       const float2 h = cadd(cmul(u1b, v2b), cmul(u2b, v1b));
       const float sx_ = a.x + b.x, dx = g.x - h.x, sy = g.y + h.y, dy = a.y - b.y;
-      buf[pa] = make_float2(sx_ - dx, sy + dy);
-      buf[pb] = make_float2(sx_ + dx, sy - dy);
+      oa = make_float2(sx_ - dx, sy + dy);
+      ob = make_float2(sx_ + dx, sy - dy);
+    };
+    // Two neighbouring slots (r, r ^ 1) per step with 16-byte loads: their mirror slots are neighbours too
+    // (even bins: top digit d <-> R - 1 - d while the lower digits are not all zero; odd bins: r <-> H - 1 - r),
+    // and the swizzle only XORs the low four bits with a per-block constant, so pairs stay pairs.
+    constexpr int PPB = LR / 4;  // slot pairs per block of LR slots with top digit < LR / 2
+#pragma unroll 2
+    for (int it = tid; it < H / 2; it += NT) {
+      int pa0, pb0;
+      if (it < H / 4) {  // even bins: m <-> (H - m) mod H; m < H/2 <=> top digit (last in scrambled order) < LR/2
+        const int r = (it / PPB) * LR + 2 * (it % PPB);
+        if (r < LR) continue;  // lower digits all zero: mirrors are d <-> R - d, done one by one below
+        const int m2 = (H - natural_bin<LOG2N>(r)) & (H - 1);
+        pa0 = swz(r);
+        pb0 = swz(scrambled_pos<LOG2N>(m2));
+      } else {  // odd bins: m <-> H - 1 - m, i.e. scrambled position r <-> H - 1 - r
+        const int r = 2 * (it - H / 4);
+        pa0 = H + swz(r);
+        pb0 = H + swz(H - 1 - r);
+      }
+      const int qa = pa0 >> 1, qb = pb0 >> 1;  // float4 index
+      const float4 U1a = __ldg(reinterpret_cast<const float4 *>(U1) + qa), U2a = __ldg(reinterpret_cast<const float4 *>(U2) + qa);
+      const float4 V1a = __ldg(reinterpret_cast<const float4 *>(V1) + qa), V2a = __ldg(reinterpret_cast<const float4 *>(V2) + qa);
+      const float4 U1b = __ldg(reinterpret_cast<const float4 *>(U1) + qb), U2b = __ldg(reinterpret_cast<const float4 *>(U2) + qb);
+      const float4 V1b = __ldg(reinterpret_cast<const float4 *>(V1) + qb), V2b = __ldg(reinterpret_cast<const float4 *>(V2) + qb);
+      // slot r sits in half (pa0 & 1) of the a-quad and its mirror in half (pb0 & 1) of the b-quad; slot r ^ 1 and
+      // its mirror sit in the other halves
+      const bool ea = pa0 & 1, eb = pb0 & 1;
+      auto lo = [](const float4 &v) { return make_float2(v.x, v.y); };
+      auto hi = [](const float4 &v) { return make_float2(v.z, v.w); };
+      auto sel = [&](const float4 &v, bool upper) { return upper ? hi(v) : lo(v); };
+      float2 oa0, ob0, oa1, ob1;
+      product(sel(U1a, ea), sel(U2a, ea), sel(V1a, ea), sel(V2a, ea), sel(U1b, eb), sel(U2b, eb), sel(V1b, eb), sel(V2b, eb),
+              oa0, ob0);
+      product(sel(U1a, !ea), sel(U2a, !ea), sel(V1a, !ea), sel(V2a, !ea), sel(U1b, !eb), sel(U2b, !eb), sel(V1b, !eb),
+              sel(V2b, !eb), oa1, ob1);
+      reinterpret_cast<float4 *>(buf)[qa] = ea ? make_float4(oa1.x, oa1.y, oa0.x, oa0.y) : make_float4(oa0.x, oa0.y, oa1.x, oa1.y);
+      reinterpret_cast<float4 *>(buf)[qb] = eb ? make_float4(ob1.x, ob1.y, ob0.x, ob0.y) : make_float4(ob0.x, ob0.y, ob1.x, ob1.y);
+    }
+    for (int r = tid; r < LR / 2; r += NT) {  // first block of the even bins, slot by slot
+      const int m2 = (H - natural_bin<LOG2N>(r)) & (H - 1);
+      const int pa = swz(r), pb = swz(scrambled_pos<LOG2N>(m2));
+      float2 oa, ob;
+      product(__ldg(U1 + pa), __ldg(U2 + pa), __ldg(V1 + pa), __ldg(V2 + pa), __ldg(U1 + pb), __ldg(U2 + pb), __ldg(V1 + pb),
+              __ldg(V2 + pb), oa, ob);
+      buf[pa] = oa;
+      buf[pb] = ob;
     }
   }
   __syncthreads();
@@ -879,7 +915,7 @@ __global__ void __launch_bounds__(NT)
     put(PH, H, make_float2(tm.q_nyq, 0.f));
   }
   __syncthreads();
-  inverse_full<LOG2N, NT>(buf, ws.wn, tid);
+  inverse_full<LOG2N, NT>(buf, ws.wn, tid, s_tw);
 
   // xc[i] = x[(i + H) mod N] / N (rescale + half rotation, CrossCorr.cc:493-505); the factor 2 above
   const float scale = 0.5f / (float)N;
@@ -898,11 +934,13 @@ __global__ void __launch_bounds__(NT)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *buf = reinterpret_cast<float2 *>(smem_raw);
   uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw + (size_t)N * sizeof(float2));  // NW words
+  float2 *s_tw = reinterpret_cast<float2 *>(mask + NW);  // TwTables<LOG2N>::TOTAL inverse-pass twiddles
   __shared__ double s_thr[NB];
   __shared__ unsigned int s_wtot[NWARP];
   __shared__ unsigned int s_base;
 
   const int tid = threadIdx.x;
+  TwTables<LOG2N>::template load<NT>(s_tw, tid);  // used after the barriers below
   const int spi = (int)direct_list[blockIdx.x];
   const SpDesc sp = sps[spi];
   const SlotMeta tm = ws.meta[sp.t_slot];
@@ -934,7 +972,7 @@ __global__ void __launch_bounds__(NT)
     buf[PH] = make_float2(tm.q_nyq, 0.f);
   }
   __syncthreads();
-  inverse_full<LOG2N, NT>(buf, ws.wn, tid);
+  inverse_full<LOG2N, NT>(buf, ws.wn, tid, s_tw);
 
   // xc[i] = Re x[(i + H) mod N] / N   (rescale + half rotation, CrossCorr.cc:493-505)
   const float scale = 1.0f / (float)N;
@@ -957,7 +995,9 @@ __global__ void __launch_bounds__(NT, 1)
   constexpr int LR = last_radix<LOG2N>();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *buf = reinterpret_cast<float2 *>(smem_raw);  // H complex: this CTA's half
+  float2 *s_tw = buf + H;                              // TwTables<LOG2N>::TOTAL inverse-pass twiddles
   const int tid = threadIdx.x, half = blockIdx.y, job = blockIdx.x;
+  TwTables<LOG2N>::template load<NT>(s_tw, tid);  // used after the barriers below
   const bool is_pair = job < n_pairs;
   const int spi = (int)(is_pair ? pair_list[job] : direct_list[job - n_pairs]);
   const SpDesc sp = sps[spi];
@@ -1031,7 +1071,7 @@ __global__ void __launch_bounds__(NT, 1)
     }
   }
   __syncthreads();
-  fft_inverse_halves<LOG2N, H, NT>(buf, tid);
+  fft_inverse_halves<LOG2N, H, NT>(buf, tid, s_tw);
   float2 *out = scratch + ((size_t)job * 2 + half) * H;
   for (int n = tid; n < H; n += NT) out[n] = buf[swz(n)];
 }
@@ -1348,7 +1388,7 @@ static cudaError_t xcorr_launch(const SpDesc *sps, const uint32_t *pair_list, in
     if (scratch == nullptr) return cudaErrorInvalidValue;
     const int jobs = n_pairs + n_direct;
     auto k1 = xcorr_half_kernel<LOG2N, NT>;
-    const size_t smem1 = (size_t)(N / 2) * 8;
+    const size_t smem1 = (size_t)(N / 2) * 8 + (size_t)TwTables<LOG2N>::TOTAL * 8;
     cudaError_t e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
     if (e != cudaSuccess) return e;
     k1<<<dim3(jobs, 2), NT, smem1, st>>>(pair_list, n_pairs, direct_list, sps, ws, scratch);
@@ -1361,7 +1401,7 @@ static cudaError_t xcorr_launch(const SpDesc *sps, const uint32_t *pair_list, in
                                                  cand_pool, pool_cap, cand_ref, ctr, xc_tap);
     return cudaGetLastError();
   } else {
-  const size_t smem = (size_t)N * 8 + (N / 32) * 4;
+  const size_t smem = (size_t)N * 8 + (N / 32) * 4 + (size_t)TwTables<LOG2N>::TOTAL * 8;
   if (n_pairs > 0) {
     auto k = xcorr_pair_kernel<LOG2N, NT>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

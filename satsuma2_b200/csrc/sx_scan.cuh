@@ -22,15 +22,16 @@
 //     word lies within those three, so the result is exact -- as straight-line code that computes only
 //     the planes that can influence it.  The pass words go to shared memory.
 //  C. runs of passing positions are the segments, exactly as the reference's sequential loop emits
-//     them.  Every run start (item, bit) is queued (slots from a warp scan); the queue is then worked
-//     off one run per lane: follow the run through the next items of the same diagonal (a word that
-//     is not an item has no passing position), then score the segment: popcounts over the planes, an
-//     FP32 pre-reject, the exact early reject and the reference's FP64 formula (score_counts).
+//     them.  Every run END (item, bit) is queued as soon as its item is evaluated (slots from a warp
+//     scan); the queue is worked off one run per lane: find the start of the run, going back through
+//     the previous items of the same diagonal if need be (a word that is not an item has no passing
+//     position), then score the segment: popcounts over the planes, an FP32 pre-reject, the exact early
+//     reject and the reference's FP64 formula (score_counts).
 #pragma once
 
 #define SX_SCAN_NT 128
 #define SX_SCAN_WARPS (SX_SCAN_NT / 32)
-#define SX_RUN_CAP 512  // runs (= segments) queued per warp and round: a batch of 32 items has at most 32 x 16
+#define SX_RUN_CAP 256  // run ends (= segments) queued per warp before they are worked off
 
 template <int LOG2N>
 struct ScanCfg {
@@ -39,7 +40,7 @@ struct ScanCfg {
   static constexpr int PW = NW + PAD + 2;                     // padded plane length (word NW + 1 is still readable)
   static constexpr int NBW = (NW + 31) / 32;                  // words of a lane's survivor bitset
   static constexpr int SPC = LOG2N <= 14 ? 2 : 1;             // strand-pairs per CTA
-  static constexpr int ITEM_CAP = NW > 512 ? NW : 512;        // items listed per round (>= the most one lane can have)
+  static constexpr int ITEM_CAP = NW > 384 ? NW : 384;        // items listed per round (>= the most one lane can have)
   static constexpr size_t WARP_BYTES = (size_t)SX_RUN_CAP * 4 + (size_t)NBW * 32 * 4 + (size_t)ITEM_CAP * 4 +
                                        (size_t)ITEM_CAP * 2 + 32 * 4;
   static constexpr size_t SMEM = (size_t)SPC * 4 * PW * 4 + SX_SCAN_WARPS * WARP_BYTES;
@@ -350,46 +351,53 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
 
     // Candidates are sorted by lag, so diagonal lengths rise and fall like a triangle.  Pairing the
     // k-th from the front with the k-th from the back keeps the 32 diagonals of a warp close in length.
-    // One queued run start (item i, bit s) -> its segment -> probability filter.  A run starts at the first
-    // passing position minus 45 ("lastStart = i - m_minLen", CrossCorr.cc:700) and ends at the first failing
-    // position or where the diagonal stops; it goes on through the next items of the same diagonal (a word
-    // that is no item has no passing position).
-    int n_round = 0;
-    auto do_run = [&](int i, int s_) {
+    // One queued run end (item i, position f in 0..32 of its word: the first failing position after the run,
+    // 32 = the run reaches the end of the word and the next word holds no passing position) -> its segment ->
+    // probability filter.  A run starts at its first passing position minus 45 ("lastStart = i - m_minLen",
+    // CrossCorr.cc:700); the start is in this word or, through words that pass everywhere, in an earlier item
+    // of the same diagonal.  The run ends at f or where the diagonal stops.
+    auto do_end = [&](int i, int f) {
       const uint32_t it = items[i], pass = passw[i];
       const Diag od = make_diag(s_shift[it & 31u], tlen, qlen);
       const int kb = (int)(it >> 5) * 32;
-      const uint32_t z = ~(pass >> s_);  // zeros shifted in at the top read as failing
-      const int run = z ? (__ffs(z) - 1) : 32;
-      int e = kb + s_ + run;
-      if (s_ + run == 32) {
-        int ni = i + 1;
-        uint32_t nit = it + 32u;
-        while (ni < n_round && items[ni] == nit) {
-          const uint32_t p2 = passw[ni];
-          if (p2 != 0xffffffffu) {
-            e += __ffs(~p2) - 1;
+      const int e = min(kb + f, od.L);
+      // highest failing position below f, if any, is right before the start
+      uint32_t below = ~pass & (f >= 32 ? 0xffffffffu : ((1u << f) - 1u));
+      int start_k;
+      if (below) {
+        start_k = kb + (32 - __clz(below));
+      } else {  // the run covers the word from bit 0: it began in an earlier item (or at bit 0 of this one)
+        int j = i - 1, back = kb;
+        uint32_t jt = it - 32u;
+        for (;;) {
+          if (j < 0 || items[j] != jt) {  // the previous word is no item: the run starts at this word's first bit
+            start_k = back;
             break;
           }
-          e += 32;
-          ni++;
-          nit += 32u;
+          const uint32_t pj = passw[j];
+          if (pj != 0xffffffffu) {
+            start_k = (pj >> 31) ? (back - __clz(~pj)) : back;
+            break;
+          }
+          back -= 32;
+          j--;
+          jt -= 32u;
         }
       }
-      e = min(e, od.L);
-      const int start_k = kb + s_ - 45;
+      start_k -= 45;
       const int start_t = od.i0 + start_k, seg_len = e - start_k;
       tap_segment(spi, start_t, od.shift, seg_len, seg_tap, seg_tap_cap, ctr);
       double prob, ident;
       if (score_fast(P, start_t, od.shift, seg_len, prm, prob, ident))
         emit_result(sp, start_t, od.shift, seg_len, prob, ident, res_pool, res_cap, ctr);
     };
-    // work off the queued run starts, one per lane (warp-collective)
+    // work off the queued run ends, one per lane (warp-collective); they only look back, so this may happen
+    // at any time
     auto flush_queue = [&]() {
       __syncwarp();
       for (int r = lane; r < (int)qn; r += 32) {
         const uint32_t rec = wq[r];
-        do_run((int)(rec & 0xffffu), (int)(rec >> 16));
+        do_end((int)(rec & 0xffffu), (int)(rec >> 16));
       }
       __syncwarp();
       qn = 0;
@@ -476,7 +484,7 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
       const unsigned int round_base = __shfl_sync(0xffffffffu, off_all, first);
       const unsigned int round_end =
           last < 32 ? __shfl_sync(0xffffffffu, off_all, last & 31) : total_items;
-      n_round = (int)(round_end - round_base);
+      const int n_round = (int)(round_end - round_base);
       if (mine) {
         unsigned int o = off_all - round_base;
         for (int w = 0; w < nbw; w++) {
@@ -489,43 +497,58 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
         }
       }
       __syncwarp();
-      // B2. exact pass words, one item per lane
+      // B2 + C1. exact pass words, one item per lane; every run end found is queued (slots from a warp scan)
+      uint32_t last_it = 0x80000000u, last_pass = 0u;  // item / pass word of the previous batch's last lane
       for (int i0 = 0; i0 < n_round; i0 += 32) {  // warp-uniform
         const int i = i0 + lane;
+        uint32_t it = 0x80000000u, pass = 0u, next_it = 0x80000000u;
         if (i < n_round) {
-          const uint32_t it = items[i];
+          it = items[i];
+          if (i + 1 < n_round) next_it = items[i + 1];
           const Diag od = make_diag(s_shift[it & 31u], tlen, qlen);
-          passw[i] = eval_word(P, od, (int)(it >> 5));
+          pass = eval_word(P, od, (int)(it >> 5));
+          passw[i] = pass;
         }
-      }
-      __syncwarp();
-      // C1. queue every run start of every item (slots from a warp scan); a full queue is worked off first
-      for (int i0 = 0; i0 < n_round; i0 += 32) {  // warp-uniform
-        const int i = i0 + lane;
-        uint32_t pass = 0, carry_in = 0;
-        if (i < n_round) {
-          const uint32_t it = items[i];
-          pass = passw[i];
-          if (i > 0 && items[i - 1] == it - 32u) carry_in = passw[i - 1] >> 31;  // same diagonal, previous word
+        // the previous item in list order: same diagonal and previous word -> its top bit carries into this word
+        uint32_t p_it = __shfl_up_sync(0xffffffffu, it, 1), p_pass = __shfl_up_sync(0xffffffffu, pass, 1);
+        if (lane == 0) {
+          p_it = last_it;
+          p_pass = last_pass;
         }
-        uint32_t rise = pass & ~((pass << 1) | carry_in);
-        const unsigned int mine_n = (unsigned int)__popc(rise);
+        last_it = __shfl_sync(0xffffffffu, it, 31);
+        last_pass = __shfl_sync(0xffffffffu, pass, 31);
+        const uint32_t carry_in = (p_it == it - 32u) ? (p_pass >> 31) : 0u;
+        uint32_t fall = ~pass & ((pass << 1) | carry_in);
+        // a run that reaches the end of the word ends there unless the next word is an item too
+        const bool edge = (pass >> 31) && next_it != it + 32u;
+        const unsigned int mine_n = (unsigned int)__popc(fall) + (edge ? 1u : 0u);
         unsigned int tot;
         unsigned int slot = warp_excl_scan(mine_n, &tot);
         if (tot != 0) {
           if (qn + tot > SX_RUN_CAP) flush_queue();
-          slot += qn;
-          qn += tot;
           my_segments += mine_n;
-          while (rise) {
-            const int s_ = __ffs(rise) - 1;
-            rise &= rise - 1u;
-            wq[slot++] = (uint32_t)i | ((uint32_t)s_ << 16);
+          if (tot > SX_RUN_CAP) {  // more run ends in one batch than the queue holds: done in place
+            __syncwarp();          // (passw of this batch is visible)
+            while (fall) {
+              const int f = __ffs(fall) - 1;
+              fall &= fall - 1u;
+              do_end(i, f);
+            }
+            if (edge) do_end(i, 32);
+          } else {
+            slot += qn;
+            qn += tot;
+            while (fall) {
+              const int f = __ffs(fall) - 1;
+              fall &= fall - 1u;
+              wq[slot++] = (uint32_t)i | ((uint32_t)f << 16);
+            }
+            if (edge) wq[slot++] = (uint32_t)i | (32u << 16);
           }
         }
         __syncwarp();
       }
-      flush_queue();  // C2. before the item list is reused
+      flush_queue();  // C2. before the item list is reused (the planes and `sp` of this group are still current)
       done_upto = round_end;
     }
   }
