@@ -4,8 +4,9 @@
 //        replaces CCSignal::SetSequence / ComputeEntropy / SeqToPCM (analysis/CrossCorr.cc:35-134,
 //        179-206), DNAVector::ReverseComplement (analysis/DNAVector.cc:482-521) and the forward
 //        FFTReal::do_fft calls of CrossCorrelation::DoOne (CrossCorr.cc:471-474)
-//   K2 xcorr_findtop_kernel   (c)+(d)  spectral product (+ reference quirk bins), channel sum,
-//        one inverse FFT, half rotation, RMS envelope, threshold, ordered compaction
+//   K2 xcorr_pair_kernel (both strands of a chunk pair from the forward query spectrum) /
+//      xcorr_findtop_kernel (one strand-pair)   (c)+(d)  spectral product (+ reference quirk bins),
+//        channel sum, one inverse FFT, half rotation, RMS envelope, threshold, ordered compaction
 //        replaces CrossCorrelation::DoOne / CrossCorrelate (CrossCorr.cc:386-507) and
 //        SeqAnalyzer::FindTop (CrossCorr.cc:878-944)
 //   K3 scan_score_kernel[_generic] (e)  diagonal sliding-window scan + match probability
@@ -13,6 +14,9 @@
 //        GetMatchProbabilityEx (analysis/AlignProbability.cc:62-127), ProbTable lookup
 //        (analysis/ProbTable.cc:58-74, 105-140) and the filter of FilterMatches
 //        (analysis/HomologyByXCorrSlave.cc:168-219)
+//
+//   N = 32768 (more complex points than one CTA's shared memory holds): encode_fft_half_kernel,
+//        xcorr_half_kernel + combine_findtop_kernel -- two CTAs per transform, one per half of the radix-2 split
 //
 // No tensor cores (nothing here is a dense contraction), no cuFFT, no CPU fallback.
 #include "sx_kernels.h"
