@@ -253,15 +253,15 @@ class XCorrEngine:
         _check(rc)
         return out[: n.value]
 
-    def align_blocks(self, blocks: Iterable[tuple], cap_hint: int = 0) -> np.ndarray:
+    def align_blocks(self, blocks: Iterable[tuple], cap_hint: int = 0, out: np.ndarray = None) -> np.ndarray:
         """blocks: (target_from, target_to, query_from, query_to, fast) with inclusive ranges (t_pair)."""
         arr = np.zeros(len(blocks), dtype=PAIR_DTYPE)
         for i, b in enumerate(blocks):
             arr[i]["target_from"], arr[i]["target_to"], arr[i]["query_from"], arr[i]["query_to"] = b[:4]
             arr[i]["fast"] = 1 if (len(b) > 4 and b[4]) else 0
         return self._collect(
-            lambda out, cap, n: self._L.sx_align_blocks(self._h, arr.ctypes.data, len(arr), out.ctypes.data, cap,
-                                                        C.byref(n)), cap_hint or 1 << 16)
+            lambda o, cap, n: self._L.sx_align_blocks(self._h, arr.ctypes.data, len(arr), o.ctypes.data, cap,
+                                                      C.byref(n)), cap_hint or 1 << 16, out)
 
     def align_pairs(self, pairs, fast: bool = False, cap_hint: int = 0, out: np.ndarray = None) -> np.ndarray:
         p = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)

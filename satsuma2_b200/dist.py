@@ -23,6 +23,20 @@ def shard_range(n_total: int, rank: int, world: int):
     return lo, min(n_total, lo + per)
 
 
+def shard_blocks_by_target(blocks, n_targets: int, rank: int, world: int):
+    """Block mode: every rank owns a contiguous range of target chunks -- and keeps the spectra of
+    exactly those resident in HBM -- so a t_pair block (tFrom, tTo, qFrom, qTo, fast), inclusive ranges, is clipped
+    to the rank's range; blocks that straddle a boundary are split between the neighbours.  The union over the
+    ranks is the original work list, pair for pair, without duplicates."""
+    lo, hi = shard_range(n_targets, rank, world)
+    out = []
+    for b in blocks:
+        t0, t1 = max(int(b[0]), lo), min(int(b[1]), hi - 1)
+        if t0 <= t1:
+            out.append((t0, t1, int(b[2]), int(b[3]), int(b[4]) if len(b) > 4 else 0))
+    return out
+
+
 class Group:
     """Thin wrapper: no-ops when world == 1."""
 

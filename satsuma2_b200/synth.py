@@ -102,3 +102,31 @@ def chunk_sequence(seq: np.ndarray, size: int, overlap: int, seq_id: int = 0):
         if lens[j] and np.all((c == ord("N")) | (c == ord("X"))):
             lens[j] = 0
     return starts.astype(np.int64), lens, starts.astype(np.int32)
+
+
+def genome_pair(length: int, seed: int = 11, divergence: float = 0.12, inversions: int = 4):
+    """config 4: a random target genome and a query that is a diverged copy of it with a few inverted
+    (reverse-complemented) stretches -- syntenic along the main diagonal.  -> (target, query) uint8 ASCII."""
+    rng = np.random.default_rng(seed)
+    t = rng.integers(0, 4, size=length, dtype=np.uint8)
+    q = t.copy()
+    mut = rng.random(length) < divergence
+    q[mut] = (q[mut] + rng.integers(1, 4, size=int(mut.sum()), dtype=np.uint8)) & 3
+    for _ in range(inversions):
+        n = int(rng.integers(length // 50, length // 20))
+        a = int(rng.integers(0, length - n))
+        q[a:a + n] = 3 - q[a:a + n][::-1]
+    return _ASCII[t], _ASCII[q]
+
+
+def diagonal_blocks(n_target_chunks: int, n_query_chunks: int, t_stride: int, q_stride: int, pixel: int = 24):
+    """t_pair blocks of pixel x pixel chunks along the syntenic diagonal, the way GridSearch issues them
+    (analysis/GridSearch.cc): query chunks [qb, qb + pixel) against the target chunks that cover the same bases."""
+    blocks = []
+    for qb in range(0, n_query_chunks, pixel):
+        q_hi = min(n_query_chunks - 1, qb + pixel - 1)
+        t_lo = max(0, (qb * q_stride) // t_stride - 1)
+        t_hi = min(n_target_chunks - 1, t_lo + pixel - 1)
+        if t_lo <= t_hi:
+            blocks.append((t_lo, t_hi, qb, q_hi, 0))
+    return blocks

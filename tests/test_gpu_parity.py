@@ -458,6 +458,36 @@ def test_grid_blocks_with_cached_target_spectra(sx, oracle_lib):
     assert len(listed) <= 2, listed
 
 
+def test_target_range_sharding_gives_the_same_matches(sx):
+    """config 4, multi-GPU rule: the block list clipped to per-rank target ranges (each rank caching only its
+    targets' spectra) yields, taken together, exactly the records of the unsharded run."""
+    from satsuma2_b200 import synth
+    from satsuma2_b200.dist import shard_blocks_by_target
+
+    tgt, qry = synth.genome_pair(300000, seed=5)
+    tcs, T = _genome_chunks(sx, tgt, 4096, 1024)
+    qcs, Q = _genome_chunks(sx, qry, 4096, 0)
+    blocks = synth.diagonal_blocks(len(T), len(Q), 3072, 4096, pixel=12)
+
+    def run(bl):
+        with sx.XCorrEngine(target_total=float(len(tgt))) as eng:
+            eng.set_targets(tcs)
+            eng.set_queries(qcs)
+            r = eng.align_blocks(bl)
+            return sorted((rec_key(x), float(x["prob"]), float(x["ident"])) for x in r), eng.stats()
+
+    whole, st = run(blocks)
+    assert len(whole) > 100 and any(k[0][6] for k in whole)
+    # cached target spectra: every target chunk is encoded once although it meets ~12 queries
+    n_pairs = sum((b[1] - b[0] + 1) * (b[3] - b[2] + 1) for b in blocks)
+    assert st["chunk_pairs"] == n_pairs and st["signals"] < 0.25 * n_pairs
+    for world in (2, 3):
+        parts = []
+        for rank in range(world):
+            parts += run(shard_blocks_by_target(blocks, len(T), rank, world))[0]
+        assert sorted(parts) == whole
+
+
 def test_pool_overflow_grows_and_retries(sx):
     """Device pools (candidates, records) that are too small are grown and the affected
     kernels re-run: nothing is truncated, the result set is the one a roomy engine returns."""

@@ -75,6 +75,29 @@ def test_shard_helpers():
     assert len({shard_seed(1, r) for r in range(8)}) == 8
 
 
+def test_block_sharding_by_target_range_partitions_the_work_list():
+    """Block mode: the t_pair work list clipped to per-rank target ranges covers every chunk pair exactly once."""
+    from satsuma2_b200 import synth
+    from satsuma2_b200.dist import shard_blocks_by_target
+
+    n_t, n_q = 431, 330
+    blocks = synth.diagonal_blocks(n_t, n_q, 3072, 4096, pixel=24)
+    assert len(blocks) == 14
+
+    def pairs(bl):
+        return [(t, q) for b in bl for q in range(b[2], b[3] + 1) for t in range(b[0], b[1] + 1)]
+
+    want = sorted(pairs(blocks))
+    for world in (1, 2, 4, 8):
+        got = []
+        for rank in range(world):
+            mine = shard_blocks_by_target(blocks, n_t, rank, world)
+            lo = (n_t + world - 1) // world * rank
+            assert all(lo <= b[0] <= b[1] < lo + (n_t + world - 1) // world for b in mine)
+            got += pairs(mine)
+        assert sorted(got) == want and len(set(got)) == len(got)
+
+
 def test_synth_generator_is_deterministic_and_plants_segments():
     from satsuma2_b200 import synth
 
