@@ -47,16 +47,17 @@ struct ScanCfg {
 };
 
 struct PlanePtrs {
-  const uint32_t *tlo, *thi, *qlo, *qhi;  // each readable from word -2 to word NW+1 (zero padded)
+  const uint2 *t, *q;  // plane words {lo, hi} of the target / query chunk, readable from word -2 to word NW+1 (zero padded)
 };
 
 // 32 positions of both sequences starting at target bit tw*32+tsh / query bit qw*32+qsh
 __device__ __forceinline__ void diag_words(const PlanePtrs &P, int tw, int tsh, int qw, int qsh, uint32_t &tl,
                                            uint32_t &th, uint32_t &ql, uint32_t &qh) {
-  tl = __funnelshift_r(P.tlo[tw], P.tlo[tw + 1], tsh);
-  th = __funnelshift_r(P.thi[tw], P.thi[tw + 1], tsh);
-  ql = __funnelshift_r(P.qlo[qw], P.qlo[qw + 1], qsh);
-  qh = __funnelshift_r(P.qhi[qw], P.qhi[qw + 1], qsh);
+  const uint2 t0 = P.t[tw], t1 = P.t[tw + 1], q0 = P.q[qw], q1 = P.q[qw + 1];
+  tl = __funnelshift_r(t0.x, t1.x, tsh);
+  th = __funnelshift_r(t0.y, t1.y, tsh);
+  ql = __funnelshift_r(q0.x, q1.x, qsh);
+  qh = __funnelshift_r(q0.y, q1.y, qsh);
 }
 
 // Counts over one segment [start_t, start_t+len) on lag `shift`, then the probability filter.
@@ -225,19 +226,16 @@ __device__ __forceinline__ unsigned int warp_excl_scan(unsigned int v, unsigned 
 // words of every plane, then only the count planes that can reach the result: word kw-2 feeds windows 2 / 4
 // (their top bits), word kw-1 windows 2 .. 16.
 __device__ __forceinline__ uint32_t eval_word(const PlanePtrs &P, const Diag &d, int kw) {
-  const uint32_t *tl = P.tlo + d.tw0 + kw - 2, *th = P.thi + d.tw0 + kw - 2;
-  const uint32_t *ql = P.qlo + d.qw0 + kw - 2, *qh = P.qhi + d.qw0 + kw - 2;
-  const uint32_t a0 = tl[0], a1 = tl[1], a2 = tl[2], a3 = tl[3];
-  const uint32_t b0 = th[0], b1 = th[1], b2 = th[2], b3 = th[3];
-  const uint32_t c0 = ql[0], c1 = ql[1], c2 = ql[2], c3 = ql[3];
-  const uint32_t e0 = qh[0], e1 = qh[1], e2 = qh[2], e3 = qh[3];
+  const uint2 *tp = P.t + d.tw0 + kw - 2, *qp = P.q + d.qw0 + kw - 2;
+  const uint2 t0 = tp[0], t1 = tp[1], t2 = tp[2], t3 = tp[3];
+  const uint2 q0 = qp[0], q1 = qp[1], q2 = qp[2], q3 = qp[3];
   const int ts = d.tsh, qs = d.qsh;
-  uint32_t mA = ~((__funnelshift_r(a0, a1, ts) ^ __funnelshift_r(c0, c1, qs)) |
-                  (__funnelshift_r(b0, b1, ts) ^ __funnelshift_r(e0, e1, qs)));
-  uint32_t mB = ~((__funnelshift_r(a1, a2, ts) ^ __funnelshift_r(c1, c2, qs)) |
-                  (__funnelshift_r(b1, b2, ts) ^ __funnelshift_r(e1, e2, qs)));
-  uint32_t mC = ~((__funnelshift_r(a2, a3, ts) ^ __funnelshift_r(c2, c3, qs)) |
-                  (__funnelshift_r(b2, b3, ts) ^ __funnelshift_r(e2, e3, qs)));
+  uint32_t mA = ~((__funnelshift_r(t0.x, t1.x, ts) ^ __funnelshift_r(q0.x, q1.x, qs)) |
+                  (__funnelshift_r(t0.y, t1.y, ts) ^ __funnelshift_r(q0.y, q1.y, qs)));
+  uint32_t mB = ~((__funnelshift_r(t1.x, t2.x, ts) ^ __funnelshift_r(q1.x, q2.x, qs)) |
+                  (__funnelshift_r(t1.y, t2.y, ts) ^ __funnelshift_r(q1.y, q2.y, qs)));
+  uint32_t mC = ~((__funnelshift_r(t2.x, t3.x, ts) ^ __funnelshift_r(q2.x, q3.x, qs)) |
+                  (__funnelshift_r(t2.y, t3.y, ts) ^ __funnelshift_r(q2.y, q3.y, qs)));
   if (kw < 2) mA = 0u;  // before the diagonal starts
   if (kw < 1) mB = 0u;
   if (kw == d.nwords - 1) mC &= d.lastmask;
@@ -270,7 +268,7 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
   constexpr int N = 1 << LOG2N, H = N / 2, NW = C::NW, PW = C::PW, NBW = C::NBW, SPC = C::SPC, PAD = C::PAD;
   constexpr int ITEM_CAP = C::ITEM_CAP;
   extern __shared__ __align__(16) unsigned char scan_smem[];
-  uint32_t *s_planes = reinterpret_cast<uint32_t *>(scan_smem);  // [SPC][tlo, thi, qlo, qhi][PW]
+  uint2 *s_planes = reinterpret_cast<uint2 *>(scan_smem);  // [SPC][target, query][PW] plane words {lo, hi}
   __shared__ unsigned int s_next;
   __shared__ int s_ncand[SPC];
 
@@ -311,14 +309,12 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
     const SpDesc sp = sps[sp0 + j];
     const uint32_t *tp = ws.planes + (size_t)sp.t_slot * 2 * NW;
     const uint32_t *qp = ws.planes + (size_t)sp.q_slot * 2 * NW;
-    uint32_t *pl = s_planes + (size_t)j * 4 * PW;
+    uint2 *pl = s_planes + (size_t)j * 2 * PW;
     for (int i = tid; i < PW; i += SX_SCAN_NT) {
       const int w = i - PAD;
       const bool in = w >= 0 && w < NW;
-      pl[i] = in ? __ldg(tp + w) : 0u;
-      pl[PW + i] = in ? __ldg(tp + NW + w) : 0u;
-      pl[2 * PW + i] = in ? __ldg(qp + w) : 0u;
-      pl[3 * PW + i] = in ? __ldg(qp + NW + w) : 0u;
+      pl[i] = in ? make_uint2(__ldg(tp + w), __ldg(tp + NW + w)) : make_uint2(0u, 0u);
+      pl[PW + i] = in ? make_uint2(__ldg(qp + w), __ldg(qp + NW + w)) : make_uint2(0u, 0u);
     }
   }
   __syncthreads();
@@ -344,10 +340,8 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
     const uint2 cref = cand_ref[spi];
     const int tlen = ws.meta[sp.t_slot].len, qlen = ws.meta[sp.q_slot].len;
     PlanePtrs P;
-    P.tlo = s_planes + (size_t)j * 4 * PW + PAD;
-    P.thi = P.tlo + PW;
-    P.qlo = P.thi + PW;
-    P.qhi = P.qlo + PW;
+    P.t = s_planes + (size_t)j * 2 * PW + PAD;
+    P.q = P.t + PW;
 
     // Candidates are sorted by lag, so diagonal lengths rise and fall like a triangle.  Pairing the
     // k-th from the front with the k-th from the back keeps the 32 diagonals of a warp close in length.
@@ -428,39 +422,52 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
       int pp_all = 0, pp_ge3 = 0, pp_ge11 = 0;  // of m[kw-1]
       int p2_ge19 = 0, p2_ge27 = 0;             // of m[kw-2]
       int q_ge19 = 0, q_ge27 = 0;               // of m[kw-1], become p2_* next step
-      const uint32_t *ptl = P.tlo + d.tw0, *pth = P.thi + d.tw0, *pql = P.qlo + d.qw0, *pqh = P.qhi + d.qw0;
-      uint32_t rtl = ptl[0], rth = pth[0], rql = pql[0], rqh = pqh[0];
-      int rem = d.L;  // positions of the diagonal at and after word kw
-      for (int w = 0; w < nbw; w++) {  // warp-uniform
-        uint32_t acc = 0, bit = 1u;
-        const int kw_end = min(nw_max, w * 32 + 32);
-#pragma unroll 2
-        for (int kw = w * 32; kw < kw_end; kw++) {  // warp-uniform trip count
-          const int kn = min(kw + 1, d.nwords);  // a shorter diagonal idles and must not read past its planes
-          const uint32_t ntl = ptl[kn], nth = pth[kn], nql = pql[kn], nqh = pqh[kn];
-          const uint32_t tl = __funnelshift_r(rtl, ntl, d.tsh), th = __funnelshift_r(rth, nth, d.tsh);
-          const uint32_t ql = __funnelshift_r(rql, nql, d.qsh), qh = __funnelshift_r(rqh, nqh, d.qsh);
-          rtl = ntl; rth = nth; rql = nql; rqh = nqh;
-          // the diagonal's last word is partial, words after it are empty
-          const uint32_t vm = rem >= 32 ? 0xffffffffu : (rem > 0 ? d.lastmask : 0u);
-          const uint32_t m = ~((tl ^ ql) | (th ^ qh)) & vm;
-          const int c_all = __popc(m), c_lo8 = __popc(m & 0xffu), c_lo16 = __popc(m & 0xffffu),
-                    c_lo24 = __popc(m & 0xffffffu);
-          const int u0 = p2_ge19 + pp_all + c_lo8;
-          const int u1 = p2_ge27 + pp_all + c_lo16;
-          const int u2 = pp_ge3 + c_lo24;
-          const int u3 = pp_ge11 + c_all;
-          if (rem > 0 && max(max(u0, u1), max(u2, u3)) >= 19) acc |= bit;
-          bit <<= 1;
-          rem -= 32;
-          p2_ge19 = q_ge19;
-          p2_ge27 = q_ge27;
-          pp_all = c_all;
-          pp_ge3 = __popc(m >> 3);
-          pp_ge11 = __popc(m >> 11);
-          q_ge19 = __popc(m >> 19);
-          q_ge27 = __popc(m >> 27);
+      const uint2 *pt = P.t + d.tw0, *pq = P.q + d.qw0;
+      uint2 rt = pt[0], rq = pq[0];
+      uint32_t acc = 0, bit = 1u;
+      // one word: FULL = every lane's diagonal covers the whole word (no masking, no clamping)
+      auto step = [&](int kw, bool full) {
+        const int kn = full ? kw + 1 : min(kw + 1, d.nwords);  // a shorter diagonal idles, never reads past its planes
+        const uint2 nt = pt[kn], nq = pq[kn];
+        const uint32_t tl = __funnelshift_r(rt.x, nt.x, d.tsh), th = __funnelshift_r(rt.y, nt.y, d.tsh);
+        const uint32_t ql = __funnelshift_r(rq.x, nq.x, d.qsh), qh = __funnelshift_r(rq.y, nq.y, d.qsh);
+        rt = nt;
+        rq = nq;
+        uint32_t m = ~((tl ^ ql) | (th ^ qh));
+        bool inside = true;
+        if (!full) {  // the diagonal's last word is partial, words after it are empty
+          inside = kw < d.nwords;
+          m &= kw < d.nwords - 1 ? 0xffffffffu : (kw == d.nwords - 1 ? d.lastmask : 0u);
         }
+        const int c_all = __popc(m), c_lo8 = __popc(m & 0xffu), c_lo16 = __popc(m & 0xffffu),
+                  c_lo24 = __popc(m & 0xffffffu);
+        const int u0 = p2_ge19 + pp_all + c_lo8;
+        const int u1 = p2_ge27 + pp_all + c_lo16;
+        const int u2 = pp_ge3 + c_lo24;
+        const int u3 = pp_ge11 + c_all;
+        if (inside && max(max(u0, u1), max(u2, u3)) >= 19) acc |= bit;
+        bit <<= 1;
+        p2_ge19 = q_ge19;
+        p2_ge27 = q_ge27;
+        pp_all = c_all;
+        pp_ge3 = __popc(m >> 3);
+        pp_ge11 = __popc(m >> 11);
+        q_ge19 = __popc(m >> 19);
+        q_ge27 = __popc(m >> 27);
+      };
+      // words [0, nw_full) are full on every diagonal of the group (empty lanes do not count: their bits are dropped)
+      const bool live = d.nwords > 0;
+      const int nw_full = min(__reduce_min_sync(0xffffffffu, live ? d.nwords - 1 : 0x7fffffff), nw_max);
+      for (int w = 0; w < nbw; w++) {  // warp-uniform
+        acc = 0;
+        bit = 1u;
+        const int kw_end = min(nw_max, w * 32 + 32), kw_full = max(w * 32, min(nw_full, kw_end));
+        int kw = w * 32;
+#pragma unroll 4
+        for (; kw < kw_full; kw++) step(kw, true);  // warp-uniform trip counts
+#pragma unroll 2
+        for (; kw < kw_end; kw++) step(kw, false);
+        if (!live) acc = 0;
         s_need[w][lane] = acc;
         n_items += __popc(acc);
       }
