@@ -541,6 +541,8 @@ static ScoreParams score_params(const sx_ctx *c) {
   p.min_len = c->cfg.min_len;
   p.use_table = (c->cfg.use_prob_table && c->have_table) ? 1 : 0;
   p.z_cut = c->z_cut;
+  p.run_cap = c->cfg.debug_small_pools ? 8 : 0;  // forces the scan kernel's queue-overflow paths
+  p.pad_ = 0;
   return p;
 }
 

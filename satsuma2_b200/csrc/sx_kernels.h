@@ -61,6 +61,8 @@ struct ScoreParams {
   int32_t min_len;
   int32_t use_table;
   double z_cut;  // early reject when the normalised deviation z exceeds this (+inf disables)
+  int32_t run_cap;  // test hook: run ends queued per warp in the scan kernel (0 = the built-in capacity)
+  int32_t pad_;
 };
 
 struct BatchCounters {  // device-side, zeroed per batch

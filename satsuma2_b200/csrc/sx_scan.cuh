@@ -40,7 +40,7 @@ struct ScanCfg {
   static constexpr int PW = NW + PAD + 2;                     // padded plane length (word NW + 1 is still readable)
   static constexpr int NBW = (NW + 31) / 32;                  // words of a lane's survivor bitset
   static constexpr int SPC = LOG2N <= 14 ? 2 : 1;             // strand-pairs per CTA
-  static constexpr int ITEM_CAP = NW > 384 ? NW : 384;        // items listed per round (>= the most one lane can have)
+  static constexpr int ITEM_CAP = NW > 512 ? NW : 512;        // items listed per round (>= the most one lane can have)
   static constexpr size_t WARP_BYTES = (size_t)SX_RUN_CAP * 4 + (size_t)NBW * 32 * 4 + (size_t)ITEM_CAP * 4 +
                                        (size_t)ITEM_CAP * 2 + 32 * 4;
   static constexpr size_t SMEM = (size_t)SPC * 4 * PW * 4 + SX_SCAN_WARPS * WARP_BYTES;
@@ -321,7 +321,8 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
 
   unsigned int my_segments = 0;
   unsigned long long my_positions = 0;
-  unsigned int qn = 0;  // segments in this warp's queue (warp-uniform)
+  unsigned int qn = 0;  // run ends in this warp's queue (warp-uniform)
+  const unsigned int run_cap = prm.run_cap > 0 ? min((unsigned int)prm.run_cap, (unsigned int)SX_RUN_CAP) : SX_RUN_CAP;
   for (;;) {  // groups of 32 candidate lags, handed out dynamically
     unsigned int g = 0;
     if (lane == 0) g = atomicAdd(&s_next, 1u);
@@ -532,9 +533,9 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
         unsigned int tot;
         unsigned int slot = warp_excl_scan(mine_n, &tot);
         if (tot != 0) {
-          if (qn + tot > SX_RUN_CAP) flush_queue();
+          if (qn + tot > run_cap) flush_queue();
           my_segments += mine_n;
-          if (tot > SX_RUN_CAP) {  // more run ends in one batch than the queue holds: done in place
+          if (tot > run_cap) {  // more run ends in one batch than the queue holds: done in place
             __syncwarp();          // (passw of this batch is visible)
             while (fall) {
               const int f = __ffs(fall) - 1;
