@@ -488,6 +488,51 @@ def test_target_range_sharding_gives_the_same_matches(sx):
         assert sorted(parts) == whole
 
 
+def test_guide_mode_style_short_chunk_pairs(sx, oracle_lib):
+    """The refinement pass of the reference (`HomologyByXCorr -guide`, tools/analysis/HomologyByXCorr.cc:206-330,
+    714-717, 786-790) runs the same path on many SHORT chunks: the gaps between chained matches cut into pieces
+    with 32-base laps (flat entropy weights below 1024 bases), chunk i compared with chunks j, |i - j| <= 3, and
+    targetSize = t_chunk.  Through the C ABI that is an explicit pair list over ragged chunk lists."""
+    from satsuma2_b200 import synth
+
+    rng = np.random.default_rng(9)
+    tgt, qry = synth.genome_pair(120000, seed=9, divergence=0.10, inversions=0)
+    tl, ql = [], []
+    pos = 0
+    while pos < len(tgt) - 5000 and len(tl) < 40:
+        gap_t, gap_q = int(rng.integers(20, 3000)), 0
+        gap_q = max(20, gap_t + int(rng.integers(-15, 16)))
+        tl.append((tgt[pos:pos + gap_t + 32].tobytes(), pos, 0, len(tgt)))
+        ql.append((qry[pos:pos + gap_q + 32].tobytes(), pos, 0, len(qry)))
+        pos += gap_t
+    n = len(tl)
+    pairs = [(i, j) for i in range(n) for j in range(max(0, i - 3), min(n, i + 4))]
+    listed = []
+    with sx.XCorrEngine(target_total=4096.0, cutoff=1.2) as eng:
+        eng.set_targets(sx.ChunkSet.from_list(tl))
+        eng.set_queries(sx.ChunkSet.from_list(ql))
+        got = eng.align_pairs(pairs)
+    params = oracle_lib.make_params(target_total=4096.0, cutoff=1.2)
+    exp = oracle_lib.align_pairs(params, tl, ql, pairs, threads=os.cpu_count() or 1)
+    assert len(exp) > 30
+    if sorted(map(rec_key, got)) != sorted(map(rec_key, exp)):
+        with sx.XCorrEngine(target_total=4096.0, cutoff=1.2) as eng:
+            eng.set_targets(sx.ChunkSet.from_list(tl))
+            eng.set_queries(sx.ChunkSet.from_list(ql))
+            for (t, q) in pairs:
+                gp = eng.align_pairs([(t, q)])
+                ep = oracle_lib.align_pairs(params, tl, ql, [(t, q)])
+                compare_pair_records(oracle_lib, gp, ep, tl[t][0], ql[q][0], tl[t][1], ql[q][1], len(qry), 4096, N, 1.2,
+                                     0.99, 4096.0, listed)
+    ge = {rec_key(r): r for r in got}
+    for r in exp:
+        if rec_key(r) in ge:
+            assert ge[rec_key(r)]["ident"] == r["ident"]
+            assert abs(ge[rec_key(r)]["prob"] - r["prob"]) <= 1e-6 * abs(r["prob"])
+    _log_listed("guide_mode_style", listed)
+    assert len(listed) <= 3, listed
+
+
 def test_pool_overflow_grows_and_retries(sx):
     """Device pools (candidates, records) that are too small are grown and the affected
     kernels re-run: nothing is truncated, the result set is the one a roomy engine returns."""
