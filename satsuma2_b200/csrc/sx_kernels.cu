@@ -441,7 +441,7 @@ __device__ __forceinline__ int encode_prepare(const SigDesc &sd, const Slots &ws
 template <int LOG2N, int NT>
 __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
     encode_fft_kernel(const SigDesc *__restrict__ sigs, Slots ws, float *__restrict__ tap) {
-  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, WIN = N / 512, NWARP = NT / 32;
+  constexpr int N = 1 << LOG2N, H = N / 2, WIN = N / 512, NWARP = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *buf = reinterpret_cast<float2 *>(smem_raw);            // N complex (swizzled slots)
   uint8_t *sb = smem_raw + (size_t)N * sizeof(float2);            // N oriented bases
@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(NT, 1)
 // RMS envelope per 256 lags (float square, double accumulate), threshold env*cutoff + 1, ballot
 // mask, block scan, ordered compaction into the candidate pool (one atomic per strand-pair).
 template <int LOG2N, int NT, class XcAt>
-__device__ __forceinline__ void findtop_impl(XcAt xc_at, double co, uint32_t *mask, double *s_thr,
+__device__ __forceinline__ void findtop_impl(XcAt xc_at, double co, uint32_t *mask,
                                              unsigned int *s_wtot, unsigned int *s_base, int spi,
                                              uint16_t *__restrict__ cand_pool, unsigned int pool_cap,
                                              uint2 *__restrict__ cand_ref, BatchCounters *ctr,
@@ -705,24 +705,23 @@ __device__ __forceinline__ void findtop_impl(XcAt xc_at, double co, uint32_t *ma
     float *o = xc_tap + (size_t)spi * N;
     for (int i = tid; i < N; i += NT) o[i] = xc_at(i);
   }
+  // one warp per block of 256 lags: its 8 values per lane stay in registers between the envelope and the
+  // threshold test (every lane gets the block sum from the butterfly reduction)
   for (int b = warp; b < NB; b += NWARP) {
+    float v[8];
     double acc = 0.;
-    if (NB > 8) {
 #pragma unroll
-      for (int r = 0; r < 8; r++) {
-        const float v = xc_at(b * 256 + r * 32 + lane);
-        acc += (double)__fmul_rn(v, v);
-      }
-      acc = warp_sum(acc);
+    for (int r = 0; r < 8; r++) {
+      v[r] = xc_at(b * 256 + r * 32 + lane);
+      if (NB > 8) acc += (double)__fmul_rn(v[r], v[r]);
     }
-    if (lane == 0) s_thr[b] = __dadd_rn(__dmul_rn(__dsqrt_rn(__ddiv_rn(acc, 256.0)), co), 1.0);
-  }
-  __syncthreads();
-  for (int w = warp; w < NW; w += NWARP) {
-    const int i = w * 32 + lane;
-    const bool hit = (double)xc_at(i) > s_thr[i >> 8];
-    const uint32_t m = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) mask[w] = m;
+    if (NB > 8) acc = warp_sum(acc);
+    const double thr = __dadd_rn(__dmul_rn(__dsqrt_rn(__ddiv_rn(acc, 256.0)), co), 1.0);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const uint32_t m = __ballot_sync(0xffffffffu, (double)v[r] > thr);
+      if (lane == 0) mask[b * 8 + r] = m;
+    }
   }
   __syncthreads();
   // ---- ordered compaction: exclusive scan of per-word popcounts -----------------------------------
@@ -780,13 +779,13 @@ __device__ __forceinline__ void findtop_impl(XcAt xc_at, double co, uint32_t *ma
       }
     }
   }
-  __syncthreads();  // mask / s_thr / s_base are reused by the next strand
+  __syncthreads();  // mask / s_base are reused by the next strand
 }
 
 // FindTop over component COMP of a swizzled complex buffer holding the unscaled inverse transform
 template <int LOG2N, int NT, int COMP>
 __device__ __forceinline__ void findtop(const float2 *buf, int off, float scale, double co, uint32_t *mask,
-                                        double *s_thr, unsigned int *s_wtot, unsigned int *s_base, int spi,
+                                        unsigned int *s_wtot, unsigned int *s_base, int spi,
                                         uint16_t *__restrict__ cand_pool, unsigned int pool_cap,
                                         uint2 *__restrict__ cand_ref, BatchCounters *ctr, float *__restrict__ xc_tap) {
   constexpr int N = 1 << LOG2N;
@@ -794,7 +793,7 @@ __device__ __forceinline__ void findtop(const float2 *buf, int off, float scale,
     const float2 v = buf[swz((i + off) & (N - 1))];
     return (COMP ? v.y : v.x) * scale;
   };
-  findtop_impl<LOG2N, NT>(xc_at, co, mask, s_thr, s_wtot, s_base, spi, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
+  findtop_impl<LOG2N, NT>(xc_at, co, mask, s_wtot, s_base, spi, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
 }
 
 // the two H-point inverses, then the radix-2 combine x[n] = e[n] + w_N^{-n} o[n], x[n+H] = e[n] - w_N^{-n} o[n]
@@ -817,13 +816,12 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
     xcorr_pair_kernel(const uint32_t *__restrict__ pair_list, const SpDesc *__restrict__ sps, Slots ws, double cutoff,
                       double cutoff_fast, uint16_t *__restrict__ cand_pool, unsigned int pool_cap,
                       uint2 *__restrict__ cand_ref, BatchCounters *ctr, float *__restrict__ xc_tap) {
-  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, NB = N / 256, NWARP = NT / 32;
+  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, NWARP = NT / 32;
   constexpr int LR = last_radix<LOG2N>();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *buf = reinterpret_cast<float2 *>(smem_raw);
   uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw + (size_t)N * sizeof(float2));  // NW words
   float2 *s_tw = reinterpret_cast<float2 *>(mask + NW);  // TwTables<LOG2N>::TOTAL inverse-pass twiddles
-  __shared__ double s_thr[NB];
   __shared__ unsigned int s_wtot[NWARP];
   __shared__ unsigned int s_base;
 
@@ -924,8 +922,8 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
   // xc[i] = x[(i + H) mod N] / N (rescale + half rotation, CrossCorr.cc:493-505); the factor 2 above
   const float scale = 0.5f / (float)N;
   const double co = (sp.flags & SP_FAST) ? cutoff_fast : cutoff;
-  findtop<LOG2N, NT, 0>(buf, H, scale, co, mask, s_thr, s_wtot, &s_base, spi, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
-  findtop<LOG2N, NT, 1>(buf, (H - (qlen - 1)) & (N - 1), scale, co, mask, s_thr, s_wtot, &s_base, spi + 1, cand_pool,
+  findtop<LOG2N, NT, 0>(buf, H, scale, co, mask, s_wtot, &s_base, spi, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
+  findtop<LOG2N, NT, 1>(buf, (H - (qlen - 1)) & (N - 1), scale, co, mask, s_wtot, &s_base, spi + 1, cand_pool,
                         pool_cap, cand_ref, ctr, xc_tap);
 }
 
@@ -934,12 +932,11 @@ __global__ void __launch_bounds__(NT)
     xcorr_findtop_kernel(const uint32_t *__restrict__ direct_list, const SpDesc *__restrict__ sps, Slots ws,
                          double cutoff, double cutoff_fast, uint16_t *__restrict__ cand_pool, unsigned int pool_cap,
                          uint2 *__restrict__ cand_ref, BatchCounters *ctr, float *__restrict__ xc_tap) {
-  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, NB = N / 256, NWARP = NT / 32;
+  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, NWARP = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *buf = reinterpret_cast<float2 *>(smem_raw);
   uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw + (size_t)N * sizeof(float2));  // NW words
   float2 *s_tw = reinterpret_cast<float2 *>(mask + NW);  // TwTables<LOG2N>::TOTAL inverse-pass twiddles
-  __shared__ double s_thr[NB];
   __shared__ unsigned int s_wtot[NWARP];
   __shared__ unsigned int s_base;
 
@@ -981,7 +978,7 @@ __global__ void __launch_bounds__(NT)
   // xc[i] = Re x[(i + H) mod N] / N   (rescale + half rotation, CrossCorr.cc:493-505)
   const float scale = 1.0f / (float)N;
   const double co = (sp.flags & SP_FAST) ? cutoff_fast : cutoff;
-  findtop<LOG2N, NT, 0>(buf, H, scale, co, mask, s_thr, s_wtot, &s_base, spi, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
+  findtop<LOG2N, NT, 0>(buf, H, scale, co, mask, s_wtot, &s_base, spi, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
 }
 
 // ---- K2 for transforms that do not fit one CTA (N = 32768) ------------------------------------------
@@ -1086,11 +1083,10 @@ __global__ void __launch_bounds__(NT, 1)
                            const SpDesc *__restrict__ sps, Slots ws, const float2 *__restrict__ scratch, double cutoff,
                            double cutoff_fast, uint16_t *__restrict__ cand_pool, unsigned int pool_cap,
                            uint2 *__restrict__ cand_ref, BatchCounters *ctr, float *__restrict__ xc_tap) {
-  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, NB = N / 256, NWARP = NT / 32;
+  constexpr int N = 1 << LOG2N, H = N / 2, NB = N / 256, NWARP = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *xs = reinterpret_cast<float *>(smem_raw);                                       // N lags
   uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw + (size_t)N * sizeof(float));  // NW words
-  __shared__ double s_thr[NB];
   __shared__ unsigned int s_wtot[NWARP];
   __shared__ unsigned int s_base;
   const int tid = threadIdx.x, sj = blockIdx.x;
@@ -1122,7 +1118,7 @@ __global__ void __launch_bounds__(NT, 1)
   __syncthreads();
   const double co = (sp.flags & SP_FAST) ? cutoff_fast : cutoff;
   auto xc_at = [&](int i) -> float { return xs[i]; };
-  findtop_impl<LOG2N, NT>(xc_at, co, mask, s_thr, s_wtot, &s_base, spi, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
+  findtop_impl<LOG2N, NT>(xc_at, co, mask, s_wtot, &s_base, spi, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
 }
 
 // =================================================================================================
