@@ -1083,7 +1083,7 @@ __global__ void __launch_bounds__(NT, 1)
                            const SpDesc *__restrict__ sps, Slots ws, const float2 *__restrict__ scratch, double cutoff,
                            double cutoff_fast, uint16_t *__restrict__ cand_pool, unsigned int pool_cap,
                            uint2 *__restrict__ cand_ref, BatchCounters *ctr, float *__restrict__ xc_tap) {
-  constexpr int N = 1 << LOG2N, H = N / 2, NB = N / 256, NWARP = NT / 32;
+  constexpr int N = 1 << LOG2N, H = N / 2, NWARP = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *xs = reinterpret_cast<float *>(smem_raw);                                       // N lags
   uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw + (size_t)N * sizeof(float));  // NW words
