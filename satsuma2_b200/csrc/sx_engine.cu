@@ -758,7 +758,7 @@ static int batch_wait(sx_ctx *c, Run &r) {
     }
     const BatchCounters ctr = *c->h_ctr.p;
     r.need_encode = false;  // spectra of this batch are in place now
-    if (r.need_xcorr) r.n_cand_seen = ctr.n_candidates;
+    if (r.need_xcorr) r.n_cand_seen = ctr.cand_used;  // every candidate reserves one pool entry, overflowing or not
     if (ctr.status & ST_CAND_OVERFLOW) {
       // the candidate pool was too small: grow to what the kernel asked for and redo K2+K3
       const size_t want = std::max<size_t>((size_t)ctr.cand_used + (ctr.cand_used >> 2), c->d_cand_pool.n * 2);

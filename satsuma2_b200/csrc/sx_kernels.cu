@@ -760,7 +760,6 @@ __device__ __forceinline__ void findtop_impl(XcAt xc_at, double co, uint32_t *ma
     }
     *s_base = base;
     cand_ref[spi] = make_uint2(base, total);
-    atomicAdd(&ctr->n_candidates, (unsigned long long)total);
   }
   __syncthreads();
   const unsigned int base = *s_base;

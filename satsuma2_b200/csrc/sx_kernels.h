@@ -73,7 +73,7 @@ struct BatchCounters {  // device-side, zeroed per batch
   unsigned int n_generic;     // strand-pairs with candidates that the byte-wise scan kernel has to do (set by the
                               // bit-parallel one; 0 lets the byte-wise kernel leave at once)
   unsigned int pad_;
-  unsigned long long n_candidates, n_segments, n_positions;  // n_positions: diagonal positions scanned
+  unsigned long long reserved_, n_segments, n_positions;  // n_positions: diagonal positions scanned
 };
 enum { ST_CAND_OVERFLOW = 1, ST_RES_OVERFLOW = 2, ST_TAP_OVERFLOW = 4, ST_INTERNAL = 16 };
 
