@@ -950,6 +950,10 @@ static void push_pair(sx_ctx *c, Batch &b, int32_t ts, int32_t qs, int32_t qlen,
 static int align_list_inner(sx_ctx *c, const PairReq *reqs, int64_t n, sx_result *out, int64_t cap, int64_t *n_out) {
   if (c->T.n == 0 && n > 0) return fail(SX_ERR_STATE, "align: no targets loaded");
   if (c->Q.n == 0 && n > 0) return fail(SX_ERR_STATE, "align: no queries loaded");
+  // every request is checked before anything is queued: a bad one must not leave half a batch behind
+  for (int64_t i = 0; i < n; i++)
+    if (reqs[i].t < 0 || reqs[i].t >= c->T.n || reqs[i].q < 0 || reqs[i].q >= c->Q.n)
+      return fail(SX_ERR_ARG, "align: pair %lld = (target %d, query %d) out of range", (long long)i, reqs[i].t, reqs[i].q);
   CU(cudaSetDevice(c->cfg.device));
   ResultSink sink;
   sink.out = out;
@@ -983,10 +987,6 @@ static int align_list_inner(sx_ctx *c, const PairReq *reqs, int64_t n, sx_result
   const size_t maxpairs = (size_t)c->cfg.max_batch_pairs;
   for (int64_t i = 0; i < n; i++) {
     const PairReq &r = reqs[i];
-    if (r.t < 0 || r.t >= c->T.n || r.q < 0 || r.q >= c->Q.n) {
-      if (have_prev) { cur ^= 1; drain(); }
-      return fail(SX_ERR_ARG, "align: pair %lld = (target %d, query %d) out of range", (long long)i, r.t, r.q);
-    }
     Batch *b = &bufs[cur];
     // worst case this pair needs 3 fresh transient slots
     if (b->pairs.size() >= maxpairs || b->transient_used + 3 > c->n_transient) {
@@ -1015,6 +1015,13 @@ static int align_list_inner(sx_ctx *c, const PairReq *reqs, int64_t n, sx_result
 
 static int align_list(sx_ctx *c, const PairReq *reqs, int64_t n, sx_result *out, int64_t cap, int64_t *n_out) {
   const int rc = align_list_inner(c, reqs, n, out, cap, n_out);
+  if (rc != SX_OK && rc != SX_ERR_CAPACITY && rc != SX_ERR_ARG) {
+    // a call that failed half way may have marked cached target spectra valid whose encode kernel never ran
+    const std::string keep = g_err;
+    cudaStreamSynchronize(c->stream);
+    std::fill(c->t_valid.begin(), c->t_valid.end(), 0);
+    g_err = keep;
+  }
   const int rc2 = finish_uploads(c);  // bases no batch asked for still leave the caller's buffers now
   return rc != SX_OK ? rc : rc2;
 }
