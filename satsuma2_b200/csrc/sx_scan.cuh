@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned char *wbase = scan_smem + (size_t)SPC * 4 * PW * 4 + (size_t)warp * C::WARP_BYTES;
-  uint32_t *wq = reinterpret_cast<uint32_t *>(wbase);                         // SX_RUN_CAP run starts: item | bit << 16
+  uint32_t *wq = reinterpret_cast<uint32_t *>(wbase);                         // SX_RUN_CAP run ends: item | position << 16
   uint32_t(*s_need)[32] = reinterpret_cast<uint32_t(*)[32]>(wq + SX_RUN_CAP);  // [NBW][32]
   uint32_t *passw = reinterpret_cast<uint32_t *>(s_need + NBW);               // ITEM_CAP
   uint16_t *items = reinterpret_cast<uint16_t *>(passw + ITEM_CAP);           // ITEM_CAP
@@ -344,8 +344,6 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
     P.t = s_planes + (size_t)j * 2 * PW + PAD;
     P.q = P.t + PW;
 
-    // Candidates are sorted by lag, so diagonal lengths rise and fall like a triangle.  Pairing the
-    // k-th from the front with the k-th from the back keeps the 32 diagonals of a warp close in length.
     // One queued run end (item i, position f in 0..32 of its word: the first failing position after the run,
     // 32 = the run reaches the end of the word and the next word holds no passing position) -> its segment ->
     // probability filter.  A run starts at its first passing position minus 45 ("lastStart = i - m_minLen",
@@ -398,6 +396,8 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
       qn = 0;
     };
 
+    // Candidates are sorted by lag, so diagonal lengths rise and fall like a triangle.  Pairing the
+    // k-th from the front with the k-th from the back keeps the 32 diagonals of a warp close in length.
     const int p = ((int)g - gbase) * 32 + lane;
     const int c = (p & 1) ? (nc - 1 - (p >> 1)) : (p >> 1);
     int shift = 0;
