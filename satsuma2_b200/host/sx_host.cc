@@ -30,6 +30,47 @@ static void split_tokens(const std::string &line, std::vector<std::string> &tok)
   }
 }
 
+// vecDNAVector::ReadQ (analysis/DNAVector.cc:1150-1173): records of four lines; the name is the WHOLE header
+// line (blanks and the leading '@' included), the bases are the whole second line exactly as written, the '+'
+// and quality lines are skipped; blank lines between records are skipped.
+static bool read_one_fastq(const std::string &file, std::vector<Sequence> &out, std::string *err) {
+  FILE *f = fopen(file.c_str(), "rb");
+  if (!f) {
+    if (err) *err = "cannot open " + file;
+    return false;
+  }
+  std::vector<std::string> lines;
+  std::string line;
+  char buf[1 << 16];
+  while (fgets(buf, sizeof(buf), f)) {
+    size_t n = strlen(buf);
+    const bool eol = n > 0 && buf[n - 1] == '\n';
+    if (eol) buf[n - 1] = 0;
+    line += buf;
+    if (eol) {
+      lines.push_back(line);
+      line.clear();
+    }
+  }
+  if (!line.empty()) lines.push_back(line);
+  fclose(f);
+  std::vector<std::string> tok;
+  for (size_t i = 0; i < lines.size();) {
+    split_tokens(lines[i], tok);
+    if (tok.empty()) {
+      i++;
+      continue;
+    }
+    Sequence s;
+    s.name = lines[i];
+    s.bases = i + 1 < lines.size() ? lines[i + 1] : std::string();
+    s.keep_case = true;
+    out.push_back(s);
+    i += 4;
+  }
+  return true;
+}
+
 static bool read_one_fasta(const std::string &file, std::vector<Sequence> &out, std::string *err) {
   FILE *f = fopen(file.c_str(), "rb");
   if (!f) {
@@ -40,12 +81,12 @@ static bool read_one_fasta(const std::string &file, std::vector<Sequence> &out, 
   std::vector<std::string> tok;
   bool have_record = false;
   char buf[1 << 16];
-  bool first_line = true;
+  bool first_line = true, is_fastq = false;
   auto flush_line = [&](const std::string &ln) -> bool {
     split_tokens(ln, tok);
     if (tok.empty()) return true;
-    if (first_line && tok[0][0] == '@') {
-      if (err) *err = file + ": FASTQ input is not supported by this loader";
+    if (first_line && tok[0][0] == '@') {  // "It's a fastq file!!!" (DNAVector.cc:1223-1228): re-read as FASTQ
+      is_fastq = true;
       return false;
     }
     first_line = false;
@@ -56,7 +97,7 @@ static bool read_one_fasta(const std::string &file, std::vector<Sequence> &out, 
       }
       std::string name = tok[0].substr(1);
       for (size_t i = 1; i < tok.size(); i++) name += "_" + tok[i];
-      out.push_back(Sequence{name, std::string()});
+      { Sequence rec; rec.name = name; out.push_back(rec); }
       have_record = true;
     } else {
       pending += tok[0];
@@ -71,14 +112,14 @@ static bool read_one_fasta(const std::string &file, std::vector<Sequence> &out, 
     if (eol) {
       if (!flush_line(line)) {
         fclose(f);
-        return false;
+        return is_fastq ? read_one_fastq(file, out, err) : false;
       }
       line.clear();
     }
   }
   if (!line.empty() && !flush_line(line)) {
     fclose(f);
-    return false;
+    return is_fastq ? read_one_fastq(file, out, err) : false;
   }
   fclose(f);
   if (have_record) out.back().bases.swap(pending);
@@ -96,7 +137,8 @@ bool read_fasta(const std::string &files, std::vector<Sequence> &out, std::strin
     pos = c + 1;
   }
   for (Sequence &s : out)
-    for (char &ch : s.bases) ch = (char)toupper((unsigned char)ch);
+    if (!s.keep_case)  // ReadQ does not upper-case
+      for (char &ch : s.bases) ch = (char)toupper((unsigned char)ch);
   return true;
 }
 

@@ -20,11 +20,13 @@ typedef sx_result t_result;  // analysis/WorkQueue.h:23-33
 
 struct Sequence {
   std::string name;   // header tokens joined by '_', leading '>' dropped
-  std::string bases;  // upper-cased
+  std::string bases;  // upper-cased (FASTA); as written (FASTQ, keep_case)
+  bool keep_case = false;
 };
 
 // Comma-separated list of FASTA files, concatenated.  Lines are split on blanks/tabs; a header's
 // tokens are joined with '_'; of a sequence line only the first token counts; bases are upper-cased.
+// A file whose first record line starts with '@' is read as FASTQ (vecDNAVector::ReadQ).
 bool read_fasta(const std::string &files, std::vector<Sequence> &out, std::string *err);
 
 struct ChunkList {

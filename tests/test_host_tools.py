@@ -71,6 +71,22 @@ def test_fasta_and_chunking(host_bins, tmp_path):
     assert [c[3] for c in T2] == [0, 0, 0, 2048, 0]
 
 
+def test_fastq_input(host_bins, tmp_path):
+    """A file whose first record line starts with '@' is read as FASTQ (vecDNAVector::ReadQ,
+    analysis/DNAVector.cc:1150-1173, 1223-1228): four lines per record, bases = the whole second line."""
+    rng = np.random.default_rng(2)
+    r1 = bytes(rng.choice(list(b"ACGT"), 5000).astype(np.uint8)).decode()
+    r2 = bytes(rng.choice(list(b"ACGT"), 100).astype(np.uint8)).decode()
+    q = tmp_path / "q.fastq"
+    with open(q, "w") as f:
+        f.write(f"@read1 some text\n{r1}\n+\n{'I' * 5000}\n\n@read2\n{r2}\n+\n{'I' * 100}\n")
+    t = tmp_path / "t.fa"
+    _write_fasta(t, [("t1", r1.encode())])
+    T, Q = _dump_chunks(host_bins["HomologyByXCorr"], str(q), str(t))
+    assert [(c[1], c[2], c[3]) for c in Q] == [(0, 0, 4096), (0, 4096, 904), (1, 0, 100)]
+    assert [(c[2], c[3]) for c in T] == [(0, 4096), (2048, 2952), (4096, 904)]
+
+
 def test_sample_chunk_counts(host_bins):
     ref = "/root/reference/samples"
     if not os.path.isdir(ref):
