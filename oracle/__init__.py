@@ -393,6 +393,14 @@ class Reference:
         n = self.lib.ref_read_match_file(path.encode(), _ptr(out), cap, C.byref(nt), C.byref(nq))
         return out[: max(n, 0)].copy(), nt.value, nq.value
 
+    def sort_collapse(self, recs: np.ndarray, collapse: bool = True) -> np.ndarray:
+        """MultiMatches::Sort (+ Collapse) of the reference on n x 10 records (layout of read_match_file)."""
+        self.lib.ref_sort_collapse.restype = C.c_long
+        self.lib.ref_sort_collapse.argtypes = [C.c_void_p, C.c_long, C.c_int]
+        io = np.ascontiguousarray(recs, dtype=np.float64).copy()
+        k = self.lib.ref_sort_collapse(_ptr(io), len(io), int(collapse))
+        return io[:k].copy()
+
     def codec(self):
         acgt = np.zeros((128, 4))
         rc = np.zeros(128, dtype=np.uint8)

@@ -341,6 +341,34 @@ long ref_read_match_file(const char *path, double *out, long cap, int *n_targets
   return n;
 }
 
+// MultiMatches::Sort + Collapse (analysis/SequenceMatch.h:211-215, SequenceMatch.cc:418-469) on n records of
+// 10 doubles (layout of ref_read_match_file); returns the number of records left, written back to `io`.
+long ref_sort_collapse(double *io, long n, int do_collapse) {
+  CoutSilencer s;
+  MultiMatches mm;
+  for (long i = 0; i < n; i++) {
+    const double *r = io + 10 * i;
+    SingleMatch m;
+    m.SetQueryTargetID((int)r[1], (int)r[0], (int)r[2]);
+    m.SetPos((int)r[4], (int)r[3], (int)r[5], r[6] != 0.);
+    m.AddMatches(r[7]);
+    m.SetProbability(r[8]);
+    m.SetIdentity(r[9]);
+    mm.AddMatch(m);
+  }
+  mm.Sort();
+  if (do_collapse && mm.GetMatchCount() > 0) mm.Collapse();
+  const long k = mm.GetMatchCount();
+  for (long i = 0; i < k; i++) {
+    const SingleMatch &m = mm.GetMatch((int)i);
+    double *o = io + 10 * i;
+    o[0] = m.GetTargetID(); o[1] = m.GetQueryID(); o[2] = m.m_queryLen; o[3] = m.GetStartTarget();
+    o[4] = m.GetStartQuery(); o[5] = m.GetLength(); o[6] = m.IsRC() ? 1 : 0; o[7] = m.GetMatches();
+    o[8] = m.GetProbability(); o[9] = m.GetIdentity();
+  }
+  return k;
+}
+
 // a4: codec tables (DNAVector.cc:13-58, 351-403) for all 256 byte values (as signed char index, i.e.
 // what DNA_A(char) sees for bytes < 128; bytes >= 128 are UB in the reference and not tabulated).
 void ref_codec(double *acgt /* 128*4 */, char *rc /* 128 */, double *equal /* 128*128 */,

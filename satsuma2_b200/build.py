@@ -59,7 +59,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 HOST = os.path.join(HERE, "host")
 BIN = os.path.join(HERE, "bin")
-HOST_PROGRAMS = {"HomologyByXCorr": "homology_by_xcorr_main.cc", "HomologyByXCorrSlave": "homology_slave_main.cc"}
+HOST_PROGRAMS = {"HomologyByXCorr": "homology_by_xcorr_main.cc", "HomologyByXCorrSlave": "homology_slave_main.cc",
+                 "XCorrMatchTool": "match_tool_main.cc"}
 
 
 def build_host(force: bool = False) -> list:

@@ -1,0 +1,40 @@
+// XCorrMatchTool: the master-side list operations on an xcorr match file (version 3) that become the next
+// bottleneck once the slaves run on GPUs: MultiMatches::Sort and MultiMatches::Collapse
+// (analysis/SequenceMatch.h:211-215, SequenceMatch.cc:418-469) as SatsumaSynteny2 and ChainMatches apply them
+// (analysis/SatsumaSynteny2.cc:468-476, 506-507, 605-606; tools/analysis/ChainMatches.cc:65-66).
+//   XCorrMatchTool -i <in> -o <out> [-sort 1] [-collapse 1]
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <string>
+
+#include "sx_host.h"
+
+int main(int argc, char **argv) {
+  std::map<std::string, std::string> a;
+  for (int i = 1; i + 1 < argc; i += 2) a[argv[i]] = argv[i + 1];
+  if (!a.count("-i") || !a.count("-o")) {
+    fprintf(stderr, "usage: %s -i <match file> -o <match file> [-sort 1] [-collapse 1]\n", argv[0]);
+    return 2;
+  }
+  const bool do_sort = !a.count("-sort") || atoi(a["-sort"].c_str()) != 0;
+  const bool do_collapse = !a.count("-collapse") || atoi(a["-collapse"].c_str()) != 0;
+  sxh::MatchFile mf;
+  std::string err;
+  if (!mf.read(a["-i"], &err)) {
+    fprintf(stderr, "%s\n", err.c_str());
+    return 1;
+  }
+  printf("Matches read: %zu\n", mf.matches.size());
+  if (do_sort) mf.sort();
+  if (do_collapse) {
+    printf("Matches before collapse: %zu\n", mf.matches.size());
+    mf.collapse();
+    printf("Matches after collapse:  %zu\n", mf.matches.size());
+  }
+  if (!mf.write(a["-o"], &err)) {
+    fprintf(stderr, "%s\n", err.c_str());
+    return 1;
+  }
+  return 0;
+}

@@ -3,6 +3,7 @@
 #include "sx_host.h"
 
 #include <cctype>
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 
@@ -321,7 +322,8 @@ bool MatchFile::write(const std::string &path, std::string *err) const {
   w.put((int32_t)query_names.size());
   for (const std::string &s : query_names) w.str(s);
   w.put((int32_t)matches.size());
-  for (const t_result &m : matches) {
+  for (size_t mi = 0; mi < matches.size(); mi++) {
+    const t_result &m = matches[mi];
     // SingleMatch::Write (SequenceMatch.cc:49-64): all coordinates are 32-bit ints in the file
     w.put((int32_t)m.target_id);
     w.put((int32_t)m.query_id);
@@ -330,7 +332,7 @@ bool MatchFile::write(const std::string &path, std::string *err) const {
     w.put((int32_t)(int64_t)m.qstart);
     w.put((int32_t)m.len);
     w.put((int32_t)(m.reverse ? 1 : 0));
-    const double nmatch = m.ident * (double)(int32_t)m.len;  // AddMatches(ident * len)
+    const double nmatch = mi < n_matches.size() ? n_matches[mi] : m.ident * (double)(int32_t)m.len;  // AddMatches(ident * len)
     w.put(nmatch);
     w.put(m.prob);
     w.put(m.ident);
@@ -340,6 +342,74 @@ bool MatchFile::write(const std::string &path, std::string *err) const {
   const bool ok = w.ok && fclose(f) == 0;
   if (!ok && err) *err = "write error on " + path;
   return ok;
+}
+
+namespace {
+struct MatchRec {
+  t_result r;
+  double nmatch;
+};
+std::vector<MatchRec> zip_matches(const MatchFile &mf) {
+  std::vector<MatchRec> v(mf.matches.size());
+  for (size_t i = 0; i < v.size(); i++) {
+    v[i].r = mf.matches[i];
+    v[i].nmatch = i < mf.n_matches.size() ? mf.n_matches[i] : mf.matches[i].ident * (double)(int32_t)mf.matches[i].len;
+  }
+  return v;
+}
+void unzip_matches(const std::vector<MatchRec> &v, MatchFile &mf) {
+  mf.matches.resize(v.size());
+  mf.n_matches.resize(v.size());
+  for (size_t i = 0; i < v.size(); i++) {
+    mf.matches[i] = v[i].r;
+    mf.n_matches[i] = v[i].nmatch;
+  }
+}
+}  // namespace
+
+void MatchFile::sort() {
+  std::vector<MatchRec> v = zip_matches(*this);
+  std::sort(v.begin(), v.end(), [](const MatchRec &x, const MatchRec &y) {
+    const t_result &a = x.r, &b = y.r;
+    // the file holds 32-bit ints (SingleMatch); compare what the reference compares
+    const int32_t at = (int32_t)a.target_id, bt = (int32_t)b.target_id, aq = (int32_t)a.query_id, bq = (int32_t)b.query_id;
+    if (at != bt) return at < bt;
+    if (aq != bq) return aq < bq;
+    if ((a.reverse != 0) != (b.reverse != 0)) return a.reverse == 0;
+    const int32_t as = (int32_t)a.tstart, bs = (int32_t)b.tstart;
+    if (as == bs) return (int32_t)a.len < (int32_t)b.len;
+    return as < bs;
+  });
+  unzip_matches(v, *this);
+}
+
+void MatchFile::collapse() {
+  if (matches.empty()) return;  // the reference reads element 0 of an empty vector here
+  auto laps = [](int32_t a, int32_t b) {
+    const int32_t c = a < b ? b - a : a - b;
+    return c < 4;
+  };
+  const std::vector<MatchRec> in = zip_matches(*this);
+  std::vector<MatchRec> out;
+  out.reserve(in.size());
+  MatchRec n = in[0];
+  for (size_t i = 1; i < in.size(); i++) {
+    const t_result &s1 = in[i - 1].r, &s2 = in[i].r;
+    if ((int32_t)s1.target_id == (int32_t)s2.target_id && (s1.reverse != 0) == (s2.reverse != 0) &&
+        laps((int32_t)s1.tstart, (int32_t)s2.tstart) && laps((int32_t)(int64_t)s1.qstart, (int32_t)(int64_t)s2.qstart)) {
+      const int32_t nq = (int32_t)(int64_t)n.r.qstart, s2q = (int32_t)(int64_t)s2.qstart;
+      if (s2q < nq) {
+        n.r.len = (uint64_t)(int64_t)(nq + (int32_t)n.r.len - s2q);
+        n.r.qstart = (uint64_t)(int64_t)s2q;
+      } else {
+        n.r.len = (uint64_t)(int64_t)(s2q + (int32_t)s2.len - nq);
+      }
+    } else {
+      out.push_back(n);
+      n = in[i];
+    }
+  }
+  unzip_matches(out, *this);  // the running match `n` is not stored: MultiMatches::Collapse ends the same way
 }
 
 bool MatchFile::read(const std::string &path, std::string *err) {
@@ -366,12 +436,15 @@ bool MatchFile::read(const std::string &path, std::string *err) {
   r.get(n);
   if (!r.ok || n < 0) n = 0;
   matches.resize((size_t)n);
-  for (t_result &m : matches) {
+  n_matches.assign((size_t)n, 0.);
+  for (size_t mi = 0; mi < matches.size(); mi++) {
+    t_result &m = matches[mi];
     int32_t tid, qid, qlen, st, sq, len, rc;
-    double nmatch;
+    double nmatch = 0.;
     memset(&m, 0, sizeof(m));
     r.get(tid); r.get(qid); r.get(qlen); r.get(st); r.get(sq); r.get(len); r.get(rc);
     r.get(nmatch); r.get(m.prob); r.get(m.ident);
+    n_matches[mi] = nmatch;
     m.target_id = (uint64_t)(int64_t)tid;
     m.query_id = (uint64_t)(int64_t)qid;
     m.query_size = (uint64_t)(int64_t)qlen;

@@ -83,8 +83,19 @@ struct MatchFile {
   std::vector<std::string> target_names, query_names;
   std::vector<int32_t> target_sizes, query_sizes;
   std::vector<t_result> matches;
+  // SingleMatch::m_matches per record (= ident * len when the slave record is turned into a match; it is NOT
+  // updated when Collapse changes the length).  Empty, or shorter than `matches`: ident * len is written.
+  std::vector<double> n_matches;
   bool write(const std::string &path, std::string *err) const;
   bool read(const std::string &path, std::string *err);
+  // MultiMatches::Sort (analysis/SequenceMatch.h:211-215): std::sort with SingleMatch::operator< (:93-109):
+  // target id, query id, forward before reverse, start in target, length.  Same comparator, same algorithm.
+  void sort();
+  // MultiMatches::Collapse (analysis/SequenceMatch.cc:418-469) on a sorted list, quirks included: neighbours
+  // are fused when they share the TARGET id and orientation and start within 3 bases of each other in both
+  // sequences (the query id is not compared); the fused match keeps the first one's scores; and the last
+  // group is dropped (the reference never stores its running match after the loop).
+  void collapse();
 };
 
 }  // namespace sxh

@@ -87,6 +87,63 @@ def test_fastq_input(host_bins, tmp_path):
     assert [(c[2], c[3]) for c in T] == [(0, 4096), (2048, 2952), (4096, 904)]
 
 
+def _write_match_file(path, recs, n_t, n_q):
+    """Version-3 MultiMatches file (analysis/SequenceMatch.cc:320-360) from n x 10 records."""
+    with open(path, "wb") as f:
+        f.write(struct.pack("<ii", 3, n_t))
+        for i in range(n_t):
+            name = f"t{i}".encode() + b"\0"
+            f.write(struct.pack("<q", len(name)) + name)
+        f.write(struct.pack("<i", n_q))
+        for i in range(n_q):
+            name = f"q{i}".encode() + b"\0"
+            f.write(struct.pack("<q", len(name)) + name)
+        f.write(struct.pack("<i", len(recs)))
+        for r in recs:
+            f.write(struct.pack("<iiiiiiiddd", int(r[0]), int(r[1]), int(r[2]), int(r[3]), int(r[4]), int(r[5]), int(r[6]),
+                                float(r[7]), float(r[8]), float(r[9])))
+        f.write(struct.pack(f"<{n_t}i", *([1000000] * n_t)))
+        f.write(struct.pack(f"<{n_q}i", *([1000000] * n_q)))
+
+
+def test_sort_and_collapse_match_the_reference(host_bins, reference_lib, tmp_path):
+    """SURVEY 8f rank 3: MultiMatches::Sort / Collapse (analysis/SequenceMatch.h:211-215, SequenceMatch.cc:418-469)
+    as the master applies them to the slaves' records every cycle -- same order, same fused matches, quirks
+    included (query id ignored when fusing, last group dropped), against the compiled reference."""
+    rng = np.random.default_rng(4)
+    n = 5000
+    recs = np.zeros((n, 10))
+    recs[:, 0] = rng.integers(0, 3, n)            # target id
+    recs[:, 1] = rng.integers(0, 3, n)            # query id
+    recs[:, 2] = 1000000
+    recs[:, 3] = rng.integers(0, 20000, n)        # start in target
+    recs[:, 4] = recs[:, 3] + rng.integers(-40, 40, n)  # start in query: near the diagonal
+    recs[:, 5] = rng.integers(46, 400, n)
+    recs[:, 6] = rng.integers(0, 2, n)
+    recs[:, 9] = rng.uniform(0.5, 1.0, n)
+    recs[:, 7] = recs[:, 9] * recs[:, 5]
+    recs[:, 8] = rng.uniform(0.99, 1.0, n)
+    # duplicates as overlapping target chunks produce them (SURVEY Q14), and near-duplicates 1-3 bases apart
+    dup = recs[rng.integers(0, n, 1500)].copy()
+    dup[:, 3] += rng.integers(0, 4, len(dup))
+    dup[:, 4] += rng.integers(-3, 4, len(dup))
+    dup[:, 5] += rng.integers(-10, 30, len(dup))
+    recs = np.concatenate([recs, dup])
+    rng.shuffle(recs)
+    src = tmp_path / "in.match"
+    _write_match_file(src, recs, 3, 3)
+    for collapse in (0, 1):
+        dst = tmp_path / f"out{collapse}.match"
+        subprocess.run([host_bins["XCorrMatchTool"], "-i", str(src), "-o", str(dst), "-sort", "1", "-collapse", str(collapse)],
+                       check=True, capture_output=True)
+        got, nt, nq = reference_lib.read_match_file(str(dst))
+        exp = reference_lib.sort_collapse(recs, bool(collapse))
+        assert (nt, nq) == (3, 3)
+        assert got.shape == exp.shape and len(exp) > 1000
+        assert np.array_equal(got, exp)
+    assert len(exp) < len(recs) - 500  # collapse fused the planted duplicates
+
+
 def test_sample_chunk_counts(host_bins):
     ref = "/root/reference/samples"
     if not os.path.isdir(ref):
