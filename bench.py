@@ -304,6 +304,10 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing hygiene: at least 3 warm-up steps
+    # stdout carries ONE JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) would precede it
+    # (any level from VERSION up prints it; INFO and above are left alone, whoever set them wants the log)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        del os.environ["NCCL_DEBUG"]
 
     if args.impl == "reference":
         return run_reference_arm(args)

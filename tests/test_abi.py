@@ -86,3 +86,29 @@ def test_prob_table_builder_matches_oracle(sx, oracle_lib):
     tab = sx.build_prob_table(800001.0)
     exp = oracle_lib.prob_table(800001.0)
     assert np.array_equal(tab[1:], exp[1:])
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The bench lines kept under profiles/ carry every key the measurement contract names."""
+    import glob
+    import json
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "profiles", "r1_bench_*.json")))
+    assert files
+    for f in files:
+        d = json.load(open(f))
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "e2e"):
+            assert k in d, (f, k)
+        assert d["metric"] == "chunk_pair_xcorrs_per_sec" and d["unit"] == "chunk-pairs/s" and d["warmup"] >= 3
+        assert "workload" in d["config"] and d["vs_baseline"] is None
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+        if d.get("impl") == "reference":
+            assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["e2e"]["h2d_bytes_per_step"] == 0
+            continue
+        assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and "clocks" in d
+        if "roofline" in d:
+            r = d["roofline"]
+            assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r)
+            assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
