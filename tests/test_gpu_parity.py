@@ -182,6 +182,60 @@ def test_random_pairs_against_oracle(sx, oracle_lib):
     assert found > 0.5 * n  # planted segments are found in most pairs
 
 
+def test_ragged_fuzz_against_oracle(sx, oracle_lib):
+    """Randomised ragged chunk pairs: lengths 30..4096 (not multiples of the entropy window or of 32, chunks at
+    unaligned blob offsets), related sequences with substitutions, an occasional IUPAC letter / N run / lower-case
+    or unknown byte, forward and reverse homology, low target_total so that many segments are kept.  Every code
+    path of the encoder (16-base fast path, byte-wise path, derived and direct reverse strands) and both scan
+    kernels meet; the record sets must equal the oracle's (borderline lags listed)."""
+    rng = np.random.default_rng(2024)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    comp = np.zeros(256, np.uint8)
+    comp[list(b"ACGT")] = list(b"TGCA")
+    n = 240
+    tl, ql = [], []
+    for i in range(n):
+        lt = int(rng.integers(30, 4097))
+        t = rng.choice(acgt, lt)
+        a, b = sorted(rng.integers(0, lt, 2))
+        seg = t[a:b].copy()
+        mut = rng.random(len(seg)) < rng.uniform(0.02, 0.3)
+        seg[mut] = rng.choice(acgt, int(mut.sum()))
+        if rng.random() < 0.5:
+            seg = comp[seg[::-1]]
+        pre, post = rng.choice(acgt, int(rng.integers(0, 600))), rng.choice(acgt, int(rng.integers(0, 600)))
+        q = np.concatenate([pre, seg, post])[:4096]
+        if len(q) < 30:
+            q = np.concatenate([q, rng.choice(acgt, 30)])
+        kind = rng.random()
+        if kind < 0.10:
+            q[int(rng.integers(0, len(q)))] = ord("R")
+        elif kind < 0.20:
+            k0 = int(rng.integers(0, len(t)))
+            t[k0:k0 + int(rng.integers(1, 60))] = ord("N")
+        elif kind < 0.25:
+            q[int(rng.integers(0, len(q)))] = ord("a")
+        elif kind < 0.30:
+            t[int(rng.integers(0, len(t)))] = 200
+        tl.append((t.tobytes(), int(rng.integers(0, 1000)), i, 100000))
+        ql.append((q.tobytes(), int(rng.integers(0, 1000)), i, 100000))
+    pairs = [(i, i) for i in range(n)]
+    listed = []
+    with sx.XCorrEngine(target_total=20000.0, max_batch_pairs=64) as eng:
+        eng.set_targets(sx.ChunkSet.from_list(tl))
+        eng.set_queries(sx.ChunkSet.from_list(ql))
+        got = eng.align_pairs(pairs)
+    params = oracle_lib.make_params(target_total=20000.0)
+    exp = oracle_lib.align_pairs(params, tl, ql, pairs, threads=os.cpu_count() or 1)
+    assert len(exp) > 200
+    for i in range(n):
+        gp, ep = got[got["query_id"] == i], exp[exp["query_id"] == i]
+        compare_pair_records(oracle_lib, gp, ep, tl[i][0], ql[i][0], tl[i][1], ql[i][1], 100000, 4096, N, 1.8, 0.99,
+                             20000.0, listed)
+    _log_listed("ragged_fuzz", listed)
+    assert len(listed) <= 4, listed
+
+
 def test_batching_is_invisible(sx):
     """Same pairs through different batch sizes / cached vs transient spectra / blocks vs pairs give
     the same set (idempotence; target-spectrum cache reuse is exact)."""
