@@ -43,6 +43,7 @@
 #undef main
 #undef private
 #undef protected
+#include "analysis/MatchDynProg.h"
 
 namespace {
 
@@ -361,6 +362,36 @@ long ref_sort_collapse(double *io, long n, int do_collapse) {
   const long k = mm.GetMatchCount();
   for (long i = 0; i < k; i++) {
     const SingleMatch &m = mm.GetMatch((int)i);
+    double *o = io + 10 * i;
+    o[0] = m.GetTargetID(); o[1] = m.GetQueryID(); o[2] = m.m_queryLen; o[3] = m.GetStartTarget();
+    o[4] = m.GetStartQuery(); o[5] = m.GetLength(); o[6] = m.IsRC() ? 1 : 0; o[7] = m.GetMatches();
+    o[8] = m.GetProbability(); o[9] = m.GetIdentity();
+  }
+  return k;
+}
+
+// RunMatchDynProg (analysis/MatchDynProg.cc:401-561) on n records (layout of ref_read_match_file) that are already
+// sorted + collapsed; sequence sizes as the match file carries them.  Returns the chain length, records in `io`.
+long ref_chain(double *io, long n, int n_targets, int n_queries, const int *tsize, const int *qsize) {
+  CoutSilencer s;
+  MultiMatches in, out;
+  in.SetCounts(n_targets, n_queries);
+  for (int i = 0; i < n_targets; i++) in.SetTargetSize(i, tsize[i]);
+  for (int i = 0; i < n_queries; i++) in.SetQuerySize(i, qsize[i]);
+  for (long i = 0; i < n; i++) {
+    const double *r = io + 10 * i;
+    SingleMatch m;
+    m.SetQueryTargetID((int)r[1], (int)r[0], (int)r[2]);
+    m.SetPos((int)r[4], (int)r[3], (int)r[5], r[6] != 0.);
+    m.AddMatches(r[7]);
+    m.SetProbability(r[8]);
+    m.SetIdentity(r[9]);
+    in.AddMatch(m);
+  }
+  RunMatchDynProg(out, in);
+  const long k = out.GetMatchCount();
+  for (long i = 0; i < k && i < n; i++) {
+    const SingleMatch &m = out.GetMatch((int)i);
     double *o = io + 10 * i;
     o[0] = m.GetTargetID(); o[1] = m.GetQueryID(); o[2] = m.m_queryLen; o[3] = m.GetStartTarget();
     o[4] = m.GetStartQuery(); o[5] = m.GetLength(); o[6] = m.IsRC() ? 1 : 0; o[7] = m.GetMatches();

@@ -4,6 +4,7 @@
 
 #include <cctype>
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 
@@ -410,6 +411,159 @@ void MatchFile::collapse() {
     }
   }
   unzip_matches(out, *this);  // the running match `n` is not stored: MultiMatches::Collapse ends the same way
+}
+
+namespace {
+// TransPenalty (MatchDynProg.cc:43-92), operation for operation
+double trans_penalty(int startT1, int startQ1, bool rc1, int startT2, int startQ2, bool rc2) {
+  if (rc1 != rc2) return 20.;  // RC_PENALTY
+  double expect = (double)(startT2 - startT1);
+  double observe = (double)(startQ2 - startQ1);
+  double sigma = 0;
+  if (expect > 1000000) sigma = std::sqrt(expect) / 10. - 100;
+  if (rc1 == true && rc2 == true) observe = -observe;
+  double diff = observe - expect;
+  if (diff < 0.) diff = -diff;
+  double flat = 0.01;
+  if (diff == 1) flat = 0;
+  if (expect < 300.) expect = 300;
+  double p = diff / expect + sigma + flat;
+  if (p > 40) p = 40;  // MAX_PENALTY
+  return p;
+}
+// GetRepeatScore (MatchDynProg.cc:94-112)
+double repeat_score(int v) {
+  if (v <= 1) return 10.;
+  if (v == 2) return 5.;
+  if (v == 3) return 2.5;
+  if (v == 4) return 1.2;
+  if (v >= 25) return 0.000001;
+  if (v >= 10) return 0.001;
+  return 0.5;
+}
+struct ChainRec {  // SingleMatchDP (MatchDynProg.cc:115-163)
+  MatchRec m;
+  double score = 999999999999999.;  // PRETTY_INFINITE
+  double pen = -1.;
+  int back = -1;
+  double rep = 100.;
+  void update(double s, int b) {
+    if (s < score) {
+      score = s;
+      back = b;
+    }
+  }
+  double get_score() {
+    if (pen < 0.) pen = -200 * std::log(m.r.prob);  // MatchPenalty
+    return score + pen;
+  }
+};
+bool match_less(const t_result &a, const t_result &b) {  // SingleMatch::operator< (SequenceMatch.h:93-109)
+  const int32_t at = (int32_t)a.target_id, bt = (int32_t)b.target_id, aq = (int32_t)a.query_id, bq = (int32_t)b.query_id;
+  if (at != bt) return at < bt;
+  if (aq != bq) return aq < bq;
+  if ((a.reverse != 0) != (b.reverse != 0)) return a.reverse == 0;
+  const int32_t as = (int32_t)a.tstart, bs = (int32_t)b.tstart;
+  if (as == bs) return (int32_t)a.len < (int32_t)b.len;
+  return as < bs;
+}
+// MatchDynProg::Chain (MatchDynProg.cc:199-243)
+void chain_one_target(std::vector<ChainRec> &v, std::vector<MatchRec> &out) {
+  std::sort(v.begin(), v.end(), [](const ChainRec &a, const ChainRec &b) { return (int32_t)a.m.r.tstart < (int32_t)b.m.r.tstart; });
+  if (v.empty()) return;
+  const int la_limit = 2000, la_dist = 250000;
+  v[0].update(0., -1);
+  const int n = (int)v.size();
+  for (int i = 0; i < n; i++) {
+    ChainRec &one = v[i];
+    double skip_score = 0.;
+    int fed = 0;
+    for (int j = i + 1; j < n; j++) {
+      ChainRec &two = v[j];
+      if ((int32_t)two.m.r.tstart - (int32_t)one.m.r.tstart > la_dist && fed > 10) break;
+      if (j - i > la_limit) break;
+      fed++;
+      double trans = 150;  // GetHighMaxPenalty
+      if ((int32_t)one.m.r.query_id == (int32_t)two.m.r.query_id)
+        trans = trans_penalty((int32_t)one.m.r.tstart, (int32_t)(int64_t)one.m.r.qstart, one.m.r.reverse != 0,
+                              (int32_t)two.m.r.tstart, (int32_t)(int64_t)two.m.r.qstart, two.m.r.reverse != 0);
+      trans += skip_score;
+      skip_score += two.rep;
+      two.update(one.get_score() + trans, i);
+    }
+  }
+  std::vector<MatchRec> chain;
+  for (int i = n - 1; i >= 0; i = v[i].back) chain.push_back(v[i].m);
+  std::sort(chain.begin(), chain.end(), [](const MatchRec &a, const MatchRec &b) { return match_less(a.r, b.r); });
+  out.insert(out.end(), chain.begin(), chain.end());
+}
+}  // namespace
+
+void MatchFile::chain(MatchFile &out) const {
+  out = MatchFile();
+  out.target_names = target_names;
+  out.query_names = query_names;
+  out.target_sizes = target_sizes;
+  out.query_sizes = query_sizes;
+  const int n_t = (int)target_sizes.size(), n_q = (int)query_sizes.size();
+  const std::vector<MatchRec> in = zip_matches(*this);
+  const int n_in = (int)in.size();
+  // "Filling out repeat lists": how many matches cover every base (saturating at 100), MatchDynProg.cc:411-481
+  std::vector<std::vector<char>> mult_t((size_t)n_t), mult_q((size_t)n_q);
+  for (int i = 0; i < n_t; i++) mult_t[i].assign((size_t)std::max(target_sizes[i], 0), 0);
+  for (int i = 0; i < n_q; i++) mult_q[i].assign((size_t)std::max(query_sizes[i], 0), 0);
+  int last_t = -1, last_q = -1, last_st = 0, last_sq = 0, last_len = 0;
+  for (const MatchRec &mr : in) {
+    const int tid = (int32_t)mr.r.target_id, qid = (int32_t)mr.r.query_id;
+    const int st = (int32_t)mr.r.tstart, sq = (int32_t)(int64_t)mr.r.qstart, len = (int32_t)mr.r.len;
+    if (qid < 0) continue;
+    int start_t = st, start_q = sq;
+    if (tid == last_t && qid == last_q && st <= last_st + last_len && sq <= last_sq + last_len && st > last_st &&
+        sq > last_sq) {
+      start_t = last_st + last_len;
+      start_q = last_sq + last_len;
+    }
+    last_t = tid; last_q = qid; last_st = st; last_sq = sq; last_len = len;
+    if (tid < 0 || tid >= n_t || qid >= n_q) continue;  // the reference indexes out of bounds here
+    std::vector<char> &t = mult_t[tid], &q = mult_q[qid];
+    for (int j = start_t; j < st + len; j++)
+      if (j > 0 && j < (int)t.size() && t[j] < 100) t[j]++;
+    for (int j = start_q; j < sq + len; j++)
+      if (j > 0 && j < (int)q.size() && q[j] < 100) q[j]++;
+  }
+  // per target: the index range its matches span in the (sorted) list
+  std::vector<int> first_i((size_t)n_t, n_in + 1), last_i((size_t)n_t, -1);
+  for (int i = 0; i < n_in; i++) {
+    const int id = (int32_t)in[i].r.target_id;
+    if (id < 0 || id >= n_t) continue;
+    if (i < first_i[id]) first_i[id] = i;
+    if (i > last_i[id]) last_i[id] = i;
+  }
+  std::vector<MatchRec> result;
+  for (int j = 0; j < n_t; j++) {
+    const int last = last_i[j], first = last == -1 ? 0 : first_i[j];
+    const std::vector<char> &t = mult_t[j];
+    std::vector<ChainRec> dp;
+    for (int i = first; i <= last; i++) {
+      const t_result &m = in[i].r;
+      const int qid = (int32_t)m.query_id;
+      if (qid < 0 || qid >= n_q) continue;  // out of bounds in the reference
+      const std::vector<char> &q = mult_q[qid];
+      const int mid_t = (int32_t)m.tstart + (int32_t)m.len / 2, mid_q = (int32_t)(int64_t)m.qstart + (int32_t)m.len / 2;
+      if (mid_t < 0 || mid_t >= (int)t.size() || mid_q < 0 || mid_q >= (int)q.size()) continue;  // ditto
+      double rep = repeat_score(t[mid_t]);
+      const double rep2 = repeat_score(q[mid_q]);
+      if (rep2 < rep) rep = rep2;
+      if (rep > 0.0001) {
+        ChainRec c;
+        c.m = in[i];
+        c.rep = rep;
+        dp.push_back(c);
+      }
+    }
+    chain_one_target(dp, result);
+  }
+  unzip_matches(result, out);
 }
 
 bool MatchFile::read(const std::string &path, std::string *err) {

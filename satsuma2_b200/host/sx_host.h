@@ -96,6 +96,12 @@ struct MatchFile {
   // sequences (the query id is not compared); the fused match keeps the first one's scores; and the last
   // group is dropped (the reference never stores its running match after the loop).
   void collapse();
+  // RunMatchDynProg (analysis/MatchDynProg.cc:401-561; Chain :199-243; penalties :24-112): the synteny chain
+  // through a sorted + collapsed match list, per target sequence: per-base coverage counts give every match a
+  // repeat score, matches in heavily covered places are dropped, a forward DP over the matches ordered by their
+  // start in the target (look-ahead 2000 matches / 250 kb) minimises transition + skip + match penalties, and the
+  // best chain is traced back from the last match.  ChainMatches = sort(); collapse(); chain().
+  void chain(MatchFile &out) const;
 };
 
 }  // namespace sxh

@@ -87,7 +87,7 @@ def test_fastq_input(host_bins, tmp_path):
     assert [(c[2], c[3]) for c in T] == [(0, 4096), (2048, 2952), (4096, 904)]
 
 
-def _write_match_file(path, recs, n_t, n_q):
+def _write_match_file(path, recs, n_t, n_q, size=1000000):
     """Version-3 MultiMatches file (analysis/SequenceMatch.cc:320-360) from n x 10 records."""
     with open(path, "wb") as f:
         f.write(struct.pack("<ii", 3, n_t))
@@ -102,8 +102,8 @@ def _write_match_file(path, recs, n_t, n_q):
         for r in recs:
             f.write(struct.pack("<iiiiiiiddd", int(r[0]), int(r[1]), int(r[2]), int(r[3]), int(r[4]), int(r[5]), int(r[6]),
                                 float(r[7]), float(r[8]), float(r[9])))
-        f.write(struct.pack(f"<{n_t}i", *([1000000] * n_t)))
-        f.write(struct.pack(f"<{n_q}i", *([1000000] * n_q)))
+        f.write(struct.pack(f"<{n_t}i", *([size] * n_t)))
+        f.write(struct.pack(f"<{n_q}i", *([size] * n_q)))
 
 
 def test_sort_and_collapse_match_the_reference(host_bins, reference_lib, tmp_path):
@@ -142,6 +142,48 @@ def test_sort_and_collapse_match_the_reference(host_bins, reference_lib, tmp_pat
         assert got.shape == exp.shape and len(exp) > 1000
         assert np.array_equal(got, exp)
     assert len(exp) < len(recs) - 500  # collapse fused the planted duplicates
+
+
+def test_chain_matches_the_reference(host_bins, reference_lib, tmp_path):
+    """SURVEY 8f rank 3, second half: ChainMatches = Sort, Collapse, RunMatchDynProg (tools/analysis/ChainMatches.cc:
+    60-75, analysis/MatchDynProg.cc:199-243, 401-561) on a synthetic synteny: true matches along a diagonal with
+    an inversion and indel drift, noise matches off the diagonal, and a repeat that piles matches onto one place."""
+    rng = np.random.default_rng(6)
+    size = 400000
+    recs = []
+    for tid, qid in ((0, 0), (1, 1), (1, 0)):
+        pos_t, drift = 500, 0
+        while pos_t < size - 2000:
+            ln = int(rng.integers(46, 600))
+            rc = 150000 < pos_t < 200000 and tid == 0
+            sq = (size - (pos_t + drift) - ln) if rc else pos_t + drift
+            ident = float(rng.uniform(0.6, 0.98))
+            if 0 < sq < size - ln:
+                recs.append([tid, qid, size, pos_t, sq, ln, int(rc), ident * ln, float(rng.uniform(0.99, 1.0)), ident])
+            pos_t += ln + int(rng.integers(50, 3000))
+            drift += int(rng.integers(-20, 21))
+    for _ in range(3000):  # noise
+        ln = int(rng.integers(46, 120))
+        ident = float(rng.uniform(0.5, 0.8))
+        recs.append([int(rng.integers(0, 2)), int(rng.integers(0, 2)), size, int(rng.integers(1, size - 200)),
+                     int(rng.integers(1, size - 200)), ln, int(rng.integers(0, 2)), ident * ln, float(rng.uniform(0.99, 1.0)),
+                     ident])
+    for _ in range(400):  # a repeat: many query places hit the same target place
+        ln = int(rng.integers(100, 300))
+        recs.append([0, 0, size, 300000 + int(rng.integers(0, 50)), int(rng.integers(1, size - 400)), ln, 0, 0.8 * ln,
+                     0.995, 0.8])
+    recs = np.array(recs, dtype=np.float64)
+    rng.shuffle(recs)
+    src, dst = tmp_path / "in.match", tmp_path / "chained.match"
+    _write_match_file(src, recs, 2, 2, size)
+    subprocess.run([host_bins["XCorrMatchTool"], "-i", str(src), "-o", str(dst), "-sort", "1", "-collapse", "1", "-chain", "1"],
+                   check=True, capture_output=True)
+    got, nt, nq = reference_lib.read_match_file(str(dst))
+    exp = reference_lib.chain(reference_lib.sort_collapse(recs, True), [size, size], [size, size])
+    assert got.shape == exp.shape and 200 < len(exp) < len(recs) // 4
+    assert np.array_equal(got, exp)
+    on_diag = np.abs(exp[:, 3] - exp[:, 4]) < 2000
+    assert on_diag[exp[:, 6] == 0].mean() > 0.9  # the chain follows the planted synteny
 
 
 def test_sample_chunk_counts(host_bins):
