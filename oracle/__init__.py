@@ -401,14 +401,14 @@ class Reference:
         k = self.lib.ref_sort_collapse(_ptr(io), len(io), int(collapse))
         return io[:k].copy()
 
-    def chain(self, recs: np.ndarray, target_sizes, query_sizes) -> np.ndarray:
-        """RunMatchDynProg of the reference on sorted + collapsed n x 10 records."""
+    def chain(self, recs: np.ndarray, target_sizes, query_sizes, dups: bool = False) -> np.ndarray:
+        """RunMatchDynProg (dups: RunMatchDynProgMult) of the reference on sorted + collapsed n x 10 records."""
         self.lib.ref_chain.restype = C.c_long
-        self.lib.ref_chain.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        self.lib.ref_chain.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         io = np.ascontiguousarray(recs, dtype=np.float64).copy()
         ts = np.ascontiguousarray(target_sizes, dtype=np.int32)
         qs = np.ascontiguousarray(query_sizes, dtype=np.int32)
-        k = self.lib.ref_chain(_ptr(io), len(io), len(ts), len(qs), _ptr(ts), _ptr(qs))
+        k = self.lib.ref_chain(_ptr(io), len(io), len(ts), len(qs), _ptr(ts), _ptr(qs), int(dups))
         return io[:k].copy()
 
     def codec(self):

@@ -372,7 +372,7 @@ long ref_sort_collapse(double *io, long n, int do_collapse) {
 
 // RunMatchDynProg (analysis/MatchDynProg.cc:401-561) on n records (layout of ref_read_match_file) that are already
 // sorted + collapsed; sequence sizes as the match file carries them.  Returns the chain length, records in `io`.
-long ref_chain(double *io, long n, int n_targets, int n_queries, const int *tsize, const int *qsize) {
+long ref_chain(double *io, long n, int n_targets, int n_queries, const int *tsize, const int *qsize, int dups) {
   CoutSilencer s;
   MultiMatches in, out;
   in.SetCounts(n_targets, n_queries);
@@ -388,7 +388,10 @@ long ref_chain(double *io, long n, int n_targets, int n_queries, const int *tsiz
     m.SetIdentity(r[9]);
     in.AddMatch(m);
   }
-  RunMatchDynProg(out, in);
+  if (dups)
+    RunMatchDynProgMult(out, in);  // analysis/MatchDynProg.cc:245-399
+  else
+    RunMatchDynProg(out, in);
   const long k = out.GetMatchCount();
   for (long i = 0; i < k && i < n; i++) {
     const SingleMatch &m = out.GetMatch((int)i);

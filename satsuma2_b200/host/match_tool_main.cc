@@ -3,8 +3,8 @@
 // (analysis/SequenceMatch.h:211-215, SequenceMatch.cc:418-469) as SatsumaSynteny2 and ChainMatches apply them
 // (analysis/SatsumaSynteny2.cc:468-476, 506-507, 605-606; tools/analysis/ChainMatches.cc:65-66).
 // and the synteny chain of ChainMatches (tools/analysis/ChainMatches.cc:60-75 = Sort, Collapse, RunMatchDynProg,
-// analysis/MatchDynProg.cc:401-561; `-dups 0` only).
-//   XCorrMatchTool -i <in> -o <out> [-sort 1] [-collapse 1] [-chain 0]
+// analysis/MatchDynProg.cc:401-561; `-dups 1` = RunMatchDynProgMult, :245-399).
+//   XCorrMatchTool -i <in> -o <out> [-sort 1] [-collapse 1] [-chain 0] [-dups 0]
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -16,7 +16,7 @@ int main(int argc, char **argv) {
   std::map<std::string, std::string> a;
   for (int i = 1; i + 1 < argc; i += 2) a[argv[i]] = argv[i + 1];
   if (!a.count("-i") || !a.count("-o")) {
-    fprintf(stderr, "usage: %s -i <match file> -o <match file> [-sort 1] [-collapse 1] [-chain 0]\n", argv[0]);
+    fprintf(stderr, "usage: %s -i <match file> -o <match file> [-sort 1] [-collapse 1] [-chain 0] [-dups 0]\n", argv[0]);
     return 2;
   }
   const bool do_sort = !a.count("-sort") || atoi(a["-sort"].c_str()) != 0;
@@ -36,7 +36,10 @@ int main(int argc, char **argv) {
   }
   if (a.count("-chain") && atoi(a["-chain"].c_str()) != 0) {
     sxh::MatchFile chained;
-    mf.chain(chained);
+    if (a.count("-dups") && atoi(a["-dups"].c_str()) != 0)
+      mf.chain_dups(chained);
+    else
+      mf.chain(chained);
     printf("Matches in the chain:    %zu\n", chained.matches.size());
     mf = chained;
   }

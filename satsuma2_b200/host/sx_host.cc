@@ -566,6 +566,45 @@ void MatchFile::chain(MatchFile &out) const {
   unzip_matches(result, out);
 }
 
+void MatchFile::chain_dups(MatchFile &out) const {
+  MatchFile tmp;
+  chain(tmp);
+  tmp.sort();
+  MatchFile rest;
+  rest.target_names = target_names;
+  rest.query_names = query_names;
+  rest.target_sizes = target_sizes;
+  rest.query_sizes = query_sizes;
+  const int n_t = (int)target_sizes.size(), n_q = (int)query_sizes.size();
+  const std::vector<MatchRec> in = zip_matches(*this);
+  std::vector<MatchRec> rest_recs;
+  for (int j = 0; j < n_t; j++) {
+    // the query with the most matches in this target's first chain ("best query"); ties keep the lowest id
+    std::vector<int> q_hits((size_t)n_q, 0);
+    for (const t_result &m : tmp.matches) {
+      if ((int32_t)m.target_id != j) continue;
+      const int q = (int32_t)m.query_id;
+      if (q >= 0 && q < n_q) q_hits[q]++;
+    }
+    int best_query = -1, max_hits = 0;
+    for (int i = 0; i < n_q; i++)
+      if (q_hits[i] > max_hits) {
+        max_hits = q_hits[i];
+        best_query = i;
+      }
+    for (const MatchRec &mr : in) {
+      if ((int32_t)mr.r.target_id != j) continue;
+      if ((int32_t)mr.r.query_id != best_query) rest_recs.push_back(mr);
+    }
+  }
+  unzip_matches(rest_recs, rest);
+  rest.chain(out);
+  std::vector<MatchRec> all = zip_matches(out), first = zip_matches(tmp);
+  all.insert(all.end(), first.begin(), first.end());
+  unzip_matches(all, out);
+  out.sort();
+}
+
 bool MatchFile::read(const std::string &path, std::string *err) {
   FILE *f = fopen(path.c_str(), "rb");
   if (!f) {

@@ -102,6 +102,9 @@ struct MatchFile {
   // start in the target (look-ahead 2000 matches / 250 kb) minimises transition + skip + match penalties, and the
   // best chain is traced back from the last match.  ChainMatches = sort(); collapse(); chain().
   void chain(MatchFile &out) const;
+  // RunMatchDynProgMult (analysis/MatchDynProg.cc:245-399), `-dups 1`: chain once, then for every target drop the
+  // matches of the query that dominates its first chain, chain what is left, and return both chains, sorted.
+  void chain_dups(MatchFile &out) const;
 };
 
 }  // namespace sxh

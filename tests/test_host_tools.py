@@ -176,14 +176,18 @@ def test_chain_matches_the_reference(host_bins, reference_lib, tmp_path):
     rng.shuffle(recs)
     src, dst = tmp_path / "in.match", tmp_path / "chained.match"
     _write_match_file(src, recs, 2, 2, size)
-    subprocess.run([host_bins["XCorrMatchTool"], "-i", str(src), "-o", str(dst), "-sort", "1", "-collapse", "1", "-chain", "1"],
-                   check=True, capture_output=True)
-    got, nt, nq = reference_lib.read_match_file(str(dst))
-    exp = reference_lib.chain(reference_lib.sort_collapse(recs, True), [size, size], [size, size])
-    assert got.shape == exp.shape and 200 < len(exp) < len(recs) // 4
-    assert np.array_equal(got, exp)
-    on_diag = np.abs(exp[:, 3] - exp[:, 4]) < 2000
-    assert on_diag[exp[:, 6] == 0].mean() > 0.9  # the chain follows the planted synteny
+    for dups in (0, 1):  # -dups 1 = RunMatchDynProgMult (config 5's master-side flag)
+        subprocess.run([host_bins["XCorrMatchTool"], "-i", str(src), "-o", str(dst), "-sort", "1", "-collapse", "1",
+                        "-chain", "1", "-dups", str(dups)], check=True, capture_output=True)
+        got, nt, nq = reference_lib.read_match_file(str(dst))
+        exp = reference_lib.chain(reference_lib.sort_collapse(recs, True), [size, size], [size, size], bool(dups))
+        assert got.shape == exp.shape and 200 < len(exp) < len(recs) // 4
+        assert np.array_equal(got, exp)
+        if not dups:
+            on_diag = np.abs(exp[:, 3] - exp[:, 4]) < 2000
+            assert on_diag[exp[:, 6] == 0].mean() > 0.9  # the chain follows the planted synteny
+            n_single = len(exp)
+    assert len(exp) > n_single  # the second pass added the secondary (duplicated) alignments
 
 
 def test_sample_chunk_counts(host_bins):
