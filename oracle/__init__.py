@@ -19,6 +19,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libsatsuma_ref.so")
+REF_TOOL = os.path.join(HERE, "_ref", "HomologyByXCorr_ref")  # the reference's standalone tool, unmodified
 REFERENCE_ROOT = "/root/reference"
 
 
@@ -26,7 +27,7 @@ def build(ref: bool = True) -> None:
     """Compile the C oracle (always) and the reference harness (when /root/reference exists)."""
     subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     if ref and os.path.isdir(REFERENCE_ROOT):
-        subprocess.check_call(["make", "-s", "-C", HERE, "ref", "-j8"])
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref", "reftool", "-j8"])
 
 
 RESULT_DTYPE = np.dtype(

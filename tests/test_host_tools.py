@@ -87,6 +87,65 @@ def test_fastq_input(host_bins, tmp_path):
     assert [(c[2], c[3]) for c in T] == [(0, 4096), (2048, 2952), (4096, 904)]
 
 
+def _equal_length_case(tmp_path, n_t=24, n_q=20, L=2000, seed=12):
+    """Many sequences of ONE length below the chunk stride: every sequence is one chunk and all chunks are equally
+    long, so the reference tool's re-used CCSignal objects never carry stale samples and its output is
+    a valid parity target.  Queries are diverged copies of the targets, every third one reverse-complemented,
+    every fourth unrelated."""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    comp = np.zeros(256, np.uint8)
+    comp[list(b"ACGT")] = list(b"TGCA")
+    T = [rng.choice(acgt, L) for _ in range(n_t)]
+    Q = []
+    for i in range(n_q):
+        q = T[i].copy()
+        mut = rng.random(L) < rng.uniform(0.05, 0.15)
+        q[mut] = rng.choice(acgt, int(mut.sum()))
+        if i % 3 == 1:
+            q = comp[q[::-1]]
+        if i % 4 == 3:
+            q = rng.choice(acgt, L)
+        Q.append(q)
+    t, q = tmp_path / "t.fa", tmp_path / "q.fa"
+    _write_fasta(t, [(f"t{i}", T[i].tobytes()) for i in range(n_t)])
+    _write_fasta(q, [(f"q{i}", Q[i].tobytes()) for i in range(n_q)])
+    return T, Q, str(t), str(q)
+
+
+def _rows(arr):
+    return sorted(tuple(float(x) for x in row) for row in arr)
+
+
+def test_oracle_matches_the_reference_standalone_tool(oracle_lib, reference_lib, tmp_path):
+    """The UNMODIFIED reference executable (tools/analysis/HomologyByXCorr, built by `make -C oracle reftool`) run
+    end to end on a FASTA pair: its match file equals what the oracle predicts under the standalone semantics
+    (-min_prob applied, RC coordinate from the real chunk length, target_total = sum of target lengths)."""
+    import oracle
+
+    if not os.path.exists(oracle.REF_TOOL):
+        pytest.skip("oracle/_ref/HomologyByXCorr_ref not built (needs /root/reference)")
+    L = 2000
+    T, Q, t, q = _equal_length_case(tmp_path, L=L)
+    out = tmp_path / "ref.match"
+    subprocess.run([oracle.REF_TOOL, "-q", q, "-t", t, "-o", str(out)], check=True, capture_output=True)
+    arr, nt, nq = reference_lib.read_match_file(str(out))
+    assert (nt, nq) == (len(T), len(Q)) and len(arr) >= 15 and arr[:, 6].sum() >= 3
+    tl = [(T[i].tobytes(), 0, i, L) for i in range(len(T))]
+    ql = [(Q[i].tobytes(), 0, i, L) for i in range(len(Q))]
+    params = oracle_lib.make_params(min_prob=0.9999, target_total=float(len(T) * L))
+    exp = oracle_lib.align_pairs(params, tl, ql, [(a, b) for a in range(len(T)) for b in range(len(Q))],
+                                 threads=os.cpu_count() or 1)
+    rows = []
+    for rr in exp:
+        k = list(rec_key(rr))
+        if k[6]:  # standalone RC coordinate uses the real chunk length (tools/...:173,799)
+            qs = k[3] if k[3] < (1 << 63) else k[3] - (1 << 64)
+            k[3] = qs + 4096 - L
+        rows.append((k[1], k[0], k[2], k[4], k[3], k[5], k[6], float(rr["ident"]) * k[5], float(rr["prob"]), float(rr["ident"])))
+    assert _rows(arr) == _rows(rows)
+
+
 def _write_match_file(path, recs, n_t, n_q, size=1000000):
     """Version-3 MultiMatches file (analysis/SequenceMatch.cc:320-360) from n x 10 records."""
     with open(path, "wb") as f:
@@ -283,6 +342,29 @@ def test_standalone_tool_writes_reference_compatible_match_file(host_bins, sx, o
         arr, nt, nq = oracle.Reference().read_match_file(str(o))
         assert (nt, nq) == (1, 1) and len(arr) == len(recs)
         assert np.allclose(arr, np.array(recs, dtype=np.float64), rtol=0, atol=0)
+
+
+@pytest.mark.gpu
+def test_standalone_tool_equals_the_reference_tool(host_bins, sx, reference_lib, tmp_path):
+    """Executable against executable: the B200 HomologyByXCorr and the unmodified reference tool on the same FASTA
+    pair write the same match file (names, sizes, every record; probabilities to 1e-6 relative)."""
+    import oracle
+
+    if not os.path.exists(oracle.REF_TOOL):
+        pytest.skip("oracle/_ref/HomologyByXCorr_ref not built")
+    T, Q, t, q = _equal_length_case(tmp_path)
+    ref_out, my_out = tmp_path / "ref.match", tmp_path / "b200.match"
+    subprocess.run([oracle.REF_TOOL, "-q", q, "-t", t, "-o", str(ref_out)], check=True, capture_output=True)
+    r = subprocess.run([host_bins["HomologyByXCorr"], "-q", q, "-t", t, "-o", str(my_out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    a = _parse_match_file(str(ref_out))
+    b = _parse_match_file(str(my_out))
+    assert a[0] == b[0] and a[1] == b[1] and a[3] == b[3] and a[4] == b[4]  # names and sizes
+    ra, rb = sorted(a[2]), sorted(b[2])
+    assert len(ra) == len(rb) >= 15
+    for x, y in zip(ra, rb):
+        assert x[:7] == y[:7] and x[9] == y[9], (x, y)          # coordinates, strand, identity
+        assert abs(x[8] - y[8]) <= 1e-6 * abs(x[8]) and abs(x[7] - y[7]) <= 1e-9
 
 
 @pytest.mark.gpu
