@@ -3,7 +3,10 @@
 // (target overlap t_chunk/2, query overlap 0, -nblocks/-block sharding), same filter (-min_prob
 // applied, RC coordinate from the real chunk length) and the same version-3 binary match file
 // (`-o`), so MergeXCorrMatches / ChainMatches consume the output unchanged.
-// Not supported here: -guide, -proteins, -select, -pairs, -line, -chain (not on the DNA hot path).
+// `-guide <chained match file>` is the refinement pass of SatsumaSynteny2 -do_refine (tools/...:206-330, 651-675,
+// 714-717, 786-790, 833-837): pieces of the gaps between chained matches, piece i against pieces i-3 .. i+3, one
+// forced orientation per piece, targetSize = t_chunk, then the guide's matches merged in and the list sorted.
+// Not supported here: -proteins, -select, -pairs, -line, -chain (not on the DNA hot path).
 // Known, documented difference: the reference tool reuses one CCSignal object, so a short chunk
 // that follows a full one keeps stale samples; this tool uses fresh signals as the
 // slave does.
@@ -25,7 +28,7 @@ static const char *flag(std::map<std::string, std::string> &a, const char *k, co
 int main(int argc, char **argv) {
   std::map<std::string, std::string> a;
   for (int i = 1; i + 1 < argc; i += 2) a[argv[i]] = argv[i + 1];
-  for (const char *bad : {"-guide", "-proteins", "-select", "-pairs", "-line", "-chain"})
+  for (const char *bad : {"-proteins", "-select", "-pairs", "-line", "-chain"})
     if (a.count(bad) && std::string(a[bad]) != "" && std::string(a[bad]) != "0" && std::string(a[bad]) != "false") {
       fprintf(stderr, "HomologyByXCorr(B200): %s is not supported by the GPU path\n", bad);
       return 2;
@@ -51,6 +54,11 @@ int main(int argc, char **argv) {
   const int nblocks = atoi(flag(a, "-nblocks", "0")), block = atoi(flag(a, "-block", "0"));
   const int nblocks_q = atoi(flag(a, "-nblocks_query", "0")), block_q = atoi(flag(a, "-block_query", "0"));
   const bool same_only = atoi(flag(a, "-same_only", "0")) != 0;
+  const std::string guide = flag(a, "-guide", "");
+  if (!guide.empty() && nblocks != 0) {
+    fprintf(stderr, "Guided mode, chunking not available!!\n");  // tools/...:605-608
+    return 2;
+  }
 
   std::vector<Sequence> qs, ts;
   std::string err;
@@ -61,6 +69,19 @@ int main(int argc, char **argv) {
   ChunkList tc, qc;
   chunk_sequences(ts, opt.t_chunk, opt.t_chunk / 2, nblocks, block, tc);  // tools/...:635
   chunk_sequences(qs, opt.q_chunk, 0, nblocks_q, block_q, qc);
+  std::vector<int> orientation;  // guided mode: per piece +1 forward only, -1 reverse only
+  MatchFile chained;
+  if (!guide.empty()) {
+    printf("Reading %s\n", guide.c_str());
+    if (!chained.read(guide, &err)) {
+      fprintf(stderr, "%s\n", err.c_str());
+      return 1;
+    }
+    printf("Done loading, recomputing chunks.\n");
+    guide_chunks(ts, qs, chained, opt.t_chunk, tc, qc, orientation);
+    opt.target_total = (double)opt.t_chunk;
+    printf("Using target size (guided) %d\n", opt.t_chunk);
+  }
   printf("Query sequence:  %s\nTarget sequence: %s\n", q.c_str(), t.c_str());
   printf("chunks: target %d query %d\n", tc.n(), qc.n());
   if (a.count("-dump_chunks")) {
@@ -93,7 +114,59 @@ int main(int argc, char **argv) {
     blocks.clear();
     return ok;
   };
-  for (int j = 0; j < tc.n(); j++) {
+  if (!guide.empty()) {
+    // piece j of the target against pieces j-3 .. j+3 of the query (bOneOnOne); a run of query pieces with the same
+    // forced orientation is one block, and only records of that orientation are kept
+    for (int pass = 0; pass < 2 && tc.n() > 0; pass++) {  // pass 0: forward-only pieces, pass 1: reverse-only
+      const int want = pass == 0 ? 1 : -1;
+      for (int j = 0; j < tc.n(); j++) {
+        if (tc.lens[j] == 0) continue;
+        const int lo = j - 3 < 0 ? 0 : j - 3, hi = j + 3 >= qc.n() ? qc.n() - 1 : j + 3;
+        for (int i = lo; i <= hi;) {
+          if (orientation[i] != want || qc.lens[i] == 0 || (same_only && tc.names[tc.seq_ids[j]] != qc.names[qc.seq_ids[i]])) {
+            i++;
+            continue;
+          }
+          int e = i;
+          while (e + 1 <= hi && orientation[e + 1] == want && qc.lens[e + 1] != 0 &&
+                 !(same_only && tc.names[tc.seq_ids[j]] != qc.names[qc.seq_ids[e + 1]]))
+            e++;
+          t_pair p;
+          memset(&p, 0, sizeof(p));
+          p.target_from = p.target_to = j;
+          p.query_from = i;
+          p.query_to = e;
+          blocks.push_back(p);
+          i = e + 1;
+        }
+      }
+      const size_t before = mf.matches.size();
+      if (!flush()) {
+        fprintf(stderr, "HomologyByXCorr(B200): %s\n", hx.error().c_str());
+        return 1;
+      }
+      size_t w = before;
+      for (size_t r = before; r < mf.matches.size(); r++)
+        if ((mf.matches[r].reverse != 0) == (want < 0)) mf.matches[w++] = mf.matches[r];
+      mf.matches.resize(w);
+    }
+    // "Merging w/ guide..." (tools/...:833-837): MultiMatches::MergeRead takes names and sizes from the guide file
+    // and appends its matches; then the list is sorted
+    printf("Merging w/ guide...\n");
+    mf.n_matches.clear();
+    for (const t_result &m : mf.matches) mf.n_matches.push_back(m.ident * (double)(int32_t)m.len);
+    mf.target_names = chained.target_names;
+    mf.query_names = chained.query_names;
+    mf.target_sizes = chained.target_sizes;
+    mf.query_sizes = chained.query_sizes;
+    for (size_t r = 0; r < chained.matches.size(); r++) {
+      mf.matches.push_back(chained.matches[r]);
+      mf.n_matches.push_back(r < chained.n_matches.size() ? chained.n_matches[r]
+                                                          : chained.matches[r].ident * (double)(int32_t)chained.matches[r].len);
+    }
+    mf.sort();
+  }
+  for (int j = 0; guide.empty() && j < tc.n(); j++) {
     if (tc.lens[j] == 0 || qc.n() == 0) continue;
     if (!same_only) {
       t_pair p;

@@ -198,6 +198,70 @@ void chunk_sequences(const std::vector<Sequence> &seqs, int size, int overlap, i
 }
 
 // ------------------------------------------------------------------------------------------------
+void guide_chunks(const std::vector<Sequence> &targets, const std::vector<Sequence> &queries, const MatchFile &chained,
+                  int size, ChunkList &t_out, ChunkList &q_out, std::vector<int> &orientation) {
+  t_out = ChunkList();
+  q_out = ChunkList();
+  orientation.clear();
+  std::vector<int64_t> t_base(targets.size()), q_base(queries.size());
+  for (size_t i = 0; i < targets.size(); i++) {
+    t_base[i] = (int64_t)t_out.blob.size();
+    t_out.blob += targets[i].bases;
+    t_out.seq_sizes.push_back((int32_t)targets[i].bases.size());
+    t_out.names.push_back(targets[i].name);
+  }
+  for (size_t i = 0; i < queries.size(); i++) {
+    q_base[i] = (int64_t)q_out.blob.size();
+    q_out.blob += queries[i].bases;
+    q_out.seq_sizes.push_back((int32_t)queries[i].bases.size());
+    q_out.names.push_back(queries[i].name);
+  }
+  const int max_len = 100000, min_len = 20, lap = 32;
+  for (size_t i = 1; i < chained.matches.size(); i++) {
+    const t_result &m = chained.matches[i], &n = chained.matches[i - 1];
+    const int t_id = (int32_t)m.target_id, q_id = (int32_t)m.query_id;
+    if (t_id != (int32_t)n.target_id || q_id != (int32_t)n.query_id || (m.reverse != 0) != (n.reverse != 0)) continue;
+    if (t_id < 0 || t_id >= (int)targets.size() || q_id < 0 || q_id >= (int)queries.size()) continue;
+    const int force = m.reverse ? -1 : 1;
+    const int len = (int32_t)n.len;
+    int start_t = (int32_t)n.tstart + len - lap, start_q = (int32_t)(int64_t)n.qstart + len - lap;
+    if (start_t < 0) start_t = 0;
+    if (start_q < 0) start_q = 0;
+    const int end_t = (int32_t)m.tstart + lap;
+    int end_q = (int32_t)(int64_t)m.qstart + lap;
+    const int target_size = end_t - start_t, query_size = end_q - start_q;
+    if (target_size > max_len || query_size > max_len) continue;
+    if (target_size < min_len || query_size < min_len) continue;
+    const int mx = target_size > query_size ? target_size : query_size;
+    const int pieces = 1 + mx / size;
+    const int t_chunk = target_size / pieces, q_chunk = query_size / pieces;
+    const int t_len = (int)targets[t_id].bases.size(), q_len = (int)queries[q_id].bases.size();
+    if (m.reverse) {  // the match's query coordinates are on the reverse strand: take the forward window
+      start_q = q_len - end_q;
+      end_q = start_q + query_size;
+    }
+    int t_iter = start_t, q_iter = start_q;
+    while (q_iter < end_q && t_iter < end_t) {
+      if (q_iter + q_chunk >= q_len) break;
+      if (t_iter + t_chunk >= t_len) break;
+      if (q_iter < 0) q_iter = 0;  // "Minor error (q)"
+      if (t_iter < 0) t_iter = 0;
+      t_out.offsets.push_back(t_base[t_id] + t_iter);
+      t_out.lens.push_back(t_chunk);
+      t_out.starts.push_back(t_iter);
+      t_out.seq_ids.push_back(t_id);
+      q_out.offsets.push_back(q_base[q_id] + q_iter);
+      q_out.lens.push_back(q_chunk);
+      q_out.starts.push_back(q_iter);
+      q_out.seq_ids.push_back(q_id);
+      orientation.push_back(force);
+      q_iter += t_chunk / 2;  // sic: each side advances by half of the OTHER side's piece
+      t_iter += q_chunk / 2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 HomologyByXCorr::HomologyByXCorr() {}
 HomologyByXCorr::~HomologyByXCorr() {
   if (ctx_) sx_destroy(ctx_);
@@ -221,6 +285,7 @@ bool HomologyByXCorr::init(const Options &o, const ChunkList &target, const Chun
   cfg.sort_results = o.sort_results ? 1 : 0;
   target_total_ = 0;  // Slave.cc:405-408: ALL target sequence lengths
   for (int32_t s : target.seq_sizes) target_total_ += (double)s;
+  if (o.target_total > 0) target_total_ = o.target_total;  // "Using target size (guided)", tools/...:714-717
   cfg.target_total = target_total_;
   if (sx_create(&cfg, &ctx_) != SX_OK) {
     err_ = sx_last_error();

@@ -44,6 +44,17 @@ struct ChunkList {
 void chunk_sequences(const std::vector<Sequence> &seqs, int size, int overlap, int n_blocks, int my_block,
                      ChunkList &out);
 
+struct MatchFile;
+// Guided refinement (tools/analysis/HomologyByXCorr.cc:206-330, SetGuideChunks): between every two consecutive
+// matches of a chained match list that share target, query and orientation, the gap (with 32-base laps into both
+// matches) is cut into `pieces = 1 + max(gap_t, gap_q) / size` pieces per side; piece k of the target list is paired
+// with piece k of the query list (same index in both lists), and `orientation[k]` (+1 forward only, -1 reverse
+// only) is forced.  Every quirk of the reference is kept: gaps above 100 000 or below 20 bases are skipped, the
+// iterators advance by HALF of the OTHER side's piece length, reverse matches take their query window from the
+// far end of the forward sequence.
+void guide_chunks(const std::vector<Sequence> &targets, const std::vector<Sequence> &queries, const MatchFile &chained,
+                  int size, ChunkList &t_out, ChunkList &q_out, std::vector<int> &orientation);
+
 // Slave-side driver with the reference's interface: load once, then align_target(t_pair).
 class HomologyByXCorr {
  public:
@@ -57,6 +68,7 @@ class HomologyByXCorr {
     bool standalone_semantics = false;  // tools/analysis/HomologyByXCorr: filter at -min_prob, RC coordinate by chunk length
     int max_batch_pairs = 0;
     bool sort_results = false;
+    double target_total = 0;  // > 0: instead of the sum of the target sequence lengths (guided mode: t_chunk)
   };
   HomologyByXCorr();
   ~HomologyByXCorr();

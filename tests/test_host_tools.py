@@ -368,6 +368,66 @@ def test_standalone_tool_equals_the_reference_tool(host_bins, sx, reference_lib,
 
 
 @pytest.mark.gpu
+def test_guided_refinement_equals_the_reference_tool(host_bins, sx, reference_lib, tmp_path):
+    """`-guide` (the refinement pass behind SatsumaSynteny2 -do_refine): executable against executable.  Chained
+    guide matches every 1500 bases make every gap -- hence every piece -- equally long, so the reference tool's
+    re-used signal objects carry no stale samples and its output is a valid target.  One sequence
+    pair is forward, the other reverse (forced orientation -1, query window taken from the far end)."""
+    import oracle
+
+    if not os.path.exists(oracle.REF_TOOL):
+        pytest.skip("oracle/_ref/HomologyByXCorr_ref not built")
+    rng = np.random.default_rng(8)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    comp = np.zeros(256, np.uint8)
+    comp[list(b"ACGT")] = list(b"TGCA")
+    t0, t1 = rng.choice(acgt, 60000), rng.choice(acgt, 40000)
+
+    def diverged(x):
+        y = x.copy()
+        mut = rng.random(len(y)) < 0.10
+        y[mut] = rng.choice(acgt, int(mut.sum()))
+        return y
+
+    q0, q1 = diverged(t0), comp[diverged(t1)[::-1]]
+    t, q = tmp_path / "t.fa", tmp_path / "q.fa"
+    _write_fasta(t, [("t0", t0.tobytes()), ("t1", t1.tobytes())])
+    _write_fasta(q, [("q0", q0.tobytes()), ("q1", q1.tobytes())])
+    recs = []
+    for k in range(36):
+        recs.append([0, 0, len(q0), 1000 + 1500 * k, 1000 + 1500 * k, 100, 0, 90.0, 0.99995, 0.9])
+    for k in range(22):  # reverse strand: query coordinates are on the reverse complement, colinear with the target
+        recs.append([1, 1, len(q1), 2000 + 1500 * k, 2000 + 1500 * k, 100, 1, 88.0, 0.99991, 0.88])
+    guide = tmp_path / "chained.match"
+    with open(guide, "wb") as f:
+        f.write(struct.pack("<ii", 3, 2))
+        for name in (b"t0\0", b"t1\0"):
+            f.write(struct.pack("<q", len(name)) + name)
+        f.write(struct.pack("<i", 2))
+        for name in (b"q0\0", b"q1\0"):
+            f.write(struct.pack("<q", len(name)) + name)
+        f.write(struct.pack("<i", len(recs)))
+        for r in recs:
+            f.write(struct.pack("<iiiiiiiddd", *[int(x) for x in r[:7]], *[float(x) for x in r[7:]]))
+        f.write(struct.pack("<2i", len(t0), len(t1)) + struct.pack("<2i", len(q0), len(q1)))
+    ref_out, my_out = tmp_path / "ref.match", tmp_path / "b200.match"
+    common = ["-q", str(q), "-t", str(t), "-guide", str(guide), "-cutoff", "1.2"]
+    subprocess.run([oracle.REF_TOOL, *common, "-o", str(ref_out)], check=True, capture_output=True)
+    r = subprocess.run([host_bins["HomologyByXCorr"], *common, "-o", str(my_out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    a, b = _parse_match_file(str(ref_out)), _parse_match_file(str(my_out))
+    assert a[0] == b[0] and a[1] == b[1] and a[3] == b[3] and a[4] == b[4]
+    ra, rb = sorted(a[2]), sorted(b[2])
+    new_fwd = [x for x in ra if x[6] == 0 and x[5] != 100]
+    new_rev = [x for x in ra if x[6] == 1 and x[5] != 100]
+    assert len(new_fwd) > 20 and len(new_rev) > 10      # the pass found matches inside the gaps, on both strands
+    assert len(ra) == len(rb)
+    for x, y in zip(ra, rb):
+        assert x[:7] == y[:7] and x[9] == y[9], (x, y)
+        assert abs(x[8] - y[8]) <= 1e-6 * abs(x[8]) and abs(x[7] - y[7]) <= 1e-9
+
+
+@pytest.mark.gpu
 def test_slave_speaks_the_reference_wire_protocol(host_bins, sx, tmp_path):
     """A scripted master hands t_pairs to the B200 slave over loopback TCP and
     gets t_result records back; they equal the in-process C-ABI results."""
