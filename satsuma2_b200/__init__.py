@@ -184,7 +184,7 @@ class XCorrEngine:
         _check(self._L.sx_create(C.byref(self.cfg), C.byref(h)))
         self._h = h
         self.N = 2 * self.cfg.t_chunk
-        self._keep = []
+        self._keep = [None, None]
 
     def close(self):
         if getattr(self, "_h", None):
@@ -204,8 +204,11 @@ class XCorrEngine:
         self.close()
 
     # ---- loading
-    def _set(self, fn, cs: ChunkSet):
+    def _set(self, fn, cs: ChunkSet, slot: int = 0):
         bases = np.ascontiguousarray(cs.bases, dtype=np.uint8)
+        # async_upload: the library reads the blob until the next sx_align_* call returns -- keep the (possibly
+        # temporary) array and the chunk set alive until then
+        self._keep[slot] = (bases, cs)
         _check(fn(self._h, bases.ctypes.data, cs.offsets.ctypes.data, cs.lens.ctypes.data, cs.starts.ctypes.data,
                   cs.seq_ids.ctypes.data, len(cs), cs.seq_sizes.ctypes.data, len(cs.seq_sizes)))
 
@@ -213,7 +216,7 @@ class XCorrEngine:
         self._set(self._L.sx_set_targets, cs)
 
     def set_queries(self, cs: ChunkSet):
-        self._set(self._L.sx_set_queries, cs)
+        self._set(self._L.sx_set_queries, cs, 1)
 
     def set_targets_raw(self, bases_ptr: int, cs: ChunkSet):
         """Same as set_targets but reads the blob from an explicit host address (e.g. pinned memory)."""

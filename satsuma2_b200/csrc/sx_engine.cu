@@ -287,10 +287,20 @@ static int set_store(sx_ctx *c, ChunkStore &S, const char *bases, const int64_t 
     if (seq_ids && (seq_ids[i] < 0 || seq_ids[i] >= n_seqs))
       return fail(SX_ERR_ARG, "%s: chunk %d refers to sequence %d of %d", what, i, seq_ids[i], n_seqs);
   }
+  if (seq_ids && (!seq_sizes || n_seqs <= 0)) return fail(SX_ERR_ARG, "%s: seq_ids given without seq_sizes", what);
+  // allocate first, commit the metadata only when the device buffer exists: a failed call leaves an empty store
+  // (and, for targets, no cached spectra) behind, never chunk lists that point at a null blob
+  S.n = 0;
+  S.async_pending = false;
+  if (&S == &c->T) std::fill(c->t_valid.begin(), c->t_valid.end(), 0);
   if (S.d_bases && S.cap_bytes < blob + 16) {  // keep the device buffer across calls when it is big enough
     cudaFree(S.d_bases);
     S.d_bases = nullptr;
     S.cap_bytes = 0;
+  }
+  if (blob > 0 && !S.d_bases) {
+    CU(cudaMalloc((void **)&S.d_bases, blob + 16));
+    S.cap_bytes = blob + 16;
   }
   S.n = n;
   S.blob_bytes = blob;
@@ -300,10 +310,6 @@ static int set_store(sx_ctx *c, ChunkStore &S, const char *bases, const int64_t 
   if (seq_ids) S.seq_ids.assign(seq_ids, seq_ids + n); else S.seq_ids.assign(n, 0);
   if (seq_sizes && n_seqs > 0) S.seq_sizes.assign(seq_sizes, seq_sizes + n_seqs); else S.seq_sizes.assign(1, 0);
   if (blob > 0) {
-    if (!S.d_bases) {
-      CU(cudaMalloc((void **)&S.d_bases, blob + 16));
-      S.cap_bytes = blob + 16;
-    }
     S.async_pending = false;
     if (c->cfg.async_upload) {
       // nothing travels yet: upload_pieces() enqueues the pieces as the batches ask for them

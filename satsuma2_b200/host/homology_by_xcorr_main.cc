@@ -185,7 +185,10 @@ int main(int argc, char **argv) {
         blocks.push_back(p);
       }
     }
-    if (blocks.size() >= 64 && !flush()) break;
+    if (blocks.size() >= 64 && !flush()) {  // a GPU failure must not end in a truncated match file and exit code 0
+      fprintf(stderr, "HomologyByXCorr(B200): %s\n", hx.error().c_str());
+      return 1;
+    }
   }
   if (!flush()) {
     fprintf(stderr, "HomologyByXCorr(B200): %s\n", hx.error().c_str());

@@ -88,3 +88,54 @@ def compare_pair_records(oracle, got, exp, tchunk, qchunk, t_start, q_start, q_s
         assert (lag in border) or near_prob, f"unexplained match difference {k} (lag {lag}, prob {rec['prob']})"
         listed.append(dict(key=k, lag=int(lag), where="gpu-only" if k in g else "oracle-only",
                            prob=float(rec["prob"]), reason="threshold" if lag in border else "min_prob"))
+
+
+def candidate_pairs(key, T, Q, q_chunk_flag):
+    """Chunk pairs (t, q) a record key can have come from.  T / Q: lists of (bases, start, seq_id, seq_size).
+    Target chunks overlap, so up to two targets qualify; the reverse-strand query coordinate is inverted
+    with the slave's RCQuery formula (Slave.cc:56-60, 180)."""
+    qid, tid, qsize, qstart, tstart, _, reverse = key
+    ts = [i for i, c in enumerate(T) if c[2] == tid and c[1] <= tstart < c[1] + len(c[0])]
+    qs = []
+    for j, c in enumerate(Q):
+        if c[2] != qid:
+            continue
+        if not reverse:
+            sq = qstart - c[1]
+        else:
+            v = qstart if qstart < (1 << 63) else qstart - (1 << 64)
+            sq = v - qsize + c[1] + q_chunk_flag
+        if 0 <= sq < len(c[0]):
+            qs.append(j)
+    return [(t, q) for t in ts for q in qs]
+
+
+def explain_set_difference(oracle, got, exp, T, Q, gpu_pair, exp_pair, q_chunk_flag, N, cutoff, min_prob, target_total,
+                           listed, max_pairs=64):
+    """Whole record sets of many chunk pairs (a block, a grid, a genome).  Identical sets pass at once;
+    otherwise every record of the symmetric difference is traced back to the chunk pair(s) it can have come
+    from, those pairs are re-run one by one on both sides (gpu_pair(t, q) / exp_pair(t, q) -> records) and
+    compare_pair_records must explain each difference by a borderline candidate lag or probability (it appends
+    to `listed`, it asserts otherwise).  A differing record that no re-run pair reproduces is unexplained."""
+    gk = {rec_key(r) for r in got}
+    ek = {rec_key(r) for r in exp}
+    diff = gk ^ ek
+    if not diff:
+        return 0
+    pairs = []
+    for k in sorted(diff):
+        cp = candidate_pairs(k, T, Q, q_chunk_flag)
+        assert cp, f"record {k} maps to no chunk pair"
+        for p in cp:
+            if p not in pairs:
+                pairs.append(p)
+    assert len(pairs) <= max_pairs, f"{len(diff)} differing records over {len(pairs)} chunk pairs: not borderline noise"
+    before = len(listed)
+    for (t, q) in pairs:
+        gp, ep = gpu_pair(t, q), exp_pair(t, q)
+        compare_pair_records(oracle, gp, ep, T[t][0], Q[q][0], T[t][1], Q[q][1], Q[q][3], q_chunk_flag, N, cutoff,
+                             min_prob, target_total, listed)
+    accounted = {tuple(item["key"]) for item in listed[before:]}
+    missing = diff - accounted
+    assert not missing, f"differences not reproduced pair by pair: {sorted(missing)[:5]}"
+    return len(diff)

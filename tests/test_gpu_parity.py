@@ -6,7 +6,8 @@ import os
 import numpy as np
 import pytest
 
-from parity import (XC_TOL, chunk_list, compare_candidates, compare_pair_records, rec_key, xc_rel_err)
+from parity import (XC_TOL, chunk_list, compare_candidates, compare_pair_records, explain_set_difference, rec_key,
+                    xc_rel_err)
 
 pytestmark = pytest.mark.gpu
 N = 8192
@@ -92,7 +93,7 @@ def test_samples_blocks_match_reference(samples_engine, golden_samples, oracle_l
     assert len(listed) <= 2, listed
 
 
-def test_samples_prob_table_mode(sx, golden_samples):
+def test_samples_prob_table_mode(sx, golden_samples, oracle_lib):
     g = golden_samples
     T = chunk_list(g["t_bases"], g["t_lens"], g["t_starts"], g["t_seq"], g["t_seqsize"])
     Q = chunk_list(g["q_bases"], g["q_lens"], g["q_starts"], g["q_seq"], g["q_seqsize"])
@@ -105,9 +106,14 @@ def test_samples_prob_table_mode(sx, golden_samples):
         b = [int(x) for x in g["block_table"]]
         got = eng.align_blocks([tuple(b)])
         exp = g["block_table_records"]
-        gk, ek = set(map(rec_key, got)), set(map(rec_key, exp))
-        # candidate sets can differ at borderline lags only: allow a handful of the ~1800 records
-        assert len(gk ^ ek) <= 0.01 * len(ek), (len(gk), len(ek), len(gk ^ ek))
+        # in table mode hundreds of records hang on one candidate lag: every differing record must trace back to a
+        # lag within 1e-4 of the FindTop threshold (listed), nothing else is tolerated
+        params = oracle_lib.make_params(target_total=float(g["target_total"]), prob_table=tab, table_value=0.9999)
+        listed = []
+        explain_set_difference(oracle_lib, got, exp, T, Q, lambda t, q: eng.align_blocks([(t, t, q, q, b[4])]),
+                               lambda t, q: oracle_lib.align_pairs(params, T, Q, [(t, q)], fast=bool(b[4])), 4096, N,
+                               2.9 if b[4] else 1.8, 0.99, float(g["target_total"]), listed)
+        _log_listed("samples_prob_table", listed)
         assert set(np.unique(got["prob"])) == {0.9999}
         ge = {rec_key(r): r for r in got}
         for r in exp:
@@ -267,8 +273,10 @@ def test_sorted_results_follow_reference_order(sx, golden_samples):
         eng.set_queries(sx.ChunkSet.from_list(Q))
         got = eng.align_blocks([(0, 7, 0, 7, 0)])
     exp = g["block_0"]
-    if sorted(map(rec_key, got)) == sorted(map(rec_key, exp)):
-        assert list(map(rec_key, got)) == list(map(rec_key, exp))
+    # block_0's record set is identical on the fixture (test_samples_blocks_match_reference explains any
+    # borderline flip); here the ORDER is the subject, so the sets must agree outright
+    assert sorted(map(rec_key, got)) == sorted(map(rec_key, exp))
+    assert list(map(rec_key, got)) == list(map(rec_key, exp))
 
 
 def test_capacity_error_reports_required_size(sx, golden_samples):
@@ -286,7 +294,11 @@ def test_capacity_error_reports_required_size(sx, golden_samples):
         out = np.zeros(3, dtype=sx.RESULT_DTYPE)
         n = C.c_int64(0)
         rc = eng._L.sx_align_blocks(eng._h, arr.ctypes.data, 1, out.ctypes.data, 3, C.byref(n))
-        assert rc == sx.SX_ERR_CAPACITY and n.value == len(g["block_0"]) or abs(n.value - len(g["block_0"])) <= 2
+        assert rc == sx.SX_ERR_CAPACITY, rc
+        assert n.value == len(g["block_0"]), (n.value, len(g["block_0"]))
+        out = np.zeros(n.value, dtype=sx.RESULT_DTYPE)  # the size it asked for is enough
+        rc = eng._L.sx_align_blocks(eng._h, arr.ctypes.data, 1, out.ctypes.data, n.value, C.byref(n))
+        assert rc == sx.SX_OK and n.value == len(out)
         with pytest.raises(sx.SatsumaError):
             eng.align_pairs([(0, 9999)])
 
@@ -455,10 +467,18 @@ def test_repeat_rich_prob_table(sx, oracle_lib):
     params = oracle_lib.make_params(target_total=total, prob_table=tab, table_value=0.9999)
     pairs = [(t, q) for q in range(nq) for t in range(nt)]
     exp = oracle_lib.align_pairs(params, T, Q, pairs, threads=os.cpu_count() or 1)
-    gk, ek = set(map(rec_key, got)), set(map(rec_key, exp))
-    assert len(ek) > 2000, len(ek)
-    # in table mode thousands of records hang on every candidate lag: allow only a sliver of borderline flips
-    assert len(gk ^ ek) <= 0.002 * len(ek), (len(gk), len(ek), len(gk ^ ek))
+    assert len(exp) > 2000, len(exp)
+    # thousands of records hang on every candidate lag in table mode: each differing record is traced to its
+    # chunk pair and must sit on a lag within 1e-4 of the FindTop threshold (listed)
+    listed = []
+    with sx.XCorrEngine(target_total=total, use_prob_table=1, prob_table_value=0.9999) as eng2:
+        eng2.set_prob_table(tab)
+        eng2.set_targets(tcs)
+        eng2.set_queries(qcs)
+        explain_set_difference(oracle_lib, got, exp, T, Q, lambda t, q: eng2.align_blocks([(t, t, q, q, 0)]),
+                               lambda t, q: oracle_lib.align_pairs(params, T, Q, [(t, q)]), 4096, N, 1.8, 0.99, total,
+                               listed)
+    _log_listed("repeat_rich_prob_table", listed)
     ge = {rec_key(r): r for r in got}
     for r in exp:
         k = rec_key(r)
@@ -625,3 +645,75 @@ def test_async_upload_matches_blocking_upload(sx):
             outs.append(np.sort(r, order=["query_id", "tstart", "qstart", "len", "reverse"]))
     assert len(outs[0]) == len(outs[1]) > n // 2
     assert outs[0].tobytes() == outs[1].tobytes()
+
+
+def _samples_full():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "samples_full.npz"))
+    tseq, qseq = g["t_seq"], g["q_seq"]
+    T = [(tseq[s:s + n].tobytes(), int(s), 0, len(tseq)) for s, n in zip(g["t_starts"], g["t_lens"])]
+    Q = [(qseq[s:s + n].tobytes(), int(s), 0, len(qseq)) for s, n in zip(g["q_starts"], g["q_lens"])]
+    return g, tseq, qseq, T, Q
+
+
+def test_full_config0_every_chunk_pair(sx, oracle_lib):
+    """configs[0] in full: all 261 x 245 = 63,945 chunk pairs of samples/dog.X.part.fasta (target) vs
+    samples/human.X.part.fasta (query), slave semantics.  Expected records: the UNMODIFIED reference
+    (oracle/_ref/libsatsuma_ref.so, HomologyByXCorr::align_target on all host cores), run live on this box and
+    first checked against the digest of what it produced in the development container
+    (tests/golden/samples_full.npz); without the compiled reference, the C restatement (which the CPU suite pins
+    against the same digest).  Every difference is traced to its chunk pair and must be a listed borderline."""
+    import oracle
+    sys_path_golden = os.path.join(ROOT, "tests", "golden")
+    import sys
+    if sys_path_golden not in sys.path:
+        sys.path.insert(0, sys_path_golden)
+    from make_samples_full import record_digest
+
+    g, tseq, qseq, T, Q = _samples_full()
+    total = float(g["target_total"])
+    nt, nq = len(T), len(Q)
+    assert (nt, nq) == (261, 245)
+    threads = os.cpu_count() or 1
+    if oracle.have_reference():
+        R = oracle.Reference()
+        R.configure()
+        R.set_chunks(True, T, [len(tseq)])
+        R.set_chunks(False, Q, [len(qseq)])
+        tp = np.array([[t, t, q, q, 0] for q in range(nq) for t in range(nt)], dtype=np.int32)
+        exp, _, n = R.align_pairs_mt(tp, threads)
+        assert n == len(exp)
+        kind = "reference"
+    else:
+        params = oracle_lib.make_params(target_total=total)
+        exp = oracle_lib.align_pairs(params, T, Q, [(t, q) for q in range(nq) for t in range(nt)], threads=threads)
+        kind = "port"
+    assert len(exp) == int(g["n_records"]) and int(exp["reverse"].sum()) == int(g["n_reverse"])
+    assert record_digest(exp) == str(g["digest"]), f"{kind} output differs from the development container's reference run"
+
+    to = np.asarray(g["t_starts"], np.int64)
+    qo = np.asarray(g["q_starts"], np.int64)
+    params = oracle_lib.make_params(target_total=total)
+    listed = []
+    with sx.XCorrEngine(target_total=total) as eng:
+        eng.set_targets(sx.ChunkSet(tseq, to, g["t_lens"], g["t_starts"], np.zeros(nt, np.int32), [len(tseq)]))
+        eng.set_queries(sx.ChunkSet(qseq, qo, g["q_lens"], g["q_starts"], np.zeros(nq, np.int32), [len(qseq)]))
+        got = eng.align_blocks([(0, nt - 1, 0, nq - 1, 0)])
+        st = eng.stats()
+        assert st["chunk_pairs"] == nt * nq
+        ndiff = explain_set_difference(oracle_lib, got, exp, T, Q, lambda t, q: eng.align_blocks([(t, t, q, q, 0)]),
+                                       lambda t, q: oracle_lib.align_pairs(params, T, Q, [(t, q)]), 4096, N, 1.8, 0.99,
+                                       total, listed)
+    ge = {rec_key(r): r for r in exp}
+    for r in got:
+        e = ge.get(rec_key(r))
+        if e is not None:
+            assert r["ident"] == e["ident"]
+            assert abs(float(r["prob"]) - float(e["prob"])) <= 1e-6 * abs(float(e["prob"]))
+    _log_listed("full_config0", listed)
+    d = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "full_config0.json"), "w") as f:
+        json.dump({"chunk_pairs": nt * nq, "expected_from": kind, "records_expected": int(len(exp)),
+                   "records_gpu": int(len(got)), "differing_records": int(ndiff), "unexplained": 0,
+                   "listed": [dict(x, key=[int(v) for v in x["key"]]) for x in listed]}, f)
+    assert len(listed) <= 8, listed

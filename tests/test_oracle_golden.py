@@ -136,3 +136,64 @@ def test_large_transforms_against_reference(oracle_lib, golden_large, NN):
     ge = {rec_key(r): r for r in exp}
     for r in got:
         assert r["prob"] == ge[rec_key(r)]["prob"] and r["ident"] == ge[rec_key(r)]["ident"]
+
+
+def test_full_config0_stripe_against_reference_digest(oracle_lib):
+    """configs[0]: every target chunk x a stripe of query chunks of the sample pair through the C restatement;
+    the sorted record keys + identities hash to what the unmodified reference produced in the development
+    container (tests/golden/make_samples_full.py).  The whole grid is checked on the GPU box (-m gpu)."""
+    import os
+    import sys
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    from make_samples_full import record_digest
+
+    g = np.load(os.path.join(here, "samples_full.npz"))
+    tseq, qseq = g["t_seq"], g["q_seq"]
+    assert (len(tseq), len(qseq)) == (800001, 1000001)
+    T = [(tseq[s:s + n].tobytes(), int(s), 0, len(tseq)) for s, n in zip(g["t_starts"], g["t_lens"])]
+    Q = [(qseq[s:s + n].tobytes(), int(s), 0, len(qseq)) for s, n in zip(g["q_starts"], g["q_lens"])]
+    q0, q1 = (int(x) for x in g["stripe_q"])
+    params = oracle_lib.make_params(target_total=float(g["target_total"]))
+    pairs = [(t, q) for q in range(q0, q1) for t in range(len(T))]
+    recs = oracle_lib.align_pairs(params, T, Q, pairs, threads=os.cpu_count() or 1)
+    assert len(recs) == int(g["stripe_n"])
+    assert record_digest(recs) == str(g["stripe_digest"])
+
+
+def test_fp32_prereject_margin():
+    """The scan kernel drops a segment before any FP64 arithmetic when a float estimate of the normalised
+    deviation z exceeds z_cut + 0.25 (csrc/sx_scan.cuh score_fast).  Brute force over (len, gcT, gcQ, matches):
+    the float32 evaluation of the same expression stays within 0.05 of the FP64 value the exact path computes
+    wherever the decision could matter (|z| < 60), so "estimate > z_cut + 0.25" implies "exact z > z_cut" with a
+    5x margin -- the pre-reject can never drop a segment the exact path would keep."""
+    f32 = np.float32
+    worst = 0.0
+    rng = np.random.default_rng(1)
+    lens = list(range(46, 200)) + [int(x) for x in rng.integers(200, 8192, 200)]
+    for ln in lens:
+        if ln < 200:
+            gt, gq = np.meshgrid(np.arange(0, ln + 1), np.arange(0, ln + 1), indexing="ij")
+            gt, gq = gt.ravel(), gq.ravel()
+        else:
+            gt, gq = rng.integers(0, ln + 1, 4000), rng.integers(0, ln + 1, 4000)
+        for m in sorted(set(int(x) for x in np.linspace(19, ln, 24))):
+            # FP64, operation order of score_counts / GetMatchProbabilityEx (AlignProbability.cc:62-127)
+            dl = float(ln)
+            gct = gt / dl
+            r = gq * gct + (dl - gq) * (1.0 - gct)
+            p = r / dl / 2.0
+            with np.errstate(divide="ignore", invalid="ignore"):
+                s = np.sqrt(p * (1.0 - p) * dl)
+                z = ((p * dl - dl * (m / dl)) / s) / 1.414213562
+                # FP32, operation order of the pre-reject
+                fl = f32(ln)
+                num = (gq * gt + (ln - gq) * (ln - gt)).astype(f32)
+                pf = num / (f32(2.0) * fl * fl)
+                zf = (pf * fl - f32(m)) * (f32(1.0) / np.sqrt(pf * (f32(1.0) - pf) * fl)) * f32(0.70710678)
+            ok = np.isfinite(z) & np.isfinite(zf) & (np.abs(z) < 60.0)
+            if ok.any():
+                worst = max(worst, float(np.abs(zf[ok].astype(np.float64) - z[ok]).max()))
+    assert worst < 0.05, worst
