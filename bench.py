@@ -301,6 +301,9 @@ def main():
                     help="pairs = configs[1] (the headline metric); grid = configs[3]-style block search of a synthetic "
                          "genome pair with target spectra cached in HBM, sharded by target range (strong scaling)")
     ap.add_argument("--genome-mb", type=float, default=24.0, help="--workload grid: bases per genome, in millions")
+    ap.add_argument("--target-total", type=float, default=0.0,
+                    help="targetTotal of the probability filter (default: pairs x chunk, i.e. every target chunk of the "
+                         "step); profiling runs with fewer pairs pass the full step's 4294967296")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing hygiene: at least 3 warm-up steps
@@ -334,7 +337,8 @@ def main():
     pairs = np.ascontiguousarray(np.stack([np.arange(n), np.arange(n)], axis=1), dtype=np.int32)
 
     # spectra are never kept across steps (cache disabled): every step redoes the whole path
-    eng = sx.XCorrEngine(device=local_rank, target_total=float(n) * CHUNK, max_batch_pairs=args.batch,
+    target_total = args.target_total if args.target_total > 0 else float(n) * CHUNK
+    eng = sx.XCorrEngine(device=local_rank, target_total=target_total, max_batch_pairs=args.batch,
                          spectra_cache_bytes=-1, async_upload=1)
     stream = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
     t_ptr, q_ptr = T.ctypes.data, Q.ctypes.data

@@ -120,6 +120,10 @@ struct sx_ctx {
   ChunkStore T, Q;
   double target_total = 0;
   double z_cut = INFINITY;
+  int run_min = 0;                 // compute_run_min() for the parameters below
+  double rm_z_cut = NAN;           // ... cached: it only changes with z_cut / the table / min_len
+  int rm_use_table = -1, rm_min_len = -1;
+  std::vector<double> h_table;     // host copy of the ProbTable (run_min in -prob_table mode)
 
   // signal slots: [0, n_persist) = cached target spectra (slot == target chunk index),
   // then two per-batch workspaces of n_transient slots each: while the device still works on batch k, batch
@@ -456,6 +460,8 @@ extern "C" int sx_set_prob_table(sx_ctx *c, const double *table) {
   if (rc != SX_OK) return rc;
   CU(cudaMemcpy(c->d_table.p, table, sizeof(double) * 512 * 2048, cudaMemcpyHostToDevice));
   c->have_table = true;
+  c->h_table.assign(table, table + (size_t)512 * 2048);
+  c->rm_use_table = -1;  // run_min depends on the table
   return SX_OK;
 }
 
@@ -538,6 +544,49 @@ static double compute_z_cut(double min_prob, double target_total) {
   return hi + 1e-9;
 }
 
+// Shortest run of passing windows whose segment can still pass the probability filter (ScoreParams::run_min).
+// A run of r consecutive passing windows that follows a failing window starts with exactly 19 matches in its
+// first window (the 46-window count moves by at most one per position), so its segment -- the union of the r
+// windows, 45 + r positions -- holds at most 18 + r matches.  r is prunable when, for EVERY base composition
+// (gcT, gcQ) that admits that many matches, score_counts rejects a segment of 45 + r positions with
+// min(18 + r, feasible) matches: more matches only lower z / raise the identity, so that is the best case.
+// The test mirrors score_counts operation for operation; "z <= z_cut" counts as kept (the exact path decides),
+// NaN counts as kept.  Returns the first r that is NOT prunable; every shorter run is never scored.
+static int compute_run_min(double z_cut, int use_table, const double *table, int min_len) {
+  const int R_MAX = 256;
+  for (int r = 1; r < R_MAX; r++) {
+    const int len = 45 + r;
+    if (len < min_len) continue;  // dropped by -l whatever its score (Slave.cc:172)
+    const double dl = (double)len;
+    bool keepable = false;
+    for (int gt = 0; gt <= len && !keepable; gt++) {
+      for (int gq = 0; gq <= len; gq++) {
+        const int feasible = std::min(gq, gt) + std::min(len - gq, len - gt);  // matches need equal bases
+        const int m = std::min(18 + r, feasible);
+        if (m < 19) continue;  // the first window alone holds 19 matches
+        const double ident = (double)m / dl;
+        const double gc_target = (double)gt / dl;
+        const double at_target = 1. - gc_target;
+        double rr = (double)gq * gc_target;
+        rr = rr + (dl - (double)gq) * at_target;
+        const double p_match = rr / dl / 2.;
+        if (use_table) {
+          const int index = (int)(p_match * 511.0);
+          if (index < 1 || index > 511) continue;
+          const int l = len >= 2048 ? 2047 : len;
+          if (!table || ident >= table[(size_t)index * 2048 + l]) { keepable = true; break; }
+        } else {
+          const double sd = std::sqrt(p_match * (1. - p_match) * dl);
+          const double z = (p_match * dl - dl * ident) / sd / 1.414213562;
+          if (!(z > z_cut)) { keepable = true; break; }
+        }
+      }
+    }
+    if (keepable) return r;
+  }
+  return R_MAX;
+}
+
 static ScoreParams score_params(const sx_ctx *c) {
   ScoreParams p;
   p.target_total = c->target_total;
@@ -548,7 +597,7 @@ static ScoreParams score_params(const sx_ctx *c) {
   p.use_table = (c->cfg.use_prob_table && c->have_table) ? 1 : 0;
   p.z_cut = c->z_cut;
   p.run_cap = c->cfg.debug_small_pools ? 8 : 0;  // forces the scan kernel's queue-overflow paths
-  p.pad_ = 0;
+  p.run_min = (c->cfg.debug_flags & 1) ? 0 : c->run_min;
   return p;
 }
 
@@ -721,6 +770,15 @@ static int batch_launch(sx_ctx *c, Run &r) {
     r.seg_tap_cap = (unsigned int)c->d_seg_tap.n;
   }
   c->z_cut = c->cfg.use_prob_table ? INFINITY : compute_z_cut(c->cfg.min_prob, c->target_total);
+  {
+    const int use_table = (c->cfg.use_prob_table && c->have_table) ? 1 : 0;
+    if (!(c->rm_z_cut == c->z_cut) || c->rm_use_table != use_table || c->rm_min_len != c->cfg.min_len) {
+      c->run_min = compute_run_min(c->z_cut, use_table, c->h_table.empty() ? nullptr : c->h_table.data(), c->cfg.min_len);
+      c->rm_z_cut = c->z_cut;
+      c->rm_use_table = use_table;
+      c->rm_min_len = c->cfg.min_len;
+    }
+  }
   r.need_xcorr = true;
   r.active = true;
   if ((rc = batch_kernels(c, r)) != SX_OK) return rc;

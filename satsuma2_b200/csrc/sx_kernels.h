@@ -62,7 +62,7 @@ struct ScoreParams {
   int32_t use_table;
   double z_cut;  // early reject when the normalised deviation z exceeds this (+inf disables)
   int32_t run_cap;  // test hook: run ends queued per warp in the scan kernel (0 = the built-in capacity)
-  int32_t pad_;
+  int32_t run_min;  // runs of fewer passing windows (behind a failing one) cannot pass the filter: never scored
 };
 
 struct BatchCounters {  // device-side, zeroed per batch

@@ -323,6 +323,8 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
   unsigned long long my_positions = 0;
   unsigned int qn = 0;  // run ends in this warp's queue (warp-uniform)
   const unsigned int run_cap = prm.run_cap > 0 ? min((unsigned int)prm.run_cap, (unsigned int)SX_RUN_CAP) : SX_RUN_CAP;
+  const int run_min = seg_tap != nullptr ? 0 : prm.run_min;  // the segment tap wants every raw segment
+  const bool byte_filter = run_min >= 15;
   for (;;) {  // groups of 32 candidate lags, handed out dynamically
     unsigned int g = 0;
     if (lane == 0) g = atomicAdd(&s_next, 1u);
@@ -377,6 +379,10 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
           jt -= 32u;
         }
       }
+      // run_min pruning (ScoreParams::run_min): a run of r passing windows that follows a failing window holds
+      // at most 18 + r matches in its 45 + r positions; the host has verified that no such segment passes the
+      // probability filter for r < run_min.  Runs that start at the first evaluated window (k = 46) are exempt.
+      if (e - start_k < run_min && start_k > 46) return;
       start_k -= 45;
       const int start_t = od.i0 + start_k, seg_len = e - start_k;
       tap_segment(spi, start_t, od.shift, seg_len, seg_tap, seg_tap_cap, ctr);
@@ -420,57 +426,133 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
     //   q3:                       m[kw-1] bits 11..31 + m[kw]
     unsigned int n_items = 0;
     {
-      int pp_all = 0, pp_ge3 = 0, pp_ge11 = 0;  // of m[kw-1]
-      int p2_ge19 = 0, p2_ge27 = 0;             // of m[kw-2]
-      int q_ge19 = 0, q_ge27 = 0;               // of m[kw-1], become p2_* next step
       const uint2 *pt = P.t + d.tw0, *pq = P.q + d.qw0;
       uint2 rt = pt[0], rq = pq[0];
-      uint32_t acc = 0, bit = 1u;
-      // one word: FULL = every lane's diagonal covers the whole word (no masking, no clamping)
-      auto step = [&](int kw, bool full) {
+      // match word kw of this lane's diagonal; FULL = every lane's diagonal covers the whole word (no masking,
+      // no clamping).  Returns false past the end of the diagonal (m = 0 there).
+      auto match_word = [&](int kw, bool full, uint32_t &m) -> bool {
         const int kn = full ? kw + 1 : min(kw + 1, d.nwords);  // a shorter diagonal idles, never reads past its planes
         const uint2 nt = pt[kn], nq = pq[kn];
         const uint32_t tl = __funnelshift_r(rt.x, nt.x, d.tsh), th = __funnelshift_r(rt.y, nt.y, d.tsh);
         const uint32_t ql = __funnelshift_r(rq.x, nq.x, d.qsh), qh = __funnelshift_r(rq.y, nq.y, d.qsh);
         rt = nt;
         rq = nq;
-        uint32_t m = ~((tl ^ ql) | (th ^ qh));
-        bool inside = true;
-        if (!full) {  // the diagonal's last word is partial, words after it are empty
-          inside = kw < d.nwords;
-          m &= kw < d.nwords - 1 ? 0xffffffffu : (kw == d.nwords - 1 ? d.lastmask : 0u);
-        }
-        const int c_all = __popc(m), c_lo8 = __popc(m & 0xffu), c_lo16 = __popc(m & 0xffffu),
-                  c_lo24 = __popc(m & 0xffffffu);
-        const int u0 = p2_ge19 + pp_all + c_lo8;
-        const int u1 = p2_ge27 + pp_all + c_lo16;
-        const int u2 = pp_ge3 + c_lo24;
-        const int u3 = pp_ge11 + c_all;
-        if (inside && max(max(u0, u1), max(u2, u3)) >= 19) acc |= bit;
-        bit <<= 1;
-        p2_ge19 = q_ge19;
-        p2_ge27 = q_ge27;
-        pp_all = c_all;
-        pp_ge3 = __popc(m >> 3);
-        pp_ge11 = __popc(m >> 11);
-        q_ge19 = __popc(m >> 19);
-        q_ge27 = __popc(m >> 27);
+        m = ~((tl ^ ql) | (th ^ qh));
+        if (full) return true;
+        // the diagonal's last word is partial, words after it are empty
+        m &= kw < d.nwords - 1 ? 0xffffffffu : (kw == d.nwords - 1 ? d.lastmask : 0u);
+        return kw < d.nwords;
       };
       // words [0, nw_full) are full on every diagonal of the group (empty lanes do not count: their bits are dropped)
       const bool live = d.nwords > 0;
       const int nw_full = min(__reduce_min_sync(0xffffffffu, live ? d.nwords - 1 : 0x7fffffff), nw_max);
-      for (int w = 0; w < nbw; w++) {  // warp-uniform
-        acc = 0;
-        bit = 1u;
-        const int kw_end = min(nw_max, w * 32 + 32), kw_full = max(w * 32, min(nw_full, kw_end));
-        int kw = w * 32;
+      if (!byte_filter) {
+        int pp_all = 0, pp_ge3 = 0, pp_ge11 = 0;  // of m[kw-1]
+        int p2_ge19 = 0, p2_ge27 = 0;             // of m[kw-2]
+        int q_ge19 = 0, q_ge27 = 0;               // of m[kw-1], become p2_* next step
+        uint32_t acc = 0, bit = 1u;
+        auto step = [&](int kw, bool full) {
+          uint32_t m;
+          const bool inside = match_word(kw, full, m);
+          const int c_all = __popc(m), c_lo8 = __popc(m & 0xffu), c_lo16 = __popc(m & 0xffffu),
+                    c_lo24 = __popc(m & 0xffffffu);
+          const int u0 = p2_ge19 + pp_all + c_lo8;
+          const int u1 = p2_ge27 + pp_all + c_lo16;
+          const int u2 = pp_ge3 + c_lo24;
+          const int u3 = pp_ge11 + c_all;
+          if (inside && max(max(u0, u1), max(u2, u3)) >= 19) acc |= bit;
+          bit <<= 1;
+          p2_ge19 = q_ge19;
+          p2_ge27 = q_ge27;
+          pp_all = c_all;
+          pp_ge3 = __popc(m >> 3);
+          pp_ge11 = __popc(m >> 11);
+          q_ge19 = __popc(m >> 19);
+          q_ge27 = __popc(m >> 27);
+        };
+        for (int w = 0; w < nbw; w++) {  // warp-uniform
+          acc = 0;
+          bit = 1u;
+          const int kw_end = min(nw_max, w * 32 + 32), kw_full = max(w * 32, min(nw_full, kw_end));
+          int kw = w * 32;
 #pragma unroll 4
-        for (; kw < kw_full; kw++) step(kw, true);  // warp-uniform trip counts
+          for (; kw < kw_full; kw++) step(kw, true);  // warp-uniform trip counts
 #pragma unroll 2
-        for (; kw < kw_end; kw++) step(kw, false);
-        if (!live) acc = 0;
-        s_need[w][lane] = acc;
-        n_items += __popc(acc);
+          for (; kw < kw_end; kw++) step(kw, false);
+          if (!live) acc = 0;
+          s_need[w][lane] = acc;
+          n_items += __popc(acc);
+        }
+      } else {
+        // Byte filter (run_min >= 15).  Only runs of >= run_min passing windows are of interest; such a run
+        // contains a whole aligned byte of positions [8g, 8g+7].  Its last window, ending at 8g+7, lies inside bytes
+        // g-5 .. g: S6(g) = sum of their match counts >= 19; its first window, ending at 8g, lies inside bytes
+        // g-6 .. g-1 plus one position of byte g: S7(g) - c(g) + 1 >= 19.  F marks the words with such a byte.
+        // A run also touches words where it covers no whole byte; every word between those and the byte's word is
+        // covered entirely, hence in F.  Where the run crosses from word i into word i+1 the top window of word i
+        // passes (its top byte has S6 >= 19: H) and the bottom window of word i+1 passes (S7 of its bottom byte
+        // >= 19: L): X(i) = H(i) & L(i+1).  items = F | X(i) & F(i+1) | X(i-1) & F(i-1).
+        // Word 1 holds the first evaluated window (k = 46, positions 1 .. 46, inside bytes 0 .. 5): a run that
+        // starts there is scored whatever its length, so word 1 is an item when those bytes hold 19 matches.
+        // Counts are kept four bytes to a register: c = match counts of the word's bytes, c * 0x01010101 their
+        // prefix sums; nothing exceeds 56, so the byte lanes never carry into each other.
+        uint32_t cp = 0, cpp = 0;  // byte counts of words kw-1, kw-2
+        uint32_t bn = 0;           // for word kw-1: {T, T, T - P0, T - P1}: what its bytes add to S6 of the next word's bytes
+        uint32_t accF = 0, accH = 0, accL = 0, bit = 1u;
+        auto step = [&](int kw, bool full) {
+          uint32_t m;
+          const bool inside = match_word(kw, full, m);
+          const uint32_t c = (uint32_t)__popc(m & 0xffu) | ((uint32_t)__popc(m & 0xff00u) << 8) |
+                             ((uint32_t)__popc(m & 0xff0000u) << 16) | ((uint32_t)__popc(m & 0xff000000u) << 24);
+          const uint32_t pre = c * 0x01010101u;                    // byte j: c0 + .. + cj
+          const uint32_t s6 = pre + bn + (cpp >> 24);               // byte j: counts of bytes g-5 .. g
+          const uint32_t s7 = s6 + __byte_perm(cpp, cp, 0x5432);    // byte j: counts of bytes g-6 .. g
+          const uint32_t t6 = (s6 + 0x6d6d6d6du) & 0x80808080u;     // bytes with S6 >= 19
+          const uint32_t t7 = (s7 - c + 0x6e6e6e6eu) & 0x80808080u;  // bytes with S7 - c >= 18
+          if (inside && (t6 & t7)) accF |= bit;
+          if (inside && (t6 >> 31)) accH |= bit;
+          if (inside && ((s7 + 0x6du) & 0x80u)) accL |= bit;
+          bit <<= 1;
+          const uint32_t tot = pre >> 24;
+          bn = tot * 0x01010101u - (pre << 16);
+          cpp = cp;
+          cp = c;
+        };
+        bool w1 = false;
+        if (d.nwords > 1) {
+          uint32_t tl, th, ql, qh;
+          diag_words(P, d.tw0, d.tsh, d.qw0, d.qsh, tl, th, ql, qh);
+          int cnt = __popc(~((tl ^ ql) | (th ^ qh)));
+          diag_words(P, d.tw0 + 1, d.tsh, d.qw0 + 1, d.qsh, tl, th, ql, qh);
+          cnt += __popc(~((tl ^ ql) | (th ^ qh)) & 0xffffu & (d.nwords == 2 ? d.lastmask : 0xffffffffu));
+          w1 = cnt >= 19;
+        }
+        uint32_t carryF = 0u, carryH = 0u;  // F / H of word 32w - 1
+        for (int w = 0; w < nbw; w++) {  // warp-uniform
+          accF = accH = accL = 0;
+          bit = 1u;
+          const int kw_end = min(nw_max, w * 32 + 32), kw_full = max(w * 32, min(nw_full, kw_end));
+          int kw = w * 32;
+#pragma unroll 4
+          for (; kw < kw_full; kw++) step(kw, true);  // warp-uniform trip counts
+#pragma unroll 2
+          for (; kw < kw_end; kw++) step(kw, false);
+          const uint32_t x = accH & (accL >> 1);  // crossings between words of this block
+          uint32_t acc = accF | (x & (accF >> 1)) | ((x & accF) << 1);
+          if (carryH & accL & 1u) {  // a run may cross from the previous block's last word into this block's first
+            if (carryF) acc |= 1u;
+            if ((accF & 1u) && live && !(s_need[w - 1][lane] >> 31)) {
+              s_need[w - 1][lane] |= 0x80000000u;
+              n_items++;
+            }
+          }
+          carryF = accF >> 31;
+          carryH = accH >> 31;
+          if (w == 0 && w1) acc |= 2u;
+          if (!live) acc = 0;
+          s_need[w][lane] = acc;
+          n_items += __popc(acc);
+        }
       }
     }
     __syncwarp();
@@ -529,12 +611,31 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
         uint32_t fall = ~pass & ((pass << 1) | carry_in);
         // a run that reaches the end of the word ends there unless the next word is an item too
         const bool edge = (pass >> 31) && next_it != it + 32u;
+        my_segments += (unsigned int)__popc(fall) + (edge ? 1u : 0u);
+        if (run_min > 1) {
+          // Runs that lie inside this word and are shorter than run_min never reach the queue (see do_end).  Kept:
+          // run ends with >= run_min passing positions right below them (erosion of the pass word), the lowest run
+          // end when the run reaches bit 0 (it may have begun in an earlier word; do_end decides) and, in word 1,
+          // the run that starts at the first evaluated window (bit 14).
+          uint32_t er = pass;
+          for (int have = 1; have < run_min && er; ) {  // warp-uniform trip count except for the early exit
+            const int sft = min(have, run_min - have);
+            er &= er >> sft;
+            have += sft;
+          }
+          uint32_t keep = run_min < 32 ? (er << run_min) : 0u;
+          keep |= (~pass) & (0u - (~pass));  // lowest failing position: the run below it (if any) reaches bit 0
+          if ((it >> 5) == 1u) {
+            const uint32_t z = ~(pass | 0x3fffu);
+            keep |= z & (0u - z);
+          }
+          fall &= keep;
+        }
         const unsigned int mine_n = (unsigned int)__popc(fall) + (edge ? 1u : 0u);
         unsigned int tot;
         unsigned int slot = warp_excl_scan(mine_n, &tot);
         if (tot != 0) {
           if (qn + tot > run_cap) flush_queue();
-          my_segments += mine_n;
           if (tot > run_cap) {  // more run ends in one batch than the queue holds: done in place
             __syncwarp();          // (passw of this batch is visible)
             while (fall) {

@@ -155,15 +155,18 @@ def test_synthetic_edge_cases(sx, golden_synthetic, oracle_lib):
     assert len(listed) <= 3, listed
 
 
-def test_random_pairs_against_oracle(sx, oracle_lib):
+@pytest.mark.parametrize("total", [768 * 4096.0, 1.5e8, 4294967296.0])
+def test_random_pairs_against_oracle(sx, oracle_lib, total):
     """config 2 shape at a size the oracle finishes in seconds: every record compared, differences
-    must be explained by borderline lags (listed)."""
+    must be explained by borderline lags (listed).  target_total as the bench's 1M-pair step has it (2^32:
+    the scan kernel's byte filter and run-length pruning, run_min = 16), as config 4's 150 Mb genome
+    (run_min = 12) and as this small set alone (run_min = 7)."""
     from satsuma2_b200 import synth
 
     n = 768
     T, Q, truth = synth.random_pairs(n, 4096, seed=5)
     listed = []
-    with sx.XCorrEngine(target_total=float(n * 4096), max_batch_pairs=200) as eng:
+    with sx.XCorrEngine(target_total=total, max_batch_pairs=200) as eng:
         eng.set_targets(sx.ChunkSet.independent(T))
         eng.set_queries(sx.ChunkSet.independent(Q))
         pairs = np.stack([np.arange(n), np.arange(n)], axis=1)
@@ -171,21 +174,84 @@ def test_random_pairs_against_oracle(sx, oracle_lib):
         st = eng.stats()
     tl = [(T[i].tobytes(), 0, i, 4096) for i in range(n)]
     ql = [(Q[i].tobytes(), 0, i, 4096) for i in range(n)]
-    params = oracle_lib.make_params(target_total=float(n * 4096))
+    params = oracle_lib.make_params(target_total=total)
     exp = oracle_lib.align_pairs(params, tl, ql, pairs, threads=os.cpu_count() or 1)
     assert st["chunk_pairs"] == n and st["strand_pairs"] == 2 * n
-    # ~292 candidates and ~2300 raw segments per strand-pair on random DNA
+    # ~292 candidates per strand-pair on random DNA; ~2300 raw segments when all are counted
+    # (the byte filter only meets the runs inside the words it evaluates)
     assert 200 < st["candidates"] / (2 * n) < 400
-    assert 1500 < st["segments"] / (2 * n) < 3500
+    if total < 1e9:
+        assert 1500 < st["segments"] / (2 * n) < 3500
     found = 0
     for i in range(n):
         gp, ep = got[got["query_id"] == i], exp[exp["query_id"] == i]
-        compare_pair_records(oracle_lib, gp, ep, tl[i][0], ql[i][0], 0, 0, 4096, 4096, N, 1.8, 0.99,
-                             float(n * 4096), listed)
+        compare_pair_records(oracle_lib, gp, ep, tl[i][0], ql[i][0], 0, 0, 4096, 4096, N, 1.8, 0.99, total, listed)
         found += int(len(gp) > 0)
     _log_listed("random_pairs", listed)
     assert len(listed) <= 4, listed
     assert found > 0.5 * n  # planted segments are found in most pairs
+
+
+def _stress_pairs(n, seed):
+    """Chunk pairs that crowd the run-length boundary of the scan kernel: per pair a handful of planted segments of
+    30-120 bases at 85-100 % identity (forward and reverse), tandem repeats, GC-rich against AT-rich stretches (the
+    compositions that lower the match threshold) and runs that start at the first window of a diagonal."""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    comp = np.zeros(256, np.uint8)
+    comp[list(b"ACGT")] = list(b"TGCA")
+    T = rng.choice(acgt, (n, 4096))
+    Q = rng.choice(acgt, (n, 4096))
+    for i in range(n):
+        kind = i % 4
+        if kind == 1:  # skewed composition: GC-rich target stretch, AT-rich query
+            T[i, 1000:3000] = rng.choice(np.frombuffer(b"GGCCGCAT", np.uint8), 2000)
+            Q[i, 500:2500] = rng.choice(np.frombuffer(b"AATTATGC", np.uint8), 2000)
+        if kind == 2:  # tandem repeat in both
+            unit = rng.choice(acgt, int(rng.integers(3, 30)))
+            rep = np.tile(unit, 600 // len(unit) + 1)[:600]
+            a, b = int(rng.integers(0, 3400)), int(rng.integers(0, 3400))
+            T[i, a:a + 600] = rep
+            Q[i, b:b + 600] = rep
+        for _ in range(int(rng.integers(3, 9))):
+            ln = int(rng.integers(30, 121))
+            a, b = int(rng.integers(0, 4096 - ln)), int(rng.integers(0, 4096 - ln))
+            if kind == 3 and rng.random() < 0.5:
+                a = 0 if rng.random() < 0.5 else a   # diagonals whose first window already passes
+                b = 0 if a else b
+            seg = T[i, a:a + ln].copy()
+            mut = rng.random(ln) < rng.uniform(0.0, 0.15)
+            seg[mut] = rng.choice(acgt, int(mut.sum()))
+            if rng.random() < 0.5:
+                seg = comp[seg[::-1]]
+            Q[i, b:b + ln] = seg
+    return np.ascontiguousarray(T), np.ascontiguousarray(Q)
+
+
+@pytest.mark.parametrize("total", [2.0e4, 1.5e8, 4294967296.0, 1.0e12])
+def test_pruned_scan_equals_exhaustive_scan(sx, total):
+    """The scan kernel never scores runs of passing windows too short to survive the probability filter
+    (ScoreParams::run_min) and, from run_min = 15 on, filters words by byte counts; debug_flags bit 0 switches both
+    off (every raw segment is scored).  On pairs built to crowd the boundary, plus config-2 pairs, the two ways give
+    bit-identical records (idempotence under pruning) for small, genome-scale and bench-scale target totals."""
+    from satsuma2_b200 import synth
+
+    Ts, Qs = _stress_pairs(1200, seed=int(total) % 1000)
+    Tr, Qr, _ = synth.random_pairs(1200, 4096, seed=77)
+    T, Q = np.concatenate([Ts, Tr]), np.concatenate([Qs, Qr])
+    n = len(T)
+    pairs = np.stack([np.arange(n), np.arange(n)], axis=1)
+    outs, segs = [], []
+    for flags in (0, 1):
+        with sx.XCorrEngine(target_total=total, debug_flags=flags, max_batch_pairs=500) as eng:
+            eng.set_targets(sx.ChunkSet.independent(T))
+            eng.set_queries(sx.ChunkSet.independent(Q))
+            r = eng.align_pairs(pairs)
+            outs.append(np.sort(r, order=["query_id", "tstart", "qstart", "len", "reverse"]))
+            segs.append(eng.stats()["segments"])
+    assert len(outs[1]) > 300, len(outs[1])
+    assert outs[0].tobytes() == outs[1].tobytes()
+    assert segs[0] <= segs[1]
 
 
 def test_ragged_fuzz_against_oracle(sx, oracle_lib):
