@@ -209,6 +209,12 @@ __device__ __forceinline__ uint32_t pass_word(const W16 &s4p, const W16 &s4, con
   const uint32_t n5 = s55 ^ (s54 & cy);
   return n5 | (n4 & (n3 | n2 | (n1 & n0)));  // count >= 19 (0b010011)
 }
+// a * b + c as one multiply-add on the FMA pipe, also when b is a power of two (the logic pipe is this kernel's limit)
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
 // exclusive prefix sum over the warp; *total = sum over all lanes
 __device__ __forceinline__ unsigned int warp_excl_scan(unsigned int v, unsigned int *total) {
   const int lane = threadIdx.x & 31;
@@ -502,9 +508,13 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
         auto step = [&](int kw, bool full) {
           uint32_t m;
           const bool inside = match_word(kw, full, m);
-          const uint32_t c = (uint32_t)__popc(m & 0xffu) | ((uint32_t)__popc(m & 0xff00u) << 8) |
-                             ((uint32_t)__popc(m & 0xff0000u) << 16) | ((uint32_t)__popc(m & 0xff000000u) << 24);
-          const uint32_t pre = c * 0x01010101u;                    // byte j: c0 + .. + cj
+          // byte j of pre: matches in bytes 0 .. j of the word (three masks, four popcounts, packed by
+          // multiply-adds, which run beside the logic pipe); c = pre - (pre << 8): the bytes' own counts
+          uint32_t pre = (uint32_t)__popc(m & 0xffu);
+          pre = mad_u32((uint32_t)__popc(m & 0xffffu), 0x100u, pre);
+          pre = mad_u32((uint32_t)__popc(m & 0xffffffu), 0x10000u, pre);
+          pre = mad_u32((uint32_t)__popc(m), 0x1000000u, pre);
+          const uint32_t c = pre * 0xffffff01u;
           const uint32_t s6 = pre + bn + (cpp >> 24);               // byte j: counts of bytes g-5 .. g
           const uint32_t s7 = s6 + __byte_perm(cpp, cp, 0x5432);    // byte j: counts of bytes g-6 .. g
           const uint32_t t6 = (s6 + 0x6d6d6d6du) & 0x80808080u;     // bytes with S6 >= 19
