@@ -154,8 +154,9 @@ def cpu_reference_rate(T, Q, n_sample: int, threads: int):
         R.set_chunks(False, ql, [CHUNK] * n_sample)
         R.lib.ref_set_target_total(total)
         tp = np.array([[i, i, i, i, 0] for i in range(n_sample)], dtype=np.int32)
-        _, secs, nrec = R.align_pairs_mt(tp, threads)
-        return n_sample / secs, "reference", secs, int(nrec)
+        recs, secs, nrec = R.align_pairs_mt(tp, threads)
+        assert nrec == len(recs)
+        return n_sample / secs, "reference", secs, recs
     O = oracle.Oracle()
     tl = [(T[i].tobytes(), 0, i, CHUNK) for i in range(n_sample)]
     ql = [(Q[i].tobytes(), 0, i, CHUNK) for i in range(n_sample)]
@@ -164,7 +165,148 @@ def cpu_reference_rate(T, Q, n_sample: int, threads: int):
     t0 = time.perf_counter()
     rec = O.align_pairs(params, tl, ql, pairs, threads=threads)
     secs = time.perf_counter() - t0
-    return n_sample / secs, "port", secs, len(rec)
+    return n_sample / secs, "port", secs, rec
+
+
+def parity_check(T, Q, n_sample, gpu_recs, cpu_recs, kind, target_total):
+    """The GPU's records of the first n_sample pairs of the timed step against the CPU reference's records of the
+    same pairs (each pair is its own sequence: query_id = pair index).  Every difference must be explained by a
+    candidate lag within 1e-4 of the FindTop threshold or a probability within 1e-4 of min_prob (tests/parity.py);
+    explained ones are listed, anything else counts as unexplained."""
+    import oracle
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from parity import compare_pair_records, rec_key
+
+    O = oracle.Oracle()
+    g = gpu_recs[gpu_recs["query_id"] < n_sample]
+    gk = {rec_key(r) for r in g}
+    ck = {rec_key(r) for r in cpu_recs}
+    listed, unexplained = [], []
+    for i in sorted({k[0] for k in gk ^ ck}):
+        try:
+            compare_pair_records(O, g[g["query_id"] == i], cpu_recs[cpu_recs["query_id"] == i], T[i].tobytes(),
+                                 Q[i].tobytes(), 0, 0, CHUNK, CHUNK, FFT_N, 1.8, 0.99, target_total, listed)
+        except AssertionError as e:
+            unexplained.append(str(e)[:200])
+    ident_ok = True
+    cmap = {rec_key(r): r for r in cpu_recs}
+    for r in g:
+        c = cmap.get(rec_key(r))
+        if c is not None and (r["ident"] != c["ident"] or abs(float(r["prob"]) - float(c["prob"])) > 1e-6 * abs(float(c["prob"]))):
+            ident_ok = False
+    return {"against": kind, "pairs": int(n_sample), "records_gpu": int(len(g)), "records_cpu": int(len(cpu_recs)),
+            "differing": len(gk ^ ck), "unexplained": len(unexplained) + (0 if ident_ok else 1),
+            "listed": [dict(x, key=[int(v) for v in x["key"]]) for x in listed], "prob_ident_equal": ident_ok,
+            "notes": unexplained}
+
+
+def pairs_workload(grp, local_rank, chunk, n, steps, warmup, batch, seed=7):
+    """configs[2]: independent random chunk pairs of a larger chunk size (FFT length 2 x chunk), one planted segment
+    each -- the headline workload's shape at N = 16384 / 32768.  -> dict (device-resident value, e2e, kernel ms)."""
+    import torch
+
+    import satsuma2_b200 as sx
+    from satsuma2_b200 import synth
+
+    dev = torch.device("cuda", local_rank)
+    tt = torch.empty((n, chunk), dtype=torch.uint8, pin_memory=True)
+    tq = torch.empty((n, chunk), dtype=torch.uint8, pin_memory=True)
+    T, Q = tt.numpy(), tq.numpy()
+    synth.random_pairs(n, chunk, seed=seed, out_t=T, out_q=Q)
+    cs_t, cs_q = sx.ChunkSet.independent(T), sx.ChunkSet.independent(Q)
+    pairs = np.ascontiguousarray(np.stack([np.arange(n), np.arange(n)], axis=1), dtype=np.int32)
+    eng = sx.XCorrEngine(device=local_rank, t_chunk=chunk, q_chunk=chunk, target_total=float(n) * chunk,
+                         max_batch_pairs=batch, spectra_cache_bytes=-1, async_upload=1)
+    stream = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
+    rec_buf = np.zeros(4 * n, dtype=sx.RESULT_DTYPE)
+
+    def step_device():
+        return eng.align_pairs(pairs, out=rec_buf)
+
+    def step_e2e():
+        eng.set_targets_raw(T.ctypes.data, cs_t)
+        eng.set_queries_raw(Q.ctypes.data, cs_q)
+        return eng.align_pairs(pairs, out=rec_buf)
+
+    eng.set_targets_raw(T.ctypes.data, cs_t)
+    eng.set_queries_raw(Q.ctypes.data, cs_q)
+    eng.set_profiling(True)
+    ms_dev, clocks, rec = _timed_steps(step_device, steps, warmup, stream, grp, local_rank, eng.reset_stats)
+    st = eng.stats()
+    eng.set_profiling(False)
+    ms_e2e, _, rec = _timed_steps(step_e2e, steps, 1, stream, grp, local_rank, eng.reset_stats)
+    st_e2e = eng.stats()
+    b = max(st["batches"], 1)
+    out = {"workload": f"configs[2]: {n} random {chunk}x{chunk} chunk pairs (FFT length {2 * chunk}), one planted "
+                       "segment each", "chunk": chunk, "fft_n": 2 * chunk, "pairs_per_step": n, "device_batch_pairs": batch,
+           "metric": METRIC, "unit": UNIT, "value": n * steps / (ms_dev / 1e3), "ms_per_step": ms_dev / steps,
+           "e2e": {"value": n * steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
+                   "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] / steps), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / steps)},
+           "kernel_ms_per_batch": {"encode_fft": st["ms_encode_fft"] / b, "xcorr_findtop": st["ms_xcorr"] / b,
+                                   "scan_score": st["ms_scan_score"] / b},
+           "records_per_step": int(len(rec)), "gpu_launches": int(st["kernel_launches"]),
+           "per_pair": {"candidates": st["candidates"] / max(st["chunk_pairs"], 1),
+                        "matches": st["matches"] / max(st["chunk_pairs"], 1)}, "clocks": clocks}
+    eng.close()
+    return out
+
+
+def repeats_workload(grp, local_rank, genome_mb, steps, warmup, batch):
+    """configs[4]: repeat-rich synthetic genome pair (tandem + interspersed repeat families, low-complexity tracts)
+    in -prob_table 1 mode (slave semantics; -dups 1 only changes the master's chaining): high candidate density,
+    thousands of kept records per block.  Blocks of 24x24 chunks along the diagonal, one GPU."""
+    import torch
+
+    import satsuma2_b200 as sx
+    from satsuma2_b200 import synth
+
+    dev = torch.device("cuda", local_rank)
+    L = int(genome_mb * 1e6)
+    a, b = synth.repeat_rich_pair(L, seed=21)
+    to, tl, ts = synth.chunk_sequence(a, CHUNK, CHUNK // 4)
+    qo, ql, qs = synth.chunk_sequence(b, CHUNK, 0)
+    ta, tb = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
+    cs_t = sx.ChunkSet(ta.numpy(), to, tl, ts, np.zeros(len(tl), np.int32), [L])
+    cs_q = sx.ChunkSet(tb.numpy(), qo, ql, qs, np.zeros(len(ql), np.int32), [L])
+    blocks = sx.make_blocks(synth.diagonal_blocks(len(tl), len(ql), CHUNK - CHUNK // 4, CHUNK, pixel=24))
+    t0 = time.perf_counter()
+    tab = sx.build_prob_table(float(L))
+    table_s = time.perf_counter() - t0
+    eng = sx.MultiEngine(devices=[local_rank], target_total=float(L), use_prob_table=1, prob_table_value=0.9999,
+                         max_batch_pairs=batch)
+    eng.set_prob_table(tab)
+    stream = torch.cuda.ExternalStream(eng.stream_handle(0), device=dev)
+    rec_buf = np.zeros(1 << 22, dtype=sx.RESULT_DTYPE)
+
+    def step_device():
+        eng.invalidate_spectra()
+        return eng.align_blocks(blocks, out=rec_buf)
+
+    def step_e2e():
+        eng.set_targets(cs_t)
+        eng.set_queries(cs_q)
+        return eng.align_blocks(blocks, out=rec_buf)
+
+    eng.set_targets(cs_t)
+    eng.set_queries(cs_q)
+    ms_dev, clocks, rec = _timed_steps(step_device, steps, warmup, stream, grp, local_rank, eng.reset_stats)
+    st = eng.stats()
+    ms_e2e, _, rec = _timed_steps(step_e2e, steps, 1, stream, grp, local_rank, eng.reset_stats)
+    st_e2e = eng.stats()
+    n = st["chunk_pairs"] / steps
+    out = {"workload": f"configs[4]: repeat-rich {genome_mb:g} Mb synthetic genome pair, -prob_table 1, 24x24-chunk blocks "
+                       "along the diagonal", "pairs_per_step": int(n), "metric": METRIC, "unit": UNIT,
+           "value": n * steps / (ms_dev / 1e3), "ms_per_step": ms_dev / steps,
+           "e2e": {"value": n * steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
+                   "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] / steps), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / steps)},
+           "per_pair": {"candidates": st["candidates"] / max(st["chunk_pairs"], 1),
+                        "segments": st["segments"] / max(st["chunk_pairs"], 1),
+                        "matches": st["matches"] / max(st["chunk_pairs"], 1)},
+           "records_per_step": int(len(rec)), "prob_table_build_s": table_s, "gpu_launches": int(st["kernel_launches"]),
+           "clocks": clocks}
+    eng.close()
+    return out
 
 
 def run_reference_arm(args):
@@ -177,7 +319,8 @@ def run_reference_arm(args):
     T, Q, _ = make_workload(n_step, seed=1000 + 0, pinned=False)
     times, kind, nrec = [], "reference", 0
     for it in range(args.warmup + args.steps):
-        rate, kind, secs, nrec = cpu_reference_rate(T, Q, n_step, cores)
+        rate, kind, secs, recs = cpu_reference_rate(T, Q, n_step, cores)
+        nrec = len(recs)
         if it >= args.warmup:
             times.append(secs)
     ms = 1e3 * sum(times) / max(len(times), 1)
@@ -199,88 +342,119 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_grid(args):
-    """Secondary workload (not the headline metric): GridSearch-style 24x24-chunk blocks along the syntenic
-    diagonal of a synthetic genome pair (BASELINE.json configs[3]).  Target spectra are cached in HBM and reused
-    by every query chunk that meets them; ranks own contiguous target ranges (no collective).  Every step starts
-    with cold spectra (sx_invalidate_spectra), so reuse happens inside the step only."""
+def _timed_steps(fn, steps, warmup, stream, grp, local_rank, reset=None):
+    """warm-up, then `steps` calls bracketed by barrier + synchronize, CUDA events on the library's stream,
+    max over ranks; nvidia-smi sampled meanwhile.  -> (ms for all steps, clocks, last result)"""
+    import torch
+
+    for _ in range(warmup):
+        res = fn()
+    if reset is not None:
+        reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    grp.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0.record(stream)
+    for _ in range(steps):
+        res = fn()
+    e1.record(stream)
+    e1.synchronize()
+    torch.cuda.synchronize()
+    grp.barrier()
+    return grp.max(e0.elapsed_time(e1)), sampler.stop(), res
+
+
+def grid_workload(args, grp, rank, local_rank, world, genome_mb, steps, warmup):
+    """configs[3]: GridSearch-style 24x24-chunk blocks along the syntenic diagonal of a synthetic genome pair.
+    STRONG scaling: the target chunk list is cut into `world` contiguous ranges (sx_multi, shard = rank); a rank is
+    sent only the bases of its target range and of the query chunks its blocks touch, keeps its target spectra in
+    HBM (cold at the start of every step) and returns its own records -- no collective.  -> dict for the JSON line."""
     import torch
 
     import satsuma2_b200 as sx
-    from satsuma2_b200 import build as sxbuild, synth
-    from satsuma2_b200.dist import Group, shard_blocks_by_target
+    from satsuma2_b200 import synth
+
+    dev = torch.device("cuda", local_rank)
+    L = int(genome_mb * 1e6)
+    tgt, qry = synth.genome_pair(L, seed=11)
+    to, tl, ts = synth.chunk_sequence(tgt, CHUNK, CHUNK // 4)  # slave / grid overlap = size / 4 (Slave.cc:400)
+    qo, ql, qs = synth.chunk_sequence(qry, CHUNK, 0)
+    # pinned host copies: the e2e leg uploads from them every step
+    tt, tq = torch.from_numpy(tgt).pin_memory(), torch.from_numpy(qry).pin_memory()
+    cs_t = sx.ChunkSet(tt.numpy(), to, tl, ts, np.zeros(len(tl), np.int32), [L])
+    cs_q = sx.ChunkSet(tq.numpy(), qo, ql, qs, np.zeros(len(ql), np.int32), [L])
+    blocks = sx.make_blocks(synth.diagonal_blocks(len(tl), len(ql), CHUNK - CHUNK // 4, CHUNK, pixel=24))
+    eng = sx.MultiEngine(devices=[local_rank], shard_rank=rank, shard_world=world, target_total=float(L),
+                         max_batch_pairs=args.batch)
+    stream = torch.cuda.ExternalStream(eng.stream_handle(0), device=dev)
+    n_all = int(((blocks["target_to"] - blocks["target_from"] + 1).astype(np.int64) *
+                 (blocks["query_to"] - blocks["query_from"] + 1)).sum())
+    rec_buf = np.zeros(max(1 << 16, 4 * n_all // world + (1 << 16)), dtype=sx.RESULT_DTYPE)
+
+    def step_device():
+        eng.invalidate_spectra()
+        return eng.align_blocks(blocks, out=rec_buf)
+
+    def step_e2e():
+        eng.set_targets(cs_t)
+        eng.set_queries(cs_q)
+        return eng.align_blocks(blocks, out=rec_buf)
+
+    eng.set_targets(cs_t)
+    eng.set_queries(cs_q)
+    ms_dev, clocks, rec = _timed_steps(step_device, steps, warmup, stream, grp, local_rank, eng.reset_stats)
+    st = eng.stats()
+    ms_e2e, clocks_e2e, rec = _timed_steps(step_e2e, steps, max(1, warmup - 2), stream, grp, local_rank, eng.reset_stats)
+    st_e2e = eng.stats()
+    mine = st["chunk_pairs"] / max(steps, 1)
+    total_pairs = grp.sum(float(mine))
+    h2d_max = grp.max(float(st_e2e["h2d_bytes"]) / max(steps, 1))
+    h2d_sum = grp.sum(float(st_e2e["h2d_bytes"]) / max(steps, 1))
+    d2h_sum = grp.sum(float(st_e2e["d2h_bytes"]) / max(steps, 1))
+    recs = grp.sum(float(len(rec)))
+    out = {
+        "workload": f"configs[3]: {genome_mb:g} Mb x {genome_mb:g} Mb synthetic genome pair, 24x24-chunk blocks along "
+                    "the diagonal, target spectra cached in HBM (cold at the start of every step), target chunk "
+                    "list split by range over the ranks (sx_multi), no collective",
+        "scaling": "strong", "metric": METRIC, "unit": UNIT, "n_gpus": world,
+        "value": total_pairs * steps / (ms_dev / 1e3), "ms_per_step": ms_dev / steps,
+        "e2e": {"value": total_pairs * steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
+                "h2d_bytes_per_step": int(h2d_sum), "h2d_bytes_per_step_max_rank": int(h2d_max),
+                "d2h_bytes_per_step": int(d2h_sum)},
+        "target_chunks": int(len(tl)), "query_chunks": int(len(ql)), "blocks": len(blocks),
+        "pairs_per_step_all_ranks": int(total_pairs), "target_total": float(L),
+        "signals_per_pair": st["signals"] / max(st["chunk_pairs"], 1), "records_per_step": int(recs),
+        "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "clocks_e2e": clocks_e2e,
+    }
+    assert int(total_pairs) == n_all, (total_pairs, n_all)
+    eng.close()
+    del tt, tq
+    return out
+
+
+def run_grid(args):
+    """--workload grid: the configs[3] line on its own (secondary workload, not the headline metric)."""
+    import torch
+
+    from satsuma2_b200 import build as sxbuild
+    from satsuma2_b200.dist import Group
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
     sxbuild.build()
     rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    grp = Group("nccl", dev)
-    L = int(args.genome_mb * 1e6)
-    tgt, qry = synth.genome_pair(L, seed=11)
-    to, tl, ts = synth.chunk_sequence(tgt, CHUNK, CHUNK // 4)  # slave / grid overlap = size / 4 (Slave.cc:400)
-    qo, ql, qs = synth.chunk_sequence(qry, CHUNK, 0)
-    cs_t = sx.ChunkSet(tgt, to, tl, ts, np.zeros(len(tl), np.int32), [L])
-    cs_q = sx.ChunkSet(qry, qo, ql, qs, np.zeros(len(ql), np.int32), [L])
-    blocks = synth.diagonal_blocks(len(tl), len(ql), CHUNK - CHUNK // 4, CHUNK, pixel=24)
-    mine = shard_blocks_by_target(blocks, len(tl), rank, world)
-    n_pairs = sum((b[1] - b[0] + 1) * (b[3] - b[2] + 1) for b in mine)
-    eng = sx.XCorrEngine(device=local_rank, target_total=float(L), max_batch_pairs=args.batch)
-    stream = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
-    rec_buf = np.zeros(max(1 << 16, 4 * n_pairs), dtype=sx.RESULT_DTYPE)
-
-    def step_device():
-        eng.invalidate_spectra()
-        return eng.align_blocks(mine, out=rec_buf)
-
-    def step_e2e():
-        eng.set_targets(cs_t)
-        eng.set_queries(cs_q)
-        return eng.align_blocks(mine, out=rec_buf)
-
-    def timed(fn):
-        for _ in range(args.warmup):
-            rec = fn()
-        eng.reset_stats()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        grp.barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        e0.record(stream)
-        for _ in range(args.steps):
-            rec = fn()
-        e1.record(stream)
-        e1.synchronize()
-        torch.cuda.synchronize()
-        grp.barrier()
-        return grp.max(e0.elapsed_time(e1)), eng.stats(), sampler.stop(), rec
-
-    eng.set_targets(cs_t)
-    eng.set_queries(cs_q)
-    ms_dev, st, clocks, rec = timed(step_device)
-    ms_e2e, st_e2e, _, _ = timed(step_e2e)
-    total_pairs = grp.sum(float(n_pairs)) * args.steps
+    grp = Group("nccl", torch.device("cuda", local_rank))
+    g = grid_workload(args, grp, rank, local_rank, world, args.genome_mb, args.steps, args.warmup)
     if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": total_pairs / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs[3]-style grid: {args.genome_mb:g} Mb synthetic genome pair, 24x24-chunk blocks "
-                                   "along the diagonal, target spectra cached in HBM (cold at the start of every step), "
-                                   "blocks sharded by target range", "chunk": CHUNK, "fft_n": FFT_N,
-                       "target_chunks": int(len(tl)), "query_chunks": int(len(ql)), "blocks": len(blocks),
-                       "pairs_per_step_all_ranks": int(total_pairs / args.steps), "device_batch_pairs": args.batch},
-            "clocks": clocks,
-            "e2e": {"value": total_pairs / (ms_e2e / 1e3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] / args.steps),
-                    "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / args.steps), "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(st["kernel_launches"]),
-            "signals_per_pair": st["signals"] / max(st["chunk_pairs"], 1),
-            "records_per_step": int(len(rec)),
-        }), flush=True)
-    eng.close()
+        line = {"metric": METRIC, "value": g["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": g["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": g["workload"], "chunk": CHUNK, "fft_n": FFT_N, "device_batch_pairs": args.batch},
+                "clocks": g["clocks"], "e2e": g["e2e"], "gpu_launches": g["gpu_launches"], "grid": g}
+        print(json.dumps(line), flush=True)
     grp.close()
     return 0
 
@@ -297,10 +471,12 @@ def main():
     ap.add_argument("--cpu-sample-per-core", type=int, default=400)
     ap.add_argument("--ref-pairs-per-core", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (grid / chunk sizes / repeats)")
     ap.add_argument("--workload", default="pairs", choices=["pairs", "grid"],
                     help="pairs = configs[1] (the headline metric); grid = configs[3]-style block search of a synthetic "
                          "genome pair with target spectra cached in HBM, sharded by target range (strong scaling)")
-    ap.add_argument("--genome-mb", type=float, default=24.0, help="--workload grid: bases per genome, in millions")
+    ap.add_argument("--genome-mb", type=float, default=150.0,
+                    help="grid workload (configs[3]): bases per genome, in millions")
     ap.add_argument("--target-total", type=float, default=0.0,
                     help="targetTotal of the probability filter (default: pairs x chunk, i.e. every target chunk of the "
                          "step); profiling runs with fewer pairs pass the full step's 4294967296")
@@ -386,6 +562,7 @@ def main():
     ms_e2e, st_e2e, clocks_e2e, rec_e2e = timed(step_e2e, args.steps, max(1, args.warmup - 2), False)
 
     total_pairs = grp.sum(float(n)) * args.steps
+    n_records = int(len(rec))
     value = total_pairs / (ms_dev / 1e3)
     e2e_value = total_pairs / (ms_e2e / 1e3)
     d2h_per_step = int(st_e2e["d2h_bytes"] / max(args.steps, 1))
@@ -447,13 +624,27 @@ def main():
                                           "frac": kern["xcorr_findtop"]["gbs"] / hbm_peak,
                                           "traffic": traffic.get("xcorr_findtop"), "peak_source": peak_kind}})
 
-    cpu_baseline = None
+    cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         ns = min(n, args.cpu_sample_per_core * cores)
-        rate, kind, secs, nrec = cpu_reference_rate(T, Q, ns, cores)
+        rate, kind, secs, cpu_recs = cpu_reference_rate(T, Q, ns, cores)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
                         "sample": f"first {ns} pairs of the same workload, {secs:.1f} s on {cores} threads"}
+        # the timed step's own output, checked: the reference's records of those pairs vs the GPU's
+        parity = parity_check(T, Q, ns, rec, cpu_recs, kind, target_total)
+
+    # ---- secondary workloads (sub-objects of the same line; the headline stays configs[1])
+    eng.close()
+    eng = None
+    del T, Q, keep, cs_t, cs_q, rec_buf
+    extras = {}
+    if not args.no_extras:
+        extras["grid"] = grid_workload(args, grp, rank, local_rank, world, args.genome_mb, args.steps, args.warmup)
+        if world == 1:
+            extras["chunk8192"] = pairs_workload(grp, local_rank, 8192, 32768, args.steps, args.warmup, 8192)
+            extras["chunk16384"] = pairs_workload(grp, local_rank, 16384, 8192, args.steps, args.warmup, 4096)
+            extras["repeats"] = repeats_workload(grp, local_rank, 8.0, args.steps, args.warmup, args.batch)
 
     if rank == 0:
         line = {
@@ -472,13 +663,16 @@ def main():
             "gpu_launches": int(st_dev["kernel_launches"]),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
-            "records_per_step": int(len(rec)),
+            "parity_check": parity,
+            "records_per_step": n_records,
             "per_pair": {"candidates": st_dev["candidates"] / max(st_dev["chunk_pairs"], 1),
                          "segments": st_dev["segments"] / max(st_dev["chunk_pairs"], 1),
                          "matches": st_dev["matches"] / max(st_dev["chunk_pairs"], 1)},
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
-    eng.close()
+    if eng is not None:
+        eng.close()
     grp.close()
     return 0
 

@@ -149,6 +149,40 @@ int sx_align_blocks(sx_ctx *ctx, const sx_pair *blocks, int32_t n_blocks, sx_res
 int sx_align_pairs(sx_ctx *ctx, const int32_t *pairs, int64_t n_pairs, int32_t fast, sx_result *out,
                    int64_t cap, int64_t *n_out);
 
+/* ------------------------------------------------------------------ several GPUs behind one handle
+ * The reference spreads the chunk-pair grid over processes by target range: `-nblocks/-block`
+ * (analysis/SeqChunk.cc:104-116) and N slaves fed by the master (analysis/WorkQueue.cc:290-312).  sx_multi does that
+ * split in one process: the flat target chunk list is cut into shard_world * n_devices contiguous ranges, this handle
+ * owns n_devices of them (those of shard_rank), one per GPU.  Every GPU is sent only the bases of its target range
+ * (spectra cached in its HBM) and, per call, only the query chunks its share of the blocks touches; blocks that
+ * straddle a range boundary are split between the neighbours; every GPU works on its own host thread; the records of
+ * all GPUs are gathered into the caller's one buffer.  No collective: GPUs never exchange data.
+ * devices == NULL or n_devices <= 0: every visible GPU.  shard_rank / shard_world = 0 / 1 for a single process; with
+ * shard_world > 1 several processes (ranks, slaves) own disjoint parts of the same split and the union of their
+ * outputs is the unsharded result.  Chunk indices in sx_pair stay those of the caller's full lists.  The caller keeps
+ * the query `bases` alive while the handle may still fetch from them (until destroy / the next sx_multi_set_queries). */
+typedef struct sx_multi sx_multi;
+int sx_multi_create(const sx_config *cfg, const int32_t *devices, int32_t n_devices, int32_t shard_rank,
+                    int32_t shard_world, sx_multi **out);
+void sx_multi_destroy(sx_multi *m);
+const char *sx_multi_last_error(void);
+int32_t sx_multi_device_count(const sx_multi *m);
+int sx_multi_target_range(const sx_multi *m, int32_t shard, int32_t *t_lo, int32_t *t_hi); /* chunks [t_lo, t_hi) of GPU `shard` */
+int sx_multi_set_targets(sx_multi *m, const char *bases, const int64_t *offsets, const int32_t *lens,
+                         const int32_t *starts, const int32_t *seq_ids, int32_t n_chunks, const int32_t *seq_sizes,
+                         int32_t n_seqs);
+int sx_multi_set_queries(sx_multi *m, const char *bases, const int64_t *offsets, const int32_t *lens,
+                         const int32_t *starts, const int32_t *seq_ids, int32_t n_chunks, const int32_t *seq_sizes,
+                         int32_t n_seqs);
+int sx_multi_set_prob_table(sx_multi *m, const double *table);
+int sx_multi_invalidate_spectra(sx_multi *m);
+/* align_target (Slave.cc:270-300) for n blocks over all GPUs of the handle; records gathered into out[0..*n_out) */
+int sx_multi_align_blocks(sx_multi *m, const sx_pair *blocks, int32_t n_blocks, sx_result *out, int64_t cap,
+                          int64_t *n_out);
+int sx_multi_get_stats(sx_multi *m, int32_t shard, sx_stats *out); /* shard < 0: counters summed, times of the slowest GPU */
+int sx_multi_reset_stats(sx_multi *m);
+int sx_multi_stream(sx_multi *m, int32_t shard, void **stream_out);
+
 /* ------------------------------------------------------------------ stage taps (parity tests)
  * strand: 0 = query as given, 1 = reverse-complemented query (DNAVector::ReverseComplement). */
 /* CCSignal::SetSequence (analysis/CrossCorr.cc:179-206): out5 = entropy[N],A[N],C[N],G[N],T[N] */

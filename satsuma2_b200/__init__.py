@@ -99,6 +99,20 @@ def load_library():
     L.sx_stream.argtypes = [vp, C.POINTER(vp)]
     L.sx_build_prob_table.argtypes = [dbl, vp]
     L.sx_set_prob_table.argtypes = [vp, vp]
+    L.sx_multi_create.argtypes = [C.POINTER(Config), vp, i32, i32, i32, C.POINTER(vp)]
+    L.sx_multi_destroy.argtypes = [vp]
+    L.sx_multi_destroy.restype = None
+    L.sx_multi_last_error.restype = C.c_char_p
+    L.sx_multi_device_count.argtypes = [vp]
+    L.sx_multi_target_range.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
+    for name in ("sx_multi_set_targets", "sx_multi_set_queries"):
+        getattr(L, name).argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, i32]
+    L.sx_multi_set_prob_table.argtypes = [vp, vp]
+    L.sx_multi_invalidate_spectra.argtypes = [vp]
+    L.sx_multi_align_blocks.argtypes = [vp, vp, i32, vp, i64, C.POINTER(i64)]
+    L.sx_multi_get_stats.argtypes = [vp, i32, C.POINTER(Stats)]
+    L.sx_multi_reset_stats.argtypes = [vp]
+    L.sx_multi_stream.argtypes = [vp, i32, C.POINTER(vp)]
     if L.sx_abi_version() != ABI_VERSION:
         raise ImportError("libsatsuma_b200.so ABI version mismatch")
     _lib = L
@@ -126,6 +140,17 @@ def build_prob_table(target_total: float) -> np.ndarray:
     tab = np.zeros((512, 2048), dtype=np.float64)
     _check(load_library().sx_build_prob_table(float(target_total), tab.ctypes.data))
     return tab
+
+
+def make_blocks(blocks) -> np.ndarray:
+    """(target_from, target_to, query_from, query_to[, fast]) tuples, inclusive ranges -> t_pair array (PAIR_DTYPE)."""
+    if isinstance(blocks, np.ndarray) and blocks.dtype == PAIR_DTYPE:
+        return np.ascontiguousarray(blocks)
+    arr = np.zeros(len(blocks), dtype=PAIR_DTYPE)
+    for i, b in enumerate(blocks):
+        arr[i]["target_from"], arr[i]["target_to"], arr[i]["query_from"], arr[i]["query_to"] = b[:4]
+        arr[i]["fast"] = 1 if (len(b) > 4 and b[4]) else 0
+    return arr
 
 
 class ChunkSet:
@@ -258,10 +283,7 @@ class XCorrEngine:
 
     def align_blocks(self, blocks: Iterable[tuple], cap_hint: int = 0, out: np.ndarray = None) -> np.ndarray:
         """blocks: (target_from, target_to, query_from, query_to, fast) with inclusive ranges (t_pair)."""
-        arr = np.zeros(len(blocks), dtype=PAIR_DTYPE)
-        for i, b in enumerate(blocks):
-            arr[i]["target_from"], arr[i]["target_to"], arr[i]["query_from"], arr[i]["query_to"] = b[:4]
-            arr[i]["fast"] = 1 if (len(b) > 4 and b[4]) else 0
+        arr = make_blocks(blocks)
         return self._collect(
             lambda o, cap, n: self._L.sx_align_blocks(self._h, arr.ctypes.data, len(arr), o.ctypes.data, cap,
                                                       C.byref(n)), cap_hint or 1 << 16, out)
@@ -314,3 +336,97 @@ class XCorrEngine:
 
     def reset_stats(self):
         _check(self._L.sx_reset_stats(self._h))
+
+
+class MultiEngine:
+    """Several GPUs behind one handle (sx_multi_*): the target chunk list is cut into shard_world * n_devices
+    contiguous ranges, this handle owns n_devices of them; every GPU is sent only its target range and the query
+    chunks its blocks touch; records of all GPUs are gathered into one array.  devices=None: every visible GPU."""
+
+    def __init__(self, devices=None, shard_rank: int = 0, shard_world: int = 1, cfg: Optional[Config] = None, **overrides):
+        self._L = load_library()
+        self.cfg = cfg if cfg is not None else default_config(**overrides)
+        if cfg is not None:
+            for k, v in overrides.items():
+                setattr(self.cfg, k, v)
+        dev = np.ascontiguousarray(devices if devices is not None else [], dtype=np.int32)
+        h = C.c_void_p()
+        self._check(self._L.sx_multi_create(C.byref(self.cfg), dev.ctypes.data if len(dev) else None, len(dev), shard_rank,
+                                            shard_world, C.byref(h)))
+        self._h = h
+        self._keep = [None, None]
+
+    def _check(self, rc: int):
+        if rc != SX_OK:
+            raise SatsumaError(rc, self._L.sx_multi_last_error().decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sx_multi_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_devices(self) -> int:
+        return int(self._L.sx_multi_device_count(self._h))
+
+    def target_range(self, shard: int):
+        lo, hi = C.c_int32(), C.c_int32()
+        self._check(self._L.sx_multi_target_range(self._h, shard, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def _set(self, fn, cs: ChunkSet, slot: int, ptr: int = 0):
+        bases = np.ascontiguousarray(cs.bases, dtype=np.uint8)
+        self._keep[slot] = (bases, cs)  # the handle fetches query ranges from this blob on demand
+        self._check(fn(self._h, ptr or bases.ctypes.data, cs.offsets.ctypes.data, cs.lens.ctypes.data, cs.starts.ctypes.data,
+                       cs.seq_ids.ctypes.data, len(cs), cs.seq_sizes.ctypes.data, len(cs.seq_sizes)))
+
+    def set_targets(self, cs: ChunkSet, ptr: int = 0):
+        self._set(self._L.sx_multi_set_targets, cs, 0, ptr)
+
+    def set_queries(self, cs: ChunkSet, ptr: int = 0):
+        self._set(self._L.sx_multi_set_queries, cs, 1, ptr)
+
+    def set_prob_table(self, table: np.ndarray):
+        t = np.ascontiguousarray(table, dtype=np.float64)
+        assert t.shape == (512, 2048)
+        self._check(self._L.sx_multi_set_prob_table(self._h, t.ctypes.data))
+
+    def invalidate_spectra(self):
+        self._check(self._L.sx_multi_invalidate_spectra(self._h))
+
+    def align_blocks(self, blocks, out: np.ndarray = None) -> np.ndarray:
+        arr = make_blocks(blocks)
+        if out is None:
+            out = np.zeros(1 << 16, dtype=RESULT_DTYPE)
+        n = C.c_int64(0)
+        rc = self._L.sx_multi_align_blocks(self._h, arr.ctypes.data, len(arr), out.ctypes.data, len(out), C.byref(n))
+        if rc == SX_ERR_CAPACITY:
+            out = np.zeros(int(n.value), dtype=RESULT_DTYPE)
+            rc = self._L.sx_multi_align_blocks(self._h, arr.ctypes.data, len(arr), out.ctypes.data, len(out), C.byref(n))
+        self._check(rc)
+        return out[: n.value]
+
+    def stats(self, shard: int = -1) -> dict:
+        s = Stats()
+        self._check(self._L.sx_multi_get_stats(self._h, shard, C.byref(s)))
+        return s.as_dict()
+
+    def reset_stats(self):
+        self._check(self._L.sx_multi_reset_stats(self._h))
+
+    def stream_handle(self, shard: int = 0) -> int:
+        p = C.c_void_p()
+        self._check(self._L.sx_multi_stream(self._h, shard, C.byref(p)))
+        return int(p.value or 0)

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsatsuma_b200.so")
-SOURCES = ["sx_kernels.cu", "sx_engine.cu"]
+SOURCES = ["sx_kernels.cu", "sx_engine.cu", "sx_multi.cu"]
 HEADERS = ["sx_kernels.h", "sx_fft.cuh", "sx_scan.cuh", os.path.join("..", "..", "include", "satsuma_xcorr.h")]
 
 NVCC_FLAGS = [
