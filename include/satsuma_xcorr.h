@@ -120,6 +120,7 @@ int sx_create(const sx_config *cfg, sx_ctx **out);
 void sx_destroy(sx_ctx *ctx);
 const char *sx_last_error(void);
 int sx_abi_version(void);
+int sx_device_count(void); /* usable CUDA devices (0 when there is none) */
 
 /* ------------------------------------------------------------------ chunk loading
  * Replaces the chunk vectors `target` / `query` + `targetInfo` / `queryInfo` that the slave

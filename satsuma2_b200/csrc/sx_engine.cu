@@ -198,6 +198,10 @@ extern "C" void sx_default_config(sx_config *c) {
 }
 
 extern "C" int sx_abi_version(void) { return SX_ABI_VERSION; }
+extern "C" int sx_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 extern "C" const char *sx_last_error(void) { return g_err.c_str(); }
 
 extern "C" int sx_create(const sx_config *cfg, sx_ctx **out) {

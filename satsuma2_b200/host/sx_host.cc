@@ -265,6 +265,7 @@ void guide_chunks(const std::vector<Sequence> &targets, const std::vector<Sequen
 HomologyByXCorr::HomologyByXCorr() {}
 HomologyByXCorr::~HomologyByXCorr() {
   if (ctx_) sx_destroy(ctx_);
+  if (multi_) sx_multi_destroy(multi_);
 }
 
 bool HomologyByXCorr::init(const Options &o, const ChunkList &target, const ChunkList &query) {
@@ -287,6 +288,32 @@ bool HomologyByXCorr::init(const Options &o, const ChunkList &target, const Chun
   for (int32_t s : target.seq_sizes) target_total_ += (double)s;
   if (o.target_total > 0) target_total_ = o.target_total;  // "Using target size (guided)", tools/...:714-717
   cfg.target_total = target_total_;
+  if (o.n_gpus > 0) {  // several GPUs behind one handle: every GPU gets its range of the target list
+    std::vector<int32_t> devs;
+    for (int d = 0; d < o.n_gpus; d++) devs.push_back(d);
+    if (sx_multi_create(&cfg, devs.data(), (int32_t)devs.size(), 0, 1, &multi_) != SX_OK) {
+      err_ = sx_multi_last_error();
+      return false;
+    }
+    if (o.prob_table) {
+      std::vector<double> tab((size_t)512 * 2048);
+      if (sx_build_prob_table(target_total_, tab.data()) != SX_OK || sx_multi_set_prob_table(multi_, tab.data()) != SX_OK) {
+        err_ = sx_multi_last_error();
+        return false;
+      }
+    }
+    query_blob_ = query.blob;  // sx_multi fetches query ranges on demand: the blob must outlive the calls
+    if (sx_multi_set_targets(multi_, target.blob.data(), target.offsets.data(), target.lens.data(), target.starts.data(),
+                             target.seq_ids.data(), target.n(), target.seq_sizes.data(),
+                             (int32_t)target.seq_sizes.size()) != SX_OK ||
+        sx_multi_set_queries(multi_, query_blob_.data(), query.offsets.data(), query.lens.data(), query.starts.data(),
+                             query.seq_ids.data(), query.n(), query.seq_sizes.data(),
+                             (int32_t)query.seq_sizes.size()) != SX_OK) {
+      err_ = sx_multi_last_error();
+      return false;
+    }
+    return true;
+  }
   if (sx_create(&cfg, &ctx_) != SX_OK) {
     err_ = sx_last_error();
     return false;
@@ -310,22 +337,25 @@ bool HomologyByXCorr::init(const Options &o, const ChunkList &target, const Chun
 }
 
 bool HomologyByXCorr::align_targets(const t_pair *p, int n, std::vector<t_result> &results) {
-  if (!ctx_) {
+  if (!ctx_ && !multi_) {
     err_ = "not initialised";
     return false;
   }
+  auto call = [&](t_result *out, int64_t cap, int64_t *got) {
+    return multi_ ? sx_multi_align_blocks(multi_, p, n, out, cap, got) : sx_align_blocks(ctx_, p, n, out, cap, got);
+  };
   const size_t base = results.size();
   int64_t cap = 1 << 16, got = 0;
   results.resize(base + (size_t)cap);
-  int rc = sx_align_blocks(ctx_, p, n, results.data() + base, cap, &got);
+  int rc = call(results.data() + base, cap, &got);
   if (rc == SX_ERR_CAPACITY) {  // never truncated: ask again with the size the library reported
     cap = got;
     results.resize(base + (size_t)cap);
-    rc = sx_align_blocks(ctx_, p, n, results.data() + base, cap, &got);
+    rc = call(results.data() + base, cap, &got);
   }
   if (rc != SX_OK) {
     results.resize(base);
-    err_ = sx_last_error();
+    err_ = multi_ ? sx_multi_last_error() : sx_last_error();
     return false;
   }
   results.resize(base + (size_t)got);
@@ -336,7 +366,10 @@ bool HomologyByXCorr::align_target(const t_pair &p, std::vector<t_result> &resul
   return align_targets(&p, 1, results);
 }
 
-bool HomologyByXCorr::stats(sx_stats *s) const { return ctx_ && sx_get_stats(ctx_, s) == SX_OK; }
+bool HomologyByXCorr::stats(sx_stats *s) const {
+  if (multi_) return sx_multi_get_stats(multi_, -1, s) == SX_OK;
+  return ctx_ && sx_get_stats(ctx_, s) == SX_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 namespace {

@@ -60,6 +60,7 @@ class HomologyByXCorr {
  public:
   struct Options {
     int device = 0;
+    int n_gpus = 0;  // > 0: drive this many GPUs (devices 0 .. n-1) through sx_multi, target list split by range
     int t_chunk = 4096, q_chunk = 4096;
     double cutoff = 1.8, cutoff_fast = 2.9;
     int min_len = 0;
@@ -83,6 +84,8 @@ class HomologyByXCorr {
 
  private:
   sx_ctx *ctx_ = nullptr;
+  sx_multi *multi_ = nullptr;
+  std::string query_blob_;  // kept for sx_multi, which fetches query ranges when a call needs them
   double target_total_ = 0;
   std::string err_;
 };

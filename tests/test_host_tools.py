@@ -6,6 +6,7 @@ import socket
 import struct
 import subprocess
 import threading
+import time
 
 import numpy as np
 import pytest
@@ -427,26 +428,26 @@ def test_guided_refinement_equals_the_reference_tool(host_bins, sx, reference_li
         assert abs(x[8] - y[8]) <= 1e-6 * abs(x[8]) and abs(x[7] - y[7]) <= 1e-9
 
 
-@pytest.mark.gpu
-def test_slave_speaks_the_reference_wire_protocol(host_bins, sx, tmp_path):
-    """A scripted master hands t_pairs to the B200 slave over loopback TCP and
-    gets t_result records back; they equal the in-process C-ABI results."""
-    rng = np.random.default_rng(5)
-    base = rng.choice(list(b"ACGT"), 30000).astype(np.uint8)
-    qry = base.copy()
-    mut = rng.random(30000) < 0.1
-    qry[mut] = rng.choice(list(b"ACGT"), int(mut.sum()))
-    q, t = tmp_path / "q.fa", tmp_path / "t.fa"
-    _write_fasta(q, [("q", qry.tobytes())])
-    _write_fasta(t, [("t", base.tobytes())])
-    blocks = [(0, 4, 0, 3, 0), (5, 9, 4, 7, 0), (0, 9, 0, 7, 1)]
-    srv = socket.socket()
-    srv.bind(("127.0.0.1", 0))
-    srv.listen(4)
-    port = srv.getsockname()[1]
-    received, state = [], {"sent": False, "done": False}
+class _ScriptedMaster:
+    """The master's side of the slave protocol (analysis/WorkQueue.cc:71-166) on loopback TCP:
+    per connection  <- uint32 slave_id, uint32 n, n x t_result ; -> int32 count, count x t_pair (one send).
+    Hands out `per_exchange` blocks per connection (the reference master: 2 x its thread count), answers 0 while the
+    slave still owes results and -1 once every block's results can have arrived."""
 
-    def recv_all(c, n):
+    def __init__(self, sx, blocks, sid, per_exchange=2, quiet_s=1.5):
+        self.sx, self.blocks, self.sid, self.per, self.quiet_s = sx, list(blocks), sid, per_exchange, quiet_s
+        self.last_data = time.monotonic()
+        self.srv = socket.socket()
+        self.srv.bind(("127.0.0.1", 0))
+        self.srv.listen(16)
+        self.port = self.srv.getsockname()[1]
+        self.received, self.connections, self.sent = [], 0, 0
+        self.done = False
+        self.thread = threading.Thread(target=self._serve, daemon=True)
+        self.thread.start()
+
+    @staticmethod
+    def _recv_all(c, n):
         buf = b""
         while len(buf) < n:
             part = c.recv(n - len(buf))
@@ -455,41 +456,117 @@ def test_slave_speaks_the_reference_wire_protocol(host_bins, sx, tmp_path):
             buf += part
         return buf
 
-    def master():
-        while not state["done"]:
-            c, _ = srv.accept()
-            sid, n = struct.unpack("<II", recv_all(c, 8))
-            assert sid == 7
+    def _serve(self):
+        sx = self.sx
+        while not self.done:
+            c, _ = self.srv.accept()
+            self.connections += 1
+            sid, n = struct.unpack("<II", self._recv_all(c, 8))
+            assert sid == self.sid
             if n:
-                received.append(np.frombuffer(recv_all(c, 72 * n), dtype=sx.RESULT_DTYPE).copy())
-            if not state["sent"]:
-                arr = np.zeros(len(blocks), dtype=sx.PAIR_DTYPE)
-                for i, b in enumerate(blocks):
-                    arr[i]["target_from"], arr[i]["target_to"], arr[i]["query_from"], arr[i]["query_to"] = b[:4]
-                    arr[i]["fast"] = b[4]
-                c.sendall(struct.pack("<i", len(blocks)) + arr.tobytes())  # one send, like the survey's fake master
-                state["sent"] = True
+                self.received.append(np.frombuffer(self._recv_all(c, 72 * n), dtype=sx.RESULT_DTYPE).copy())
+            now = time.monotonic()
+            if n:
+                self.last_data = now
+            if self.sent < len(self.blocks):
+                part = self.blocks[self.sent:self.sent + self.per]
+                self.sent += len(part)
+                self.last_data = now
+                c.sendall(struct.pack("<i", len(part)) + sx.make_blocks(part).tobytes())
+            elif now - self.last_data < self.quiet_s:
+                # everything handed out: keep answering "nothing now" until no records have arrived for a while
+                # (the reference slave's workers poll their queue once a second)
+                time.sleep(0.2)
+                c.sendall(struct.pack("<i", 0))
             else:
                 c.sendall(struct.pack("<i", -1))
-                state["done"] = True
+                self.done = True
             c.close()
 
-    th = threading.Thread(target=master, daemon=True)
-    th.start()
-    r = subprocess.run([host_bins["HomologyByXCorrSlave"], "-master", "127.0.0.1", "-port", str(port), "-sid", "7", "-q",
-                        str(q), "-t", str(t)], capture_output=True, text=True, timeout=300)
-    th.join(timeout=30)
-    srv.close()
-    assert r.returncode == 0, r.stderr
-    got = np.concatenate(received) if received else np.zeros(0, dtype=sx.RESULT_DTYPE)
-    # the same blocks through the Python binding of the C ABI
-    from satsuma2_b200 import synth
+    def records(self):
+        self.thread.join(timeout=60)
+        self.srv.close()
+        return np.concatenate(self.received) if self.received else np.zeros(0, dtype=self.sx.RESULT_DTYPE)
 
-    to, tl, tst = synth.chunk_sequence(base, 4096, 1024)
-    qo, ql, qst = synth.chunk_sequence(qry, 4096, 0)
-    with sx.XCorrEngine(target_total=30000.0) as eng:
-        eng.set_targets(sx.ChunkSet(base, to, tl, tst, np.zeros(len(tl)), [30000]))
-        eng.set_queries(sx.ChunkSet(qry, qo, ql, qst, np.zeros(len(ql)), [30000]))
-        exp = eng.align_blocks(blocks)
-    assert len(got) == len(exp) > 0
+
+def _slave_case(tmp_path):
+    rng = np.random.default_rng(5)
+    base = rng.choice(list(b"ACGT"), 60000).astype(np.uint8)
+    qry = base.copy()
+    mut = rng.random(len(base)) < 0.1
+    qry[mut] = rng.choice(list(b"ACGT"), int(mut.sum()))
+    qry[30000:40000] = np.frombuffer(bytes(qry[30000:40000][::-1]).translate(bytes.maketrans(b"ACGT", b"TGCA")), np.uint8)
+    q, t = tmp_path / "q.fa", tmp_path / "t.fa"
+    _write_fasta(q, [("q", qry.tobytes())])
+    _write_fasta(t, [("t", base.tobytes())])
+    # 20 target chunks (overlap 1024), 15 query chunks; blocks tile the grid, one of them in "fast" mode
+    blocks = [(t0, min(t0 + 4, 19), q0, min(q0 + 3, 14), 0) for t0 in range(0, 20, 5) for q0 in range(0, 15, 4)]
+    blocks.append((0, 19, 0, 14, 1))
+    return str(q), str(t), blocks
+
+
+def _reference_block_records(q, t, blocks):
+    """What the UNMODIFIED reference emits for these t_pairs: its own FASTA loader + ChunkManager +
+    HomologyByXCorr::align_target (oracle/_ref/libsatsuma_ref.so)."""
+    import oracle
+
+    R = oracle.Reference()
+    R.configure()
+    R.load_fasta(t, q)
+    return np.concatenate([R.align_block(*b[:4], fast=bool(b[4])) for b in blocks])
+
+
+@pytest.mark.gpu
+def test_slave_speaks_the_reference_wire_protocol(host_bins, sx, reference_lib, tmp_path):
+    """A scripted master hands t_pairs to the B200 slave over loopback TCP, two per connection like the reference's
+    WorkQueue; the slave queues them over several connections, aligns them in batches on the GPU while it keeps
+    exchanging, and delivers every record.  Expected: the unmodified reference's align_target on the same FASTA."""
+    q, t, blocks = _slave_case(tmp_path)
+    exp = _reference_block_records(q, t, blocks)
+    m = _ScriptedMaster(sx, blocks, sid=7)
+    r = subprocess.run([host_bins["HomologyByXCorrSlave"], "-master", "127.0.0.1", "-port", str(m.port), "-sid", "7", "-q",
+                        q, "-t", t, "-device", "0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = m.records()
+    assert len(exp) > 100
     assert sorted(map(rec_key, got)) == sorted(map(rec_key, exp))
+    ge = {rec_key(x): x for x in got}
+    for x in exp:
+        assert ge[rec_key(x)]["ident"] == x["ident"]
+        assert abs(float(ge[rec_key(x)]["prob"]) - float(x["prob"])) <= 1e-6 * abs(float(x["prob"]))
+    # several blocks per GPU batch although the master hands out two per connection
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("exchanges")][0]
+    nb = float(line.split("(")[1].split()[0])
+    assert nb > 2.0, line
+
+
+@pytest.mark.gpu
+def test_reference_slave_with_the_binding_compiled_in(sx, reference_lib, tmp_path):
+    """INTEGRATION.md section 2, built for real: the reference's own HomologyByXCorrSlave.cc with
+    HomologyByXCorr::align_target calling sx_align_blocks (oracle/make_refslave_b200.py patches the translation unit
+    where it lies under /root/reference; flag parsing, FASTA loader, ChunkManager, worker threads and the TCP loop
+    stay the reference's).  Driven by the scripted master; records identical to the unmodified reference's."""
+    import oracle
+
+    exe = os.path.join(os.path.dirname(oracle.REF_SO), "HomologyByXCorrSlave_b200bind")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/HomologyByXCorrSlave_b200bind not built (make -C oracle refslave_b200, needs /root/reference)")
+    q, t, blocks = _slave_case(tmp_path)
+    exp = _reference_block_records(q, t, blocks)
+    # the reference slave asks for more whenever fewer than 2 x p blocks are queued and otherwise sleeps 10 s
+    # (Slave.cc:451, 524); its workers poll once a second: a generous quiet period before "terminate"
+    m = _ScriptedMaster(sx, blocks, sid=1, per_exchange=8, quiet_s=4.0)
+    env = dict(os.environ, SX_DEVICE="0")
+    p = subprocess.Popen([exe, "-master", "127.0.0.1", "-port", str(m.port), "-sid", "1", "-p", "8", "-q", q, "-t", t],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+    try:
+        out, err = p.communicate(timeout=300)
+    except subprocess.TimeoutExpired:
+        p.kill()
+        raise
+    got = m.records()
+    assert p.returncode == 0, err[-2000:]
+    assert sorted(map(rec_key, got)) == sorted(map(rec_key, exp))
+    ge = {rec_key(x): x for x in got}
+    for x in exp:
+        assert ge[rec_key(x)]["ident"] == x["ident"]
