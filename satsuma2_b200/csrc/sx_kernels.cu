@@ -163,6 +163,18 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// ---- bulk asynchronous copy shared -> global (the TMA engine without a tensor map) ------------------------
+__device__ __forceinline__ void bulk_store_fence() {  // generic-proxy writes to shared memory -> visible to the copy engine
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, int bytes) {  // 16-byte aligned, multiple of 16
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // =================================================================================================
 // K1: encode + forward transform.  One CTA per chunk signal.
 // =================================================================================================
@@ -550,10 +562,19 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
     }
     __syncthreads();
     fft_forward_halves<LOG2N, N, NT>(buf, tid);
-    // spectra out in shared-memory slot order ([even | odd] halves, scrambled bins, swizzled slots)
-    float4 *dst = reinterpret_cast<float4 *>(ws.spec + ((size_t)sd.slot * 2 + pr) * N);
-    const float4 *s4p = reinterpret_cast<const float4 *>(buf);
-    for (int k = tid; k < N / 2; k += NT) dst[k] = s4p[k];
+    // spectra out in shared-memory slot order ([even | odd] halves, scrambled bins, swizzled slots): one bulk
+    // asynchronous copy (TMA, shared -> global) issued by one thread instead of 16 load/store pairs per thread;
+    // the threads go on while the copy engine drains the buffer, and only wait for it to have READ the buffer
+    // before the next signal is generated into it
+    bulk_store_fence();
+    __syncthreads();
+    if (tid == 0) {
+      float2 *dst = ws.spec + ((size_t)sd.slot * 2 + pr) * N;
+      constexpr int PIECE = N < 4096 ? N : 4096;  // float2 per copy (at most 32 KiB)
+#pragma unroll
+      for (int o = 0; o < N; o += PIECE) bulk_store(dst + o, buf + o, PIECE * (int)sizeof(float2));
+      bulk_store_commit();
+    }
     if (tid == 0) {
       // per-channel bins from the packed transform: X_re-channel[k] + X_im-channel[k]
       //   = (a+b)/2 - i (a-b)/2  with a = Z[k], b = conj(Z[N-k])
@@ -563,6 +584,7 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
       acc_re += 0.5f * s.x + 0.5f * d.y;
       acc_im += 0.5f * s.y - 0.5f * d.x;
       acc_ny += zn.x + zn.y;
+      bulk_store_wait_read();  // the buffer may be overwritten (and, after the last round, the CTA may leave)
     }
     __syncthreads();
   }
@@ -717,9 +739,11 @@ __device__ __forceinline__ void findtop_impl(XcAt xc_at, double co, uint32_t *ma
     }
     if (NB > 8) acc = warp_sum(acc);
     const double thr = __dadd_rn(__dmul_rn(__dsqrt_rn(__ddiv_rn(acc, 256.0)), co), 1.0);
+    // (double)v > thr for a float v is v > (largest float <= thr): exact, and the compares stay in FP32
+    const float thr_f = __double2float_rd(thr);
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-      const uint32_t m = __ballot_sync(0xffffffffu, (double)v[r] > thr);
+      const uint32_t m = __ballot_sync(0xffffffffu, v[r] > thr_f);
       if (lane == 0) mask[b * 8 + r] = m;
     }
   }

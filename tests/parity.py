@@ -36,27 +36,27 @@ def xc_rel_err(got, ref):
     return float(np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() / scale)
 
 
-def borderline_lags(oracle, xc, cutoff):
-    """Lag indices whose correlation is within BORDER (relative) of the FindTop threshold."""
+def borderline_lags(oracle, xc, cutoff, border=BORDER):
+    """Lag indices whose correlation is within `border` (relative; the contract's 1e-4 unless a test documents a wider
+    allowance, as for N = 32768 against the reference's own drifting FFT) of the FindTop threshold."""
     _, env = oracle.findtop(xc, cutoff, with_env=True)
     N = xc.shape[0]
     thr = env[np.arange(N) // 256] * cutoff + 1.0 if N // 256 > 8 else np.ones(N)
-    return set(np.nonzero(np.abs(xc.astype(np.float64) - thr) <= BORDER * np.abs(thr))[0].tolist())
+    return set(np.nonzero(np.abs(xc.astype(np.float64) - thr) <= border * np.abs(thr))[0].tolist())
 
 
-def compare_candidates(oracle, got_idx, ref_xc, cutoff):
+def compare_candidates(oracle, got_idx, ref_xc, cutoff, border=BORDER):
     """Candidate sets must agree except for borderline lags. Returns the listed borderline lags."""
     exp = set(oracle.findtop(ref_xc, cutoff).tolist())
     got = set(int(i) for i in got_idx)
     diff = exp ^ got
-    border = borderline_lags(oracle, ref_xc, cutoff)
-    unexplained = diff - border
+    unexplained = diff - borderline_lags(oracle, ref_xc, cutoff, border)
     assert not unexplained, f"candidate lags differ away from the threshold: {sorted(unexplained)[:10]}"
     return sorted(diff)
 
 
 def compare_pair_records(oracle, got, exp, tchunk, qchunk, t_start, q_start, q_seqsize, q_chunk_flag, N, cutoff,
-                         min_prob, target_total, listed):
+                         min_prob, target_total, listed, border_tol=BORDER):
     """Records of ONE chunk pair (both strands).  got/exp: structured arrays (t_result layout).
     Differences must be explained by a borderline candidate lag or borderline probability."""
     g = {rec_key(r): r for r in got}
@@ -82,7 +82,7 @@ def compare_pair_records(oracle, got, exp, tchunk, qchunk, t_start, q_start, q_s
             qstart = k[3] if k[3] < (1 << 63) else k[3] - (1 << 64)
             start_q = qstart - q_seqsize + q_start + q_chunk_flag
         lag = start_q - start_t + N // 2
-        border = borderline_lags(oracle, xc, cutoff)
+        border = borderline_lags(oracle, xc, cutoff, border_tol)
         rec = g.get(k, e.get(k))
         near_prob = abs(float(rec["prob"]) - min_prob) <= 1e-4
         assert (lag in border) or near_prob, f"unexplained match difference {k} (lag {lag}, prob {rec['prob']})"

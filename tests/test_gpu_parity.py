@@ -783,3 +783,49 @@ def test_full_config0_every_chunk_pair(sx, oracle_lib):
                    "records_gpu": int(len(got)), "differing_records": int(ndiff), "unexplained": 0,
                    "listed": [dict(x, key=[int(v) for v in x["key"]]) for x in listed]}, f)
     assert len(listed) <= 8, listed
+
+
+@pytest.mark.parametrize("NN", [16384, 32768])
+def test_large_transforms_32_pairs_against_the_live_reference(sx, oracle_lib, reference_lib, NN):
+    """config 3 against the unmodified reference run on this box (oracle/_ref/libsatsuma_ref.so): 32 seeded chunk
+    pairs per transform size, both strands -- correlation vectors within REF_XC_TOL of the reference's own
+    (its float FFT uses rotation-recurrence twiddles from N = 16384 on), candidate lists identical up to
+    listed borderline lags, match records identical up to listed borderlines."""
+    from conftest import REF_XC_TOL
+    from satsuma2_b200 import synth
+
+    chunk, n = NN // 2, 32
+    T, Q, _ = synth.random_pairs(n, chunk, seed=NN + 1)
+    tl = [(T[i].tobytes(), 0, i, chunk) for i in range(n)]
+    ql = [(Q[i].tobytes(), 0, i, chunk) for i in range(n)]
+    R = reference_lib
+    R.configure(t_chunk=chunk, q_chunk=chunk)
+    R.set_chunks(True, tl, [chunk] * n)
+    R.set_chunks(False, ql, [chunk] * n)
+    R.lib.ref_set_target_total(1e6)
+    listed, worst = [], 0.0
+    with sx.XCorrEngine(t_chunk=chunk, q_chunk=chunk, target_total=1e6) as eng:
+        eng.set_targets(sx.ChunkSet.independent(T))
+        eng.set_queries(sx.ChunkSet.independent(Q))
+        for i in range(n):
+            for strand in (0, 1):
+                qs = R.revcomp(ql[i][0]) if strand else ql[i][0]
+                ref_xc = R.xcorr(tl[i][0], qs, NN)
+                err = xc_rel_err(eng.tap_xcorr(i, i, strand), ref_xc)
+                worst = max(worst, err)
+                assert err < REF_XC_TOL[NN], (i, strand, err)
+                # the candidate threshold inherits the allowance of the correlation values it is compared with
+                compare_candidates(oracle_lib, eng.tap_candidates(i, i, strand), ref_xc, 1.8, border=REF_XC_TOL[NN])
+        got = eng.align_pairs([(i, i) for i in range(n)])
+    exp = np.concatenate([R.align_block(i, i, i, i) for i in range(n)])
+    assert len(exp) > n // 2
+    for i in range(n):
+        compare_pair_records(oracle_lib, got[got["query_id"] == i], exp[exp["query_id"] == i], tl[i][0], ql[i][0], 0, 0,
+                             chunk, chunk, NN, 1.8, 0.99, 1e6, listed, border_tol=REF_XC_TOL[NN])
+    _log_listed(f"live_reference_{NN}", listed)
+    d = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, f"large_n_{NN}.json"), "w") as f:
+        json.dump({"fft_n": NN, "pairs": n, "worst_xc_rel_err_vs_reference": worst, "tolerance": REF_XC_TOL[NN],
+                   "records": int(len(exp)), "listed": len(listed)}, f)
+    assert len(listed) <= 4, listed
