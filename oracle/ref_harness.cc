@@ -370,6 +370,42 @@ long ref_sort_collapse(double *io, long n, int do_collapse) {
   return k;
 }
 
+// Timing of the list operations alone (no marshalling): Sort, Collapse, RunMatchDynProg[Mult] on n records.
+// secs[0] = Sort, secs[1] = Collapse, secs[2] = chain.  Returns the chain length.
+long ref_sort_collapse_chain_timed(const double *in, long n, int n_targets, int n_queries, const int *tsize,
+                                   const int *qsize, int dups, double *secs, long *n_collapsed) {
+  CoutSilencer s;
+  MultiMatches mm, out;
+  mm.SetCounts(n_targets, n_queries);
+  for (int i = 0; i < n_targets; i++) mm.SetTargetSize(i, tsize[i]);
+  for (int i = 0; i < n_queries; i++) mm.SetQuerySize(i, qsize[i]);
+  for (long i = 0; i < n; i++) {
+    const double *r = in + 10 * i;
+    SingleMatch m;
+    m.SetQueryTargetID((int)r[1], (int)r[0], (int)r[2]);
+    m.SetPos((int)r[4], (int)r[3], (int)r[5], r[6] != 0.);
+    m.AddMatches(r[7]);
+    m.SetProbability(r[8]);
+    m.SetIdentity(r[9]);
+    mm.AddMatch(m);
+  }
+  auto t0 = std::chrono::steady_clock::now();
+  mm.Sort();
+  auto t1 = std::chrono::steady_clock::now();
+  mm.Collapse();
+  auto t2 = std::chrono::steady_clock::now();
+  if (n_collapsed) *n_collapsed = mm.GetMatchCount();
+  if (dups)
+    RunMatchDynProgMult(out, mm);
+  else
+    RunMatchDynProg(out, mm);
+  auto t3 = std::chrono::steady_clock::now();
+  secs[0] = std::chrono::duration<double>(t1 - t0).count();
+  secs[1] = std::chrono::duration<double>(t2 - t1).count();
+  secs[2] = std::chrono::duration<double>(t3 - t2).count();
+  return out.GetMatchCount();
+}
+
 // RunMatchDynProg (analysis/MatchDynProg.cc:401-561) on n records (layout of ref_read_match_file) that are already
 // sorted + collapsed; sequence sizes as the match file carries them.  Returns the chain length, records in `io`.
 long ref_chain(double *io, long n, int n_targets, int n_queries, const int *tsize, const int *qsize, int dups) {

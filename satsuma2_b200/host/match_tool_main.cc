@@ -5,6 +5,7 @@
 // and the synteny chain of ChainMatches (tools/analysis/ChainMatches.cc:60-75 = Sort, Collapse, RunMatchDynProg,
 // analysis/MatchDynProg.cc:401-561; `-dups 1` = RunMatchDynProgMult, :245-399).
 //   XCorrMatchTool -i <in> -o <out> [-sort 1] [-collapse 1] [-chain 0] [-dups 0]
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -28,12 +29,19 @@ int main(int argc, char **argv) {
     return 1;
   }
   printf("Matches read: %zu\n", mf.matches.size());
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a0, std::chrono::steady_clock::time_point a1) {
+    return std::chrono::duration<double>(a1 - a0).count();
+  };
+  auto t0 = now();
   if (do_sort) mf.sort();
+  auto t1 = now();
   if (do_collapse) {
     printf("Matches before collapse: %zu\n", mf.matches.size());
     mf.collapse();
     printf("Matches after collapse:  %zu\n", mf.matches.size());
   }
+  auto t2 = now();
   if (a.count("-chain") && atoi(a["-chain"].c_str()) != 0) {
     sxh::MatchFile chained;
     if (a.count("-dups") && atoi(a["-dups"].c_str()) != 0)
@@ -43,6 +51,8 @@ int main(int argc, char **argv) {
     printf("Matches in the chain:    %zu\n", chained.matches.size());
     mf = chained;
   }
+  auto t3 = now();
+  printf("seconds: sort %.4f collapse %.4f chain %.4f\n", secs(t0, t1), secs(t1, t2), secs(t2, t3));
   if (!mf.write(a["-o"], &err)) {
     fprintf(stderr, "%s\n", err.c_str());
     return 1;

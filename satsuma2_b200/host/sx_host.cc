@@ -4,6 +4,8 @@
 
 #include <cctype>
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -637,8 +639,14 @@ void MatchFile::chain(MatchFile &out) const {
     if (i < first_i[id]) first_i[id] = i;
     if (i > last_i[id]) last_i[id] = i;
   }
-  std::vector<MatchRec> result;
-  for (int j = 0; j < n_t; j++) {
+  // One chain per target sequence (MatchDynProg.cc:483-557); the chains do not depend on each other, so they run on
+  // as many host threads as there are targets (at most the core count) and are appended in target order -- the
+  // output is the sequential one, record for record.  (The reference does them one after the other on one thread.)
+  std::vector<std::vector<MatchRec>> per_target((size_t)n_t);
+  std::atomic<int> next_target(0);
+  auto worker = [&]() {
+  for (int j = next_target.fetch_add(1); j < n_t; j = next_target.fetch_add(1)) {
+    std::vector<MatchRec> &result = per_target[(size_t)j];
     const int last = last_i[j], first = last == -1 ? 0 : first_i[j];
     const std::vector<char> &t = mult_t[j];
     std::vector<ChainRec> dp;
@@ -661,6 +669,14 @@ void MatchFile::chain(MatchFile &out) const {
     }
     chain_one_target(dp, result);
   }
+  };
+  const int n_threads = std::max(1, std::min<int>(n_t, (int)std::thread::hardware_concurrency()));
+  std::vector<std::thread> pool;
+  for (int w = 1; w < n_threads; w++) pool.emplace_back(worker);
+  worker();
+  for (std::thread &th : pool) th.join();
+  std::vector<MatchRec> result;
+  for (const std::vector<MatchRec> &r : per_target) result.insert(result.end(), r.begin(), r.end());
   unzip_matches(result, out);
 }
 
