@@ -55,11 +55,12 @@ def load_peaks():
 
 def load_traffic():
     """dram__bytes_read+write per launch (device batch of 16384 pairs) from profiles/*_traffic.json."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    try:
-        return json.load(open(p)).get("dram_bytes_per_launch", {})
-    except Exception:
-        return {}
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name))).get("dram_bytes_per_launch", {})
+        except Exception:
+            continue
+    return {}
 
 
 class ClockSampler:

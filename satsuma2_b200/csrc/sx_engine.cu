@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -301,14 +302,14 @@ static int set_store(sx_ctx *c, ChunkStore &S, const char *bases, const int64_t 
   S.n = 0;
   S.async_pending = false;
   if (&S == &c->T) std::fill(c->t_valid.begin(), c->t_valid.end(), 0);
-  if (S.d_bases && S.cap_bytes < blob + 16) {  // keep the device buffer across calls when it is big enough
+  if (S.d_bases && S.cap_bytes < blob + 32) {  // keep the device buffer across calls when it is big enough
     cudaFree(S.d_bases);
     S.d_bases = nullptr;
     S.cap_bytes = 0;
   }
   if (blob > 0 && !S.d_bases) {
-    CU(cudaMalloc((void **)&S.d_bases, blob + 16));
-    S.cap_bytes = blob + 16;
+    CU(cudaMalloc((void **)&S.d_bases, blob + 32));
+    S.cap_bytes = blob + 32;
   }
   S.n = n;
   S.blob_bytes = blob;

@@ -223,7 +223,7 @@ __device__ __forceinline__ int encode_prepare(const SigDesc &sd, const Slots &ws
   bool fast_done = false;
   if (sd.strand == 0) {
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
-    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src - mis);  // chunk stores are padded by 16 bytes
+    const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src - mis);  // chunk stores are padded by 32 bytes (the funnel below reads up to 20 bytes past the last base)
     const bool al16 = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
     uint32_t bad = 0;
     for (int t = tid; t < (len32 >> 4); t += NT) {

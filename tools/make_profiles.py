@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Regenerates profiles/r1_* from the ncu captures of one gpurun call (tools/ncu_capture.sh <tag> + launch list).
+"""Regenerates profiles/<round>_* from the ncu captures of one gpurun call (tools/ncu_capture.sh <tag> + launch list).
 
-    python tools/make_profiles.py <tag> [bench-json ...]
+    python tools/make_profiles.py <tag> [bench-json ...]      (round prefix = first two characters of the tag, e.g. r2)
 """
 import collections
 import csv
@@ -15,15 +15,16 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 tag = sys.argv[1]
+RND = tag[:2]
 kernels = {"encode_fft": "encode_fft_kernel", "xcorr_findtop": "xcorr_pair_kernel", "scan_score": "scan_score_kernel"}
 traffic = {}
 for key, k in kernels.items():
     rep = os.path.join(G, f"prof_{k}_{tag}.ncu-rep")
     txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep, "30"],
                          capture_output=True, text=True).stdout
-    open(os.path.join(P, f"r1_ncu_{k}.txt"), "w").write(
+    open(os.path.join(P, f"{RND}_ncu_{k}.txt"), "w").write(
         f"# ncu --set full --clock-control none --import-source on -k regex:{k} -s 4 -c 1  python bench.py --pairs 32768 "
-        f"--steps 1 --warmup 3   (capture tag {tag}; tools/ncu_summary.py)\n" + txt)
+        f"--target-total 4294967296 --steps 1 --warmup 3 --no-cpu-baseline --no-extras   (capture tag {tag}; tools/ncu_summary.py)\n" + txt)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     h, u, v = rows[0], rows[1], rows[2]
@@ -36,15 +37,15 @@ for key, k in kernels.items():
     traffic[key] = int(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
 json.dump({
     "source": f"ncu --set full --clock-control none, one launch each of a 16384-pair device batch (32768 strand-pairs, "
-              f"32768 signals: target + forward query per pair); capture tag {tag}; profiles/r1_ncu_*.txt",
+              f"32768 signals: target + forward query per pair); capture tag {tag}; profiles/{RND}_ncu_*.txt",
     "dram_bytes_per_launch": traffic,
     "algorithmic_bytes_per_launch": {"scan_score": 32768 * 4224 + 2 * 581 * 16384,
                                      "xcorr_findtop": 16384 * 2 * 131072, "encode_fft": 32768 * (131072 + 4096)},
     "note": "xcorr_findtop = xcorr_pair_kernel: one CTA per chunk pair reads the target and the forward-query spectra "
             "once (2 x 128 KiB) and derives both strands; encode_fft writes 128 KiB of spectra + planes per signal",
-}, open(os.path.join(P, "r1_traffic.json"), "w"), indent=2)
+}, open(os.path.join(P, f"{RND}_traffic.json"), "w"), indent=2)
 src = os.path.join(G, f"launches_{tag}.csv")
-shutil.copy(src, os.path.join(P, "r1_launches.csv"))
+shutil.copy(src, os.path.join(P, f"{RND}_launches.csv"))
 rows = [r for r in csv.reader(open(src)) if len(r) > 10 and r[0].isdigit()]
 agg = collections.OrderedDict()
 for r in rows:
@@ -52,12 +53,12 @@ for r in rows:
     a[0] += 1
     a[1] += float(r[-1]) / 1e6
 tot = sum(x[1] for x in agg.values())
-with open(os.path.join(P, "r1_launch_summary.txt"), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 400  python bench.py --pairs 65536 --steps 2 "
-            "--warmup 3 --no-cpu-baseline\n# per-launch times are cold-cache and serialised: compare SHARES with "
+with open(os.path.join(P, f"{RND}_launch_summary.txt"), "w") as f:
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 400  python bench.py --pairs 65536 --target-total "
+            "4294967296 --steps 2 --warmup 3 --no-cpu-baseline --no-extras\n# per-launch times are cold-cache and serialised: compare SHARES with "
             "bench.py's live CUDA-event shares (roofline.kernels.*.share)\n")
     for k, x in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"{k:62s} launches={x[0]:4d} total_ms={x[1]:9.3f} share={x[1] / tot:5.3f} avg_ms={x[1] / x[0]:.3f}\n")
 for b in sys.argv[2:]:
-    shutil.copy(b, os.path.join(P, "r1_" + os.path.basename(b)))
-print(open(os.path.join(P, "r1_launch_summary.txt")).read(), json.dumps(traffic))
+    shutil.copy(b, os.path.join(P, RND + "_" + os.path.basename(b)))
+print(open(os.path.join(P, f"{RND}_launch_summary.txt")).read(), json.dumps(traffic))
