@@ -179,6 +179,117 @@ static void fft_c(cplx *a, int n, int sign) {
   }
 }
 
+/* ---- the reference's twiddle drift from N = 16384 on ---------------------------------
+ * FFTReal builds a real transform of length 2M from two of length M ("pass" p, M = 2^p) with twiddles
+ * cos/sin(i*pi/M), i < M/2.  Up to p = 12 they come from an exact table; for p > 12 (FFTReal.h:78) from
+ * OscSinCos (OscSinCos.hpp:88-96): a float rotation recurrence restarted at (1, 0) for every group
+ * (FFTReal.hpp:605-656 forward, 783-830 inverse), whose rounding errors accumulate to ~1e-4 after some
+ * thousand steps.  The model below keeps every other operation in float64 and uses exactly those float
+ * twiddles, so it follows the reference (not the ideal transform) at N = 16384 / 32768. */
+static void osc_twiddles(int M, double *wr, double *wi) { /* w[i] = c_i + j s_i for i < M/2; i = 0 exact */
+  const float sc = (float)cos(M_PI / (double)M), ss = (float)sin(M_PI / (double)M);
+  float pc = 1.f, ps = 0.f;
+  wr[0] = 1.;
+  wi[0] = 0.;
+  for (int i = 1; i < M / 2; i++) {
+    const float oc = pc, os = ps;
+    const float a = oc * sc, b = os * ss, c = oc * ss, d = os * sc; /* separate roundings: no FMA on x86-64 */
+    pc = a - b;
+    ps = c + d;
+    wr[i] = (double)pc;
+    wi[i] = (double)ps;
+  }
+}
+/* twiddle the reference effectively applies to bin i < M of the odd half when it builds length 2M:
+ * i < M/2: the oscillator value; i = M/2: exact (the "extreme coefficients" are handled separately,
+ * FFTReal.hpp:622-626); i > M/2: -conj of the value at M - i (those bins are produced as conjugates of the
+ * lower ones, dfi[-i] / dfi[nbr_coef - i]).  `osc` = NULL: the exact twiddle (passes <= 12). */
+static void eff_twiddle(const double *owr, const double *owi, int M, int i, double *re, double *im) {
+  if (!owr || i == 0 || 2 * i == M) {
+    const double ang = M_PI * (double)i / (double)M;
+    *re = cos(ang);
+    *im = sin(ang);
+  } else if (2 * i < M) {
+    *re = owr[i];
+    *im = owi[i];
+  } else {
+    *re = -owr[M - i];
+    *im = owi[M - i];
+  }
+}
+/* forward transform as FFTReal::do_fft computes it (positive exponent): exact below M = 8192, oscillator
+ * twiddles in the passes that build lengths 16384 and 32768 */
+static void fft_ref_forward(cplx *a, int n) {
+  if (n < 16384) {
+    fft_c(a, n, +1);
+    return;
+  }
+  for (int i = 1, j = 0; i < n; i++) { /* bit reversal */
+    int bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) {
+      cplx t = a[i];
+      a[i] = a[j];
+      a[j] = t;
+    }
+  }
+  for (int len = 2; len <= n; len <<= 1) {
+    const int half = len >> 1; /* = M */
+    double *owr = NULL, *owi = NULL;
+    if (half >= 8192) { /* pass p = log2(M) > 12 */
+      owr = (double *)malloc(sizeof(double) * half);
+      owi = (double *)malloc(sizeof(double) * half);
+      osc_twiddles(half, owr, owi);
+    }
+    for (int k = 0; k < half; k++) {
+      double wr, wi;
+      eff_twiddle(owr, owi, half, k, &wr, &wi);
+      for (int s = 0; s < n; s += len) {
+        cplx u = a[s + k], v = a[s + k + half];
+        const double tr = v.re * wr - v.im * wi, ti = v.re * wi + v.im * wr;
+        a[s + k].re = u.re + tr;
+        a[s + k].im = u.im + ti;
+        a[s + k + half].re = u.re - tr;
+        a[s + k + half].im = u.im - ti;
+      }
+    }
+    free(owr);
+    free(owi);
+  }
+}
+/* inverse as FFTReal::do_ifft computes it (negative exponent, unscaled): it SPLITS first -- E = G[k] + G[k+M],
+ * O = (G[k] - G[k+M]) * conj(twiddle) -- so the oscillator twiddles act on the spectrum, level by level, before
+ * the exact shorter transforms; even time samples come from E, odd ones from O. */
+static void fft_ref_inverse(cplx *g, int n) {
+  if (n < 16384) {
+    fft_c(g, n, -1);
+    return;
+  }
+  const int M = n / 2;
+  double *owr = (double *)malloc(sizeof(double) * M), *owi = (double *)malloc(sizeof(double) * M);
+  osc_twiddles(M, owr, owi);
+  cplx *e = (cplx *)malloc(sizeof(cplx) * M), *o = (cplx *)malloc(sizeof(cplx) * M);
+  for (int k = 0; k < M; k++) {
+    double wr, wi;
+    eff_twiddle(owr, owi, M, k, &wr, &wi);
+    const cplx s = {g[k].re + g[k + M].re, g[k].im + g[k + M].im}, d = {g[k].re - g[k + M].re, g[k].im - g[k + M].im};
+    e[k] = s;
+    o[k].re = d.re * wr + d.im * wi; /* d * conj(w) */
+    o[k].im = d.im * wr - d.re * wi;
+  }
+  free(owr);
+  free(owi);
+  fft_ref_inverse(e, M);
+  fft_ref_inverse(o, M);
+  for (int m = 0; m < M; m++) {
+    g[2 * m] = e[m];
+    g[2 * m + 1] = o[m];
+  }
+  free(e);
+  free(o);
+}
+
 void sxo_xcorr(const float *tsig4, const float *qsig4, int N, float *out) {
   int H = N / 2;
   cplx *f1 = (cplx *)malloc(sizeof(cplx) * N);
@@ -195,8 +306,8 @@ void sxo_xcorr(const float *tsig4, const float *qsig4, int N, float *out) {
       f2[i].im = 0;
     }
     /* FFTReal::do_fft uses the positive exponent (extern/RealFFT/readme.txt:127) */
-    fft_c(f1, N, +1);
-    fft_c(f2, N, +1);
+    fft_ref_forward(f1, N);
+    fft_ref_forward(f2, N);
     /* DoOne, CrossCorr.cc:477-492: DC real*real; bins 1..H-2 get conj(F1)*F2;
      * bins H-1 and H are left as F1 (quirk Q1). */
     g[0].re = f1[0].re * f2[0].re;
@@ -214,7 +325,7 @@ void sxo_xcorr(const float *tsig4, const float *qsig4, int N, float *out) {
       g[N - k].im = -g[k].im;
     }
     /* do_ifft: negative exponent, unscaled; rescale by 1/N (FFTReal.hpp:206-293) */
-    fft_c(g, N, -1);
+    fft_ref_inverse(g, N);
     /* rotation by H (cc:500-505) and float accumulation over channels in order A,C,G,T (cc:395-403) */
     for (int i = 0; i < N; i++) {
       float x = (float)(g[(i + H) % N].re / (double)N);

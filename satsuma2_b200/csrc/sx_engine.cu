@@ -136,6 +136,7 @@ struct sx_ctx {
   DevBuf<SlotMeta> meta;
   DevBuf<float2> wn;  // e^{-2 pi i n / N}, n < N/2
   DevBuf<double> ent_table;  // fill_ent_table()
+  DevBuf<float2> drift;      // fill_drift_table() (N = 32768)
   std::vector<uint8_t> t_valid;  // persistent target slot holds a spectrum
 
   // per-batch device buffers
@@ -167,6 +168,7 @@ struct sx_ctx {
     s.meta = meta.p;
     s.wn = wn.p;
     s.ent_table = ent_table.p;
+    s.drift = drift.p;
     return s;
   }
 };
@@ -253,6 +255,13 @@ extern "C" int sx_create(const sx_config *cfg, sx_ctx **out) {
     if (cudaMemcpy(c->ent_table.p, et.data(), sizeof(double) * et.size(), cudaMemcpyHostToDevice) != cudaSuccess)
       rc = fail(SX_ERR_CUDA, "sx_create: entropy table upload failed");
   }
+  if (rc == SX_OK && drift_table_elems(c->log2n) > 0) {
+    std::vector<float2> dt(drift_table_elems(c->log2n));
+    fill_drift_table(c->log2n, dt.data());
+    rc = c->drift.ensure(dt.size());
+    if (rc == SX_OK && cudaMemcpy(c->drift.p, dt.data(), sizeof(float2) * dt.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+      rc = fail(SX_ERR_CUDA, "sx_create: drift table upload failed");
+  }
   if (rc != SX_OK) {
     delete c;
     return rc;
@@ -271,7 +280,7 @@ extern "C" void sx_destroy(sx_ctx *c) {
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->T.d_bases) cudaFree(c->T.d_bases);
   if (c->Q.d_bases) cudaFree(c->Q.d_bases);
-  c->spec.release(); c->planes.release(); c->sbytes.release(); c->meta.release(); c->wn.release(); c->ent_table.release();
+  c->spec.release(); c->planes.release(); c->sbytes.release(); c->meta.release(); c->wn.release(); c->ent_table.release(); c->drift.release();
   c->d_lists.release(); c->h_lists[0].release(); c->h_lists[1].release();
   c->d_sigs[0].release(); c->d_sigs[1].release(); c->d_sps.release(); c->d_cand_ref.release(); c->d_cand_pool.release();
   c->d_scratch.release(); c->d_res.release(); c->d_seg_tap.release(); c->d_ctr.release(); c->d_table.release(); c->d_tap.release();
@@ -973,6 +982,9 @@ static int32_t target_slot(sx_ctx *c, Batch &b, int32_t t) {
 // length is a multiple of the window (N/512), or below 1024 where every weight is 1.  Then
 // no reverse spectrum is computed at all: xcorr_pair_kernel derives both strands from the forward one.
 static bool rc_derivable(const sx_ctx *c, int32_t len) {
+  // N = 32768 reproduces the reference's twiddle drift (sx_kernels.h), which is not symmetric under reversal: the
+  // reverse-complement signal gets its own transform there
+  if (log2n_split(c->log2n)) return false;
   const int win = c->N / 512;
   return len >= 1 && (len % win == 0 || len < 1024);
 }

@@ -25,6 +25,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <vector>
+
 namespace sx {
 
 // ------------------------------------------------------------------------------------------------
@@ -129,6 +131,62 @@ void fill_wn_table(int log2n, float2 *out) {
   }
 }
 size_t slot_spec_elems(int log2n) { return (size_t)2 << log2n; }
+
+// ---- the reference's oscillator twiddles (sx_kernels.h) ---------------------------------------------------------
+// w~[i] = OscSinCos after i steps of angle pi / M from (1, 0), all in float, i < M / 2
+static void osc_twiddles(int M, std::vector<double> &wr, std::vector<double> &wi) {
+  const float sc = (float)cos(3.14159265358979323846 / (double)M), ss = (float)sin(3.14159265358979323846 / (double)M);
+  volatile float pc = 1.f, ps = 0.f;  // volatile: every product and sum rounded to float on its own (no FMA, no excess precision)
+  wr.assign((size_t)M / 2, 1.);
+  wi.assign((size_t)M / 2, 0.);
+  for (int i = 1; i < M / 2; i++) {
+    const float oc = pc, os = ps;
+    volatile float a = oc * sc, b = os * ss, c2 = oc * ss, d = os * sc;
+    pc = a - b;
+    ps = c2 + d;
+    wr[(size_t)i] = (double)pc;
+    wi[(size_t)i] = (double)ps;
+  }
+}
+// ratio (twiddle the reference effectively applies to bin i < M when it builds length 2M) / (exact twiddle), in the
+// reference's convention e^{+j pi i / M}: the oscillator value for i < M/2, exact at i = 0 and i = M/2 (FFTReal.hpp:
+// 622-626), -conj(value at M - i) above (those bins are produced as conjugates of the lower ones)
+static void drift_ratio(const std::vector<double> &wr, const std::vector<double> &wi, int M, int i, double *re, double *im) {
+  if (i == 0 || 2 * i == M) {
+    *re = 1.;
+    *im = 0.;
+    return;
+  }
+  double er, ei;
+  if (2 * i < M) {
+    er = wr[(size_t)i];
+    ei = wi[(size_t)i];
+  } else {
+    er = -wr[(size_t)(M - i)];
+    ei = wi[(size_t)(M - i)];
+  }
+  const double ang = 3.14159265358979323846 * (double)i / (double)M, cr = cos(ang), ci = sin(ang);
+  *re = er * cr + ei * ci;  // eff * conj(exact)
+  *im = ei * cr - er * ci;
+}
+size_t drift_table_elems(int log2n) { return log2n == 15 ? (size_t)3 << (log2n - 2) : 0; }
+void fill_drift_table(int log2n, float2 *out) {
+  if (log2n != 15) return;
+  const int N = 1 << log2n, H = N / 2, Q = N / 4;
+  std::vector<double> w14r, w14i, w13r, w13i;
+  osc_twiddles(H, w14r, w14i);      // the pass that builds length N from two of length H
+  osc_twiddles(H / 2, w13r, w13i);  // the pass below it
+  for (int k = 0; k < Q; k++) {
+    double re, im;
+    // standard-DFT convention (negative exponent) = conjugates of the reference-convention ratios
+    drift_ratio(w14r, w14i, H, k, &re, &im);
+    out[k] = make_float2((float)re, (float)-im);              // rho0
+    drift_ratio(w14r, w14i, H, k + Q, &re, &im);
+    out[Q + k] = make_float2((float)re, (float)-im);          // rho1
+    drift_ratio(w13r, w13i, H / 2, k, &re, &im);
+    out[2 * Q + k] = make_float2((float)(0.5 * (re - 1.)), (float)(-0.5 * im));  // phi
+  }
+}
 
 // Entropy terms of CCSignal::ComputeEntropy (analysis/CrossCorr.cc:28-33, 70-88) for integer base counts:
 // out[k * (WIN + 1) + c] = p < 0.001 ? 0 : p * log(p) / 0.69314718056 with p = c / k, for window lengths
@@ -600,6 +658,58 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
   }
 }
 
+// ---- the reference's twiddle drift at N = 32768, applied to one half (bins of one parity) of a spectrum held in
+// shared memory in scrambled order (sx_kernels.h, fill_drift_table).  Bins k, k + N/4, k + N/2, k + 3N/4 (k < N/4)
+// form a quad: the reference's last pass ties k to k + N/2, the pass below it ties k to k + N/4.  In this half's
+// H-point transform they are m, m + H/4, m + H/2, m + 3H/4 with m = k >> 1: the top digit of the scrambled order
+// moves by 2, so a quad is positions r, r+2, r+4, r+6 of a block of 8.
+//   FORWARD: exact spectrum -> what the reference's two oscillator passes produce
+//   INVERSE: product -> the spectrum whose EXACT inverse equals the reference's inverse with its oscillator passes
+template <int LOG2N, int NT, bool INVERSE>
+__device__ __forceinline__ void drift_correct_half(float2 *buf, const float2 *__restrict__ drift, int half, int tid) {
+  constexpr int N = 1 << LOG2N, H = N / 2, Q = N / 4;
+  static_assert(LOG2N == 15, "the quad layout below is that of Plan<15> (last radix 8)");
+  for (int q = tid; q < H / 4; q += NT) {
+    const int r = ((q >> 1) << 3) | (q & 1);  // block of 8 positions, quad 0 (even positions) or 1 (odd)
+    const int k = 2 * natural_bin<LOG2N>(r) + half;  // < N/4
+    float2 rho0 = __ldg(drift + k), rho1 = __ldg(drift + Q + k), phi = __ldg(drift + 2 * Q + k);
+    if (INVERSE) {
+      rho0.y = -rho0.y;
+      rho1.y = -rho1.y;
+      phi.y = -phi.y;
+    }
+    const int pa = swz(r), pb = swz(r + 2), pc = swz(r + 4), pd = swz(r + 6);
+    const float2 xa = buf[pa], xb = buf[pb], xc = buf[pc], xd = buf[pd];
+    float2 s0 = cadd(xa, xc), d0 = csub(xa, xc), s1 = cadd(xb, xd), d1 = csub(xb, xd);
+    if (!INVERSE) {
+      s0 = make_float2(0.5f * s0.x, 0.5f * s0.y);
+      d0 = make_float2(0.5f * d0.x, 0.5f * d0.y);
+      s1 = make_float2(0.5f * s1.x, 0.5f * s1.y);
+      d1 = make_float2(0.5f * d1.x, 0.5f * d1.y);
+      const float2 w = cmul(phi, make_float2(d0.x + d1.y, d0.y - d1.x));  // phi (D0 - i D1)
+      const float2 t0 = cmul(rho0, cadd(d0, w));
+      const float2 t1 = cmul(rho1, make_float2(d1.x - w.y, d1.y + w.x));  // rho1 (D1 + i W)
+      const float2 de = cmul(phi, csub(s0, s1));
+      const float2 e0 = cadd(s0, de), e1 = csub(s1, de);
+      buf[pa] = cadd(e0, t0);
+      buf[pc] = csub(e0, t0);
+      buf[pb] = cadd(e1, t1);
+      buf[pd] = csub(e1, t1);
+    } else {
+      const float2 a0 = cmul(rho0, d0), a1 = cmul(rho1, d1);
+      const float2 v = cmul(phi, make_float2(a0.x + a1.y, a0.y - a1.x));  // chi (A0 - i A1)
+      const float2 u0 = cadd(a0, v), u1 = make_float2(a1.x - v.y, a1.y + v.x);  // A1 + i V
+      const float2 ds = cmul(phi, csub(s0, s1));
+      const float2 e0 = cadd(s0, ds), e1 = csub(s1, ds);
+      buf[pa] = make_float2(0.5f * (e0.x + u0.x), 0.5f * (e0.y + u0.y));
+      buf[pc] = make_float2(0.5f * (e0.x - u0.x), 0.5f * (e0.y - u0.y));
+      buf[pb] = make_float2(0.5f * (e1.x + u1.x), 0.5f * (e1.y + u1.y));
+      buf[pd] = make_float2(0.5f * (e1.x - u1.x), 0.5f * (e1.y - u1.y));
+    }
+  }
+  __syncthreads();
+}
+
 // K1 for transforms that do not fit one CTA's shared memory (N = 32768: 256 KiB of complex points): the
 // two H-point transforms of the split (sx_fft.cuh) are independent, so a signal is handled by TWO CTAs,
 // blockIdx.y = half: 0 builds e[n] = z[n] + z[n+H] (even bins), 1 builds o[n] = (z[n] - z[n+H]) w_N^n (odd
@@ -675,6 +785,7 @@ __global__ void __launch_bounds__(NT, 1)
     }
     __syncthreads();
     fft_forward_halves<LOG2N, H, NT>(buf, tid);
+    if constexpr (LOG2N == 15) drift_correct_half<LOG2N, NT, false>(buf, ws.drift, half, tid);
     float4 *dst = reinterpret_cast<float4 *>(ws.spec + ((size_t)sd.slot * 2 + pr) * N + (size_t)half * H);
     const float4 *s4p = reinterpret_cast<const float4 *>(buf);
     for (int k = tid; k < H / 2; k += NT) dst[k] = s4p[k];
@@ -1095,6 +1206,7 @@ __global__ void __launch_bounds__(NT, 1)
     }
   }
   __syncthreads();
+  if constexpr (LOG2N == 15) drift_correct_half<LOG2N, NT, true>(buf, ws.drift, half, tid);
   fft_inverse_halves<LOG2N, H, NT>(buf, tid, s_tw);
   float2 *out = scratch + ((size_t)job * 2 + half) * H;
   for (int n = tid; n < H; n += NT) out[n] = buf[swz(n)];

@@ -27,6 +27,7 @@ struct Slots {
   SlotMeta *meta;
   const float2 *wn;  // e^{-2 pi i n / N}, n < N/2 (per context: the radix-2 split / combine twiddles)
   const double *ent_table;  // entropy terms for integer base counts, fill_ent_table()
+  const float2 *drift;      // N = 32768 only: [3][N/4] = rho0, rho1, phi of fill_drift_table(); nullptr otherwise
 };
 
 struct SigDesc {  // one chunk signal to encode + transform
@@ -95,6 +96,13 @@ cudaError_t launch_xcorr_findtop(int log2n, const SpDesc *sps, const uint32_t *p
                                  uint2 *cand_ref, BatchCounters *ctr, float *xc_tap, float2 *scratch,
                                  cudaStream_t stream);
 void fill_wn_table(int log2n, float2 *host_out);  // N/2 entries
+// The reference's float FFT drifts from the exact transform from N = 16384 on: its last passes take their twiddles
+// from a float rotation recurrence (extern/RealFFT/OscSinCos.hpp:88-96, FFTReal.hpp:605-656, 783-830).  At N = 32768
+// the deviation (2e-4 of max|xc|) exceeds the 1e-4 parity contract, so the kernels reproduce it: the exact spectrum
+// of every signal is corrected bin quad by bin quad to what the reference's two oscillator passes give, and the
+// product is pre-corrected for the two oscillator passes of its inverse.  Table: 3 x N/4 complex factors.
+size_t drift_table_elems(int log2n);  // 0 unless the transform size uses the correction
+void fill_drift_table(int log2n, float2 *host_out);
 size_t ent_table_elems(int log2n);
 void fill_ent_table(int log2n, double *host_out);  // ent_table_elems() entries
 cudaError_t launch_scan_score(int log2n, const SpDesc *sps, int nsp, Slots ws, const uint16_t *cand_pool,

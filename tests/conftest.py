@@ -46,11 +46,12 @@ def golden_large():
     return np.load(os.path.join(GOLDEN, "large_n.npz"))
 
 
-# from N = 16384 on the reference's own float FFT (rotation-recurrence twiddles for passes > 12)
-# drifts from the exact transform: measured 1.6e-5 (N = 16384) and 2.0e-4 (N = 32768) of max|xc|.  Against
-# the reference's vectors the tolerance is therefore 1e-4 up to N = 16384 and the documented 3e-4 at 32768;
-# against the float64 oracle it is 1e-4 everywhere.
-REF_XC_TOL = {8192: 1e-4, 16384: 1e-4, 32768: 3e-4}
+# from N = 16384 on the reference's own float FFT (rotation-recurrence twiddles for passes > 12) drifts
+# from the exact transform: 1.6e-5 (N = 16384) and 2.0e-4 (N = 32768) of max|xc|.  The oracle models that drift
+# exactly (oracle/sx_oracle.c fft_ref_forward / fft_ref_inverse: 2e-7 from the reference at both sizes) and the CUDA
+# path reproduces it at N = 32768 (csrc/sx_kernels.cu drift_correct_half), so the contract's 1e-4 holds at every size
+# against the reference's own vectors.
+REF_XC_TOL = {8192: 1e-4, 16384: 1e-4, 32768: 1e-4}
 
 
 @pytest.fixture(scope="session")
