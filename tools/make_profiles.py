@@ -18,6 +18,7 @@ tag = sys.argv[1]
 RND = tag[:2]
 kernels = {"encode_fft": "encode_fft_kernel", "xcorr_findtop": "xcorr_pair_kernel", "scan_score": "scan_score_kernel"}
 traffic = {}
+metrics = {}
 for key, k in kernels.items():
     rep = os.path.join(G, f"prof_{k}_{tag}.ncu-rep")
     txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep, "30"],
@@ -35,10 +36,23 @@ for key, k in kernels.items():
         return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u[i], 1)
 
     traffic[key] = int(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
+    metrics[key] = {m.split(".")[0].replace("sm__inst_executed_", "").replace("smsp__", "").replace("sm__", ""): round(val(m), 3)
+                    for m in ("gpu__time_duration.sum", "launch__registers_per_thread",
+                              "sm__warps_active.avg.pct_of_peak_sustained_active",
+                              "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                              "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+                              "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+                              "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+                              "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+                              "dram__throughput.avg.pct_of_peak_sustained_elapsed") if m in h}
+    if "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum" in h:
+        metrics[key]["smem_conflict_wavefront_frac"] = round(
+            val("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum") / max(val("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"), 1), 4)
 json.dump({
     "source": f"ncu --set full --clock-control none, one launch each of a 16384-pair device batch (32768 strand-pairs, "
               f"32768 signals: target + forward query per pair); capture tag {tag}; profiles/{RND}_ncu_*.txt",
     "dram_bytes_per_launch": traffic,
+    "ncu_per_launch": metrics,
     "algorithmic_bytes_per_launch": {"scan_score": 32768 * 4224 + 2 * 581 * 16384,
                                      "xcorr_findtop": 16384 * 2 * 131072, "encode_fft": 32768 * (131072 + 4096)},
     "note": "xcorr_findtop = xcorr_pair_kernel: one CTA per chunk pair reads the target and the forward-query spectra "
