@@ -63,7 +63,8 @@ typedef struct {
   int32_t async_upload;    /* != 0: sx_set_targets/queries return before the host->device copy has finished;
                               the caller keeps `bases` alive and unmodified until the next sx_align_* call on
                               this context returns.  Batches start as soon as the bases they need have arrived. */
-  int32_t debug_flags;     /* test hooks; bit 0: score every raw segment (no run-length pruning in the scan kernel) */
+  int32_t debug_flags;     /* test hooks; bit 0: score every raw segment (no run-length pruning in the scan
+                              kernel); bit 1: prepare every signal inside the transform kernel (no preparation kernel) */
   int32_t reserved[4];
 } sx_config;
 

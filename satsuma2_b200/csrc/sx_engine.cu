@@ -141,6 +141,9 @@ struct sx_ctx {
 
   // per-batch device buffers
   DevBuf<SigDesc> d_sigs[2];  // one per batch in flight (the next batch's encode is queued behind the current scan)
+  DevBuf<int32_t> d_prep_flag;  // preparation kernel -> transform kernel (PrepBuf); one set: the two kernels of a batch
+  DevBuf<float> d_prep_went;    // run back to back on the stream
+  DevBuf<double> d_prep_off;
   DevBuf<SpDesc> d_sps;
   DevBuf<uint2> d_cand_ref;
   DevBuf<uint32_t> d_lists;  // [pair list | direct list] of strand-pair indices (launch_xcorr_findtop)
@@ -282,7 +285,7 @@ extern "C" void sx_destroy(sx_ctx *c) {
   if (c->Q.d_bases) cudaFree(c->Q.d_bases);
   c->spec.release(); c->planes.release(); c->sbytes.release(); c->meta.release(); c->wn.release(); c->ent_table.release(); c->drift.release();
   c->d_lists.release(); c->h_lists[0].release(); c->h_lists[1].release();
-  c->d_sigs[0].release(); c->d_sigs[1].release(); c->d_sps.release(); c->d_cand_ref.release(); c->d_cand_pool.release();
+  c->d_sigs[0].release(); c->d_sigs[1].release(); c->d_prep_flag.release(); c->d_prep_went.release(); c->d_prep_off.release(); c->d_sps.release(); c->d_cand_ref.release(); c->d_cand_pool.release();
   c->d_scratch.release(); c->d_res.release(); c->d_seg_tap.release(); c->d_ctr.release(); c->d_table.release(); c->d_tap.release();
   c->h_sigs[0].release(); c->h_sigs[1].release(); c->h_sps[0].release(); c->h_sps[1].release(); c->h_res.release(); c->h_ctr.release();
   for (int i = 0; i < 10; i++)
@@ -741,8 +744,17 @@ static int batch_launch_early(sx_ctx *c, Run &r) {
   }
   if (c->profiling) CU(cudaEventRecord(c->ev[r.stage][0], st));
   if (nsig) {
-    CU(launch_encode_fft(c->log2n, c->d_sigs[r.stage].p, nsig, c->slots(), r.d_sig_tap, st));
-    c->stats.kernel_launches += 1;
+    PrepBuf prep = {nullptr, nullptr, nullptr};
+    if (!log2n_split(c->log2n) && r.d_sig_tap == nullptr && !(c->cfg.debug_flags & 2)) {
+      if ((rc = c->d_prep_flag.ensure((size_t)nsig)) != SX_OK) return rc;
+      if ((rc = c->d_prep_went.ensure((size_t)nsig * 256)) != SX_OK) return rc;
+      if ((rc = c->d_prep_off.ensure((size_t)nsig * 4)) != SX_OK) return rc;
+      prep.flag = c->d_prep_flag.p;
+      prep.went = c->d_prep_went.p;
+      prep.off = c->d_prep_off.p;
+    }
+    CU(launch_encode_fft(c->log2n, c->d_sigs[r.stage].p, nsig, c->slots(), r.d_sig_tap, prep, st));
+    c->stats.kernel_launches += prep.flag ? 2 : 1;
   }
   r.need_encode = nsig > 0;  // only tells batch_wait that this batch had an encode kernel to account for
   r.early_done = true;

@@ -508,9 +508,144 @@ __device__ __forceinline__ int encode_prepare(const SigDesc &sd, const Slots &ws
   return flags;
 }
 
+// K0: preparation of the common case -- forward strand, pure A/C/G/T, at most H bases -- one WARP per signal, no
+// block barriers.  These steps are a chain of dependent latencies (bases from HBM, plane words, window counts, table
+// look-ups, reductions); inside the transform kernel they held a whole CTA and its 75 KB of shared memory idle for a
+// third of its time.  Here thousands of warps are in flight and hide them; the transform kernel only picks up the
+// planes, 256 window weights and four means.  Same arithmetic as encode_prepare, statement for statement.
+template <int LOG2N>
+__global__ void __launch_bounds__(256) encode_prep_kernel(const SigDesc *__restrict__ sigs, int nsig, Slots ws, PrepBuf prep) {
+  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, WIN = N / 512, WMAX = H / WIN;
+  static_assert(WIN <= 32, "one plane word per entropy window");
+  __shared__ uint32_t s_plw[8][2 * (NW / 2)];  // plane words of at most H bases, per warp
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sig = blockIdx.x * 8 + warp;
+  if (sig >= nsig) return;
+  const SigDesc sd = sigs[sig];
+  const int len = sd.len;
+  if (sd.strand != 0 || len > H || len <= 0) {
+    if (lane == 0) prep.flag[sig] = 0;
+    return;
+  }
+  constexpr int NWH = NW / 2;
+  uint32_t *s_pl = s_plw[warp];
+  const uint8_t *__restrict__ src = sd.src;
+  const int len32 = (len + 31) & ~31, nwords = len32 >> 5;
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+  const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src - mis);  // chunk stores are padded by 32 bytes
+  const bool al16 = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+  uint32_t bad = 0;
+  for (int t = lane; t < (len32 >> 4); t += 32) {
+    uint32_t w4[4] = {0u, 0u, 0u, 0u};
+    if (t * 16 < len) {
+      if (al16) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src) + t);
+        w4[0] = v.x; w4[1] = v.y; w4[2] = v.z; w4[3] = v.w;
+      } else {
+        uint32_t x[5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) x[i] = __ldg(s32 + t * 4 + i);
+#pragma unroll
+        for (int i = 0; i < 4; i++) w4[i] = __funnelshift_r(x[i], x[i + 1], 8 * mis);
+      }
+    }
+    uint32_t lo16 = 0, hi16 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int nv = min(max(len - (t * 16 + i * 4), 0), 4);  // bases of this word inside the chunk
+      const uint32_t bm = nv == 0 ? 0u : (0xffffffffu >> (8 * (4 - nv)));
+      const uint32_t w = w4[i] & bm;
+      const uint32_t c = ((w >> 1) & 0x03030303u) ^ ((w >> 2) & 0x01010101u);
+      const uint32_t c0 = c & 0x01010101u & bm, c1 = (c >> 1) & 0x01010101u & bm, c01 = c0 & c1;
+      const uint32_t letters = (0x41414141u & bm) + 2u * c0 + 6u * c1 + 11u * c01;  // A, C = A+2, G = A+6, T = A+19
+      bad |= letters ^ w;
+      lo16 |= ((c0 * 0x01020408u) >> 24) << (4 * i);
+      hi16 |= ((c1 * 0x01020408u) >> 24) << (4 * i);
+    }
+    reinterpret_cast<uint16_t *>(s_pl)[t] = (uint16_t)lo16;
+    reinterpret_cast<uint16_t *>(s_pl + NWH)[t] = (uint16_t)hi16;
+  }
+  if (__any_sync(0xffffffffu, bad != 0u)) {  // a letter other than A/C/G/T: the general path of the transform kernel
+    if (lane == 0) prep.flag[sig] = 0;
+    return;
+  }
+  __syncwarp();
+  {
+    uint32_t *planes = ws.planes + (size_t)sd.slot * 2 * NW;
+    for (int w = lane; w < NW; w += 32) {
+      planes[w] = w < nwords ? s_pl[w] : 0u;
+      planes[NW + w] = w < nwords ? s_pl[NWH + w] : 0u;
+    }
+  }
+  if (sd.rc_slot1) {  // planes and meta of the other orientation (see encode_prepare)
+    const int oslot = sd.rc_slot1 - 1;
+    uint32_t *planes = ws.planes + (size_t)oslot * 2 * NW;
+    const int q = (len - 1) >> 5, r = (len - 1) & 31;
+    for (int j = lane; j < NW; j += 32) {
+      uint32_t lo = 0u, hi = 0u;
+      if (j <= q) {
+        const uint32_t l0 = __brev(~s_pl[q - j]), h0 = __brev(~s_pl[NWH + q - j]);
+        const uint32_t l1 = j < q ? __brev(~s_pl[q - j - 1]) : 0u, h1 = j < q ? __brev(~s_pl[NWH + q - j - 1]) : 0u;
+        lo = __funnelshift_r(l0, l1, 31 - r);
+        hi = __funnelshift_r(h0, h1, 31 - r);
+        if (j == q) {
+          const uint32_t vm = r == 31 ? 0xffffffffu : ((2u << r) - 1u);
+          lo &= vm;
+          hi &= vm;
+        }
+      }
+      planes[j] = lo;
+      planes[NW + j] = hi;
+    }
+    if (lane == 0) {
+      SlotMeta m;
+      m.len = len;
+      m.flags = 0;
+      m.q_re = m.q_im = m.q_nyq = 0.f;
+      m.pad[0] = m.pad[1] = m.pad[2] = 0;
+      ws.meta[oslot] = m;
+    }
+  }
+  // entropy weights per window and base totals (integer counts are the exact double sums of the reference)
+  int totC = 0, totG = 0, totT = 0;
+  const int nwin = (len + WIN - 1) / WIN;
+  float *wout = prep.went + (size_t)sig * WMAX;
+  for (int w = lane; w < WMAX; w += 32) {
+    float v = 0.f;
+    if (w < nwin) {
+      const int i0 = w * WIN, k = min(WIN, len - i0);
+      const uint32_t wm = k >= 32 ? 0xffffffffu : ((1u << k) - 1u);
+      const uint32_t lo = (s_pl[i0 >> 5] >> (i0 & 31)) & wm, hi = (s_pl[NWH + (i0 >> 5)] >> (i0 & 31)) & wm;
+      const int cntT = __popc(lo & hi), cntC = __popc(lo & ~hi), cntG = __popc(hi & ~lo);
+      const int cnt[4] = {k - cntT - cntC - cntG, cntC, cntG, cntT};
+      totC += cntC;
+      totG += cntG;
+      totT += cntT;
+      const double *et = ws.ent_table + (size_t)k * (WIN + 1);
+      double s = 0.;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const double e = __ldg(et + cnt[c]);
+        s = (c == 0) ? e : __dadd_rn(s, e);
+      }
+      v = __double2float_rn(-s);
+      if (v < 0.f) v = 0.f;
+    }
+    wout[w] = v;
+  }
+  totC = __reduce_add_sync(0xffffffffu, totC);
+  totG = __reduce_add_sync(0xffffffffu, totG);
+  totT = __reduce_add_sync(0xffffffffu, totT);
+  if (lane < 4) {
+    const int cnt = lane == 0 ? len - totC - totG - totT : lane == 1 ? totC : lane == 2 ? totG : totT;
+    prep.off[(size_t)sig * 4 + lane] = __ddiv_rn((double)cnt, (double)len);
+  }
+  if (lane == 0) prep.flag[sig] = 1;
+}
+
 template <int LOG2N, int NT>
 __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
-    encode_fft_kernel(const SigDesc *__restrict__ sigs, Slots ws, float *__restrict__ tap) {
+    encode_fft_kernel(const SigDesc *__restrict__ sigs, Slots ws, float *__restrict__ tap, PrepBuf prep) {
   constexpr int N = 1 << LOG2N, H = N / 2, WIN = N / 512, NWARP = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *buf = reinterpret_cast<float2 *>(smem_raw);            // N complex (swizzled slots)
@@ -528,7 +663,21 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
   const int len = sd.len;
   const float2 *__restrict__ wn = ws.wn;
 
-  const int flags = encode_prepare<LOG2N, NT>(sd, ws, smem_raw, sb, went, s_fcode, s_comp, s_base2, s_red, s_off, &s_flags, true);
+  // prepared by encode_prep_kernel (the common case): pick up planes, window weights and means; otherwise do it here
+  const bool prepared = prep.flag != nullptr && tap == nullptr && prep.flag[blockIdx.x] != 0;
+  uint32_t *s_pl2 = reinterpret_cast<uint32_t *>(sb);  // prepared: plane words [2][NW] in place of the bases
+  int flags = 0;
+  if (prepared) {
+    constexpr int NWp = N / 32;
+    const uint32_t *pl = ws.planes + (size_t)sd.slot * 2 * NWp;
+    for (int w = tid; w < 2 * NWp; w += NT) s_pl2[w] = pl[w];
+    const float *wsrc = prep.went + (size_t)blockIdx.x * (H / WIN);
+    for (int w = tid; w < H / WIN; w += NT) went[w] = wsrc[w];
+    if (tid < 4) s_off[tid] = prep.off[(size_t)blockIdx.x * 4 + tid];
+    __syncthreads();
+  } else {
+    flags = encode_prepare<LOG2N, NT>(sd, ws, smem_raw, sb, went, s_fcode, s_comp, s_base2, s_red, s_off, &s_flags, true);
+  }
   const bool flat = len < 1024;  // "Skip entropy": weight 1 everywhere (CrossCorr.cc:39-44)
 
   if (tap != nullptr) {
@@ -560,14 +709,25 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
         const float h0 = __double2float_rn(__dmul_rn(e, hit0)), m0 = __double2float_rn(__dmul_rn(e, miss0));
         const float h1 = __double2float_rn(__dmul_rn(e, hit1)), m1 = __double2float_rn(__dmul_rn(e, miss1));
         const float2 wb = __ldg(wn + k0);  // w_N^{k0}; w_N^{k0 + j} = wb * (compile-time) w_N^j
-        uint32_t packed[(WIN + 3) / 4];
+        // the window's base codes, two bits each (A,C,G,T -> 0,1,2,3): from the plane words (prepared) or the bytes
+        uint64_t codes = 0;
+        if (prepared) {
+          constexpr int NWp = N / 32;
+          const uint32_t lo = s_pl2[k0 >> 5] >> (k0 & 31), hi = s_pl2[NWp + (k0 >> 5)] >> (k0 & 31);
 #pragma unroll
-        for (int j = 0; j < (WIN + 3) / 4; j++) packed[j] = reinterpret_cast<const uint32_t *>(sb + k0)[j];
+          for (int j = 0; j < WIN; j++) codes |= (uint64_t)(((lo >> j) & 1u) | (((hi >> j) & 1u) << 1)) << (2 * j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < (WIN + 3) / 4; j++) {
+            const uint32_t p4 = reinterpret_cast<const uint32_t *>(sb + k0)[j];
+            const uint32_t c4 = ((p4 >> 1) & 0x03030303u) ^ ((p4 >> 2) & 0x01010101u);
+            codes |= (uint64_t)((c4 & 3u) | ((c4 >> 6) & 0xcu) | ((c4 >> 12) & 0x30u) | ((c4 >> 18) & 0xc0u)) << (8 * j);
+          }
+        }
 #pragma unroll
         for (int j = 0; j < WIN; j++) {
           const int k = k0 + j;
-          const uint32_t b = (packed[j >> 2] >> (8 * (j & 3))) & 0xffu;
-          const uint32_t code = ((b >> 1) & 3u) ^ ((b >> 2) & 1u);  // A,C,G,T -> 0,1,2,3
+          const uint32_t code = (uint32_t)(codes >> (2 * j)) & 3u;
           float2 v;
           v.x = k < len ? (code == c0 ? h0 : m0) : 0.f;
           v.y = k < len ? (code == c1 ? h1 : m1) : 0.f;
@@ -1494,7 +1654,7 @@ struct Cfg {
 };
 
 template <int LOG2N>
-static cudaError_t encode_launch(const SigDesc *sigs, int nsig, Slots ws, float *tap, cudaStream_t st) {
+static cudaError_t encode_launch(const SigDesc *sigs, int nsig, Slots ws, float *tap, PrepBuf prep, cudaStream_t st) {
   constexpr int N = 1 << LOG2N, NT = Cfg<LOG2N>::NT;
   if constexpr (Cfg<LOG2N>::SPLIT) {  // one CTA per half signal
     const size_t smem = (size_t)(N / 2) * 8 + N + 512 * 4 + 128 * 2 + 256;
@@ -1508,7 +1668,12 @@ static cudaError_t encode_launch(const SigDesc *sigs, int nsig, Slots ws, float 
   auto k = encode_fft_kernel<LOG2N, NT>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<nsig, NT, smem, st>>>(sigs, ws, tap);
+  if (tap != nullptr) prep.flag = nullptr;  // the signal tap shows the in-kernel route, stage by stage
+  if (prep.flag != nullptr) {
+    encode_prep_kernel<LOG2N><<<(nsig + 7) / 8, 256, 0, st>>>(sigs, nsig, ws, prep);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  k<<<nsig, NT, smem, st>>>(sigs, ws, tap, prep);
   return cudaGetLastError();
   }
 }
@@ -1591,10 +1756,10 @@ static cudaError_t scan_launch(const SpDesc *sps, int nsp, Slots ws, const uint1
     default: return cudaErrorInvalidValue; \
   }
 
-cudaError_t launch_encode_fft(int log2n, const SigDesc *sigs, int nsig, Slots ws, float *tap5n,
+cudaError_t launch_encode_fft(int log2n, const SigDesc *sigs, int nsig, Slots ws, float *tap5n, PrepBuf prep,
                               cudaStream_t stream) {
   if (nsig <= 0) return cudaSuccess;
-#define CALL(L) encode_launch<L>(sigs, nsig, ws, tap5n, stream)
+#define CALL(L) encode_launch<L>(sigs, nsig, ws, tap5n, prep, stream)
   SX_DISPATCH(log2n, CALL)
 #undef CALL
 }

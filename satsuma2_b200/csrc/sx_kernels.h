@@ -86,7 +86,15 @@ bool log2n_split(int log2n);  // transforms handled by two CTAs (N = 32768): lau
                               // N float2 per chunk-pair job / single strand-pair job
 size_t slot_spec_elems(int log2n);  // float2 elements per slot
 
-cudaError_t launch_encode_fft(int log2n, const SigDesc *sigs, int nsig, Slots ws, float *tap5n,
+// Per-signal results of the preparation kernel (one warp per signal: load, validate, 2-bit planes, entropy weights,
+// channel means) that the transform kernel picks up; flag[i] == 0: signal i is prepared inside the transform kernel
+// (letters other than A/C/G/T, explicit reverse-strand signals, chunks longer than half the transform)
+struct PrepBuf {
+  int32_t *flag;  // [nsig]
+  float *went;    // [nsig][256] entropy weight per window
+  double *off;    // [nsig][4] channel means
+};
+cudaError_t launch_encode_fft(int log2n, const SigDesc *sigs, int nsig, Slots ws, float *tap5n, PrepBuf prep,
                               cudaStream_t stream);
 // pair_list: index of the forward strand-pair of every chunk pair whose reverse strand is derived from the
 // forward query spectrum (one CTA does both strands); direct_list: strand-pairs correlated one by one

@@ -829,3 +829,42 @@ def test_large_transforms_32_pairs_against_the_live_reference(sx, oracle_lib, re
         json.dump({"fft_n": NN, "pairs": n, "worst_xc_rel_err_vs_reference": worst, "tolerance": REF_XC_TOL[NN],
                    "records": int(len(exp)), "listed": len(listed)}, f)
     assert len(listed) <= 4, listed
+
+
+def test_preparation_kernel_equals_in_kernel_preparation(sx):
+    """Signals are prepared (validated, 2-bit planes, entropy weights, channel means) by a warp-per-signal kernel ahead
+    of the transform kernel; debug_flags bit 1 keeps everything inside the transform kernel, as sx_tap_signal always
+    does.  Ragged lengths (every residue mod 16 / 32, below and above 1024, up to the full chunk), unaligned blob
+    offsets, forward and reverse homology: bit-identical records either way (probabilities included)."""
+    rng = np.random.default_rng(314)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    comp = np.zeros(256, np.uint8)
+    comp[list(b"ACGT")] = list(b"TGCA")
+    n = 400
+    tl, ql = [], []
+    for i in range(n):
+        lt = int(rng.integers(47, 4097)) if i % 5 else 4096
+        t = rng.choice(acgt, lt)
+        a, b = sorted(rng.integers(0, lt, 2))
+        seg = t[a:b].copy()
+        mut = rng.random(len(seg)) < rng.uniform(0.02, 0.25)
+        seg[mut] = rng.choice(acgt, int(mut.sum()))
+        if rng.random() < 0.5:
+            seg = comp[seg[::-1]]
+        q = np.concatenate([rng.choice(acgt, int(rng.integers(0, 900))), seg, rng.choice(acgt, int(rng.integers(0, 900)))])[:4096]
+        if len(q) < 47:
+            q = np.concatenate([q, rng.choice(acgt, 47)])
+        if i % 17 == 0:
+            q[int(rng.integers(0, len(q)))] = ord("N")  # falls back to the in-kernel route on its own
+        tl.append((t.tobytes(), int(rng.integers(0, 1000)), i, 100000))
+        ql.append((q.tobytes(), int(rng.integers(0, 1000)), i, 100000))
+    pairs = [(i, i) for i in range(n)]
+    outs = []
+    for flags in (0, 2):
+        with sx.XCorrEngine(target_total=50000.0, debug_flags=flags, max_batch_pairs=96) as eng:
+            eng.set_targets(sx.ChunkSet.from_list(tl))
+            eng.set_queries(sx.ChunkSet.from_list(ql))
+            r = eng.align_pairs(pairs)
+            outs.append(np.sort(r, order=["query_id", "tstart", "qstart", "len", "reverse"]))
+    assert len(outs[0]) > 300
+    assert outs[0].tobytes() == outs[1].tobytes()
