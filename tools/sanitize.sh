@@ -7,4 +7,4 @@ echo "memcheck rc=$?" >> gpurun_out/sanitizer_memcheck_${tag}.log
 SEL2='synthetic_edge or periodic_sequences_overflow_unit_list[4096] or split_transform or random_pairs_against_oracle[4294967296.0]'
 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "$SEL2" > gpurun_out/sanitizer_racecheck_${tag}.log 2>&1
 echo "racecheck rc=$?" >> gpurun_out/sanitizer_racecheck_${tag}.log
-tail -4 gpurun_out/sanitizer_memcheck_${tag}.log gpurun_out/sanitizer_racecheck_${tag}.log
+tail -n 4 gpurun_out/sanitizer_memcheck_${tag}.log; tail -n 4 gpurun_out/sanitizer_racecheck_${tag}.log
