@@ -20,6 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libsatsuma_ref.so")
 REF_TOOL = os.path.join(HERE, "_ref", "HomologyByXCorr_ref")  # the reference's standalone tool, unmodified
+REF_KMATCH = os.path.join(HERE, "_ref", "KMatch_ref")  # the reference's k-mer seeding program, unmodified
 REFERENCE_ROOT = "/root/reference"
 
 
@@ -27,7 +28,7 @@ def build(ref: bool = True) -> None:
     """Compile the C oracle (always) and the reference harness (when /root/reference exists)."""
     subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     if ref and os.path.isdir(REFERENCE_ROOT):
-        subprocess.check_call(["make", "-s", "-C", HERE, "ref", "reftool", "-j8"])
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref", "reftool", "refkmatch", "-j8"])
         # the reference's own slave with libsatsuma_b200 bound in (INTEGRATION.md section 2); needs the product
         # library, so it is (re)built only when that exists and is newer
         lib = os.path.join(os.path.dirname(HERE), "satsuma2_b200", "libsatsuma_b200.so")

@@ -11,8 +11,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsatsuma_b200.so")
-SOURCES = ["sx_kernels.cu", "sx_engine.cu", "sx_multi.cu"]
-HEADERS = ["sx_kernels.h", "sx_fft.cuh", "sx_scan.cuh", os.path.join("..", "..", "include", "satsuma_xcorr.h")]
+SOURCES = ["sx_kernels.cu", "sx_engine.cu", "sx_multi.cu", "sx_kmatch.cu"]
+HEADERS = ["sx_kernels.h", "sx_fft.cuh", "sx_scan.cuh", os.path.join("..", "..", "include", "satsuma_xcorr.h"),
+           os.path.join("..", "..", "include", "satsuma_kmatch.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -60,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 HOST = os.path.join(HERE, "host")
 BIN = os.path.join(HERE, "bin")
 HOST_PROGRAMS = {"HomologyByXCorr": "homology_by_xcorr_main.cc", "HomologyByXCorrSlave": "homology_slave_main.cc",
-                 "XCorrMatchTool": "match_tool_main.cc"}
+                 "XCorrMatchTool": "match_tool_main.cc", "KMatch": "kmatch_main.cc"}
 
 
 def build_host(force: bool = False) -> list:
@@ -71,7 +72,7 @@ def build_host(force: bool = False) -> list:
     common = [os.path.join(HOST, "sx_host.cc")]
     for name, main in HOST_PROGRAMS.items():
         exe = os.path.join(BIN, name)
-        srcs = common + [os.path.join(HOST, main)]
+        srcs = ([] if name == "KMatch" else common) + [os.path.join(HOST, main)]  # KMatch only needs the C ABI
         deps = srcs + [os.path.join(HOST, "sx_host.h"), LIB]
         if force or not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
             cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", exe] + srcs + [
