@@ -390,12 +390,16 @@ def grid_workload(args, grp, rank, local_rank, world, genome_mb, steps, warmup):
     cs_t = sx.ChunkSet(tt.numpy(), to, tl, ts, np.zeros(len(tl), np.int32), [L])
     cs_q = sx.ChunkSet(tq.numpy(), qo, ql, qs, np.zeros(len(ql), np.int32), [L])
     blocks = sx.make_blocks(synth.diagonal_blocks(len(tl), len(ql), CHUNK - CHUNK // 4, CHUNK, pixel=24))
-    eng = sx.MultiEngine(devices=[local_rank], shard_rank=rank, shard_world=world, target_total=float(L),
+    # one process per GPU (torchrun: shard = rank) or, with --inproc N, ONE process driving N GPUs through the same handle
+    devices = list(range(args.inproc)) if args.inproc > 0 else [local_rank]
+    eng = sx.MultiEngine(devices=devices, shard_rank=rank, shard_world=world, target_total=float(L),
                          max_batch_pairs=args.batch)
     stream = torch.cuda.ExternalStream(eng.stream_handle(0), device=dev)
     n_all = int(((blocks["target_to"] - blocks["target_from"] + 1).astype(np.int64) *
                  (blocks["query_to"] - blocks["query_from"] + 1)).sum())
     rec_buf = np.zeros(max(1 << 16, 4 * n_all // world + (1 << 16)), dtype=sx.RESULT_DTYPE)
+    if len(devices) > 1:
+        torch.cuda.synchronize()
 
     def step_device():
         eng.invalidate_spectra()
@@ -422,7 +426,8 @@ def grid_workload(args, grp, rank, local_rank, world, genome_mb, steps, warmup):
         "workload": f"configs[3]: {genome_mb:g} Mb x {genome_mb:g} Mb synthetic genome pair, 24x24-chunk blocks along "
                     "the diagonal, target spectra cached in HBM (cold at the start of every step), target chunk "
                     "list split by range over the ranks (sx_multi), no collective",
-        "scaling": "strong", "metric": METRIC, "unit": UNIT, "n_gpus": world,
+        "scaling": "strong", "metric": METRIC, "unit": UNIT, "n_gpus": world * len(devices),
+        "processes": world, "gpus_per_process": len(devices),
         "value": total_pairs * steps / (ms_dev / 1e3), "ms_per_step": ms_dev / steps,
         "e2e": {"value": total_pairs * steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": int(h2d_sum), "h2d_bytes_per_step_max_rank": int(h2d_max),
@@ -481,6 +486,9 @@ def main():
                          "genome pair with target spectra cached in HBM, sharded by target range (strong scaling)")
     ap.add_argument("--genome-mb", type=float, default=150.0,
                     help="grid workload (configs[3]): bases per genome, in millions")
+    ap.add_argument("--inproc", type=int, default=0,
+                    help="--workload grid: ONE process drives this many GPUs through sx_multi (host threads + host gather) "
+                         "instead of one torchrun rank per GPU")
     ap.add_argument("--target-total", type=float, default=0.0,
                     help="targetTotal of the probability filter (default: pairs x chunk, i.e. every target chunk of the "
                          "step); profiling runs with fewer pairs pass the full step's 4294967296")
