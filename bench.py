@@ -236,20 +236,20 @@ def pairs_workload(grp, local_rank, chunk, n, steps, warmup, batch, seed=7):
     eng.set_targets_raw(T.ctypes.data, cs_t)
     eng.set_queries_raw(Q.ctypes.data, cs_q)
     eng.set_profiling(True)
-    ms_dev, clocks, rec = _timed_steps(step_device, steps, warmup, stream, grp, local_rank, eng.reset_stats)
+    ms_dev, clocks, rec, n_dev = _timed_steps(step_device, steps, warmup, stream, grp, local_rank, eng.reset_stats, 1.0)
     st = eng.stats()
     eng.set_profiling(False)
-    ms_e2e, _, rec = _timed_steps(step_e2e, steps, 1, stream, grp, local_rank, eng.reset_stats)
+    ms_e2e, _, rec, n_e2e = _timed_steps(step_e2e, steps, 1, stream, grp, local_rank, eng.reset_stats, 1.0)
     st_e2e = eng.stats()
     b = max(st["batches"], 1)
     out = {"workload": f"configs[2]: {n} random {chunk}x{chunk} chunk pairs (FFT length {2 * chunk}), one planted "
                        "segment each", "chunk": chunk, "fft_n": 2 * chunk, "pairs_per_step": n, "device_batch_pairs": batch,
-           "metric": METRIC, "unit": UNIT, "value": n * steps / (ms_dev / 1e3), "ms_per_step": ms_dev / steps,
-           "e2e": {"value": n * steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
-                   "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] / steps), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / steps)},
+           "metric": METRIC, "unit": UNIT, "value": n / (ms_dev / 1e3), "ms_per_step": ms_dev, "steps": n_dev,
+           "e2e": {"value": n / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e, "steps": n_e2e,
+                   "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] / n_e2e), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / n_e2e)},
            "kernel_ms_per_batch": {"encode_fft": st["ms_encode_fft"] / b, "xcorr_findtop": st["ms_xcorr"] / b,
                                    "scan_score": st["ms_scan_score"] / b},
-           "records_per_step": int(len(rec)), "gpu_launches": int(st["kernel_launches"]),
+           "records_per_step": int(len(rec)), "gpu_launches": int(st["kernel_launches"] / max(n_dev, 1)),
            "per_pair": {"candidates": st["candidates"] / max(st["chunk_pairs"], 1),
                         "matches": st["matches"] / max(st["chunk_pairs"], 1)}, "clocks": clocks}
     eng.close()
@@ -294,20 +294,21 @@ def repeats_workload(grp, local_rank, genome_mb, steps, warmup, batch):
 
     eng.set_targets(cs_t)
     eng.set_queries(cs_q)
-    ms_dev, clocks, rec = _timed_steps(step_device, steps, warmup, stream, grp, local_rank, eng.reset_stats)
+    ms_dev, clocks, rec, n_dev = _timed_steps(step_device, steps, warmup, stream, grp, local_rank, eng.reset_stats, 1.0)
     st = eng.stats()
-    ms_e2e, _, rec = _timed_steps(step_e2e, steps, 1, stream, grp, local_rank, eng.reset_stats)
+    ms_e2e, _, rec, n_e2e = _timed_steps(step_e2e, steps, 1, stream, grp, local_rank, eng.reset_stats, 1.0)
     st_e2e = eng.stats()
-    n = st["chunk_pairs"] / steps
+    n = st["chunk_pairs"] / n_dev
     out = {"workload": f"configs[4]: repeat-rich {genome_mb:g} Mb synthetic genome pair, -prob_table 1, 24x24-chunk blocks "
                        "along the diagonal", "pairs_per_step": int(n), "metric": METRIC, "unit": UNIT,
-           "value": n * steps / (ms_dev / 1e3), "ms_per_step": ms_dev / steps,
-           "e2e": {"value": n * steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
-                   "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] / steps), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / steps)},
+           "value": n / (ms_dev / 1e3), "ms_per_step": ms_dev, "steps": n_dev,
+           "e2e": {"value": n / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e, "steps": n_e2e,
+                   "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] / n_e2e), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"] / n_e2e)},
            "per_pair": {"candidates": st["candidates"] / max(st["chunk_pairs"], 1),
                         "segments": st["segments"] / max(st["chunk_pairs"], 1),
                         "matches": st["matches"] / max(st["chunk_pairs"], 1)},
-           "records_per_step": int(len(rec)), "prob_table_build_s": table_s, "gpu_launches": int(st["kernel_launches"]),
+           "records_per_step": int(len(rec)), "prob_table_build_s": table_s,
+           "gpu_launches": int(st["kernel_launches"] / max(n_dev, 1)),
            "clocks": clocks}
     eng.close()
     return out
@@ -346,13 +347,23 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def _timed_steps(fn, steps, warmup, stream, grp, local_rank, reset=None):
+def _timed_steps(fn, steps, warmup, stream, grp, local_rank, reset=None, min_seconds=0.0):
     """warm-up, then `steps` calls bracketed by barrier + synchronize, CUDA events on the library's stream,
-    max over ranks; nvidia-smi sampled meanwhile.  -> (ms for all steps, clocks, last result)"""
+    max over ranks; nvidia-smi sampled meanwhile.  -> (ms PER STEP, clocks, last result, steps timed).
+    min_seconds: short steps are repeated until the timed region is long enough for the clock sampler
+    (nvidia-smi reports every 200 ms); every rank derives the same count from the slowest rank's warm-up step."""
     import torch
 
     for _ in range(warmup):
         res = fn()
+    if min_seconds > 0:
+        torch.cuda.synchronize()
+        grp.barrier()
+        t0 = time.perf_counter()
+        res = fn()
+        torch.cuda.synchronize()
+        one = grp.max(time.perf_counter() - t0)
+        steps = int(max(steps, min(200, np.ceil(min_seconds / max(one, 1e-4)))))
     if reset is not None:
         reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -367,7 +378,7 @@ def _timed_steps(fn, steps, warmup, stream, grp, local_rank, reset=None):
     e1.synchronize()
     torch.cuda.synchronize()
     grp.barrier()
-    return grp.max(e0.elapsed_time(e1)), sampler.stop(), res
+    return grp.max(e0.elapsed_time(e1)) / steps, sampler.stop(), res, steps
 
 
 def grid_workload(args, grp, rank, local_rank, world, genome_mb, steps, warmup):
@@ -412,15 +423,16 @@ def grid_workload(args, grp, rank, local_rank, world, genome_mb, steps, warmup):
 
     eng.set_targets(cs_t)
     eng.set_queries(cs_q)
-    ms_dev, clocks, rec = _timed_steps(step_device, steps, warmup, stream, grp, local_rank, eng.reset_stats)
+    ms_dev, clocks, rec, n_dev = _timed_steps(step_device, steps, warmup, stream, grp, local_rank, eng.reset_stats, 1.5)
     st = eng.stats()
-    ms_e2e, clocks_e2e, rec = _timed_steps(step_e2e, steps, max(1, warmup - 2), stream, grp, local_rank, eng.reset_stats)
+    ms_e2e, clocks_e2e, rec, n_e2e = _timed_steps(step_e2e, steps, max(1, warmup - 2), stream, grp, local_rank,
+                                                 eng.reset_stats, 1.5)
     st_e2e = eng.stats()
-    mine = st["chunk_pairs"] / max(steps, 1)
+    mine = st["chunk_pairs"] / max(n_dev, 1)
     total_pairs = grp.sum(float(mine))
-    h2d_max = grp.max(float(st_e2e["h2d_bytes"]) / max(steps, 1))
-    h2d_sum = grp.sum(float(st_e2e["h2d_bytes"]) / max(steps, 1))
-    d2h_sum = grp.sum(float(st_e2e["d2h_bytes"]) / max(steps, 1))
+    h2d_max = grp.max(float(st_e2e["h2d_bytes"]) / max(n_e2e, 1))
+    h2d_sum = grp.sum(float(st_e2e["h2d_bytes"]) / max(n_e2e, 1))
+    d2h_sum = grp.sum(float(st_e2e["d2h_bytes"]) / max(n_e2e, 1))
     recs = grp.sum(float(len(rec)))
     out = {
         "workload": f"configs[3]: {genome_mb:g} Mb x {genome_mb:g} Mb synthetic genome pair, 24x24-chunk blocks along "
@@ -428,14 +440,14 @@ def grid_workload(args, grp, rank, local_rank, world, genome_mb, steps, warmup):
                     "list split by range over the ranks (sx_multi), no collective",
         "scaling": "strong", "metric": METRIC, "unit": UNIT, "n_gpus": world * len(devices),
         "processes": world, "gpus_per_process": len(devices),
-        "value": total_pairs * steps / (ms_dev / 1e3), "ms_per_step": ms_dev / steps,
-        "e2e": {"value": total_pairs * steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
+        "value": total_pairs / (ms_dev / 1e3), "ms_per_step": ms_dev, "steps": n_dev,
+        "e2e": {"value": total_pairs / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e, "steps": n_e2e,
                 "h2d_bytes_per_step": int(h2d_sum), "h2d_bytes_per_step_max_rank": int(h2d_max),
                 "d2h_bytes_per_step": int(d2h_sum)},
         "target_chunks": int(len(tl)), "query_chunks": int(len(ql)), "blocks": len(blocks),
         "pairs_per_step_all_ranks": int(total_pairs), "target_total": float(L),
         "signals_per_pair": st["signals"] / max(st["chunk_pairs"], 1), "records_per_step": int(recs),
-        "gpu_launches": int(st["kernel_launches"]), "clocks": clocks, "clocks_e2e": clocks_e2e,
+        "gpu_launches": int(st["kernel_launches"] / max(n_dev, 1)), "clocks": clocks, "clocks_e2e": clocks_e2e,
     }
     assert int(total_pairs) == n_all, (total_pairs, n_all)
     eng.close()
@@ -458,7 +470,7 @@ def run_grid(args):
     grp = Group("nccl", torch.device("cuda", local_rank))
     g = grid_workload(args, grp, rank, local_rank, world, args.genome_mb, args.steps, args.warmup)
     if rank == 0:
-        line = {"metric": METRIC, "value": g["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {"metric": METRIC, "value": g["value"], "unit": UNIT, "n_gpus": g["n_gpus"], "steps": g["steps"],
                 "warmup": args.warmup, "ms_per_step": g["ms_per_step"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": g["workload"], "chunk": CHUNK, "fft_n": FFT_N, "device_batch_pairs": args.batch},

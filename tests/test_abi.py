@@ -101,7 +101,7 @@ def test_committed_bench_lines_follow_the_contract():
     import json
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    files = sorted(glob.glob(os.path.join(root, "profiles", "r1_bench_*.json")))
+    files = sorted(glob.glob(os.path.join(root, "profiles", "r[12]_bench_*.json")))
     assert files
     for f in files:
         d = json.load(open(f))
