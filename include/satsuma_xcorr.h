@@ -199,6 +199,12 @@ int sx_tap_candidates(sx_ctx *ctx, int32_t target, int32_t query, int32_t strand
 int sx_tap_segments(sx_ctx *ctx, int32_t target, int32_t query, int32_t strand, int32_t fast,
                     sx_segment *out, int32_t cap, int32_t *n_out);
 
+/* SeqAnalyzer::MatchUp(out, query, target, xc) with the CALLER's correlation vector (CrossCorr.cc:583-605): FindTop
+ * of xc[0..N) at `cutoff` (SeqAnalyzer::SetTopCutoff), then the diagonal scan of every candidate; the query chunk is
+ * taken as given (the reference's callers pass the reverse complement themselves).  Same order as sx_tap_segments. */
+int sx_tap_matchup(sx_ctx *ctx, int32_t target, int32_t query, double cutoff, const float *xc, sx_segment *out,
+                   int32_t cap, int32_t *n_out);
+
 /* ------------------------------------------------------------------ measurement */
 int sx_set_profiling(sx_ctx *ctx, int32_t enabled); /* per-kernel CUDA-event timing on/off */
 int sx_get_stats(sx_ctx *ctx, sx_stats *out);

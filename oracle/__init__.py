@@ -34,7 +34,8 @@ def build(ref: bool = True) -> None:
         lib = os.path.join(os.path.dirname(HERE), "satsuma2_b200", "libsatsuma_b200.so")
         exe = os.path.join(HERE, "_ref", "HomologyByXCorrSlave_b200bind")
         bind = os.path.join(os.path.dirname(HERE), "satsuma2_b200", "host", "binding")
-        deps = [lib, os.path.join(HERE, "make_refslave_b200.py")] + [os.path.join(bind, f) for f in sorted(os.listdir(bind))]
+        deps = [lib, os.path.join(HERE, "make_refslave_b200.py"), os.path.join(HERE, "shim_check.cc")] + [
+            os.path.join(bind, f) for f in sorted(os.listdir(bind))]
         if os.path.exists(lib) and (not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps)):
             subprocess.check_call(["make", "-s", "-C", HERE, "refslave_b200"])
 

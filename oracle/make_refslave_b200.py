@@ -67,7 +67,25 @@ def build() -> str:
     return EXE
 
 
+SHIM_EXE = os.path.join(OUT_DIR, "shim_check")
+
+
+def build_shim_check() -> str:
+    """oracle/shim_check.cc: the class-level shims (crosscorr_shim.h) side by side with the reference's own classes."""
+    os.makedirs(OUT_DIR, exist_ok=True)
+    srcs = [os.path.join(HERE, "shim_check.cc")] + [os.path.join(REF, p) for p in (
+        "analysis/CrossCorr.cc", "analysis/DNAVector.cc", "analysis/CodonTranslate.cc", "base/FileParser.cc",
+        "base/StringUtil.cc", "util/mutil.cc")]
+    lib_dir = os.path.join(ROOT, "satsuma2_b200")
+    cmd = ["g++", "-O2", "-w", "-std=c++14", "-pthread", "-include", "cstdint", "-include", "memory", "-I" + REF,
+           "-I" + os.path.join(REF, "analysis"), "-I" + BIND, "-I" + os.path.join(ROOT, "include"), "-o", SHIM_EXE] + srcs + [
+           "-L" + lib_dir, "-lsatsuma_b200", "-Wl,-rpath," + lib_dir, "-Wl,-rpath,$ORIGIN/../../satsuma2_b200"]
+    subprocess.run(cmd, check=True)
+    return SHIM_EXE
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit(f"{REF} not found: this target needs the reference sources")
     print(build())
+    print(build_shim_check())

@@ -93,6 +93,7 @@ def load_library():
     L.sx_tap_xcorr.argtypes = [vp, i32, i32, i32, vp]
     L.sx_tap_candidates.argtypes = [vp, i32, i32, i32, i32, vp, i32, C.POINTER(i32)]
     L.sx_tap_segments.argtypes = [vp, i32, i32, i32, i32, vp, i32, C.POINTER(i32)]
+    L.sx_tap_matchup.argtypes = [vp, i32, i32, dbl, vp, vp, i32, C.POINTER(i32)]
     L.sx_set_profiling.argtypes = [vp, i32]
     L.sx_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.sx_reset_stats.argtypes = [vp]

@@ -541,6 +541,8 @@ struct TapRequest {
   std::vector<int32_t> *cands = nullptr;
   std::vector<SegRec> *segs = nullptr;
   int sp_select = -1;  // >= 0: xc / cands / segs of this strand-pair only
+  const float *ext_xc = nullptr;  // host, N floats: candidates of strand-pair sp_select come from THIS vector
+  double ext_cutoff = 0;
 };
 
 }  // namespace
@@ -672,7 +674,18 @@ static int batch_kernels(sx_ctx *c, Run &r) {
   cudaEvent_t *ev = c->ev[r.stage];
   CU(cudaMemsetAsync(c->d_ctr.p, 0, sizeof(BatchCounters), st));
   if (prof) CU(cudaEventRecord(ev[1], st));
-  if (r.nsp && r.need_xcorr) {
+  if (r.nsp && r.need_xcorr && r.tap && r.tap->ext_xc) {
+    // SeqAnalyzer::MatchUp with the caller's correlation vector: no strand-pair has candidates except the selected
+    // one, whose candidates are FindTop of that vector
+    const size_t N = (size_t)c->N;
+    int rc = c->d_tap.ensure(N);
+    if (rc != SX_OK) return rc;
+    CU(cudaMemcpyAsync(c->d_tap.p, r.tap->ext_xc, sizeof(float) * N, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(c->d_cand_ref.p, 0, sizeof(uint2) * (size_t)r.nsp, st));
+    CU(launch_findtop_external(c->log2n, c->d_tap.p, r.tap->sp_select, r.tap->ext_cutoff, c->d_cand_pool.p,
+                               (unsigned int)std::min<size_t>(c->d_cand_pool.n, 0xfffffff0u), c->d_cand_ref.p, c->d_ctr.p, st));
+    c->stats.kernel_launches += 1;
+  } else if (r.nsp && r.need_xcorr) {
     CU(launch_xcorr_findtop(c->log2n, c->d_sps.p, c->d_lists.p, r.n_pairlist, c->d_lists.p + r.n_pairlist, r.n_direct, ws,
                             c->cfg.cutoff, c->cfg.cutoff_fast, c->d_cand_pool.p,
                             (unsigned int)std::min<size_t>(c->d_cand_pool.n, 0xfffffff0u), c->d_cand_ref.p, c->d_ctr.p,
@@ -1258,6 +1271,34 @@ extern "C" int sx_tap_segments(sx_ctx *c, int32_t target, int32_t query, int32_t
   });
   *n_out = (int32_t)segs.size();
   if ((int32_t)segs.size() > cap) return fail(SX_ERR_CAPACITY, "sx_tap_segments: %zu segments", segs.size());
+  for (size_t i = 0; i < segs.size() && out; i++) {
+    out[i].start_target = segs[i].start_t;
+    out[i].start_query = segs[i].start_t + segs[i].shift;
+    out[i].len = segs[i].len;
+  }
+  return SX_OK;
+}
+
+extern "C" int sx_tap_matchup(sx_ctx *c, int32_t target, int32_t query, double cutoff, const float *xc, sx_segment *out,
+                              int32_t cap, int32_t *n_out) {
+  if (!c || !n_out || !xc) return fail(SX_ERR_ARG, "sx_tap_matchup: null argument");
+  std::lock_guard<std::mutex> lk(c->mu);
+  Batch b;
+  int rc = tap_prepare(c, target, query, 0, 0, b);
+  if (rc != SX_OK) return rc;
+  std::vector<SegRec> segs;
+  TapRequest t;
+  t.segs = &segs;
+  t.sp_select = 0;  // the query as given; the caller passes the reverse complement itself, as the reference does
+  t.ext_xc = xc;
+  t.ext_cutoff = cutoff;
+  if ((rc = run_batch(c, b, nullptr, &t)) != SX_OK) return rc;
+  std::sort(segs.begin(), segs.end(), [](const SegRec &a, const SegRec &b2) {
+    if (a.shift != b2.shift) return a.shift < b2.shift;
+    return a.start_t < b2.start_t;
+  });
+  *n_out = (int32_t)segs.size();
+  if ((int32_t)segs.size() > cap) return fail(SX_ERR_CAPACITY, "sx_tap_matchup: %zu segments", segs.size());
   for (size_t i = 0; i < segs.size() && out; i++) {
     out[i].start_target = segs[i].start_t;
     out[i].start_query = segs[i].start_t + segs[i].shift;

@@ -1221,6 +1221,20 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
                         pool_cap, cand_ref, ctr, xc_tap);
 }
 
+// FindTop alone over a correlation vector the CALLER supplies (SeqAnalyzer::MatchUp takes `xc` as an argument,
+// analysis/CrossCorr.h:261): the candidates of strand-pair `spi` come from it instead of from the pair kernel.
+template <int LOG2N, int NT>
+__global__ void __launch_bounds__(NT)
+    findtop_external_kernel(const float *__restrict__ xc, int spi, double co, uint16_t *__restrict__ cand_pool,
+                            unsigned int pool_cap, uint2 *__restrict__ cand_ref, BatchCounters *ctr) {
+  constexpr int N = 1 << LOG2N, NW = N / 32, NWARP = NT / 32;
+  __shared__ uint32_t mask[NW];
+  __shared__ unsigned int s_wtot[NWARP];
+  __shared__ unsigned int s_base;
+  auto xc_at = [&](int i) -> float { return xc[i]; };
+  findtop_impl<LOG2N, NT>(xc_at, co, mask, s_wtot, &s_base, spi, cand_pool, pool_cap, cand_ref, ctr, nullptr);
+}
+
 template <int LOG2N, int NT>
 __global__ void __launch_bounds__(NT)
     xcorr_findtop_kernel(const uint32_t *__restrict__ direct_list, const SpDesc *__restrict__ sps, Slots ws,
@@ -1771,6 +1785,19 @@ cudaError_t launch_xcorr_findtop(int log2n, const SpDesc *sps, const uint32_t *p
                                  cudaStream_t stream) {
   if (n_pairs <= 0 && n_direct <= 0) return cudaSuccess;
 #define CALL(L) xcorr_launch<L>(sps, pair_list, n_pairs, direct_list, n_direct, ws, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, xc_tap, scratch, stream)
+  SX_DISPATCH(log2n, CALL)
+#undef CALL
+}
+
+template <int LOG2N>
+static cudaError_t findtop_external_launch(const float *xc, int spi, double co, uint16_t *cand_pool, unsigned int pool_cap,
+                                           uint2 *cand_ref, BatchCounters *ctr, cudaStream_t st) {
+  findtop_external_kernel<LOG2N, 256><<<1, 256, 0, st>>>(xc, spi, co, cand_pool, pool_cap, cand_ref, ctr);
+  return cudaGetLastError();
+}
+cudaError_t launch_findtop_external(int log2n, const float *xc, int spi, double cutoff, uint16_t *cand_pool,
+                                    unsigned int pool_cap, uint2 *cand_ref, BatchCounters *ctr, cudaStream_t stream) {
+#define CALL(L) findtop_external_launch<L>(xc, spi, cutoff, cand_pool, pool_cap, cand_ref, ctr, stream)
   SX_DISPATCH(log2n, CALL)
 #undef CALL
 }

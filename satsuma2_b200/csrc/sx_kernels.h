@@ -103,6 +103,9 @@ cudaError_t launch_xcorr_findtop(int log2n, const SpDesc *sps, const uint32_t *p
                                  double cutoff_fast, uint16_t *cand_pool, unsigned int pool_cap,
                                  uint2 *cand_ref, BatchCounters *ctr, float *xc_tap, float2 *scratch,
                                  cudaStream_t stream);
+// candidates of strand-pair `spi` from a correlation vector supplied by the caller (N floats, device memory)
+cudaError_t launch_findtop_external(int log2n, const float *xc, int spi, double cutoff, uint16_t *cand_pool,
+                                    unsigned int pool_cap, uint2 *cand_ref, BatchCounters *ctr, cudaStream_t stream);
 void fill_wn_table(int log2n, float2 *host_out);  // N/2 entries
 // The reference's float FFT drifts from the exact transform from N = 16384 on: its last passes take their twiddles
 // from a float rotation recurrence (extern/RealFFT/OscSinCos.hpp:88-96, FFTReal.hpp:605-656, 783-830).  At N = 32768

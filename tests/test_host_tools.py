@@ -570,3 +570,30 @@ def test_reference_slave_with_the_binding_compiled_in(sx, reference_lib, tmp_pat
     ge = {rec_key(x): x for x in got}
     for x in exp:
         assert ge[rec_key(x)]["ident"] == x["ident"]
+
+
+@pytest.mark.gpu
+def test_class_level_shims_match_the_reference_classes(sx, reference_lib, tmp_path):
+    """INTEGRATION.md section 3: sx_shim::CCSignal / CrossCorrelation / SeqAnalyzer (host/binding/crosscorr_shim.h), the
+    reference's class interfaces on top of the C ABI, in one program with the reference's own classes
+    (oracle/shim_check.cc, compiled against the reference headers): signals bit-equal, correlation within 1e-4,
+    MatchUp on the reference's correlation vector gives identical segment lists, both strands."""
+    import oracle
+
+    exe = os.path.join(os.path.dirname(oracle.REF_SO), "shim_check")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/shim_check not built (python oracle/make_refslave_b200.py, needs /root/reference)")
+    rng = np.random.default_rng(8)
+    t = rng.choice(list(b"ACGT"), 4096).astype(np.uint8)
+    q = np.concatenate([rng.choice(list(b"ACGT"), 700).astype(np.uint8), t[500:3000]])
+    mut = rng.random(len(q)) < 0.08
+    q[mut] = rng.choice(list(b"ACGT"), int(mut.sum()))
+    q[100] = ord("N")
+    tf, qf = tmp_path / "t.fa", tmp_path / "q.fa"
+    _write_fasta(tf, [("t", t.tobytes())])
+    _write_fasta(qf, [("q", q.tobytes())])
+    r = subprocess.run([exe, str(tf), str(qf)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "SHIM OK" in r.stdout
+    n_seg = int(r.stdout.split("err")[1].split(",")[1].split()[0])
+    assert n_seg > 1000
