@@ -868,3 +868,34 @@ def test_preparation_kernel_equals_in_kernel_preparation(sx):
             outs.append(np.sort(r, order=["query_id", "tstart", "qstart", "len", "reverse"]))
     assert len(outs[0]) > 300
     assert outs[0].tobytes() == outs[1].tobytes()
+
+
+@pytest.mark.parametrize("min_len,total", [(100, 1.6e6), (300, 4294967296.0), (47, 2.0e4)])
+def test_min_length_flag(sx, oracle_lib, min_len, total):
+    """`-l` (Slave.cc:172): segments shorter than min_len are dropped whatever their probability -- also the shortest
+    segment the scan kernel's run-length pruning has to look at.  Against the oracle, and pruned == exhaustive."""
+    from satsuma2_b200 import synth
+
+    n = 500
+    T, Q, _ = synth.random_pairs(n, 4096, seed=1000 + min_len)
+    pairs = np.stack([np.arange(n), np.arange(n)], axis=1)
+    outs = []
+    for flags in (0, 1):
+        with sx.XCorrEngine(target_total=total, min_len=min_len, debug_flags=flags) as eng:
+            eng.set_targets(sx.ChunkSet.independent(T))
+            eng.set_queries(sx.ChunkSet.independent(Q))
+            outs.append(eng.align_pairs(pairs))
+    got = outs[0]
+    assert np.sort(outs[0], order=["query_id", "tstart", "qstart", "len", "reverse"]).tobytes() == \
+        np.sort(outs[1], order=["query_id", "tstart", "qstart", "len", "reverse"]).tobytes()
+    tl = [(T[i].tobytes(), 0, i, 4096) for i in range(n)]
+    ql = [(Q[i].tobytes(), 0, i, 4096) for i in range(n)]
+    params = oracle_lib.make_params(target_total=total, min_len=min_len)
+    exp = oracle_lib.align_pairs(params, tl, ql, pairs, threads=os.cpu_count() or 1)
+    assert len(exp) > 50 and int(exp["len"].min()) >= min_len
+    listed = []
+    for i in range(n):
+        compare_pair_records(oracle_lib, got[got["query_id"] == i], exp[exp["query_id"] == i], tl[i][0], ql[i][0], 0, 0,
+                             4096, 4096, N, 1.8, 0.99, total, listed)
+    _log_listed(f"min_len_{min_len}", listed)
+    assert len(listed) <= 3, listed
