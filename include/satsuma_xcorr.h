@@ -64,7 +64,8 @@ typedef struct {
                               the caller keeps `bases` alive and unmodified until the next sx_align_* call on
                               this context returns.  Batches start as soon as the bases they need have arrived. */
   int32_t debug_flags;     /* test hooks; bit 0: score every raw segment (no run-length pruning in the scan
-                              kernel); bit 1: prepare every signal inside the transform kernel (no preparation kernel) */
+                              kernel); bit 1: prepare every signal inside the transform kernel (no preparation kernel);
+                              bit 2: transform all four channels of every chunk (no three-channel form) */
   int32_t reserved[4];
 } sx_config;
 

@@ -703,6 +703,34 @@ static int batch_kernels(sx_ctx *c, Run &r) {
   return SX_OK;
 }
 
+// Three-channel pairing (sx_kernels.h): the four channel signals of a pure A/C/G/T chunk sum to zero, so only A, C
+// and G are transformed and the G channels of two chunks share one complex transform.  The host proposes the pairs --
+// consecutive eligible signals of the batch, which in pair mode are the target and the query of one chunk pair, so
+// the pair kernel reads three spectra instead of four -- and the device settles them (a chunk with any other
+// letter keeps all four channels; the transform kernel looks at the preparation kernel's verdict on both partners).
+// A cached target's G must live in a cached slot: when one partner is persistent it is the owner.
+static void propose_g_partners(const sx_ctx *c, Batch &b, bool enable) {
+  const int32_t H = c->N / 2;
+  int open = -1;
+  for (size_t i = 0; i < b.sigs.size(); i++) {
+    SigDesc &s = b.sigs[i];
+    s.g_mode = G_NONE;
+    s.g_partner = -1;
+    if (!enable || s.strand != 0 || s.len <= 0 || s.len > H) continue;
+    if (open < 0) {
+      open = (int)i;
+      continue;
+    }
+    int o = open, m = (int)i;
+    if ((size_t)b.sigs[m].slot < c->n_persist && (size_t)b.sigs[o].slot >= c->n_persist) std::swap(o, m);
+    b.sigs[o].g_mode = G_OWNER;
+    b.sigs[o].g_partner = m;
+    b.sigs[m].g_mode = G_MEMBER;
+    b.sigs[m].g_partner = o;
+    open = -1;
+  }
+}
+
 // host part of a launch: copy the descriptors of a batch into pinned staging buffer `stage`
 static int batch_stage(sx_ctx *c, Run &r, Batch &b, TapRequest *tap, int stage) {
   r = Run();
@@ -710,6 +738,7 @@ static int batch_stage(sx_ctx *c, Run &r, Batch &b, TapRequest *tap, int stage) 
   r.tap = tap;
   r.stage = stage;
   const int nsig = r.nsig = (int)b.sigs.size(), nsp = r.nsp = (int)b.sps.size();
+  propose_g_partners(c, b, !log2n_split(c->log2n) && !(c->cfg.debug_flags & 4));
   int rc;
   if ((rc = c->h_sigs[stage].ensure(std::max(nsig, 1))) != SX_OK) return rc;
   if ((rc = c->h_sps[stage].ensure(std::max(nsp, 1))) != SX_OK) return rc;

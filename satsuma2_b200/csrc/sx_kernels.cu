@@ -419,7 +419,9 @@ __device__ __forceinline__ int encode_prepare(const SigDesc &sd, const Slots &ws
       m.len = len;
       m.flags = flags & SLOT_NONACGT;  // same letters in both orientations (complement keeps the class)
       m.q_re = m.q_im = m.q_nyq = 0.f;
-      m.pad[0] = m.pad[1] = m.pad[2] = 0;
+      m.zmode = ZM_FOUR;
+      m.zslot = 0;
+      m.pad = 0;
       ws.meta[oslot] = m;
     }
   }
@@ -602,7 +604,9 @@ __global__ void __launch_bounds__(256) encode_prep_kernel(const SigDesc *__restr
       m.len = len;
       m.flags = 0;
       m.q_re = m.q_im = m.q_nyq = 0.f;
-      m.pad[0] = m.pad[1] = m.pad[2] = 0;
+      m.zmode = ZM_FOUR;
+      m.zslot = 0;
+      m.pad = 0;
       ws.meta[oslot] = m;
     }
   }
@@ -656,6 +660,7 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
   uint8_t *s_base2 = s_comp + 128;                                // 128
   __shared__ double s_red[4][NWARP];
   __shared__ double s_off[4];
+  __shared__ double s_poff;  // three-channel form: the partner's G mean
   __shared__ int s_flags;
 
   const int tid = threadIdx.x;
@@ -667,13 +672,31 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
   const bool prepared = prep.flag != nullptr && tap == nullptr && prep.flag[blockIdx.x] != 0;
   uint32_t *s_pl2 = reinterpret_cast<uint32_t *>(sb);  // prepared: plane words [2][NW] in place of the bases
   int flags = 0;
+  // Three-channel form (sx_kernels.h): a prepared signal is pure A/C/G/T, its four channels sum to zero, so the T
+  // spectrum is never transformed; the second transform carries G of this signal and G of its partner.
+  int zmode = ZM_FOUR, partner = -1, plen = 0;
   if (prepared) {
+    if (sd.g_mode == G_OWNER) {
+      zmode = ZM_RE;
+      if (sd.g_partner >= 0 && prep.flag[sd.g_partner] != 0) partner = sd.g_partner;
+    } else if (sd.g_mode == G_MEMBER && sd.g_partner >= 0) {
+      zmode = prep.flag[sd.g_partner] != 0 ? ZM_IM : ZM_RE;  // owner not pure: this signal transforms (G + i 0) itself
+    }
     constexpr int NWp = N / 32;
     const uint32_t *pl = ws.planes + (size_t)sd.slot * 2 * NWp;
     for (int w = tid; w < 2 * NWp; w += NT) s_pl2[w] = pl[w];
     const float *wsrc = prep.went + (size_t)blockIdx.x * (H / WIN);
     for (int w = tid; w < H / WIN; w += NT) went[w] = wsrc[w];
     if (tid < 4) s_off[tid] = prep.off[(size_t)blockIdx.x * 4 + tid];
+    if (partner >= 0) {  // the partner's planes, weights and G mean behind this signal's
+      const SigDesc pd = sigs[partner];
+      plen = pd.len;
+      const uint32_t *ppl = ws.planes + (size_t)pd.slot * 2 * NWp;
+      for (int w = tid; w < 2 * NWp; w += NT) s_pl2[2 * NWp + w] = ppl[w];
+      const float *pw = prep.went + (size_t)partner * (H / WIN);
+      for (int w = tid; w < H / WIN; w += NT) went[H / WIN + w] = pw[w];
+      if (tid == 4) s_poff = prep.off[(size_t)partner * 4 + 2];
+    }
     __syncthreads();
   } else {
     flags = encode_prepare<LOG2N, NT>(sd, ws, smem_raw, sb, went, s_fcode, s_comp, s_base2, s_red, s_off, &s_flags, true);
@@ -692,9 +715,15 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
   constexpr int PH1 = bin_slot<LOG2N>(H - 1), PH = bin_slot<LOG2N>(H), PH2 = bin_slot<LOG2N>(H + 1);
   const bool pure = !(flags & SLOT_NONACGT);
   const bool fastgen = pure && len <= H;
+  const int rounds = zmode == ZM_IM ? 1 : 2;  // a member's G rides its owner's second transform
 #pragma unroll 1
-  for (int pr = 0; pr < 2; pr++) {
-    const double off0 = s_off[2 * pr], off1 = s_off[2 * pr + 1];
+  for (int pr = 0; pr < rounds; pr++) {
+    // the channel in the real part (c0) and in the imaginary part (c1) of this round's packed signal; in the
+    // three-channel form the second round is (G of this signal) + i (G of the partner, or nothing)
+    const bool g_round = pr == 1 && zmode != ZM_FOUR;
+    const uint32_t c0 = 2 * pr, c1 = g_round ? 2u : 2 * pr + 1;
+    const double off0 = s_off[c0], off1 = g_round ? (partner >= 0 ? s_poff : 0.0) : s_off[c1];
+    const int len1 = g_round ? plen : len;  // plen = 0 without a partner: imaginary part all zero
     // sample = (float)(weight * (fraction - mean)); for A/C/G/T the fraction is 1 or 0
     const double hit0 = __dsub_rn(1.0, off0), miss0 = __dsub_rn(0.0, off0);
     const double hit1 = __dsub_rn(1.0, off1), miss1 = __dsub_rn(0.0, off1);
@@ -702,35 +731,44 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
       // Fast path: one thread per entropy window (N/512 bases).  Inside a window the sample is one of
       // two floats per channel -- (float)(w*(1-mean)) or (float)(w*(0-mean)) -- rounded exactly as the
       // per-base double product of the reference; the base only selects between them.
-      const uint32_t c0 = 2 * pr, c1 = 2 * pr + 1;
+      const bool flat1 = g_round ? plen < 1024 : flat;
+      const int src1 = (g_round && partner >= 0) ? 1 : 0;  // whose planes / weights feed the imaginary part
       for (int w = tid; w < H / WIN; w += NT) {
         const int k0 = w * WIN;
-        const double e = flat ? 1.0 : (double)went[w];
-        const float h0 = __double2float_rn(__dmul_rn(e, hit0)), m0 = __double2float_rn(__dmul_rn(e, miss0));
-        const float h1 = __double2float_rn(__dmul_rn(e, hit1)), m1 = __double2float_rn(__dmul_rn(e, miss1));
+        const double e0 = flat ? 1.0 : (double)went[w];
+        const double e1 = flat1 ? 1.0 : (double)went[src1 * (H / WIN) + w];
+        const float h0 = __double2float_rn(__dmul_rn(e0, hit0)), m0 = __double2float_rn(__dmul_rn(e0, miss0));
+        const float h1 = __double2float_rn(__dmul_rn(e1, hit1)), m1 = __double2float_rn(__dmul_rn(e1, miss1));
         const float2 wb = __ldg(wn + k0);  // w_N^{k0}; w_N^{k0 + j} = wb * (compile-time) w_N^j
-        // the window's base codes, two bits each (A,C,G,T -> 0,1,2,3): from the plane words (prepared) or the bytes
-        uint64_t codes = 0;
+        // bit j of sel0 / sel1: base k0 + j is the channel's letter (codes A,C,G,T -> 0,1,2,3 as two bit planes)
+        uint32_t sel0, sel1;
         if (prepared) {
           constexpr int NWp = N / 32;
           const uint32_t lo = s_pl2[k0 >> 5] >> (k0 & 31), hi = s_pl2[NWp + (k0 >> 5)] >> (k0 & 31);
-#pragma unroll
-          for (int j = 0; j < WIN; j++) codes |= (uint64_t)(((lo >> j) & 1u) | (((hi >> j) & 1u) << 1)) << (2 * j);
+          const uint32_t *p1 = s_pl2 + src1 * 2 * NWp;
+          const uint32_t lo1 = p1[k0 >> 5] >> (k0 & 31), hi1 = p1[NWp + (k0 >> 5)] >> (k0 & 31);
+          sel0 = ((c0 & 1u) ? lo : ~lo) & ((c0 & 2u) ? hi : ~hi);
+          sel1 = ((c1 & 1u) ? lo1 : ~lo1) & ((c1 & 2u) ? hi1 : ~hi1);
         } else {
+          sel0 = sel1 = 0u;
 #pragma unroll
           for (int j = 0; j < (WIN + 3) / 4; j++) {
             const uint32_t p4 = reinterpret_cast<const uint32_t *>(sb + k0)[j];
             const uint32_t c4 = ((p4 >> 1) & 0x03030303u) ^ ((p4 >> 2) & 0x01010101u);
-            codes |= (uint64_t)((c4 & 3u) | ((c4 >> 6) & 0xcu) | ((c4 >> 12) & 0x30u) | ((c4 >> 18) & 0xc0u)) << (8 * j);
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+              const uint32_t code = (c4 >> (8 * b)) & 3u;
+              sel0 |= (uint32_t)(code == c0) << (4 * j + b);
+              sel1 |= (uint32_t)(code == c1) << (4 * j + b);
+            }
           }
         }
 #pragma unroll
         for (int j = 0; j < WIN; j++) {
           const int k = k0 + j;
-          const uint32_t code = (uint32_t)(codes >> (2 * j)) & 3u;
           float2 v;
-          v.x = k < len ? (code == c0 ? h0 : m0) : 0.f;
-          v.y = k < len ? (code == c1 ? h1 : m1) : 0.f;
+          v.x = k < len ? (((sel0 >> j) & 1u) ? h0 : m0) : 0.f;
+          v.y = k < len1 ? (((sel1 >> j) & 1u) ? h1 : m1) : 0.f;
           constexpr double ang = -2.0 * 3.14159265358979323846 / (double)N;
           const float2 st = make_float2((float)cx_cos_small(ang * j), (float)cx_sin_small(ang * j));
           const float2 wk = j == 0 ? wb : cmul(wb, st);
@@ -810,10 +848,13 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
     SlotMeta m;
     m.len = len;
     m.flags = flags & SLOT_NONACGT;
-    m.q_re = acc_re;
-    m.q_im = acc_im;
-    m.q_nyq = acc_ny;
-    m.pad[0] = m.pad[1] = m.pad[2] = 0;
+    // three-channel form: the channel sum of the spectrum is zero by construction (the reference's is float noise)
+    m.q_re = zmode == ZM_FOUR ? acc_re : 0.f;
+    m.q_im = zmode == ZM_FOUR ? acc_im : 0.f;
+    m.q_nyq = zmode == ZM_FOUR ? acc_ny : 0.f;
+    m.zmode = zmode;
+    m.zslot = zmode == ZM_IM ? sigs[sd.g_partner].slot : sd.slot;
+    m.pad = 0;
     ws.meta[sd.slot] = m;
   }
 }
@@ -969,7 +1010,9 @@ __global__ void __launch_bounds__(NT, 1)
       m->len = len;
       m->flags = flags & SLOT_NONACGT;
       m->q_nyq = acc_ny;
-      m->pad[0] = m->pad[1] = m->pad[2] = 0;
+      m->zmode = ZM_FOUR;
+      m->zslot = 0;
+      m->pad = 0;
     } else {
       m->q_re = acc_re;
       m->q_im = acc_im;
@@ -1105,6 +1148,126 @@ __device__ __forceinline__ void inverse_full(float2 *buf, const float2 *__restri
   __syncthreads();
 }
 
+// ---- spectral product of a chunk pair from the stored spectra, bin pair (k, N - k) by bin pair -----------------
+// Where the spectra of a signal live: Z1 = spectrum of (A + iC); Z3 = spectrum of (G + iT) (four-channel form) or
+// of (G_owner + i G_member) shared with another signal (three-channel form, sx_kernels.h).
+struct SpecSrc {
+  const float2 *z1, *z3;
+  int mode;  // ZM_FOUR / ZM_RE / ZM_IM
+};
+__device__ __forceinline__ SpecSrc spec_src(const Slots &ws, int slot, const SlotMeta &m, int n) {
+  SpecSrc r;
+  r.z1 = ws.spec + ((size_t)slot * 2) * n;
+  r.z3 = ws.spec + ((size_t)(m.zmode == ZM_FOUR ? slot : m.zslot) * 2 + 1) * n;
+  r.mode = m.zmode;
+  return r;
+}
+// Twice the per-channel spectra at bin k from the packed values at bin k (a) and at its mirror N - k (b):
+// a real sequence has X[N-k] = conj X[k], so for Z = X + iY: 2X = Za + conj(Zb), 2Y = -i (Za - conj(Zb)).
+// Three-channel form: T = -(A + C + G).
+struct Chan4 { float2 a, c, g, t; };
+__device__ __forceinline__ Chan4 channels2(float2 z1a, float2 z1b, float2 z3a, float2 z3b, int mode) {
+  Chan4 r;
+  r.a = make_float2(z1a.x + z1b.x, z1a.y - z1b.y);
+  r.c = make_float2(z1a.y + z1b.y, z1b.x - z1a.x);
+  const float2 re = make_float2(z3a.x + z3b.x, z3a.y - z3b.y), im = make_float2(z3a.y + z3b.y, z3b.x - z3a.x);
+  if (mode == ZM_FOUR) {
+    r.g = re;
+    r.t = im;
+  } else {
+    r.g = mode == ZM_RE ? re : im;
+    r.t = make_float2(-(r.a.x + r.c.x + r.g.x), -(r.a.y + r.c.y + r.g.y));
+  }
+  return r;
+}
+// One bin pair -> the values the inverse transform gets at bin k (oa) and at N - k (ob), times 4:
+//   forward strand  Pf[k]  = conj(At) Aq + conj(Ct) Cq + conj(Gt) Gq + conj(Tt) Tq
+//   reverse strand  the reverse-complement signal is the forward one reversed with the channels swapped A<->T,
+//                   C<->G (exact when the entropy windows line up, which the host checks); reversed about index 0
+//                   its channel spectra are conj(Tq), conj(Gq), conj(Cq), conj(Aq), so
+//                   Pr'[k] = conj(At Tq + Ct Gq + Gt Cq + Tt Aq), and its correlation is the true one rotated by
+//                   qlen - 1 lags.
+// Both are spectra of real sequences (P[N-k] = conj P[k]); BOTH packs them as Pf + i Pr' so that ONE inverse
+// transform gives the forward strand in its real part and the reverse strand in its imaginary part.
+template <bool BOTH>
+__device__ __forceinline__ void pair_product(const Chan4 &t, const Chan4 &q, float2 &oa, float2 &ob) {
+  float2 pf;
+  pf.x = (t.a.x * q.a.x + t.a.y * q.a.y) + (t.c.x * q.c.x + t.c.y * q.c.y) + (t.g.x * q.g.x + t.g.y * q.g.y) +
+         (t.t.x * q.t.x + t.t.y * q.t.y);
+  pf.y = (t.a.x * q.a.y - t.a.y * q.a.x) + (t.c.x * q.c.y - t.c.y * q.c.x) + (t.g.x * q.g.y - t.g.y * q.g.x) +
+         (t.t.x * q.t.y - t.t.y * q.t.x);
+  if (BOTH) {
+    float2 rr;
+    rr.x = (t.a.x * q.t.x - t.a.y * q.t.y) + (t.c.x * q.g.x - t.c.y * q.g.y) + (t.g.x * q.c.x - t.g.y * q.c.y) +
+           (t.t.x * q.a.x - t.t.y * q.a.y);
+    rr.y = (t.a.x * q.t.y + t.a.y * q.t.x) + (t.c.x * q.g.y + t.c.y * q.g.x) + (t.g.x * q.c.y + t.g.y * q.c.x) +
+           (t.t.x * q.a.y + t.t.y * q.a.x);
+    oa = make_float2(pf.x + rr.y, pf.y + rr.x);  // Pf + i conj(Rr)
+    ob = make_float2(pf.x - rr.y, rr.x - pf.y);  // conj(Pf) + i Rr
+  } else {
+    oa = pf;
+    ob = make_float2(pf.x, -pf.y);
+  }
+}
+// The whole product into the (swizzled, scrambled-order) transform buffer.  Two neighbouring slots (r, r ^ 1) per
+// step with 16-byte loads: their mirror slots are neighbours too (even bins: top digit d <-> R - 1 - d while the
+// lower digits are not all zero; odd bins: r <-> H - 1 - r), and the swizzle only XORs the low four bits with a
+// per-block constant, so pairs stay pairs.  The caller synchronises.
+template <int LOG2N, int NT, bool BOTH>
+__device__ __forceinline__ void spectral_product(float2 *buf, const SpecSrc T, const SpecSrc Q, int tid) {
+  constexpr int N = 1 << LOG2N, H = N / 2;
+  constexpr int LR = last_radix<LOG2N>();
+  constexpr int PPB = LR / 4;  // slot pairs per block of LR slots with top digit < LR / 2
+  const bool same3 = T.z3 == Q.z3;  // partners: one shared G transform
+  const float4 *T1 = reinterpret_cast<const float4 *>(T.z1), *T3 = reinterpret_cast<const float4 *>(T.z3);
+  const float4 *Q1 = reinterpret_cast<const float4 *>(Q.z1), *Q3 = reinterpret_cast<const float4 *>(Q.z3);
+  auto lo = [](const float4 &v) { return make_float2(v.x, v.y); };
+  auto hi = [](const float4 &v) { return make_float2(v.z, v.w); };
+  auto sel = [&](const float4 &v, bool upper) { return upper ? hi(v) : lo(v); };
+#pragma unroll 2
+  for (int it = tid; it < H / 2; it += NT) {
+    int pa0, pb0;
+    if (it < H / 4) {  // even bins: m <-> (H - m) mod H; m < H/2 <=> top digit (last in scrambled order) < LR/2
+      const int r = (it / PPB) * LR + 2 * (it % PPB);
+      if (r < LR) continue;  // lower digits all zero: mirrors are d <-> R - d, done one by one below
+      const int m2 = (H - natural_bin<LOG2N>(r)) & (H - 1);
+      pa0 = swz(r);
+      pb0 = swz(scrambled_pos<LOG2N>(m2));
+    } else {  // odd bins: m <-> H - 1 - m, i.e. scrambled position r <-> H - 1 - r
+      const int r = 2 * (it - H / 4);
+      pa0 = H + swz(r);
+      pb0 = H + swz(H - 1 - r);
+    }
+    const int qa = pa0 >> 1, qb = pb0 >> 1;  // float4 index
+    const float4 t1a = __ldg(T1 + qa), t1b = __ldg(T1 + qb), t3a = __ldg(T3 + qa), t3b = __ldg(T3 + qb);
+    const float4 q1a = __ldg(Q1 + qa), q1b = __ldg(Q1 + qb);
+    float4 q3a = t3a, q3b = t3b;
+    if (!same3) {
+      q3a = __ldg(Q3 + qa);
+      q3b = __ldg(Q3 + qb);
+    }
+    // slot r sits in half (pa0 & 1) of the a-quad and its mirror in half (pb0 & 1) of the b-quad; slot r ^ 1 and
+    // its mirror sit in the other halves
+    const bool ea = pa0 & 1, eb = pb0 & 1;
+    float2 oa0, ob0, oa1, ob1;
+    pair_product<BOTH>(channels2(sel(t1a, ea), sel(t1b, eb), sel(t3a, ea), sel(t3b, eb), T.mode),
+                       channels2(sel(q1a, ea), sel(q1b, eb), sel(q3a, ea), sel(q3b, eb), Q.mode), oa0, ob0);
+    pair_product<BOTH>(channels2(sel(t1a, !ea), sel(t1b, !eb), sel(t3a, !ea), sel(t3b, !eb), T.mode),
+                       channels2(sel(q1a, !ea), sel(q1b, !eb), sel(q3a, !ea), sel(q3b, !eb), Q.mode), oa1, ob1);
+    reinterpret_cast<float4 *>(buf)[qa] = ea ? make_float4(oa1.x, oa1.y, oa0.x, oa0.y) : make_float4(oa0.x, oa0.y, oa1.x, oa1.y);
+    reinterpret_cast<float4 *>(buf)[qb] = eb ? make_float4(ob1.x, ob1.y, ob0.x, ob0.y) : make_float4(ob0.x, ob0.y, ob1.x, ob1.y);
+  }
+  for (int r = tid; r < LR / 2; r += NT) {  // first block of the even bins, slot by slot (bins 0 and H/2 mirror themselves)
+    const int m2 = (H - natural_bin<LOG2N>(r)) & (H - 1);
+    const int pa = swz(r), pb = swz(scrambled_pos<LOG2N>(m2));
+    float2 oa, ob;
+    pair_product<BOTH>(channels2(__ldg(T.z1 + pa), __ldg(T.z1 + pb), __ldg(T.z3 + pa), __ldg(T.z3 + pb), T.mode),
+                       channels2(__ldg(Q.z1 + pa), __ldg(Q.z1 + pb), __ldg(Q.z3 + pa), __ldg(Q.z3 + pb), Q.mode), oa, ob);
+    buf[pa] = oa;
+    buf[pb] = ob;
+  }
+}
+
 template <int LOG2N, int NT>
 __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
     xcorr_pair_kernel(const uint32_t *__restrict__ pair_list, const SpDesc *__restrict__ sps, Slots ws, double cutoff,
@@ -1123,77 +1286,11 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
   TwTables<LOG2N>::template load<NT>(s_tw, tid);  // used after the barriers below
   const int spi = (int)pair_list[blockIdx.x];  // forward strand-pair; the reverse one is spi + 1
   const SpDesc sp = sps[spi];
-  const SlotMeta tm = ws.meta[sp.t_slot];
-  const int qlen = ws.meta[sp.q_slot].len;
+  const SlotMeta tm = ws.meta[sp.t_slot], qm = ws.meta[sp.q_slot];
+  const int qlen = qm.len;
 
-  // ---- products of both strands, Hermitian-symmetrised and packed: buf = 2 (Pf_h + i Pr_h) ---------
-  //   forward   Pf[k] = conj(U1) V1 + conj(U2) V2
-  //   reverse   the reverse-complement signal is the forward one reversed with channels swapped A<->T,
-  //             C<->G (exact when the entropy windows line up, which the host checks); reversed about
-  //             index 0 its packed spectra are i conj(V2), i conj(V1), so
-  //             Pr'[k] = i conj(U1 V2 + U2 V1), and its correlation is the true one rotated by qlen - 1 lags.
-  //   X_h[k] = (X[k] + conj X[N-k]) / 2 keeps exactly the real part of the inverse transform.
-  {
-    const float2 *U1 = ws.spec + ((size_t)sp.t_slot * 2) * N, *U2 = U1 + N;
-    const float2 *V1 = ws.spec + ((size_t)sp.q_slot * 2) * N, *V2 = V1 + N;
-    // one bin pair (slot a, its mirror slot b) -> the two packed values
-    auto product = [](float2 u1a, float2 u2a, float2 v1a, float2 v2a, float2 u1b, float2 u2b, float2 v1b, float2 v2b,
-                      float2 &oa, float2 &ob) {
-      const float2 a = cadd(cmulc(v1a, u1a), cmulc(v2a, u2a));
-      const float2 b = cadd(cmulc(v1b, u1b), cmulc(v2b, u2b));
-      const float2 g = cadd(cmul(u1a, v2a), cmul(u2a, v1a));
-      const float2 h = cadd(cmul(u1b, v2b), cmul(u2b, v1b));
-      const float sx_ = a.x + b.x, dx = g.x - h.x, sy = g.y + h.y, dy = a.y - b.y;
-      oa = make_float2(sx_ - dx, sy + dy);
-      ob = make_float2(sx_ + dx, sy - dy);
-    };
-    // Two neighbouring slots (r, r ^ 1) per step with 16-byte loads: their mirror slots are neighbours too
-    // (even bins: top digit d <-> R - 1 - d while the lower digits are not all zero; odd bins: r <-> H - 1 - r),
-    // and the swizzle only XORs the low four bits with a per-block constant, so pairs stay pairs.
-    constexpr int PPB = LR / 4;  // slot pairs per block of LR slots with top digit < LR / 2
-#pragma unroll 2
-    for (int it = tid; it < H / 2; it += NT) {
-      int pa0, pb0;
-      if (it < H / 4) {  // even bins: m <-> (H - m) mod H; m < H/2 <=> top digit (last in scrambled order) < LR/2
-        const int r = (it / PPB) * LR + 2 * (it % PPB);
-        if (r < LR) continue;  // lower digits all zero: mirrors are d <-> R - d, done one by one below
-        const int m2 = (H - natural_bin<LOG2N>(r)) & (H - 1);
-        pa0 = swz(r);
-        pb0 = swz(scrambled_pos<LOG2N>(m2));
-      } else {  // odd bins: m <-> H - 1 - m, i.e. scrambled position r <-> H - 1 - r
-        const int r = 2 * (it - H / 4);
-        pa0 = H + swz(r);
-        pb0 = H + swz(H - 1 - r);
-      }
-      const int qa = pa0 >> 1, qb = pb0 >> 1;  // float4 index
-      const float4 U1a = __ldg(reinterpret_cast<const float4 *>(U1) + qa), U2a = __ldg(reinterpret_cast<const float4 *>(U2) + qa);
-      const float4 V1a = __ldg(reinterpret_cast<const float4 *>(V1) + qa), V2a = __ldg(reinterpret_cast<const float4 *>(V2) + qa);
-      const float4 U1b = __ldg(reinterpret_cast<const float4 *>(U1) + qb), U2b = __ldg(reinterpret_cast<const float4 *>(U2) + qb);
-      const float4 V1b = __ldg(reinterpret_cast<const float4 *>(V1) + qb), V2b = __ldg(reinterpret_cast<const float4 *>(V2) + qb);
-      // slot r sits in half (pa0 & 1) of the a-quad and its mirror in half (pb0 & 1) of the b-quad; slot r ^ 1 and
-      // its mirror sit in the other halves
-      const bool ea = pa0 & 1, eb = pb0 & 1;
-      auto lo = [](const float4 &v) { return make_float2(v.x, v.y); };
-      auto hi = [](const float4 &v) { return make_float2(v.z, v.w); };
-      auto sel = [&](const float4 &v, bool upper) { return upper ? hi(v) : lo(v); };
-      float2 oa0, ob0, oa1, ob1;
-      product(sel(U1a, ea), sel(U2a, ea), sel(V1a, ea), sel(V2a, ea), sel(U1b, eb), sel(U2b, eb), sel(V1b, eb), sel(V2b, eb),
-              oa0, ob0);
-      product(sel(U1a, !ea), sel(U2a, !ea), sel(V1a, !ea), sel(V2a, !ea), sel(U1b, !eb), sel(U2b, !eb), sel(V1b, !eb),
-              sel(V2b, !eb), oa1, ob1);
-      reinterpret_cast<float4 *>(buf)[qa] = ea ? make_float4(oa1.x, oa1.y, oa0.x, oa0.y) : make_float4(oa0.x, oa0.y, oa1.x, oa1.y);
-      reinterpret_cast<float4 *>(buf)[qb] = eb ? make_float4(ob1.x, ob1.y, ob0.x, ob0.y) : make_float4(ob0.x, ob0.y, ob1.x, ob1.y);
-    }
-    for (int r = tid; r < LR / 2; r += NT) {  // first block of the even bins, slot by slot
-      const int m2 = (H - natural_bin<LOG2N>(r)) & (H - 1);
-      const int pa = swz(r), pb = swz(scrambled_pos<LOG2N>(m2));
-      float2 oa, ob;
-      product(__ldg(U1 + pa), __ldg(U2 + pa), __ldg(V1 + pa), __ldg(V2 + pa), __ldg(U1 + pb), __ldg(U2 + pb), __ldg(V1 + pb),
-              __ldg(V2 + pb), oa, ob);
-      buf[pa] = oa;
-      buf[pb] = ob;
-    }
-  }
+  // ---- products of both strands packed for one inverse transform: buf = 4 (Pf + i Pr') --------------------------
+  spectral_product<LOG2N, NT, true>(buf, spec_src(ws, sp.t_slot, tm, N), spec_src(ws, sp.q_slot, qm, N), tid);
   __syncthreads();
   // ---- reference quirk (CrossCorr.cc:480-492): bins H-1 and H keep the TARGET spectrum, on both strands;
   //      the reverse strand's copy carries the rotation phase e^{+2 pi i k (qlen-1) / N}
@@ -1204,7 +1301,7 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
       float sn, cs;
       sincospif(2.0f * (float)(((long long)k * rot) & (N - 1)) / (float)N, &sn, &cs);
       const float2 tr = cmul(t, make_float2(cs, sn));
-      buf[slot] = make_float2(2.f * (t.x - tr.y), 2.f * (t.y + tr.x));  // 2 (t + i tr)
+      buf[slot] = make_float2(4.f * (t.x - tr.y), 4.f * (t.y + tr.x));  // 4 (t + i tr)
     };
     put(PH1, H - 1, make_float2(tm.q_re, tm.q_im));
     put(PH2, H + 1, make_float2(tm.q_re, -tm.q_im));
@@ -1213,8 +1310,8 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
   __syncthreads();
   inverse_full<LOG2N, NT>(buf, ws.wn, tid, s_tw);
 
-  // xc[i] = x[(i + H) mod N] / N (rescale + half rotation, CrossCorr.cc:493-505); the factor 2 above
-  const float scale = 0.5f / (float)N;
+  // xc[i] = x[(i + H) mod N] / N (rescale + half rotation, CrossCorr.cc:493-505); the factor 4 above
+  const float scale = 0.25f / (float)N;
   const double co = (sp.flags & SP_FAST) ? cutoff_fast : cutoff;
   findtop<LOG2N, NT, 0>(buf, H, scale, co, mask, s_wtot, &s_base, spi, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
   findtop<LOG2N, NT, 1>(buf, (H - (qlen - 1)) & (N - 1), scale, co, mask, s_wtot, &s_base, spi + 1, cand_pool,
@@ -1254,37 +1351,21 @@ __global__ void __launch_bounds__(NT)
   const SpDesc sp = sps[spi];
   const SlotMeta tm = ws.meta[sp.t_slot];
 
-  // ---- product: P = conj(U1) V1 + conj(U2) V2 (bin order is irrelevant here) ----------------------
-  {
-    const float4 *U1 = reinterpret_cast<const float4 *>(ws.spec + ((size_t)sp.t_slot * 2) * N);
-    const float4 *U2 = U1 + N / 2;
-    const float4 *V1 = reinterpret_cast<const float4 *>(ws.spec + ((size_t)sp.q_slot * 2) * N);
-    const float4 *V2 = V1 + N / 2;
-    float4 *dst = reinterpret_cast<float4 *>(buf);
-#pragma unroll 2
-    for (int k = tid; k < N / 2; k += NT) {
-      const float4 u1 = __ldg(U1 + k), u2 = __ldg(U2 + k), v1 = __ldg(V1 + k), v2 = __ldg(V2 + k);
-      float4 p;
-      p.x = (v1.x * u1.x + v1.y * u1.y) + (v2.x * u2.x + v2.y * u2.y);
-      p.y = (v1.y * u1.x - v1.x * u1.y) + (v2.y * u2.x - v2.x * u2.y);
-      p.z = (v1.z * u1.z + v1.w * u1.w) + (v2.z * u2.z + v2.w * u2.w);
-      p.w = (v1.w * u1.z - v1.z * u1.w) + (v2.w * u2.z - v2.z * u2.w);
-      dst[k] = p;
-    }
-  }
+  // ---- product of one strand: buf = 4 Pf (the spectrum of a real sequence) ------------------------------------
+  spectral_product<LOG2N, NT, false>(buf, spec_src(ws, sp.t_slot, tm, N), spec_src(ws, sp.q_slot, ws.meta[sp.q_slot], N), tid);
   __syncthreads();
   // ---- reference quirk (CrossCorr.cc:480-492): bins H-1 and H keep the TARGET spectrum ------------
   if (tid == 0) {
     constexpr int PH1 = bin_slot<LOG2N>(H - 1), PH = bin_slot<LOG2N>(H), PH2 = bin_slot<LOG2N>(H + 1);
-    buf[PH1] = make_float2(tm.q_re, tm.q_im);
-    buf[PH2] = make_float2(tm.q_re, -tm.q_im);
-    buf[PH] = make_float2(tm.q_nyq, 0.f);
+    buf[PH1] = make_float2(4.f * tm.q_re, 4.f * tm.q_im);
+    buf[PH2] = make_float2(4.f * tm.q_re, -4.f * tm.q_im);
+    buf[PH] = make_float2(4.f * tm.q_nyq, 0.f);
   }
   __syncthreads();
   inverse_full<LOG2N, NT>(buf, ws.wn, tid, s_tw);
 
-  // xc[i] = Re x[(i + H) mod N] / N   (rescale + half rotation, CrossCorr.cc:493-505)
-  const float scale = 1.0f / (float)N;
+  // xc[i] = Re x[(i + H) mod N] / N   (rescale + half rotation, CrossCorr.cc:493-505); the factor 4 above
+  const float scale = 0.25f / (float)N;
   const double co = (sp.flags & SP_FAST) ? cutoff_fast : cutoff;
   findtop<LOG2N, NT, 0>(buf, H, scale, co, mask, s_wtot, &s_base, spi, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
 }

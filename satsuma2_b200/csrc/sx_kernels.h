@@ -8,7 +8,12 @@ namespace sx {
 // ---- HBM layout -------------------------------------------------------------------------------
 // A "signal slot" holds everything later kernels need about one chunk in one orientation:
 //   spec   [slot][2][N] float2 : spectra of (A + iC) and (G + iT); each as [even bins | odd bins], every
-//                                half in the scrambled (DIF) order of the H-point transform (sx_fft.cuh)
+//                                half in the scrambled (DIF) order of the H-point transform (sx_fft.cuh).
+//                                THREE-CHANNEL form (pure A/C/G/T chunks, SlotMeta::zmode != 0): the four channel
+//                                signals of such a chunk sum to zero sample by sample (weight * (1 - sum of means)),
+//                                so T = -(A + C + G) and only three real transforms are needed: spec[slot][0] =
+//                                (A + iC) as before, and the G channels of TWO chunks share one complex transform
+//                                (G_owner + i G_member) kept in spec[owner slot][1]; the member's spec[.][1] is unused
 //   planes [slot][2][N/32] u32 : 2-bit base codes as two bit-planes (lo, hi); A=0 C=1 G=2 T=3
 //   bytes  [slot][N] u8        : the oriented bases (only the first len are meaningful)
 //   meta   [slot]              : length, flags, the three "quirk" spectrum values
@@ -16,9 +21,13 @@ struct SlotMeta {
   int32_t len;
   int32_t flags;  // bit0: contains a byte other than A,C,G,T
   float q_re, q_im, q_nyq;  // sum over channels of the target spectrum at bins H-1 (complex) and H (real)
-  int32_t pad[3];
+  int32_t zmode;  // ZM_FOUR: spec[slot][1] = (G + iT); ZM_RE / ZM_IM: three-channel form, the G spectrum is the
+                  // real-sequence / imaginary-sequence part of spec[zslot][1]
+  int32_t zslot;
+  int32_t pad;
 };
 enum { SLOT_NONACGT = 1 };
+enum { ZM_FOUR = 0, ZM_RE = 1, ZM_IM = 2 };
 
 struct Slots {
   float2 *spec;
@@ -37,7 +46,13 @@ struct SigDesc {  // one chunk signal to encode + transform
   int32_t slot;
   int32_t rc_slot1;  // != 0: also write the reverse-complement planes / bytes / meta (no spectrum) to slot
                      // rc_slot1 - 1; its correlation is derived from the forward spectrum (xcorr_pair_kernel)
+  // three-channel pairing proposed by the host (honoured only for signals the preparation kernel accepted, i.e. pure
+  // A/C/G/T; decided on the device from PrepBuf::flag of both partners): G_OWNER transforms (G_self + i G_partner)
+  // into its own spec[.][1], G_MEMBER skips its second transform when its owner is pure too
+  int32_t g_mode = 0;      // G_NONE / G_OWNER / G_MEMBER
+  int32_t g_partner = -1;  // index of the partner in the same descriptor array (-1: none)
 };
+enum { G_NONE = 0, G_OWNER = 1, G_MEMBER = 2 };
 
 struct SpDesc {  // one strand-pair = target slot x query slot
   int32_t t_slot, q_slot;

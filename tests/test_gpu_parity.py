@@ -860,7 +860,7 @@ def test_preparation_kernel_equals_in_kernel_preparation(sx):
         ql.append((q.tobytes(), int(rng.integers(0, 1000)), i, 100000))
     pairs = [(i, i) for i in range(n)]
     outs = []
-    for flags in (0, 2):
+    for flags in (4, 6):  # bit 2: four channels per chunk on both sides (the three-channel form needs the preparation kernel)
         with sx.XCorrEngine(target_total=50000.0, debug_flags=flags, max_batch_pairs=96) as eng:
             eng.set_targets(sx.ChunkSet.from_list(tl))
             eng.set_queries(sx.ChunkSet.from_list(ql))
@@ -868,6 +868,67 @@ def test_preparation_kernel_equals_in_kernel_preparation(sx):
             outs.append(np.sort(r, order=["query_id", "tstart", "qstart", "len", "reverse"]))
     assert len(outs[0]) > 300
     assert outs[0].tobytes() == outs[1].tobytes()
+
+
+def _ragged_mixed_pairs(seed, n):
+    """pure A/C/G/T pairs of ragged lengths with forward / reverse homology, every 7th chunk with an IUPAC letter"""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    comp = np.zeros(256, np.uint8)
+    comp[list(b"ACGT")] = list(b"TGCA")
+    tl, ql = [], []
+    for i in range(n):
+        lt = int(rng.integers(47, 4097)) if i % 3 else 4096
+        t = rng.choice(acgt, lt)
+        a, b = sorted(rng.integers(0, lt, 2))
+        seg = t[a:b].copy()
+        mut = rng.random(len(seg)) < rng.uniform(0.02, 0.25)
+        seg[mut] = rng.choice(acgt, int(mut.sum()))
+        if rng.random() < 0.5:
+            seg = comp[seg[::-1]]
+        lq = 4096 if i % 4 else int(rng.integers(1100, 4097))  # i % 4 == 0: mostly not a multiple of 16 -> explicit reverse signal
+        q = np.concatenate([rng.choice(acgt, int(rng.integers(0, 900))), seg, rng.choice(acgt, 4096)])[:lq]
+        if i % 7 == 3:
+            t[int(rng.integers(0, len(t)))] = ord("R")  # this chunk keeps four channels, its partner stays on three
+        if i % 7 == 5:
+            q[int(rng.integers(0, len(q)))] = ord("N")
+        tl.append((t.tobytes(), int(rng.integers(0, 1000)), i, 100000))
+        ql.append((q.tobytes(), int(rng.integers(0, 1000)), i, 100000))
+    return tl, ql
+
+
+def test_three_channel_form_equals_four_channels(sx):
+    """Pure A/C/G/T chunks are transformed in three-channel form (T = -(A + C + G) sample by sample, the G channels of
+    two chunks share one complex transform, sx_kernels.h); debug_flags bit 2 transforms all four channels of every
+    chunk.  Correlation vectors agree to 2e-6 of their maximum and the records are identical -- in pair mode (partners =
+    target and query of a pair), with cached target spectra on a grid (partners = neighbouring targets / queries, a
+    cached target owning a query's G), with chunks that keep four channels (IUPAC letters), explicit reverse-strand
+    signals and odd signal counts mixed in."""
+    n = 301
+    tl, ql = _ragged_mixed_pairs(2718, n)
+    pairs = [(i, i) for i in range(n)]
+    grid = [(t, q) for t in range(0, 40) for q in range(20, 47)]
+    outs, xcs = [], []
+    for flags in (0, 4):
+        with sx.XCorrEngine(target_total=50000.0, debug_flags=flags, max_batch_pairs=96) as eng:
+            eng.set_targets(sx.ChunkSet.from_list(tl))
+            eng.set_queries(sx.ChunkSet.from_list(ql))
+            r1 = eng.align_pairs(pairs)
+            r2 = eng.align_pairs(grid)  # target spectra cached by now
+            xcs.append([eng.tap_xcorr(i, i, st) for i in (0, 1, 2, 3, 4, 5, 8, 12) for st in (0, 1)])
+        with sx.XCorrEngine(target_total=50000.0, debug_flags=flags, max_batch_pairs=96, spectra_cache_bytes=1) as eng:
+            eng.set_targets(sx.ChunkSet.from_list(tl))  # no cache: every batch transforms its own targets
+            eng.set_queries(sx.ChunkSet.from_list(ql))
+            r3 = eng.align_pairs(pairs + grid)
+        key = ["query_id", "target_id", "tstart", "qstart", "len", "reverse"]
+        outs.append([np.sort(r, order=key) for r in (r1, r2, r3)])
+    for a, b in zip(xcs[0], xcs[1]):
+        assert xc_rel_err(a, b) < 2e-6
+    assert len(outs[0][0]) > 200 and len(outs[0][1]) > 20
+    for a, b in zip(outs[0], outs[1]):
+        assert a.tobytes() == b.tobytes()
+    both = np.sort(np.concatenate([outs[0][0], outs[0][1]]), order=["query_id", "target_id", "tstart", "qstart", "len", "reverse"])
+    assert both.tobytes() == outs[0][2].tobytes()
 
 
 @pytest.mark.parametrize("min_len,total", [(100, 1.6e6), (300, 4294967296.0), (47, 2.0e4)])
