@@ -38,7 +38,11 @@ FFT_N = 8192
 # Algorithmic work per chunk pair (SURVEY 8d / DESIGN.md): real N-point FFT = 2.5 N log2 N flop.
 FLOP_FWD_PER_SIGNAL = 4 * 2.5 * FFT_N * 13            # 4 channels
 FLOP_XCORR_PER_STRAND = 2.5 * FFT_N * 13 + 4 * 4097 * 8  # one inverse + spectral MAC over 4 channels
-SPECTRA_BYTES_PER_SIGNAL = 2 * FFT_N * 8               # two packed complex spectra, fp32
+SPECTRUM_BYTES = FFT_N * 8                             # one packed complex spectrum (two real channels), fp32
+# Three-channel form: a pure A/C/G/T chunk stores (A + iC) of its own and shares one (G + iG') spectrum
+# with its partner -- in this workload the other chunk of its pair -- so a chunk pair writes and reads THREE spectra
+# (the four-channel form of round 1: four).  The flop figures above stay the reference's algorithmic work.
+SPECTRA_PER_CHUNK_PAIR = 3
 SCAN_ALU_OPS_PER_POSITION = 88.0 / 32.0                # bit-sliced window count: 57 LOP3 + 24 SHF + 7 match per 32 positions
 
 
@@ -56,7 +60,7 @@ def load_peaks():
 def load_traffic(key="dram_bytes_per_launch"):
     """dram__bytes_read+write per launch (device batch of 16384 pairs) and the pipe utilisation figures of the same
     `ncu --set full` captures, from profiles/*_traffic.json (tools/make_profiles.py)."""
-    for name in ("r2_traffic.json", "r1_traffic.json"):
+    for name in ("r3_traffic.json", "r2_traffic.json", "r1_traffic.json"):
         try:
             d = json.load(open(os.path.join(ROOT, "profiles", name)))
             if key in d:
@@ -599,11 +603,11 @@ def main():
     kern = {
         "encode_fft": {"ms": st_dev["ms_encode_fft"], "launches": batches,
                        "flop": FLOP_FWD_PER_SIGNAL * st_dev["signals"],
-                       "bytes": (SPECTRA_BYTES_PER_SIGNAL + CHUNK) * st_dev["signals"]},
+                       "bytes": (SPECTRA_PER_CHUNK_PAIR * SPECTRUM_BYTES / 2 + CHUNK) * st_dev["signals"]},
         "xcorr_findtop": {"ms": st_dev["ms_xcorr"], "launches": batches,
                           "flop": FLOP_XCORR_PER_STRAND * st_dev["strand_pairs"],
-                          # target + forward-query spectra read once per chunk pair (both strands derived from them)
-                          "bytes": 2 * SPECTRA_BYTES_PER_SIGNAL * st_dev["chunk_pairs"]},
+                          # the spectra of a chunk pair read once (both strands derived from them)
+                          "bytes": SPECTRA_PER_CHUNK_PAIR * SPECTRUM_BYTES * st_dev["chunk_pairs"]},
         "scan_score": {"ms": st_dev["ms_scan_score"], "launches": batches, "flop": 0.0,
                        "bytes": (4 * (FFT_N // 32) * 4) * st_dev["strand_pairs"] + 2 * st_dev["candidates"],
                        "positions": float(st_dev["positions"])},
@@ -685,7 +689,7 @@ def main():
                        "pairs_per_gpu_per_step": n, "chunk": CHUNK, "fft_n": FFT_N, "cutoff": 1.8, "min_prob": 0.99,
                        "device_batch_pairs": args.batch, "parallelism": f"pairs sharded over {world} GPU(s), no collective",
                        "l2": f"inputs larger than L2: {h2d_per_step >> 20} MiB of bases and "
-                             f"{(2 * args.batch * SPECTRA_BYTES_PER_SIGNAL) >> 20} MiB of spectra per device batch"},
+                             f"{(args.batch * SPECTRA_PER_CHUNK_PAIR * SPECTRUM_BYTES) >> 20} MiB of spectra per device batch"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_per_step,
                     "d2h_bytes_per_step": d2h_per_step, "ms_per_step": ms_e2e / args.steps},

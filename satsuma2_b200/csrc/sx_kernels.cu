@@ -1166,16 +1166,17 @@ __device__ __forceinline__ SpecSrc spec_src(const Slots &ws, int slot, const Slo
 // a real sequence has X[N-k] = conj X[k], so for Z = X + iY: 2X = Za + conj(Zb), 2Y = -i (Za - conj(Zb)).
 // Three-channel form: T = -(A + C + G).
 struct Chan4 { float2 a, c, g, t; };
-__device__ __forceinline__ Chan4 channels2(float2 z1a, float2 z1b, float2 z3a, float2 z3b, int mode) {
+template <int MODE>
+__device__ __forceinline__ Chan4 channels2(float2 z1a, float2 z1b, float2 z3a, float2 z3b) {
   Chan4 r;
   r.a = make_float2(z1a.x + z1b.x, z1a.y - z1b.y);
   r.c = make_float2(z1a.y + z1b.y, z1b.x - z1a.x);
   const float2 re = make_float2(z3a.x + z3b.x, z3a.y - z3b.y), im = make_float2(z3a.y + z3b.y, z3b.x - z3a.x);
-  if (mode == ZM_FOUR) {
+  if (MODE == ZM_FOUR) {
     r.g = re;
     r.t = im;
   } else {
-    r.g = mode == ZM_RE ? re : im;
+    r.g = MODE == ZM_RE ? re : im;
     r.t = make_float2(-(r.a.x + r.c.x + r.g.x), -(r.a.y + r.c.y + r.g.y));
   }
   return r;
@@ -1213,8 +1214,8 @@ __device__ __forceinline__ void pair_product(const Chan4 &t, const Chan4 &q, flo
 // step with 16-byte loads: their mirror slots are neighbours too (even bins: top digit d <-> R - 1 - d while the
 // lower digits are not all zero; odd bins: r <-> H - 1 - r), and the swizzle only XORs the low four bits with a
 // per-block constant, so pairs stay pairs.  The caller synchronises.
-template <int LOG2N, int NT, bool BOTH>
-__device__ __forceinline__ void spectral_product(float2 *buf, const SpecSrc T, const SpecSrc Q, int tid) {
+template <int LOG2N, int NT, bool BOTH, int TM, int QM>
+__device__ __forceinline__ void spectral_product_m(float2 *buf, const SpecSrc T, const SpecSrc Q, int tid) {
   constexpr int N = 1 << LOG2N, H = N / 2;
   constexpr int LR = last_radix<LOG2N>();
   constexpr int PPB = LR / 4;  // slot pairs per block of LR slots with top digit < LR / 2
@@ -1223,7 +1224,6 @@ __device__ __forceinline__ void spectral_product(float2 *buf, const SpecSrc T, c
   const float4 *Q1 = reinterpret_cast<const float4 *>(Q.z1), *Q3 = reinterpret_cast<const float4 *>(Q.z3);
   auto lo = [](const float4 &v) { return make_float2(v.x, v.y); };
   auto hi = [](const float4 &v) { return make_float2(v.z, v.w); };
-  auto sel = [&](const float4 &v, bool upper) { return upper ? hi(v) : lo(v); };
 #pragma unroll 2
   for (int it = tid; it < H / 2; it += NT) {
     int pa0, pb0;
@@ -1239,33 +1239,58 @@ __device__ __forceinline__ void spectral_product(float2 *buf, const SpecSrc T, c
       pb0 = H + swz(H - 1 - r);
     }
     const int qa = pa0 >> 1, qb = pb0 >> 1;  // float4 index
-    const float4 t1a = __ldg(T1 + qa), t1b = __ldg(T1 + qb), t3a = __ldg(T3 + qa), t3b = __ldg(T3 + qb);
-    const float4 q1a = __ldg(Q1 + qa), q1b = __ldg(Q1 + qb);
+    const float4 t1a = __ldg(T1 + qa), t3a = __ldg(T3 + qa), q1a = __ldg(Q1 + qa);
+    float4 t1b = __ldg(T1 + qb), t3b = __ldg(T3 + qb), q1b = __ldg(Q1 + qb);
     float4 q3a = t3a, q3b = t3b;
     if (!same3) {
       q3a = __ldg(Q3 + qa);
       q3b = __ldg(Q3 + qb);
     }
     // slot r sits in half (pa0 & 1) of the a-quad and its mirror in half (pb0 & 1) of the b-quad; slot r ^ 1 and
-    // its mirror sit in the other halves
-    const bool ea = pa0 & 1, eb = pb0 & 1;
+    // its mirror sit in the other halves: the lower slot of the a-quad mirrors the lower slot of the b-quad when the
+    // two parities agree, the upper one otherwise -- one conditional swap of the b-quads instead of per-value selects
+    const bool x = (pa0 ^ pb0) & 1;
+    auto swp = [&](float4 &v) {
+      if (x) v = make_float4(v.z, v.w, v.x, v.y);
+    };
+    swp(t1b);
+    swp(t3b);
+    swp(q1b);
+    if (!same3) swp(q3b); else q3b = t3b;
     float2 oa0, ob0, oa1, ob1;
-    pair_product<BOTH>(channels2(sel(t1a, ea), sel(t1b, eb), sel(t3a, ea), sel(t3b, eb), T.mode),
-                       channels2(sel(q1a, ea), sel(q1b, eb), sel(q3a, ea), sel(q3b, eb), Q.mode), oa0, ob0);
-    pair_product<BOTH>(channels2(sel(t1a, !ea), sel(t1b, !eb), sel(t3a, !ea), sel(t3b, !eb), T.mode),
-                       channels2(sel(q1a, !ea), sel(q1b, !eb), sel(q3a, !ea), sel(q3b, !eb), Q.mode), oa1, ob1);
-    reinterpret_cast<float4 *>(buf)[qa] = ea ? make_float4(oa1.x, oa1.y, oa0.x, oa0.y) : make_float4(oa0.x, oa0.y, oa1.x, oa1.y);
-    reinterpret_cast<float4 *>(buf)[qb] = eb ? make_float4(ob1.x, ob1.y, ob0.x, ob0.y) : make_float4(ob0.x, ob0.y, ob1.x, ob1.y);
+    pair_product<BOTH>(channels2<TM>(lo(t1a), lo(t1b), lo(t3a), lo(t3b)), channels2<QM>(lo(q1a), lo(q1b), lo(q3a), lo(q3b)),
+                       oa0, ob0);
+    pair_product<BOTH>(channels2<TM>(hi(t1a), hi(t1b), hi(t3a), hi(t3b)), channels2<QM>(hi(q1a), hi(q1b), hi(q3a), hi(q3b)),
+                       oa1, ob1);
+    reinterpret_cast<float4 *>(buf)[qa] = make_float4(oa0.x, oa0.y, oa1.x, oa1.y);
+    reinterpret_cast<float4 *>(buf)[qb] = x ? make_float4(ob1.x, ob1.y, ob0.x, ob0.y) : make_float4(ob0.x, ob0.y, ob1.x, ob1.y);
   }
   for (int r = tid; r < LR / 2; r += NT) {  // first block of the even bins, slot by slot (bins 0 and H/2 mirror themselves)
     const int m2 = (H - natural_bin<LOG2N>(r)) & (H - 1);
     const int pa = swz(r), pb = swz(scrambled_pos<LOG2N>(m2));
     float2 oa, ob;
-    pair_product<BOTH>(channels2(__ldg(T.z1 + pa), __ldg(T.z1 + pb), __ldg(T.z3 + pa), __ldg(T.z3 + pb), T.mode),
-                       channels2(__ldg(Q.z1 + pa), __ldg(Q.z1 + pb), __ldg(Q.z3 + pa), __ldg(Q.z3 + pb), Q.mode), oa, ob);
+    pair_product<BOTH>(channels2<TM>(__ldg(T.z1 + pa), __ldg(T.z1 + pb), __ldg(T.z3 + pa), __ldg(T.z3 + pb)),
+                       channels2<QM>(__ldg(Q.z1 + pa), __ldg(Q.z1 + pb), __ldg(Q.z3 + pa), __ldg(Q.z3 + pb)), oa, ob);
     buf[pa] = oa;
     buf[pb] = ob;
   }
+}
+// the loop specialised for the forms of both chunks (uniform over the CTA)
+template <int LOG2N, int NT, bool BOTH>
+__device__ __forceinline__ void spectral_product(float2 *buf, const SpecSrc T, const SpecSrc Q, int tid) {
+#define SX_PM(TM, QM) spectral_product_m<LOG2N, NT, BOTH, TM, QM>(buf, T, Q, tid)
+  switch (T.mode * 3 + Q.mode) {
+    case ZM_FOUR * 3 + ZM_FOUR: SX_PM(ZM_FOUR, ZM_FOUR); break;
+    case ZM_FOUR * 3 + ZM_RE: SX_PM(ZM_FOUR, ZM_RE); break;
+    case ZM_FOUR * 3 + ZM_IM: SX_PM(ZM_FOUR, ZM_IM); break;
+    case ZM_RE * 3 + ZM_FOUR: SX_PM(ZM_RE, ZM_FOUR); break;
+    case ZM_RE * 3 + ZM_RE: SX_PM(ZM_RE, ZM_RE); break;
+    case ZM_RE * 3 + ZM_IM: SX_PM(ZM_RE, ZM_IM); break;
+    case ZM_IM * 3 + ZM_FOUR: SX_PM(ZM_IM, ZM_FOUR); break;
+    case ZM_IM * 3 + ZM_RE: SX_PM(ZM_IM, ZM_RE); break;
+    default: SX_PM(ZM_IM, ZM_IM); break;
+  }
+#undef SX_PM
 }
 
 template <int LOG2N, int NT>

@@ -54,9 +54,10 @@ json.dump({
     "dram_bytes_per_launch": traffic,
     "ncu_per_launch": metrics,
     "algorithmic_bytes_per_launch": {"scan_score": 32768 * 4224 + 2 * 581 * 16384,
-                                     "xcorr_findtop": 16384 * 2 * 131072, "encode_fft": 32768 * (131072 + 4096)},
-    "note": "xcorr_findtop = xcorr_pair_kernel: one CTA per chunk pair reads the target and the forward-query spectra "
-            "once (2 x 128 KiB) and derives both strands; encode_fft writes 128 KiB of spectra + planes per signal",
+                                     "xcorr_findtop": 16384 * 3 * 65536, "encode_fft": 16384 * 3 * 65536 + 32768 * 4096},
+    "note": "three-channel form: a chunk pair owns three packed spectra of 64 KiB ((A + iC) of the target, (A + iC) of the "
+            "query, (G_target + i G_query)); xcorr_findtop = xcorr_pair_kernel: one CTA per chunk pair reads them once and "
+            "derives both strands; encode_fft writes them (+ planes) and reads the bases",
 }, open(os.path.join(P, f"{RND}_traffic.json"), "w"), indent=2)
 src = os.path.join(G, f"launches_{tag}.csv")
 shutil.copy(src, os.path.join(P, f"{RND}_launches.csv"))
