@@ -65,7 +65,8 @@ typedef struct {
                               this context returns.  Batches start as soon as the bases they need have arrived. */
   int32_t debug_flags;     /* test hooks; bit 0: score every raw segment (no run-length pruning in the scan
                               kernel); bit 1: prepare every signal inside the transform kernel (no preparation kernel);
-                              bit 2: transform all four channels of every chunk (no three-channel form) */
+                              bit 2: transform all four channels of every chunk (no three-channel form);
+                              bit 3: separate transform and correlation kernels for every pair (no fused kernel) */
   int32_t reserved[4];
 } sx_config;
 
@@ -114,7 +115,8 @@ typedef struct {
   double ms_scan_score;   /* kernel (e) */
   double ms_total;        /* first launch to last kernel end, per batch, summed */
   int64_t positions;      /* diagonal positions (base comparisons) scanned by kernel (e) */
-  int64_t spilled_segments; /* reserved (always 0: the scan kernel works its segment queue off before it fills) */
+  int64_t fused_pairs;    /* chunk pairs handled by the fused transform + correlation kernel (their device time is
+                             in ms_xcorr; ms_encode_fft then only holds the preparation kernel) */
 } sx_stats;
 
 /* ------------------------------------------------------------------ lifecycle */

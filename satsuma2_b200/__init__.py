@@ -51,7 +51,7 @@ class Stats(C.Structure):
         ("segments", C.c_int64), ("matches", C.c_int64), ("kernel_launches", C.c_int64), ("batches", C.c_int64),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("retries", C.c_int64), ("ms_encode_fft", C.c_double),
         ("ms_xcorr", C.c_double), ("ms_scan_score", C.c_double), ("ms_total", C.c_double), ("positions", C.c_int64),
-        ("spilled_segments", C.c_int64),
+        ("fused_pairs", C.c_int64),
     ]
 
     def as_dict(self):

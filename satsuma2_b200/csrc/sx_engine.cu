@@ -141,9 +141,17 @@ struct sx_ctx {
 
   // per-batch device buffers
   DevBuf<SigDesc> d_sigs[2];  // one per batch in flight (the next batch's encode is queued behind the current scan)
-  DevBuf<int32_t> d_prep_flag;  // preparation kernel -> transform kernel (PrepBuf); one set: the two kernels of a batch
-  DevBuf<float> d_prep_went;    // run back to back on the stream
-  DevBuf<double> d_prep_off;
+  DevBuf<int32_t> d_prep_flag[2];  // preparation kernel -> transform / fused kernel (PrepBuf), one set per batch in
+  DevBuf<float> d_prep_went[2];    // flight: a batch that is re-run after a pool overflow still finds its own
+  DevBuf<double> d_prep_off[2];
+  // fused transform + correlation kernel (pair_fused_kernel)
+  DevBuf<FusedJob> d_fused;
+  DevBuf<uint32_t> d_enc_list[2];   // signals left to the transform kernel when a batch has fused pairs
+  DevBuf<unsigned int> d_fail_ctr;  // {pairs, signals} handed back by the fused kernel
+  DevBuf<uint32_t> d_fail_pairs, d_fail_sigs;
+  DevBuf<float2> d_fused_scratch;   // one parked half-transform per resident CTA
+  int fused_grid = 0;               // 2 CTAs per SM
+  std::vector<int32_t> sig_of_slot, slot_uses;  // per slot, for the batch being staged (propose_fused)
   DevBuf<SpDesc> d_sps;
   DevBuf<uint2> d_cand_ref;
   DevBuf<uint32_t> d_lists;  // [pair list | direct list] of strand-pair indices (launch_xcorr_findtop)
@@ -159,6 +167,8 @@ struct sx_ctx {
   PinBuf<SigDesc> h_sigs[2];  // descriptor staging, one per batch in flight / being assembled
   PinBuf<SpDesc> h_sps[2];
   PinBuf<uint32_t> h_lists[2];
+  PinBuf<FusedJob> h_fused[2];
+  PinBuf<uint32_t> h_enc[2];
   PinBuf<ResultRec> h_res;
   PinBuf<BatchCounters> h_ctr;
 
@@ -238,6 +248,11 @@ extern "C" int sx_create(const sx_config *cfg, sx_ctx **out) {
   if (ce == cudaSuccess)
     for (int i = 0; i < 10 && ce == cudaSuccess; i++) ce = cudaEventCreate(&c->ev[i / 5][i % 5]);
   if (ce == cudaSuccess) ce = upload_tables();
+  if (ce == cudaSuccess) {
+    int sms = 0;
+    ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    c->fused_grid = 2 * sms;  // pair_fused_kernel: two resident CTAs per SM stride over the pairs
+  }
   if (ce != cudaSuccess) {
     delete c;
     return fail(SX_ERR_CUDA, "sx_create: %s", cudaGetErrorString(ce));
@@ -285,7 +300,8 @@ extern "C" void sx_destroy(sx_ctx *c) {
   if (c->Q.d_bases) cudaFree(c->Q.d_bases);
   c->spec.release(); c->planes.release(); c->sbytes.release(); c->meta.release(); c->wn.release(); c->ent_table.release(); c->drift.release();
   c->d_lists.release(); c->h_lists[0].release(); c->h_lists[1].release();
-  c->d_sigs[0].release(); c->d_sigs[1].release(); c->d_prep_flag.release(); c->d_prep_went.release(); c->d_prep_off.release(); c->d_sps.release(); c->d_cand_ref.release(); c->d_cand_pool.release();
+  c->d_sigs[0].release(); c->d_sigs[1].release(); for (int i = 0; i < 2; i++) { c->d_prep_flag[i].release(); c->d_prep_went[i].release(); c->d_prep_off[i].release(); c->d_enc_list[i].release(); c->h_fused[i].release(); c->h_enc[i].release(); }
+  c->d_fused.release(); c->d_fail_ctr.release(); c->d_fail_pairs.release(); c->d_fail_sigs.release(); c->d_fused_scratch.release(); c->d_sps.release(); c->d_cand_ref.release(); c->d_cand_pool.release();
   c->d_scratch.release(); c->d_res.release(); c->d_seg_tap.release(); c->d_ctr.release(); c->d_table.release(); c->d_tap.release();
   c->h_sigs[0].release(); c->h_sigs[1].release(); c->h_sps[0].release(); c->h_sps[1].release(); c->h_res.release(); c->h_ctr.release();
   for (int i = 0; i < 10; i++)
@@ -516,6 +532,8 @@ struct Batch {
   std::vector<SpDesc> sps;
   std::vector<PairReq> pairs;  // batch-local pair index -> chunk indices
   std::vector<uint32_t> pair_list, direct_list;  // strand-pair indices for the two correlation kernels
+  std::vector<FusedJob> fused;      // chunk pairs handed to the fused kernel (taken out of pair_list)
+  std::vector<uint32_t> enc_list;   // signals the transform kernel still does (when fused is not empty)
   size_t slot_base = 0;  // first slot of this batch's workspace
   size_t transient_used = 0;
   size_t t_need = 0, q_need = 0;  // highest byte of the target / query blob this batch reads (+1)
@@ -523,6 +541,7 @@ struct Batch {
   std::unordered_map<int32_t, int32_t> qslot;  // query chunk  -> forward slot (rc slot = +1)
   void clear() {
     sigs.clear(); sps.clear(); pairs.clear(); tslot.clear(); qslot.clear(); pair_list.clear(); direct_list.clear();
+    fused.clear(); enc_list.clear();
     transient_used = 0;
     t_need = q_need = 0;
   }
@@ -649,7 +668,7 @@ namespace {
 struct Run {  // one batch on the device: launched asynchronously, completed by batch_finish
   Batch *b = nullptr;
   TapRequest *tap = nullptr;
-  int nsig = 0, nsp = 0, n_pairlist = 0, n_direct = 0;
+  int nsig = 0, nsp = 0, n_pairlist = 0, n_direct = 0, n_fused = 0, n_enc = 0;
   bool need_encode = false, need_xcorr = true, active = false;
   bool early_done = false;  // descriptors of the signals uploaded and the encode kernel queued
   unsigned long long n_cand_seen = 0;
@@ -686,6 +705,17 @@ static int batch_kernels(sx_ctx *c, Run &r) {
                                (unsigned int)std::min<size_t>(c->d_cand_pool.n, 0xfffffff0u), c->d_cand_ref.p, c->d_ctr.p, st));
     c->stats.kernel_launches += 1;
   } else if (r.nsp && r.need_xcorr) {
+    if (r.n_fused) {
+      // chunk pairs whose spectra nobody else needs: transforms, product, inverse and FindTop in one kernel; the pairs
+      // it hands back (letters other than A/C/G/T) go through the separate kernels queued right behind it
+      CU(cudaMemsetAsync(c->d_fail_ctr.p, 0, 2 * sizeof(unsigned int), st));
+      PrepBuf prep = {c->d_prep_flag[r.stage].p, c->d_prep_went[r.stage].p, c->d_prep_off[r.stage].p};
+      FusedFail ff = {c->d_fail_ctr.p, c->d_fail_ctr.p + 1, c->d_fail_pairs.p, c->d_fail_sigs.p};
+      CU(launch_pair_fused(c->log2n, c->d_fused.p, r.n_fused, c->d_sigs[r.stage].p, c->d_sps.p, ws, prep, c->d_fused_scratch.p,
+                           std::min(c->fused_grid, r.n_fused), c->cfg.cutoff, c->cfg.cutoff_fast, c->d_cand_pool.p,
+                           (unsigned int)std::min<size_t>(c->d_cand_pool.n, 0xfffffff0u), c->d_cand_ref.p, c->d_ctr.p, ff, st));
+      c->stats.kernel_launches += 3;
+    }
     CU(launch_xcorr_findtop(c->log2n, c->d_sps.p, c->d_lists.p, r.n_pairlist, c->d_lists.p + r.n_pairlist, r.n_direct, ws,
                             c->cfg.cutoff, c->cfg.cutoff_fast, c->d_cand_pool.p,
                             (unsigned int)std::min<size_t>(c->d_cand_pool.n, 0xfffffff0u), c->d_cand_ref.p, c->d_ctr.p,
@@ -703,19 +733,77 @@ static int batch_kernels(sx_ctx *c, Run &r) {
   return SX_OK;
 }
 
+// Fused pairs (sx_kernels.cu, pair_fused_kernel): a chunk pair whose two spectra nobody else in the batch needs -- the
+// target is not cached, target and query each take part in this one pair -- is transformed, multiplied and searched
+// for peaks by ONE kernel; its spectra never reach HBM.  That is pair mode (independent chunk pairs, the guided
+// refinement pass).  The host proposes (it cannot see the letters); pairs with a chunk that is not pure A/C/G/T are
+// handed back by the kernel and done by the separate kernels.
+static void propose_fused(sx_ctx *c, Batch &b, bool enable) {
+  b.fused.clear();
+  b.enc_list.clear();
+  for (SigDesc &s : b.sigs) {
+    s.g_mode = G_NONE;
+    s.g_partner = -1;
+  }
+  const size_t n_slots = c->n_persist + 2 * c->n_transient;
+  if (!enable || b.pair_list.empty() || n_slots == 0) return;
+  const int32_t H = c->N / 2;
+  // per slot: the signal of this batch that fills it, and how many chunk pairs of the batch read it (entries touched
+  // here are reset below; the vectors stay all -1 / 0 between calls)
+  if (c->sig_of_slot.size() != n_slots) {
+    c->sig_of_slot.assign(n_slots, -1);
+    c->slot_uses.assign(n_slots, 0);
+  }
+  for (size_t i = 0; i < b.sigs.size(); i++) c->sig_of_slot[(size_t)b.sigs[i].slot] = (int32_t)i;
+  for (const SpDesc &sp : b.sps) {
+    if (sp.flags & SP_REVERSE) continue;  // one forward strand-pair per chunk pair
+    c->slot_uses[(size_t)sp.t_slot]++;
+    c->slot_uses[(size_t)sp.q_slot]++;
+  }
+  size_t kept = 0;
+  for (const uint32_t spi : b.pair_list) {
+    const SpDesc &sp = b.sps[spi];
+    const int32_t ti = c->sig_of_slot[(size_t)sp.t_slot], qi = c->sig_of_slot[(size_t)sp.q_slot];
+    bool ok = ti >= 0 && qi >= 0 && c->slot_uses[(size_t)sp.t_slot] == 1 && c->slot_uses[(size_t)sp.q_slot] == 1;
+    if (ok) {
+      const SigDesc &t = b.sigs[(size_t)ti], &q = b.sigs[(size_t)qi];
+      ok = t.strand == 0 && q.strand == 0 && t.len > 0 && t.len <= H && q.len > 0 && q.len <= H;
+    }
+    if (!ok) {
+      b.pair_list[kept++] = spi;
+      continue;
+    }
+    FusedJob j;
+    j.spi = spi;
+    j.t_sig = (uint32_t)ti;
+    j.q_sig = (uint32_t)qi;
+    b.fused.push_back(j);
+    b.sigs[(size_t)ti].g_mode = b.sigs[(size_t)qi].g_mode = G_FUSED;
+    b.sigs[(size_t)ti].g_partner = qi;
+    b.sigs[(size_t)qi].g_partner = ti;
+    // a cacheable target that goes through the fused kernel leaves no spectrum behind: a later batch that needs it
+    // transforms it then
+    if ((size_t)sp.t_slot < c->n_persist) c->t_valid[(size_t)sp.t_slot] = 0;
+  }
+  b.pair_list.resize(kept);
+  for (const SigDesc &sd : b.sigs) c->sig_of_slot[(size_t)sd.slot] = -1;
+  for (const SpDesc &sp : b.sps) c->slot_uses[(size_t)sp.t_slot] = c->slot_uses[(size_t)sp.q_slot] = 0;
+  if (!b.fused.empty())
+    for (size_t i = 0; i < b.sigs.size(); i++)
+      if (b.sigs[i].g_mode != G_FUSED) b.enc_list.push_back((uint32_t)i);
+}
+
 // Three-channel pairing (sx_kernels.h): the four channel signals of a pure A/C/G/T chunk sum to zero, so only A, C
 // and G are transformed and the G channels of two chunks share one complex transform.  The host proposes the pairs --
-// consecutive eligible signals of the batch, which in pair mode are the target and the query of one chunk pair, so
-// the pair kernel reads three spectra instead of four -- and the device settles them (a chunk with any other
-// letter keeps all four channels; the transform kernel looks at the preparation kernel's verdict on both partners).
+// consecutive eligible signals of the batch -- and the device settles them (a chunk with any other letter keeps all
+// four channels; the transform kernel looks at the preparation kernel's verdict on both partners).
 // A cached target's G must live in a cached slot: when one partner is persistent it is the owner.
 static void propose_g_partners(const sx_ctx *c, Batch &b, bool enable) {
   const int32_t H = c->N / 2;
   int open = -1;
   for (size_t i = 0; i < b.sigs.size(); i++) {
     SigDesc &s = b.sigs[i];
-    s.g_mode = G_NONE;
-    s.g_partner = -1;
+    if (s.g_mode == G_FUSED) continue;
     if (!enable || s.strand != 0 || s.len <= 0 || s.len > H) continue;
     if (open < 0) {
       open = (int)i;
@@ -738,7 +826,11 @@ static int batch_stage(sx_ctx *c, Run &r, Batch &b, TapRequest *tap, int stage) 
   r.tap = tap;
   r.stage = stage;
   const int nsig = r.nsig = (int)b.sigs.size(), nsp = r.nsp = (int)b.sps.size();
-  propose_g_partners(c, b, !log2n_split(c->log2n) && !(c->cfg.debug_flags & 4));
+  // the three-channel form and the fused kernel both build on the preparation kernel (batch_launch_early)
+  const bool prep_on = !log2n_split(c->log2n) && !(c->cfg.debug_flags & 2) && !(tap && tap->sig5n);
+  const bool three = prep_on && !(c->cfg.debug_flags & 4);
+  propose_fused(c, b, three && !(c->cfg.debug_flags & 8) && log2n_fusable(c->log2n) && tap == nullptr && c->fused_grid > 0);
+  propose_g_partners(c, b, three);
   int rc;
   if ((rc = c->h_sigs[stage].ensure(std::max(nsig, 1))) != SX_OK) return rc;
   if ((rc = c->h_sps[stage].ensure(std::max(nsp, 1))) != SX_OK) return rc;
@@ -749,6 +841,12 @@ static int batch_stage(sx_ctx *c, Run &r, Batch &b, TapRequest *tap, int stage) 
   if ((rc = c->h_lists[stage].ensure(std::max(r.n_pairlist + r.n_direct, 1))) != SX_OK) return rc;
   if (r.n_pairlist) memcpy(c->h_lists[stage].p, b.pair_list.data(), sizeof(uint32_t) * r.n_pairlist);
   if (r.n_direct) memcpy(c->h_lists[stage].p + r.n_pairlist, b.direct_list.data(), sizeof(uint32_t) * r.n_direct);
+  r.n_fused = (int)b.fused.size();
+  r.n_enc = (int)b.enc_list.size();
+  if ((rc = c->h_fused[stage].ensure(std::max(r.n_fused, 1))) != SX_OK) return rc;
+  if ((rc = c->h_enc[stage].ensure(std::max(r.n_enc, 1))) != SX_OK) return rc;
+  if (r.n_fused) memcpy(c->h_fused[stage].p, b.fused.data(), sizeof(FusedJob) * r.n_fused);
+  if (r.n_enc) memcpy(c->h_enc[stage].p, b.enc_list.data(), sizeof(uint32_t) * r.n_enc);
   r.staged = true;
   return SX_OK;
 }
@@ -788,15 +886,24 @@ static int batch_launch_early(sx_ctx *c, Run &r) {
   if (nsig) {
     PrepBuf prep = {nullptr, nullptr, nullptr};
     if (!log2n_split(c->log2n) && r.d_sig_tap == nullptr && !(c->cfg.debug_flags & 2)) {
-      if ((rc = c->d_prep_flag.ensure((size_t)nsig)) != SX_OK) return rc;
-      if ((rc = c->d_prep_went.ensure((size_t)nsig * 256)) != SX_OK) return rc;
-      if ((rc = c->d_prep_off.ensure((size_t)nsig * 4)) != SX_OK) return rc;
-      prep.flag = c->d_prep_flag.p;
-      prep.went = c->d_prep_went.p;
-      prep.off = c->d_prep_off.p;
+      if ((rc = c->d_prep_flag[r.stage].ensure((size_t)nsig)) != SX_OK) return rc;
+      if ((rc = c->d_prep_went[r.stage].ensure((size_t)nsig * 256)) != SX_OK) return rc;
+      if ((rc = c->d_prep_off[r.stage].ensure((size_t)nsig * 4)) != SX_OK) return rc;
+      prep.flag = c->d_prep_flag[r.stage].p;
+      prep.went = c->d_prep_went[r.stage].p;
+      prep.off = c->d_prep_off[r.stage].p;
     }
-    CU(launch_encode_fft(c->log2n, c->d_sigs[r.stage].p, nsig, c->slots(), r.d_sig_tap, prep, st));
-    c->stats.kernel_launches += prep.flag ? 2 : 1;
+    const uint32_t *enc_list = nullptr;
+    if (r.n_fused) {  // the transform kernel only does the signals the fused kernel does not take
+      if ((rc = c->d_enc_list[r.stage].ensure((size_t)std::max(r.n_enc, 1))) != SX_OK) return rc;
+      if (r.n_enc) {
+        CU(cudaMemcpyAsync(c->d_enc_list[r.stage].p, c->h_enc[r.stage].p, sizeof(uint32_t) * r.n_enc, cudaMemcpyHostToDevice, st));
+        c->stats.h2d_bytes += (int64_t)(sizeof(uint32_t) * r.n_enc);
+      }
+      enc_list = c->d_enc_list[r.stage].p;
+    }
+    CU(launch_encode_fft(c->log2n, c->d_sigs[r.stage].p, nsig, c->slots(), r.d_sig_tap, prep, enc_list, r.n_enc, st));
+    c->stats.kernel_launches += (prep.flag ? 1 : 0) + ((enc_list == nullptr || r.n_enc > 0) ? 1 : 0);
   }
   r.need_encode = nsig > 0;  // only tells batch_wait that this batch had an encode kernel to account for
   r.early_done = true;
@@ -826,8 +933,19 @@ static int batch_launch(sx_ctx *c, Run &r) {
       return rc;
     if (c->d_res.n == 0 && (rc = c->d_res.ensure(std::max<size_t>((size_t)nsp * 8, 1 << 16))) != SX_OK) return rc;
   }
+  if (r.n_fused) {
+    if ((rc = c->d_fused.ensure((size_t)r.n_fused)) != SX_OK) return rc;
+    if ((rc = c->d_fail_ctr.ensure(2)) != SX_OK) return rc;
+    if ((rc = c->d_fail_pairs.ensure((size_t)r.n_fused)) != SX_OK) return rc;
+    if ((rc = c->d_fail_sigs.ensure((size_t)2 * r.n_fused)) != SX_OK) return rc;
+    if ((rc = c->d_fused_scratch.ensure((size_t)c->fused_grid * (N / 2))) != SX_OK) return rc;
+  }
   cudaStream_t st = c->stream;
   if (nsp) CU(cudaMemcpyAsync(c->d_sps.p, c->h_sps[r.stage].p, sizeof(SpDesc) * nsp, cudaMemcpyHostToDevice, st));
+  if (r.n_fused) {
+    CU(cudaMemcpyAsync(c->d_fused.p, c->h_fused[r.stage].p, sizeof(FusedJob) * r.n_fused, cudaMemcpyHostToDevice, st));
+    c->stats.h2d_bytes += (int64_t)(sizeof(FusedJob) * r.n_fused);
+  }
   if (r.n_pairlist + r.n_direct)
     CU(cudaMemcpyAsync(c->d_lists.p, c->h_lists[r.stage].p, sizeof(uint32_t) * (r.n_pairlist + r.n_direct),
                        cudaMemcpyHostToDevice, st));
@@ -914,6 +1032,7 @@ static int batch_wait(sx_ctx *c, Run &r) {
     c->stats.signals += nsig;
     c->stats.strand_pairs += nsp;
     c->stats.chunk_pairs += (int64_t)r.b->pairs.size();
+    c->stats.fused_pairs += (int64_t)r.n_fused;
     c->stats.candidates += (int64_t)r.n_cand_seen;
     c->stats.segments += (int64_t)ctr.n_segments;
     c->stats.positions += (int64_t)ctr.n_positions;

@@ -25,6 +25,9 @@
 #include <math.h>
 #include <string.h>
 
+#include <stdlib.h>
+
+#include <algorithm>
 #include <vector>
 
 namespace sx {
@@ -649,7 +652,8 @@ __global__ void __launch_bounds__(256) encode_prep_kernel(const SigDesc *__restr
 
 template <int LOG2N, int NT>
 __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
-    encode_fft_kernel(const SigDesc *__restrict__ sigs, Slots ws, float *__restrict__ tap, PrepBuf prep) {
+    encode_fft_kernel(const SigDesc *__restrict__ sigs, Slots ws, float *__restrict__ tap, PrepBuf prep,
+                      const uint32_t *__restrict__ jobs, const unsigned int *__restrict__ njobs) {
   constexpr int N = 1 << LOG2N, H = N / 2, WIN = N / 512, NWARP = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *buf = reinterpret_cast<float2 *>(smem_raw);            // N complex (swizzled slots)
@@ -664,12 +668,16 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
   __shared__ int s_flags;
 
   const int tid = threadIdx.x;
-  const SigDesc sd = sigs[blockIdx.x];
+  // which signals: jobs == nullptr: signal blockIdx.x; jobs given: signal jobs[blockIdx.x]; jobs and njobs given: a fixed
+  // grid strides over the *njobs entries of a list written on the device (the fused kernel's fall-backs, normally none)
+  for (int jb = blockIdx.x; njobs != nullptr ? jb < (int)*njobs : jb == (int)blockIdx.x; jb += gridDim.x) {
+  const int sig = jobs != nullptr ? (int)jobs[jb] : jb;
+  const SigDesc sd = sigs[sig];
   const int len = sd.len;
   const float2 *__restrict__ wn = ws.wn;
 
   // prepared by encode_prep_kernel (the common case): pick up planes, window weights and means; otherwise do it here
-  const bool prepared = prep.flag != nullptr && tap == nullptr && prep.flag[blockIdx.x] != 0;
+  const bool prepared = prep.flag != nullptr && tap == nullptr && prep.flag[sig] != 0;
   uint32_t *s_pl2 = reinterpret_cast<uint32_t *>(sb);  // prepared: plane words [2][NW] in place of the bases
   int flags = 0;
   // Three-channel form (sx_kernels.h): a prepared signal is pure A/C/G/T, its four channels sum to zero, so the T
@@ -685,9 +693,9 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
     constexpr int NWp = N / 32;
     const uint32_t *pl = ws.planes + (size_t)sd.slot * 2 * NWp;
     for (int w = tid; w < 2 * NWp; w += NT) s_pl2[w] = pl[w];
-    const float *wsrc = prep.went + (size_t)blockIdx.x * (H / WIN);
+    const float *wsrc = prep.went + (size_t)sig * (H / WIN);
     for (int w = tid; w < H / WIN; w += NT) went[w] = wsrc[w];
-    if (tid < 4) s_off[tid] = prep.off[(size_t)blockIdx.x * 4 + tid];
+    if (tid < 4) s_off[tid] = prep.off[(size_t)sig * 4 + tid];
     if (partner >= 0) {  // the partner's planes, weights and G mean behind this signal's
       const SigDesc pd = sigs[partner];
       plen = pd.len;
@@ -704,7 +712,7 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
   const bool flat = len < 1024;  // "Skip entropy": weight 1 everywhere (CrossCorr.cc:39-44)
 
   if (tap != nullptr) {
-    float *te = tap + (size_t)blockIdx.x * 5 * N;
+    float *te = tap + (size_t)sig * 5 * N;
     for (int k = tid; k < N; k += NT) te[k] = flat ? 1.f : (k < len ? went[k / WIN] : 0.f);
   }
 
@@ -778,7 +786,7 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
       }
       if (tap != nullptr) {  // taps read back exactly what the transform is about to see
         __syncthreads();
-        float *ts = tap + (size_t)blockIdx.x * 5 * N + (size_t)(1 + 2 * pr) * N;
+        float *ts = tap + (size_t)sig * 5 * N + (size_t)(1 + 2 * pr) * N;
         for (int k = tid; k < N; k += NT) {
           const float2 v = k < H ? buf[swz(k)] : make_float2(0.f, 0.f);
           ts[k] = v.x;
@@ -804,7 +812,7 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
         }
         buf[swz(k)] = v;
         if (tap != nullptr) {
-          float *ts = tap + (size_t)blockIdx.x * 5 * N + (size_t)(1 + 2 * pr) * N;
+          float *ts = tap + (size_t)sig * 5 * N + (size_t)(1 + 2 * pr) * N;
           ts[k] = v.x;
           ts[N + k] = v.y;
         }
@@ -856,6 +864,8 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
     m.zslot = zmode == ZM_IM ? sigs[sd.g_partner].slot : sd.slot;
     m.pad = 0;
     ws.meta[sd.slot] = m;
+  }
+  __syncthreads();  // list mode: the shared-memory state of this signal is dead
   }
 }
 
@@ -1297,9 +1307,9 @@ template <int LOG2N, int NT>
 __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
     xcorr_pair_kernel(const uint32_t *__restrict__ pair_list, const SpDesc *__restrict__ sps, Slots ws, double cutoff,
                       double cutoff_fast, uint16_t *__restrict__ cand_pool, unsigned int pool_cap,
-                      uint2 *__restrict__ cand_ref, BatchCounters *ctr, float *__restrict__ xc_tap) {
+                      uint2 *__restrict__ cand_ref, BatchCounters *ctr, float *__restrict__ xc_tap,
+                      const unsigned int *__restrict__ n_listed) {
   constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, NWARP = NT / 32;
-  constexpr int LR = last_radix<LOG2N>();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *buf = reinterpret_cast<float2 *>(smem_raw);
   uint32_t *mask = reinterpret_cast<uint32_t *>(smem_raw + (size_t)N * sizeof(float2));  // NW words
@@ -1309,7 +1319,10 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
 
   const int tid = threadIdx.x;
   TwTables<LOG2N>::template load<NT>(s_tw, tid);  // used after the barriers below
-  const int spi = (int)pair_list[blockIdx.x];  // forward strand-pair; the reverse one is spi + 1
+  // n_listed == nullptr: one CTA per entry of pair_list; otherwise a fixed grid strides over the *n_listed entries of a
+  // list written on the device (the fused kernel's fall-backs, normally none).  FindTop ends with a barrier.
+  for (int jb = blockIdx.x; n_listed != nullptr ? jb < (int)*n_listed : jb == (int)blockIdx.x; jb += gridDim.x) {
+  const int spi = (int)pair_list[jb];  // forward strand-pair; the reverse one is spi + 1
   const SpDesc sp = sps[spi];
   const SlotMeta tm = ws.meta[sp.t_slot], qm = ws.meta[sp.q_slot];
   const int qlen = qm.len;
@@ -1341,6 +1354,7 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
   findtop<LOG2N, NT, 0>(buf, H, scale, co, mask, s_wtot, &s_base, spi, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
   findtop<LOG2N, NT, 1>(buf, (H - (qlen - 1)) & (N - 1), scale, co, mask, s_wtot, &s_base, spi + 1, cand_pool,
                         pool_cap, cand_ref, ctr, xc_tap);
+  }
 }
 
 // FindTop alone over a correlation vector the CALLER supplies (SeqAnalyzer::MatchUp takes `xc` as an argument,
@@ -1393,6 +1407,266 @@ __global__ void __launch_bounds__(NT)
   const float scale = 0.25f / (float)N;
   const double co = (sp.flags & SP_FAST) ? cutoff_fast : cutoff;
   findtop<LOG2N, NT, 0>(buf, H, scale, co, mask, s_wtot, &s_base, spi, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
+}
+
+// =================================================================================================
+// K1 + K2 fused for chunk pairs whose spectra nobody else needs (pair mode: independent chunk pairs, the guided
+// refinement pass): one CTA per chunk pair, the spectra never leave the SM.
+//   Three-channel form: the pair needs three complex N-point transforms, (A + iC) of the target, (A + iC) of the
+//   query and (G_target + i G_query).  Every N-point transform is two independent H-point transforms (even / odd bins,
+//   sx_fft.cuh) and the spectral product pairs bin k with N - k, which stay inside a half.  So the CTA works half by
+//   half: three thread groups of 128 transform one signal each into three 32 KiB buffers (own named barriers, they
+//   exchange nothing), the whole CTA forms the product in place and runs its H-point inverse.  The inverse of the even
+//   half (32 KiB) is parked in an L2-resident scratch line of this CTA while the odd half goes through the same
+//   buffers; the radix-2 combine then writes both strands' correlation vectors over the two free buffers and FindTop
+//   runs on them.  96 KiB of transform buffers -> two CTAs (24 warps) per SM; per chunk pair 8 KB of bases are read
+//   and 64 KB go through L2, against 384 KB through HBM for separate kernels.
+//   Chunks the preparation kernel did not accept (a letter other than A/C/G/T) are handed back: the pair is appended to
+//   the fall-back lists, which the separate kernels work off right behind this one.
+// =================================================================================================
+#define SX_FUSED_NT 384
+#define SX_FUSED_NG 128
+template <int LOG2N>
+struct FusedCfg {
+  static constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32;
+  static constexpr size_t SMEM = (size_t)3 * H * sizeof(float2) + (size_t)2 * 2 * NW * 4 + (size_t)2 * 256 * 4 +
+                                 (size_t)TwTables<LOG2N>::TOTAL * sizeof(float2) + (size_t)NW * 4;
+};
+
+__device__ __forceinline__ void fused_group_barrier(int grp) {  // literal ids (a register id reserves all 16 barriers)
+  if (grp == 0)
+    asm volatile("bar.sync 1, %0;" ::"n"(SX_FUSED_NG) : "memory");
+  else if (grp == 1)
+    asm volatile("bar.sync 2, %0;" ::"n"(SX_FUSED_NG) : "memory");
+  else
+    asm volatile("bar.sync 3, %0;" ::"n"(SX_FUSED_NG) : "memory");
+}
+
+template <int LOG2N>
+__global__ void __launch_bounds__(SX_FUSED_NT, 2)
+    pair_fused_kernel(const FusedJob *__restrict__ jobs, int njobs, const SigDesc *__restrict__ sigs,
+                      const SpDesc *__restrict__ sps, Slots ws, PrepBuf prep, float2 *__restrict__ scratch, double cutoff,
+                      double cutoff_fast, uint16_t *__restrict__ cand_pool, unsigned int pool_cap,
+                      uint2 *__restrict__ cand_ref, BatchCounters *ctr, FusedFail fail) {
+  constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, WIN = N / 512, NT = SX_FUSED_NT, NG = SX_FUSED_NG, NWARP = NT / 32;
+  constexpr int LR = last_radix<LOG2N>(), PPB = LR / 4;
+  using P = Plan<LOG2N>;
+  using TW = TwTables<LOG2N>;
+  constexpr int L1 = H / P::R0, L2 = L1 / P::R1, L3 = L2 / P::R2;
+  static_assert(WIN <= 32, "one plane word per entropy window");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *buf = reinterpret_cast<float2 *>(smem_raw);                          // [3][H] swizzled slots
+  uint32_t *s_pl = reinterpret_cast<uint32_t *>(buf + 3 * H);                  // [2 chunks][2 planes][NW]
+  float *s_went = reinterpret_cast<float *>(s_pl + 2 * 2 * NW);                // [2][256] window weights
+  float2 *s_tw = reinterpret_cast<float2 *>(s_went + 2 * 256);                 // inverse-pass twiddles
+  uint32_t *mask = reinterpret_cast<uint32_t *>(s_tw + TW::TOTAL);             // NW words (FindTop)
+  float *xf = reinterpret_cast<float *>(buf), *xr = reinterpret_cast<float *>(buf + H);  // N lags each, over buffers 0 / 1
+  __shared__ double s_off[2][4];
+  __shared__ unsigned int s_wtot[NWARP];
+  __shared__ unsigned int s_base;
+
+  const int tid = threadIdx.x, grp = tid / NG, gt = tid - grp * NG;
+  const float2 *__restrict__ wn = ws.wn;
+  TW::template load<NT>(s_tw, tid);
+  float4 *park = reinterpret_cast<float4 *>(scratch + (size_t)blockIdx.x * H);  // this CTA's scratch line (L2-resident)
+
+  for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+    __syncthreads();  // the previous pair's shared-memory contents are dead
+    const FusedJob J = jobs[job];
+    if (prep.flag[J.t_sig] == 0 || prep.flag[J.q_sig] == 0) {  // not pure A/C/G/T (or otherwise not prepared): hand back
+      if (tid == 0) {
+        const unsigned int i = atomicAdd(fail.n_pairs, 1u);
+        fail.pairs[i] = J.spi;
+        const unsigned int k = atomicAdd(fail.n_sigs, 2u);
+        fail.sigs[k] = J.t_sig;
+        fail.sigs[k + 1] = J.q_sig;
+      }
+      continue;
+    }
+    const SigDesc td = sigs[J.t_sig], qd = sigs[J.q_sig];
+    const int tlen = td.len, qlen = qd.len;
+    {
+      const uint32_t *pt = ws.planes + (size_t)td.slot * 2 * NW, *pq = ws.planes + (size_t)qd.slot * 2 * NW;
+      for (int w = tid; w < 2 * NW; w += NT) {
+        s_pl[w] = pt[w];
+        s_pl[2 * NW + w] = pq[w];
+      }
+      const float *wt = prep.went + (size_t)J.t_sig * 256, *wq = prep.went + (size_t)J.q_sig * 256;
+      for (int w = tid; w < 256; w += NT) {
+        s_went[w] = wt[w];
+        s_went[256 + w] = wq[w];
+      }
+      if (tid < 8) s_off[tid >> 2][tid & 3] = prep.off[(size_t)(tid < 4 ? J.t_sig : J.q_sig) * 4 + (tid & 3)];
+    }
+    __syncthreads();
+
+    // what this thread's group transforms: group 0 (A + iC) of the target, 1 (A + iC) of the query, 2 (G_t + i G_q)
+    const int sx_ = grp == 1 ? 1 : 0, sy = grp == 0 ? 0 : 1;  // chunk feeding the real / imaginary part
+    const uint32_t c0 = grp == 2 ? 2u : 0u, c1 = grp == 2 ? 2u : 1u;
+    const int len0 = sx_ ? qlen : tlen, len1 = sy ? qlen : tlen;
+    const bool flat0 = len0 < 1024, flat1 = len1 < 1024;  // "Skip entropy": weight 1 everywhere (CrossCorr.cc:39-44)
+    const double off0 = s_off[sx_][c0], off1 = s_off[sy][c1];
+    const double hit0 = __dsub_rn(1.0, off0), miss0 = __dsub_rn(0.0, off0);
+    const double hit1 = __dsub_rn(1.0, off1), miss1 = __dsub_rn(0.0, off1);
+    float2 *gb = buf + grp * H;
+    float4 *B0 = reinterpret_cast<float4 *>(buf), *B1 = reinterpret_cast<float4 *>(buf + H),
+           *B2 = reinterpret_cast<float4 *>(buf + 2 * H);
+
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+      // ---- signal of this half: e[n] = z[n] (even bins) / o[n] = z[n] w_N^n (odd bins); a chunk has z[n + H] = 0.
+      //      Same arithmetic as encode_fft_kernel's fast path, sample for sample.
+      for (int w = gt; w < H / WIN; w += NG) {
+        const int k0 = w * WIN;
+        const double e0 = flat0 ? 1.0 : (double)s_went[sx_ * 256 + w];
+        const double e1 = flat1 ? 1.0 : (double)s_went[sy * 256 + w];
+        const float h0 = __double2float_rn(__dmul_rn(e0, hit0)), m0 = __double2float_rn(__dmul_rn(e0, miss0));
+        const float h1 = __double2float_rn(__dmul_rn(e1, hit1)), m1 = __double2float_rn(__dmul_rn(e1, miss1));
+        const uint32_t *p0 = s_pl + sx_ * 2 * NW, *p1 = s_pl + sy * 2 * NW;
+        const uint32_t lo0 = p0[k0 >> 5] >> (k0 & 31), hi0 = p0[NW + (k0 >> 5)] >> (k0 & 31);
+        const uint32_t lo1 = p1[k0 >> 5] >> (k0 & 31), hi1 = p1[NW + (k0 >> 5)] >> (k0 & 31);
+        const uint32_t sel0 = ((c0 & 1u) ? lo0 : ~lo0) & ((c0 & 2u) ? hi0 : ~hi0);
+        const uint32_t sel1 = ((c1 & 1u) ? lo1 : ~lo1) & ((c1 & 2u) ? hi1 : ~hi1);
+        const float2 wb = half ? __ldg(wn + k0) : make_float2(1.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < WIN; j++) {
+          const int k = k0 + j;
+          float2 v;
+          v.x = k < len0 ? (((sel0 >> j) & 1u) ? h0 : m0) : 0.f;
+          v.y = k < len1 ? (((sel1 >> j) & 1u) ? h1 : m1) : 0.f;
+          if (half) {
+            constexpr double ang = -2.0 * 3.14159265358979323846 / (double)N;
+            const float2 st = make_float2((float)cx_cos_small(ang * j), (float)cx_sin_small(ang * j));
+            const float2 wk = j == 0 ? wb : cmul(wb, st);
+            v = cmul(v, wk);
+          }
+          gb[swz(k)] = v;
+        }
+      }
+      fused_group_barrier(grp);
+      // ---- forward H-point transform of this group's buffer
+      fft_pass<H, H, P::R0, false, NG>(gb, gt);
+      fused_group_barrier(grp);
+      fft_pass<H, L1, P::R1, false, NG>(gb, gt);
+      fused_group_barrier(grp);
+      fft_pass<H, L2, P::R2, false, NG>(gb, gt);
+      if constexpr (P::R3 > 1) {
+        fused_group_barrier(grp);
+        fft_pass<H, L3, P::R3, false, NG>(gb, gt);
+      }
+      __syncthreads();
+      // ---- product of this half in place over buffer 2 (see spectral_product): 4 (Pf + i Pr')
+      for (int it = tid; it < H / 4; it += NT) {
+        int pa0, pb0;
+        if (half == 0) {
+          const int r = (it / PPB) * LR + 2 * (it % PPB);
+          if (r < LR) continue;
+          const int m2 = (H - natural_bin<LOG2N>(r)) & (H - 1);
+          pa0 = swz(r);
+          pb0 = swz(scrambled_pos<LOG2N>(m2));
+        } else {
+          const int r = 2 * it;
+          pa0 = swz(r);
+          pb0 = swz(H - 1 - r);
+        }
+        const int qa = pa0 >> 1, qb = pb0 >> 1;
+        const float4 t1a = B0[qa], q1a = B1[qa], z3a = B2[qa];
+        float4 t1b = B0[qb], q1b = B1[qb], z3b = B2[qb];
+        const bool x = (pa0 ^ pb0) & 1;
+        if (x) {
+          t1b = make_float4(t1b.z, t1b.w, t1b.x, t1b.y);
+          q1b = make_float4(q1b.z, q1b.w, q1b.x, q1b.y);
+          z3b = make_float4(z3b.z, z3b.w, z3b.x, z3b.y);
+        }
+        auto lo = [](const float4 &v) { return make_float2(v.x, v.y); };
+        auto hi = [](const float4 &v) { return make_float2(v.z, v.w); };
+        float2 oa0, ob0, oa1, ob1;
+        pair_product<true>(channels2<ZM_RE>(lo(t1a), lo(t1b), lo(z3a), lo(z3b)), channels2<ZM_IM>(lo(q1a), lo(q1b), lo(z3a), lo(z3b)),
+                           oa0, ob0);
+        pair_product<true>(channels2<ZM_RE>(hi(t1a), hi(t1b), hi(z3a), hi(z3b)), channels2<ZM_IM>(hi(q1a), hi(q1b), hi(z3a), hi(z3b)),
+                           oa1, ob1);
+        B2[qa] = make_float4(oa0.x, oa0.y, oa1.x, oa1.y);
+        B2[qb] = x ? make_float4(ob1.x, ob1.y, ob0.x, ob0.y) : make_float4(ob0.x, ob0.y, ob1.x, ob1.y);
+      }
+      if (half == 0) {
+        for (int r = tid; r < LR / 2; r += NT) {  // first block of the even bins, slot by slot
+          const int m2 = (H - natural_bin<LOG2N>(r)) & (H - 1);
+          const int pa = swz(r), pb = swz(scrambled_pos<LOG2N>(m2));
+          float2 oa, ob;
+          pair_product<true>(channels2<ZM_RE>(buf[pa], buf[pb], buf[2 * H + pa], buf[2 * H + pb]),
+                             channels2<ZM_IM>(buf[H + pa], buf[H + pb], buf[2 * H + pa], buf[2 * H + pb]), oa, ob);
+          buf[2 * H + pa] = oa;
+          buf[2 * H + pb] = ob;
+        }
+      }
+      __syncthreads();
+      // reference quirk (CrossCorr.cc:480-492): bins H-1, H (and the mirror H+1) keep the target spectrum summed over
+      // the channels -- zero in the three-channel form
+      if (tid == 0) {
+        if (half == 0) {
+          buf[2 * H + bin_slot<LOG2N>(H)] = make_float2(0.f, 0.f);
+        } else {
+          buf[2 * H + bin_slot<LOG2N>(H - 1) - H] = make_float2(0.f, 0.f);
+          buf[2 * H + bin_slot<LOG2N>(H + 1) - H] = make_float2(0.f, 0.f);
+        }
+      }
+      __syncthreads();
+      // ---- inverse H-point transform of the product
+      if constexpr (P::R3 > 1) {
+        fft_pass<H, L3, P::R3, true, NT, true>(buf + 2 * H, tid, s_tw + TW::OFF3);
+        __syncthreads();
+      }
+      fft_pass<H, L2, P::R2, true, NT, true>(buf + 2 * H, tid, s_tw + TW::OFF2);
+      __syncthreads();
+      fft_pass<H, L1, P::R1, true, NT, true>(buf + 2 * H, tid, s_tw + TW::OFF1);
+      __syncthreads();
+      fft_pass<H, H, P::R0, true, NT, true>(buf + 2 * H, tid, s_tw + TW::OFF0);
+      __syncthreads();
+      if (half == 0) {  // park e[n]; every thread reads back exactly what it wrote
+        for (int i = tid; i < H / 2; i += NT) park[i] = B2[i];
+        __syncthreads();  // buffer 2 is generated into next
+      }
+    }
+    // ---- radix-2 combine x[n] = e[n] + w_N^{-n} o[n], x[n + H] = e[n] - w_N^{-n} o[n]; forward strand = real part,
+    //      reverse strand = imaginary part rotated by qlen - 1 lags; xc[i] = x[(i + H) mod N] / N (rescale + half
+    //      rotation, CrossCorr.cc:493-505), the factor 4 of the product
+    {
+      const float scale = 0.25f / (float)N;
+      const int offr = (H - (qlen - 1)) & (N - 1);
+      for (int i = tid; i < H / 2; i += NT) {
+        const float4 e4 = park[i], o4 = B2[i];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const int n = swz(2 * i + c);  // logical index of this physical slot (the swizzle is its own inverse)
+          const float2 e = c ? make_float2(e4.z, e4.w) : make_float2(e4.x, e4.y);
+          const float2 o = c ? make_float2(o4.z, o4.w) : make_float2(o4.x, o4.y);
+          const float2 t = cmulc(o, __ldg(wn + n));
+          const float2 lo = cadd(e, t), hi = csub(e, t);
+          xf[n + H] = lo.x * scale;
+          xf[n] = hi.x * scale;
+          xr[(n - offr) & (N - 1)] = lo.y * scale;
+          xr[(n + H - offr) & (N - 1)] = hi.y * scale;
+        }
+      }
+    }
+    __syncthreads();
+    const SpDesc sp = sps[J.spi];
+    const double co = (sp.flags & SP_FAST) ? cutoff_fast : cutoff;
+    auto at_f = [&](int i) -> float { return xf[i]; };
+    auto at_r = [&](int i) -> float { return xr[i]; };
+    findtop_impl<LOG2N, NT>(at_f, co, mask, s_wtot, &s_base, (int)J.spi, cand_pool, pool_cap, cand_ref, ctr, nullptr);
+    findtop_impl<LOG2N, NT>(at_r, co, mask, s_wtot, &s_base, (int)J.spi + 1, cand_pool, pool_cap, cand_ref, ctr, nullptr);
+    if (tid < 2) {  // what the scan kernel reads of the two slots (the planes are the preparation kernel's)
+      SlotMeta m;
+      m.len = tid ? qlen : tlen;
+      m.flags = 0;
+      m.q_re = m.q_im = m.q_nyq = 0.f;
+      m.zmode = ZM_FOUR;  // no stored spectrum
+      m.zslot = 0;
+      m.pad = 0;
+      ws.meta[tid ? qd.slot : td.slot] = m;
+    }
+  }
 }
 
 // ---- K2 for transforms that do not fit one CTA (N = 32768) ------------------------------------------
@@ -1765,6 +2039,16 @@ __global__ void __launch_bounds__(NT)
 // =================================================================================================
 // Launchers
 // =================================================================================================
+// Experiment knob (tools/dual_context_probe.py): SX_FFT_SMEM_KB=<n> requests at least n KiB of dynamic shared memory for
+// the transform kernels, i.e. caps their CTAs per SM so that CTAs of another context's scan kernel fit beside them.
+static size_t fft_smem_floor() {
+  static const size_t v = [] {
+    const char *e = getenv("SX_FFT_SMEM_KB");
+    return e ? (size_t)atoi(e) * 1024 : (size_t)0;
+  }();
+  return v;
+}
+
 template <int LOG2N>
 struct Cfg {
   static constexpr int NT = (LOG2N >= 14) ? 512 : 256;
@@ -1774,7 +2058,8 @@ struct Cfg {
 };
 
 template <int LOG2N>
-static cudaError_t encode_launch(const SigDesc *sigs, int nsig, Slots ws, float *tap, PrepBuf prep, cudaStream_t st) {
+static cudaError_t encode_launch(const SigDesc *sigs, int nsig, Slots ws, float *tap, PrepBuf prep, const uint32_t *enc_list,
+                                 int n_enc, cudaStream_t st) {
   constexpr int N = 1 << LOG2N, NT = Cfg<LOG2N>::NT;
   if constexpr (Cfg<LOG2N>::SPLIT) {  // one CTA per half signal
     const size_t smem = (size_t)(N / 2) * 8 + N + 512 * 4 + 128 * 2 + 256;
@@ -1784,7 +2069,7 @@ static cudaError_t encode_launch(const SigDesc *sigs, int nsig, Slots ws, float 
     k<<<dim3(nsig, 2), NT, smem, st>>>(sigs, ws, tap);
     return cudaGetLastError();
   } else {
-  const size_t smem = (size_t)N * 8 + N + 512 * 4 + 128 * 2 + 256;
+  const size_t smem = std::max((size_t)N * 8 + N + 512 * 4 + 128 * 2 + 256, fft_smem_floor());
   auto k = encode_fft_kernel<LOG2N, NT>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -1793,7 +2078,8 @@ static cudaError_t encode_launch(const SigDesc *sigs, int nsig, Slots ws, float 
     encode_prep_kernel<LOG2N><<<(nsig + 7) / 8, 256, 0, st>>>(sigs, nsig, ws, prep);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
-  k<<<nsig, NT, smem, st>>>(sigs, ws, tap, prep);
+  if (enc_list != nullptr && n_enc == 0) return cudaSuccess;
+  k<<<enc_list != nullptr ? n_enc : nsig, NT, smem, st>>>(sigs, ws, tap, prep, enc_list, nullptr);
   return cudaGetLastError();
   }
 }
@@ -1821,12 +2107,12 @@ static cudaError_t xcorr_launch(const SpDesc *sps, const uint32_t *pair_list, in
                                                  cand_pool, pool_cap, cand_ref, ctr, xc_tap);
     return cudaGetLastError();
   } else {
-  const size_t smem = (size_t)N * 8 + (N / 32) * 4 + (size_t)TwTables<LOG2N>::TOTAL * 8;
+  const size_t smem = std::max((size_t)N * 8 + (N / 32) * 4 + (size_t)TwTables<LOG2N>::TOTAL * 8, fft_smem_floor());
   if (n_pairs > 0) {
     auto k = xcorr_pair_kernel<LOG2N, NT>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<n_pairs, NT, smem, st>>>(pair_list, sps, ws, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
+    k<<<n_pairs, NT, smem, st>>>(pair_list, sps, ws, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, xc_tap, nullptr);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   if (n_direct > 0) {
@@ -1837,6 +2123,37 @@ static cudaError_t xcorr_launch(const SpDesc *sps, const uint32_t *pair_list, in
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   return cudaSuccess;
+  }
+}
+
+template <int LOG2N>
+static cudaError_t fused_launch(const FusedJob *jobs, int njobs, const SigDesc *sigs, const SpDesc *sps, Slots ws, PrepBuf prep,
+                                float2 *scratch, int grid, double cutoff, double cutoff_fast, uint16_t *cand_pool,
+                                unsigned int pool_cap, uint2 *cand_ref, BatchCounters *ctr, FusedFail fail, cudaStream_t st) {
+  if constexpr (LOG2N > 13) {
+    return cudaErrorInvalidValue;  // 3 x H complex points do not fit two CTAs per SM: the separate kernels do these sizes
+  } else {
+    constexpr int N = 1 << LOG2N, NT = Cfg<LOG2N>::NT;
+    auto k = pair_fused_kernel<LOG2N>;
+    const size_t smem = FusedCfg<LOG2N>::SMEM;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, SX_FUSED_NT, smem, st>>>(jobs, njobs, sigs, sps, ws, prep, scratch, cutoff, cutoff_fast, cand_pool, pool_cap,
+                                       cand_ref, ctr, fail);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // fall-backs (chunks with a letter other than A/C/G/T), normally none: fixed grids that leave at once
+    const int fb_grid = 148;
+    auto k1 = encode_fft_kernel<LOG2N, NT>;
+    const size_t smem1 = std::max((size_t)N * 8 + N + 512 * 4 + 128 * 2 + 256, fft_smem_floor());
+    if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1)) != cudaSuccess) return e;
+    k1<<<fb_grid, NT, smem1, st>>>(sigs, ws, nullptr, prep, fail.sigs, fail.n_sigs);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    auto k2 = xcorr_pair_kernel<LOG2N, NT>;
+    const size_t smem2 = std::max((size_t)N * 8 + (N / 32) * 4 + (size_t)TwTables<LOG2N>::TOTAL * 8, fft_smem_floor());
+    if ((e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)) != cudaSuccess) return e;
+    k2<<<fb_grid, NT, smem2, st>>>(fail.pairs, sps, ws, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, nullptr,
+                                   fail.n_pairs);
+    return cudaGetLastError();
   }
 }
 
@@ -1877,9 +2194,9 @@ static cudaError_t scan_launch(const SpDesc *sps, int nsp, Slots ws, const uint1
   }
 
 cudaError_t launch_encode_fft(int log2n, const SigDesc *sigs, int nsig, Slots ws, float *tap5n, PrepBuf prep,
-                              cudaStream_t stream) {
+                              const uint32_t *enc_list, int n_enc, cudaStream_t stream) {
   if (nsig <= 0) return cudaSuccess;
-#define CALL(L) encode_launch<L>(sigs, nsig, ws, tap5n, prep, stream)
+#define CALL(L) encode_launch<L>(sigs, nsig, ws, tap5n, prep, enc_list, n_enc, stream)
   SX_DISPATCH(log2n, CALL)
 #undef CALL
 }
@@ -1891,6 +2208,17 @@ cudaError_t launch_xcorr_findtop(int log2n, const SpDesc *sps, const uint32_t *p
                                  cudaStream_t stream) {
   if (n_pairs <= 0 && n_direct <= 0) return cudaSuccess;
 #define CALL(L) xcorr_launch<L>(sps, pair_list, n_pairs, direct_list, n_direct, ws, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, xc_tap, scratch, stream)
+  SX_DISPATCH(log2n, CALL)
+#undef CALL
+}
+
+bool log2n_fusable(int log2n) { return log2n >= 11 && log2n <= 13; }
+cudaError_t launch_pair_fused(int log2n, const FusedJob *jobs, int njobs, const SigDesc *sigs, const SpDesc *sps, Slots ws,
+                              PrepBuf prep, float2 *scratch, int grid, double cutoff, double cutoff_fast, uint16_t *cand_pool,
+                              unsigned int pool_cap, uint2 *cand_ref, BatchCounters *ctr, FusedFail fail,
+                              cudaStream_t stream) {
+  if (njobs <= 0) return cudaSuccess;
+#define CALL(L) fused_launch<L>(jobs, njobs, sigs, sps, ws, prep, scratch, grid, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, fail, stream)
   SX_DISPATCH(log2n, CALL)
 #undef CALL
 }

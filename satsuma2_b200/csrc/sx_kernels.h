@@ -52,7 +52,8 @@ struct SigDesc {  // one chunk signal to encode + transform
   int32_t g_mode = 0;      // G_NONE / G_OWNER / G_MEMBER
   int32_t g_partner = -1;  // index of the partner in the same descriptor array (-1: none)
 };
-enum { G_NONE = 0, G_OWNER = 1, G_MEMBER = 2 };
+enum { G_NONE = 0, G_OWNER = 1, G_MEMBER = 2, G_FUSED = 3 };  // G_FUSED: handled by pair_fused_kernel (g_partner = the
+                                                               // other chunk of the pair); the transform kernel skips it
 
 struct SpDesc {  // one strand-pair = target slot x query slot
   int32_t t_slot, q_slot;
@@ -109,7 +110,25 @@ struct PrepBuf {
   float *went;    // [nsig][256] entropy weight per window
   double *off;    // [nsig][4] channel means
 };
+// enc_list != nullptr: only the n_enc signals listed there are transformed (the preparation kernel still sees all nsig)
 cudaError_t launch_encode_fft(int log2n, const SigDesc *sigs, int nsig, Slots ws, float *tap5n, PrepBuf prep,
+                              const uint32_t *enc_list, int n_enc, cudaStream_t stream);
+
+// Fused transform + correlation of chunk pairs whose spectra nobody else needs (sx_kernels.cu, pair_fused_kernel).
+struct FusedJob {
+  uint32_t spi;           // forward strand-pair of the chunk pair (the reverse one is spi + 1)
+  uint32_t t_sig, q_sig;  // indices of the target / query signal in the batch's SigDesc array
+};
+struct FusedFail {  // pairs the fused kernel hands back (a chunk was not pure A/C/G/T); counters zeroed by the caller
+  unsigned int *n_pairs, *n_sigs;
+  uint32_t *pairs;  // forward strand-pair indices
+  uint32_t *sigs;   // signal indices, two per pair
+};
+bool log2n_fusable(int log2n);
+// grid CTAs (<= 2 per SM) stride over the jobs; scratch: grid x N/2 float2.  Also queues the fall-back kernels.
+cudaError_t launch_pair_fused(int log2n, const FusedJob *jobs, int njobs, const SigDesc *sigs, const SpDesc *sps, Slots ws,
+                              PrepBuf prep, float2 *scratch, int grid, double cutoff, double cutoff_fast, uint16_t *cand_pool,
+                              unsigned int pool_cap, uint2 *cand_ref, BatchCounters *ctr, FusedFail fail,
                               cudaStream_t stream);
 // pair_list: index of the forward strand-pair of every chunk pair whose reverse strand is derived from the
 // forward query spectrum (one CTA does both strands); direct_list: strand-pairs correlated one by one

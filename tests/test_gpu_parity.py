@@ -931,6 +931,32 @@ def test_three_channel_form_equals_four_channels(sx):
     assert both.tobytes() == outs[0][2].tobytes()
 
 
+def test_fused_pair_kernel_equals_separate_kernels(sx):
+    """Chunk pairs whose spectra nobody else in the batch needs go through ONE kernel (transforms, product, inverse,
+    FindTop; sx_kernels.cu pair_fused_kernel); debug_flags bit 3 keeps the separate transform and correlation kernels.
+    Identical records either way -- with pairs the fused kernel hands back (an IUPAC letter in one chunk), queries
+    whose reverse strand needs its own signal (never fused), chunks shared between pairs (never fused), ragged
+    lengths, several device batches, and with the target cache on and off."""
+    n = 500
+    tl, ql = _ragged_mixed_pairs(1618, n)
+    pairs = [(i, i) for i in range(n)] + [(i, i + 1) for i in range(0, 40, 2)]  # the first 40 chunks take part twice
+    key = ["query_id", "target_id", "tstart", "qstart", "len", "reverse"]
+    outs, fused = [], []
+    for flags in (0, 8):
+        for cache in (0, 1):
+            with sx.XCorrEngine(target_total=50000.0, debug_flags=flags, max_batch_pairs=128, spectra_cache_bytes=cache) as eng:
+                eng.set_targets(sx.ChunkSet.from_list(tl))
+                eng.set_queries(sx.ChunkSet.from_list(ql))
+                outs.append(np.sort(eng.align_pairs(pairs), order=key))
+                outs.append(np.sort(eng.align_pairs(pairs[:100]), order=key))  # second call on the same context
+                fused.append(eng.stats()["fused_pairs"])
+    assert fused[0] > 300 and fused[1] > 300 and fused[2] == 0 and fused[3] == 0, fused
+    assert len(outs[0]) > 300
+    for k in range(2, 8, 2):
+        assert outs[k].tobytes() == outs[0].tobytes(), k
+        assert outs[k + 1].tobytes() == outs[1].tobytes(), k
+
+
 @pytest.mark.parametrize("min_len,total", [(100, 1.6e6), (300, 4294967296.0), (47, 2.0e4)])
 def test_min_length_flag(sx, oracle_lib, min_len, total):
     """`-l` (Slave.cc:172): segments shorter than min_len are dropped whatever their probability -- also the shortest
