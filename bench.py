@@ -496,6 +496,10 @@ def main():
     ap.add_argument("--cpu-sample-per-core", type=int, default=400)
     ap.add_argument("--ref-pairs-per-core", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--debug-flags", type=int, default=0,
+                    help="sx_config::debug_flags of the headline engine (A/B runs: 4 = four channels per chunk)")
+    ap.add_argument("--fuse-pairs", type=int, default=0,
+                    help="sx_config::fuse_pairs of the headline engine (A/B runs: 1 = fused transform + correlation kernel)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (grid / chunk sizes / repeats)")
     ap.add_argument("--workload", default="pairs", choices=["pairs", "grid"],
                     help="pairs = configs[1] (the headline metric); grid = configs[3]-style block search of a synthetic "
@@ -543,7 +547,7 @@ def main():
     # spectra are never kept across steps (cache disabled): every step redoes the whole path
     target_total = args.target_total if args.target_total > 0 else float(n) * CHUNK
     eng = sx.XCorrEngine(device=local_rank, target_total=target_total, max_batch_pairs=args.batch,
-                         spectra_cache_bytes=-1, async_upload=1)
+                         spectra_cache_bytes=-1, async_upload=1, debug_flags=args.debug_flags, fuse_pairs=args.fuse_pairs)
     stream = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
     t_ptr, q_ptr = T.ctypes.data, Q.ctypes.data
     h2d_per_step = int(T.nbytes + Q.nbytes)

@@ -65,9 +65,12 @@ typedef struct {
                               this context returns.  Batches start as soon as the bases they need have arrived. */
   int32_t debug_flags;     /* test hooks; bit 0: score every raw segment (no run-length pruning in the scan
                               kernel); bit 1: prepare every signal inside the transform kernel (no preparation kernel);
-                              bit 2: transform all four channels of every chunk (no three-channel form);
-                              bit 3: separate transform and correlation kernels for every pair (no fused kernel) */
-  int32_t reserved[4];
+                              bit 2: transform all four channels of every chunk (no three-channel form) */
+  int32_t fuse_pairs;      /* 1: chunk pairs whose spectra nobody else in the batch needs (independent pairs, the guided
+                              refinement pass) go through ONE kernel -- transforms, product, inverse, peak scan -- and
+                              their spectra never reach HBM.  Identical records.  Default 0: on B200 the separate
+                              kernels are 3 % faster (both are bound by instruction issue, not by HBM) */
+  int32_t reserved[3];
 } sx_config;
 
 /* Fills *cfg with the reference's defaults (slave semantics). */

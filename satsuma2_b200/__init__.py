@@ -41,7 +41,7 @@ class Config(C.Structure):
         ("min_prob", C.c_double), ("prob_table_value", C.c_double), ("target_total", C.c_double),
         ("rc_coord_mode", C.c_int32), ("max_batch_pairs", C.c_int32), ("spectra_cache_bytes", C.c_int64),
         ("sort_results", C.c_int32), ("debug_small_pools", C.c_int32), ("async_upload", C.c_int32),
-        ("debug_flags", C.c_int32), ("reserved", C.c_int32 * 4),
+        ("debug_flags", C.c_int32), ("fuse_pairs", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 

@@ -114,7 +114,16 @@ struct sx_ctx {
   std::mutex mu;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // async_upload: host->device copies of the chunk blobs
-  cudaEvent_t ev[2][5] = {{nullptr, nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr, nullptr}};  // per batch in flight
+  // Descriptor uploads and the read-back of counters / records run on their own stream, tied to the compute stream by
+  // events: queued in the compute stream they would sit between the kernels of consecutive batches (measured: 0.19 ms
+  // of idle device per 5 ms batch)
+  cudaStream_t aux_stream = nullptr;   // read-backs (waits for the batch's last kernel)
+  cudaStream_t desc_stream = nullptr;  // descriptor uploads (never wait for a kernel)
+  cudaEvent_t ev_desc[2] = {nullptr, nullptr};  // descriptors of the batch are on the device
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};  // the last kernel of the batch has finished
+  cudaEvent_t ev_ctr[2] = {nullptr, nullptr};   // its counter block is on the host
+  cudaEvent_t ev_res = nullptr;                 // the records of the last fetched batch have left the result pool
+  cudaEvent_t ev[2][7] = {};  // per batch in flight: 0 early start, 1 transforms done, 5 fused kernel done, 6 rest starts, 2 correlation done, 3 scan done, 4 records fetched
   bool profiling = false;
   sx_stats stats;
 
@@ -145,20 +154,21 @@ struct sx_ctx {
   DevBuf<float> d_prep_went[2];    // flight: a batch that is re-run after a pool overflow still finds its own
   DevBuf<double> d_prep_off[2];
   // fused transform + correlation kernel (pair_fused_kernel)
-  DevBuf<FusedJob> d_fused;
+  DevBuf<FusedJob> d_fused[2];      // (the buffers marked [2] exist once per batch in flight: the fused kernel of the next
+                                    // batch is queued while the current one still scans)
   DevBuf<uint32_t> d_enc_list[2];   // signals left to the transform kernel when a batch has fused pairs
-  DevBuf<unsigned int> d_fail_ctr;  // {pairs, signals} handed back by the fused kernel
-  DevBuf<uint32_t> d_fail_pairs, d_fail_sigs;
+  DevBuf<unsigned int> d_fail_ctr[2];  // {pairs, signals} handed back by the fused kernel
+  DevBuf<uint32_t> d_fail_pairs[2], d_fail_sigs[2];
   DevBuf<float2> d_fused_scratch;   // one parked half-transform per resident CTA
   int fused_grid = 0;               // 2 CTAs per SM
   std::vector<int32_t> sig_of_slot, slot_uses;  // per slot, for the batch being staged (propose_fused)
-  DevBuf<SpDesc> d_sps;
-  DevBuf<uint2> d_cand_ref;
-  DevBuf<uint32_t> d_lists;  // [pair list | direct list] of strand-pair indices (launch_xcorr_findtop)
-  DevBuf<uint16_t> d_cand_pool;
+  DevBuf<SpDesc> d_sps[2];
+  DevBuf<uint2> d_cand_ref[2];
+  DevBuf<uint32_t> d_lists[2];  // [pair list | direct list] of strand-pair indices (launch_xcorr_findtop)
+  DevBuf<uint16_t> d_cand_pool[2];
   DevBuf<ResultRec> d_res;
   DevBuf<SegRec> d_seg_tap;
-  DevBuf<BatchCounters> d_ctr;
+  DevBuf<BatchCounters> d_ctr[2];
   DevBuf<double> d_table;
   DevBuf<float> d_tap;
   DevBuf<float2> d_scratch;  // split transforms (N = 32768): e[n] / o[n] of every correlation job between the two kernels
@@ -245,8 +255,16 @@ extern "C" int sx_create(const sx_config *cfg, sx_ctx **out) {
   c->target_total = cfg->target_total;
   cudaError_t ce = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&c->desc_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && ce == cudaSuccess; i++) {
+    ce = cudaEventCreateWithFlags(&c->ev_desc[i], cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_ctr[i], cudaEventDisableTiming);
+  }
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&c->ev_res, cudaEventDisableTiming);
   if (ce == cudaSuccess)
-    for (int i = 0; i < 10 && ce == cudaSuccess; i++) ce = cudaEventCreate(&c->ev[i / 5][i % 5]);
+    for (int i = 0; i < 14 && ce == cudaSuccess; i++) ce = cudaEventCreate(&c->ev[i / 7][i % 7]);
   if (ce == cudaSuccess) ce = upload_tables();
   if (ce == cudaSuccess) {
     int sms = 0;
@@ -257,7 +275,8 @@ extern "C" int sx_create(const sx_config *cfg, sx_ctx **out) {
     delete c;
     return fail(SX_ERR_CUDA, "sx_create: %s", cudaGetErrorString(ce));
   }
-  int rc = c->d_ctr.ensure(1);
+  int rc = c->d_ctr[0].ensure(1);
+  if (rc == SX_OK) rc = c->d_ctr[1].ensure(1);
   if (rc == SX_OK) rc = c->h_ctr.ensure(1);
   if (rc == SX_OK) rc = c->wn.ensure((size_t)c->N / 2);
   if (rc == SX_OK) {
@@ -293,19 +312,30 @@ extern "C" void sx_destroy(sx_ctx *c) {
   cudaSetDevice(c->cfg.device);
   cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
+  if (c->desc_stream) cudaStreamSynchronize(c->desc_stream);
   for (ChunkStore *S : {&c->T, &c->Q})
     for (cudaEvent_t e : S->piece_ev) cudaEventDestroy(e);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  if (c->desc_stream) cudaStreamDestroy(c->desc_stream);
+  for (int i = 0; i < 2; i++) {
+    if (c->ev_desc[i]) cudaEventDestroy(c->ev_desc[i]);
+    if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+    if (c->ev_ctr[i]) cudaEventDestroy(c->ev_ctr[i]);
+  }
+  if (c->ev_res) cudaEventDestroy(c->ev_res);
   if (c->T.d_bases) cudaFree(c->T.d_bases);
   if (c->Q.d_bases) cudaFree(c->Q.d_bases);
   c->spec.release(); c->planes.release(); c->sbytes.release(); c->meta.release(); c->wn.release(); c->ent_table.release(); c->drift.release();
-  c->d_lists.release(); c->h_lists[0].release(); c->h_lists[1].release();
+  c->d_lists[0].release(); c->d_lists[1].release(); c->h_lists[0].release(); c->h_lists[1].release();
   c->d_sigs[0].release(); c->d_sigs[1].release(); for (int i = 0; i < 2; i++) { c->d_prep_flag[i].release(); c->d_prep_went[i].release(); c->d_prep_off[i].release(); c->d_enc_list[i].release(); c->h_fused[i].release(); c->h_enc[i].release(); }
-  c->d_fused.release(); c->d_fail_ctr.release(); c->d_fail_pairs.release(); c->d_fail_sigs.release(); c->d_fused_scratch.release(); c->d_sps.release(); c->d_cand_ref.release(); c->d_cand_pool.release();
-  c->d_scratch.release(); c->d_res.release(); c->d_seg_tap.release(); c->d_ctr.release(); c->d_table.release(); c->d_tap.release();
+  for (int i = 0; i < 2; i++) { c->d_fused[i].release(); c->d_fail_ctr[i].release(); c->d_fail_pairs[i].release(); c->d_fail_sigs[i].release(); c->d_sps[i].release(); c->d_cand_ref[i].release(); c->d_cand_pool[i].release(); c->d_ctr[i].release(); }
+  c->d_fused_scratch.release();
+  c->d_scratch.release(); c->d_res.release(); c->d_seg_tap.release(); c->d_table.release(); c->d_tap.release();
   c->h_sigs[0].release(); c->h_sigs[1].release(); c->h_sps[0].release(); c->h_sps[1].release(); c->h_res.release(); c->h_ctr.release();
-  for (int i = 0; i < 10; i++)
-    if (c->ev[i / 5][i % 5]) cudaEventDestroy(c->ev[i / 5][i % 5]);
+  for (int i = 0; i < 14; i++)
+    if (c->ev[i / 7][i % 7]) cudaEventDestroy(c->ev[i / 7][i % 7]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -671,6 +701,8 @@ struct Run {  // one batch on the device: launched asynchronously, completed by 
   int nsig = 0, nsp = 0, n_pairlist = 0, n_direct = 0, n_fused = 0, n_enc = 0;
   bool need_encode = false, need_xcorr = true, active = false;
   bool early_done = false;  // descriptors of the signals uploaded and the encode kernel queued
+  bool fused_valid = false;  // the fused kernel queued by batch_launch_early has filled this batch's candidate pool;
+                             // the counter block was zeroed there
   unsigned long long n_cand_seen = 0;
   float *d_sig_tap = nullptr, *d_xc_tap = nullptr;
   SegRec *d_seg_tap = nullptr;
@@ -683,16 +715,54 @@ struct Run {  // one batch on the device: launched asynchronously, completed by 
 };
 }  // namespace
 
+// device pools of a batch (per batch in flight); debug_small_pools starts with pools that must overflow
+static int ensure_pools(sx_ctx *c, Run &r) {
+  const int nsp = r.nsp;
+  int rc;
+  if ((rc = c->d_sps[r.stage].ensure(std::max(nsp, 1))) != SX_OK) return rc;
+  if ((rc = c->d_cand_ref[r.stage].ensure(std::max(nsp, 1))) != SX_OK) return rc;
+  if (c->cfg.debug_small_pools) {  // test hook: start with pools that must overflow, so the grow-and-retry paths run
+    if (c->d_cand_pool[r.stage].n == 0 && (rc = c->d_cand_pool[r.stage].ensure(64)) != SX_OK) return rc;
+  } else if (c->d_cand_pool[r.stage].n < std::max<size_t>((size_t)nsp * 640, 1 << 16)) {
+    if ((rc = c->d_cand_pool[r.stage].ensure(std::max<size_t>((size_t)nsp * 640, 1 << 16))) != SX_OK) return rc;
+  }
+  if (r.n_fused) {
+    if ((rc = c->d_fused[r.stage].ensure((size_t)r.n_fused)) != SX_OK) return rc;
+    if ((rc = c->d_fail_ctr[r.stage].ensure(2)) != SX_OK) return rc;
+    if ((rc = c->d_fail_pairs[r.stage].ensure((size_t)r.n_fused)) != SX_OK) return rc;
+    if ((rc = c->d_fail_sigs[r.stage].ensure((size_t)2 * r.n_fused)) != SX_OK) return rc;
+    if ((rc = c->d_fused_scratch.ensure((size_t)c->fused_grid * ((size_t)c->N / 2))) != SX_OK) return rc;
+  }
+  return SX_OK;
+}
+
+// The fused kernel of a batch (chunk pairs whose spectra nobody else needs: transforms, product, inverse and FindTop
+// in one kernel) and, right behind it, the separate kernels over the pairs it hands back (letters other than A/C/G/T).
+// Writes this batch's own candidate pool and counter block.
+static int launch_fused(sx_ctx *c, Run &r) {
+  cudaStream_t st = c->stream;
+  CU(cudaMemsetAsync(c->d_fail_ctr[r.stage].p, 0, 2 * sizeof(unsigned int), st));
+  PrepBuf prep = {c->d_prep_flag[r.stage].p, c->d_prep_went[r.stage].p, c->d_prep_off[r.stage].p};
+  FusedFail ff = {c->d_fail_ctr[r.stage].p, c->d_fail_ctr[r.stage].p + 1, c->d_fail_pairs[r.stage].p, c->d_fail_sigs[r.stage].p};
+  CU(launch_pair_fused(c->log2n, c->d_fused[r.stage].p, r.n_fused, c->d_sigs[r.stage].p, c->d_sps[r.stage].p, c->slots(), prep,
+                       c->d_fused_scratch.p, std::min(c->fused_grid, r.n_fused), c->cfg.cutoff, c->cfg.cutoff_fast,
+                       c->d_cand_pool[r.stage].p, (unsigned int)std::min<size_t>(c->d_cand_pool[r.stage].n, 0xfffffff0u),
+                       c->d_cand_ref[r.stage].p, c->d_ctr[r.stage].p, ff, st));
+  c->stats.kernel_launches += 3;
+  return SX_OK;
+}
+
 // (re)launch the correlation and scan kernels of a batch and the asynchronous read-back of its counter block
-// (the encode kernel has been queued by batch_launch_early)
+// (the encode kernel -- and the fused kernel, the first time round -- have been queued by batch_launch_early)
 static int batch_kernels(sx_ctx *c, Run &r) {
   cudaStream_t st = c->stream;
   const bool prof = c->profiling;
   const Slots ws = c->slots();
   const ScoreParams prm = score_params(c);
   cudaEvent_t *ev = c->ev[r.stage];
-  CU(cudaMemsetAsync(c->d_ctr.p, 0, sizeof(BatchCounters), st));
-  if (prof) CU(cudaEventRecord(ev[1], st));
+  if (prof) CU(cudaEventRecord(ev[6], st));
+  const bool keep_fused = r.fused_valid && r.need_xcorr;  // first attempt: counters and candidates of the fused pairs stand
+  if (!keep_fused) CU(cudaMemsetAsync(c->d_ctr[r.stage].p, 0, sizeof(BatchCounters), st));
   if (r.nsp && r.need_xcorr && r.tap && r.tap->ext_xc) {
     // SeqAnalyzer::MatchUp with the caller's correlation vector: no strand-pair has candidates except the selected
     // one, whose candidates are FindTop of that vector
@@ -700,36 +770,35 @@ static int batch_kernels(sx_ctx *c, Run &r) {
     int rc = c->d_tap.ensure(N);
     if (rc != SX_OK) return rc;
     CU(cudaMemcpyAsync(c->d_tap.p, r.tap->ext_xc, sizeof(float) * N, cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(c->d_cand_ref.p, 0, sizeof(uint2) * (size_t)r.nsp, st));
-    CU(launch_findtop_external(c->log2n, c->d_tap.p, r.tap->sp_select, r.tap->ext_cutoff, c->d_cand_pool.p,
-                               (unsigned int)std::min<size_t>(c->d_cand_pool.n, 0xfffffff0u), c->d_cand_ref.p, c->d_ctr.p, st));
+    CU(cudaMemsetAsync(c->d_cand_ref[r.stage].p, 0, sizeof(uint2) * (size_t)r.nsp, st));
+    CU(launch_findtop_external(c->log2n, c->d_tap.p, r.tap->sp_select, r.tap->ext_cutoff, c->d_cand_pool[r.stage].p,
+                               (unsigned int)std::min<size_t>(c->d_cand_pool[r.stage].n, 0xfffffff0u), c->d_cand_ref[r.stage].p, c->d_ctr[r.stage].p, st));
     c->stats.kernel_launches += 1;
   } else if (r.nsp && r.need_xcorr) {
-    if (r.n_fused) {
-      // chunk pairs whose spectra nobody else needs: transforms, product, inverse and FindTop in one kernel; the pairs
-      // it hands back (letters other than A/C/G/T) go through the separate kernels queued right behind it
-      CU(cudaMemsetAsync(c->d_fail_ctr.p, 0, 2 * sizeof(unsigned int), st));
-      PrepBuf prep = {c->d_prep_flag[r.stage].p, c->d_prep_went[r.stage].p, c->d_prep_off[r.stage].p};
-      FusedFail ff = {c->d_fail_ctr.p, c->d_fail_ctr.p + 1, c->d_fail_pairs.p, c->d_fail_sigs.p};
-      CU(launch_pair_fused(c->log2n, c->d_fused.p, r.n_fused, c->d_sigs[r.stage].p, c->d_sps.p, ws, prep, c->d_fused_scratch.p,
-                           std::min(c->fused_grid, r.n_fused), c->cfg.cutoff, c->cfg.cutoff_fast, c->d_cand_pool.p,
-                           (unsigned int)std::min<size_t>(c->d_cand_pool.n, 0xfffffff0u), c->d_cand_ref.p, c->d_ctr.p, ff, st));
-      c->stats.kernel_launches += 3;
+    if (r.n_fused && !keep_fused) {  // a re-run after a pool overflow
+      int rc = launch_fused(c, r);
+      if (rc != SX_OK) return rc;
     }
-    CU(launch_xcorr_findtop(c->log2n, c->d_sps.p, c->d_lists.p, r.n_pairlist, c->d_lists.p + r.n_pairlist, r.n_direct, ws,
-                            c->cfg.cutoff, c->cfg.cutoff_fast, c->d_cand_pool.p,
-                            (unsigned int)std::min<size_t>(c->d_cand_pool.n, 0xfffffff0u), c->d_cand_ref.p, c->d_ctr.p,
+    CU(launch_xcorr_findtop(c->log2n, c->d_sps[r.stage].p, c->d_lists[r.stage].p, r.n_pairlist, c->d_lists[r.stage].p + r.n_pairlist, r.n_direct, ws,
+                            c->cfg.cutoff, c->cfg.cutoff_fast, c->d_cand_pool[r.stage].p,
+                            (unsigned int)std::min<size_t>(c->d_cand_pool[r.stage].n, 0xfffffff0u), c->d_cand_ref[r.stage].p, c->d_ctr[r.stage].p,
                             r.d_xc_tap, c->d_scratch.p, st));
     c->stats.kernel_launches += log2n_split(c->log2n) ? 2 : (r.n_pairlist > 0) + (r.n_direct > 0);
   }
+  r.fused_valid = false;  // any further attempt starts from zeroed counters
   if (prof) CU(cudaEventRecord(ev[2], st));
   if (r.nsp) {
-    CU(launch_scan_score(c->log2n, c->d_sps.p, r.nsp, ws, c->d_cand_pool.p, c->d_cand_ref.p, prm, c->d_res.p,
-                         (unsigned int)std::min<size_t>(c->d_res.n, 0xfffffff0u), r.d_seg_tap, r.seg_tap_cap, c->d_ctr.p, st));
+    CU(cudaStreamWaitEvent(st, c->ev_res, 0));  // the previous batch's records have left the result pool
+    CU(launch_scan_score(c->log2n, c->d_sps[r.stage].p, r.nsp, ws, c->d_cand_pool[r.stage].p, c->d_cand_ref[r.stage].p, prm, c->d_res.p,
+                         (unsigned int)std::min<size_t>(c->d_res.n, 0xfffffff0u), r.d_seg_tap, r.seg_tap_cap, c->d_ctr[r.stage].p, st));
     c->stats.kernel_launches += 2;
   }
   if (prof) CU(cudaEventRecord(ev[3], st));
-  CU(cudaMemcpyAsync(c->h_ctr.p, c->d_ctr.p, sizeof(BatchCounters), cudaMemcpyDeviceToHost, st));
+  // the counter block comes back on the auxiliary stream: the compute stream goes straight on to the next batch
+  CU(cudaEventRecord(c->ev_done[r.stage], st));
+  CU(cudaStreamWaitEvent(c->aux_stream, c->ev_done[r.stage], 0));
+  CU(cudaMemcpyAsync(c->h_ctr.p, c->d_ctr[r.stage].p, sizeof(BatchCounters), cudaMemcpyDeviceToHost, c->aux_stream));
+  CU(cudaEventRecord(c->ev_ctr[r.stage], c->aux_stream));
   return SX_OK;
 }
 
@@ -829,7 +898,7 @@ static int batch_stage(sx_ctx *c, Run &r, Batch &b, TapRequest *tap, int stage) 
   // the three-channel form and the fused kernel both build on the preparation kernel (batch_launch_early)
   const bool prep_on = !log2n_split(c->log2n) && !(c->cfg.debug_flags & 2) && !(tap && tap->sig5n);
   const bool three = prep_on && !(c->cfg.debug_flags & 4);
-  propose_fused(c, b, three && !(c->cfg.debug_flags & 8) && log2n_fusable(c->log2n) && tap == nullptr && c->fused_grid > 0);
+  propose_fused(c, b, three && c->cfg.fuse_pairs == 1 && log2n_fusable(c->log2n) && tap == nullptr && c->fused_grid > 0);
   propose_g_partners(c, b, three);
   int rc;
   if ((rc = c->h_sigs[stage].ensure(std::max(nsig, 1))) != SX_OK) return rc;
@@ -878,9 +947,27 @@ static int batch_launch_early(sx_ctx *c, Run &r) {
     if ((rc = upload_pieces(c, S, upto)) != SX_OK) return rc;
     CU(cudaStreamWaitEvent(st, S.piece_ev[upto - 1], 0));
   }
-  if (nsig) {
-    CU(cudaMemcpyAsync(c->d_sigs[r.stage].p, c->h_sigs[r.stage].p, sizeof(SigDesc) * nsig, cudaMemcpyHostToDevice, st));
-    c->stats.h2d_bytes += (int64_t)(sizeof(SigDesc) * nsig);
+  // every descriptor of the batch travels on the auxiliary stream, beside whatever the compute stream is still doing
+  // for the previous batch; the compute stream picks them up through an event
+  if ((rc = ensure_pools(c, r)) != SX_OK) return rc;
+  if ((rc = c->d_lists[r.stage].ensure(std::max(r.n_pairlist + r.n_direct, 1))) != SX_OK) return rc;
+  if (r.n_fused && (rc = c->d_enc_list[r.stage].ensure((size_t)std::max(r.n_enc, 1))) != SX_OK) return rc;
+  {
+    cudaStream_t ax = c->desc_stream;
+    int64_t bytes = 0;
+    auto up = [&](void *dst, const void *src, size_t n) -> cudaError_t {
+      if (n == 0) return cudaSuccess;
+      bytes += (int64_t)n;
+      return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, ax);
+    };
+    CU(up(c->d_sigs[r.stage].p, c->h_sigs[r.stage].p, sizeof(SigDesc) * nsig));
+    if (r.n_fused) CU(up(c->d_enc_list[r.stage].p, c->h_enc[r.stage].p, sizeof(uint32_t) * r.n_enc));
+    CU(up(c->d_sps[r.stage].p, c->h_sps[r.stage].p, sizeof(SpDesc) * nsp));
+    CU(up(c->d_fused[r.stage].p, c->h_fused[r.stage].p, sizeof(FusedJob) * r.n_fused));
+    CU(up(c->d_lists[r.stage].p, c->h_lists[r.stage].p, sizeof(uint32_t) * (r.n_pairlist + r.n_direct)));
+    c->stats.h2d_bytes += bytes;
+    CU(cudaEventRecord(c->ev_desc[r.stage], ax));
+    CU(cudaStreamWaitEvent(st, c->ev_desc[r.stage], 0));
   }
   if (c->profiling) CU(cudaEventRecord(c->ev[r.stage][0], st));
   if (nsig) {
@@ -893,17 +980,19 @@ static int batch_launch_early(sx_ctx *c, Run &r) {
       prep.went = c->d_prep_went[r.stage].p;
       prep.off = c->d_prep_off[r.stage].p;
     }
-    const uint32_t *enc_list = nullptr;
-    if (r.n_fused) {  // the transform kernel only does the signals the fused kernel does not take
-      if ((rc = c->d_enc_list[r.stage].ensure((size_t)std::max(r.n_enc, 1))) != SX_OK) return rc;
-      if (r.n_enc) {
-        CU(cudaMemcpyAsync(c->d_enc_list[r.stage].p, c->h_enc[r.stage].p, sizeof(uint32_t) * r.n_enc, cudaMemcpyHostToDevice, st));
-        c->stats.h2d_bytes += (int64_t)(sizeof(uint32_t) * r.n_enc);
-      }
-      enc_list = c->d_enc_list[r.stage].p;
-    }
+    // with fused pairs the transform kernel only does the signals the fused kernel does not take
+    const uint32_t *enc_list = r.n_fused ? c->d_enc_list[r.stage].p : nullptr;
     CU(launch_encode_fft(c->log2n, c->d_sigs[r.stage].p, nsig, c->slots(), r.d_sig_tap, prep, enc_list, r.n_enc, st));
     c->stats.kernel_launches += (prep.flag ? 1 : 0) + ((enc_list == nullptr || r.n_enc > 0) ? 1 : 0);
+  }
+  if (c->profiling) CU(cudaEventRecord(c->ev[r.stage][1], st));
+  // the fused kernel fills this batch's own candidate pool: the device goes from the previous batch's scan straight
+  // into it
+  if (r.n_fused) {
+    CU(cudaMemsetAsync(c->d_ctr[r.stage].p, 0, sizeof(BatchCounters), st));
+    if ((rc = launch_fused(c, r)) != SX_OK) return rc;
+    r.fused_valid = true;
+    if (c->profiling) CU(cudaEventRecord(c->ev[r.stage][5], st));
   }
   r.need_encode = nsig > 0;  // only tells batch_wait that this batch had an encode kernel to account for
   r.early_done = true;
@@ -919,37 +1008,13 @@ static int batch_launch(sx_ctx *c, Run &r) {
   const size_t N = (size_t)c->N;
   int rc;
   if ((rc = batch_launch_early(c, r)) != SX_OK) return rc;
-  if ((rc = c->d_sps.ensure(std::max(nsp, 1))) != SX_OK) return rc;
-  if ((rc = c->d_cand_ref.ensure(std::max(nsp, 1))) != SX_OK) return rc;
-  if ((rc = c->d_lists.ensure(std::max(r.n_pairlist + r.n_direct, 1))) != SX_OK) return rc;
   if (log2n_split(c->log2n) && (rc = c->d_scratch.ensure((size_t)std::max(r.n_pairlist + r.n_direct, 1) * N)) != SX_OK)
     return rc;
-  if (c->cfg.debug_small_pools) {  // test hook: start with pools that must overflow, so the grow-and-retry paths run
-    if (c->d_cand_pool.n == 0 && (rc = c->d_cand_pool.ensure(64)) != SX_OK) return rc;
+  if (c->cfg.debug_small_pools) {
     if (c->d_res.n == 0 && (rc = c->d_res.ensure(4)) != SX_OK) return rc;
   } else {
-    if (c->d_cand_pool.n < std::max<size_t>((size_t)nsp * 640, 1 << 16) &&
-        (rc = c->d_cand_pool.ensure(std::max<size_t>((size_t)nsp * 640, 1 << 16))) != SX_OK)
-      return rc;
     if (c->d_res.n == 0 && (rc = c->d_res.ensure(std::max<size_t>((size_t)nsp * 8, 1 << 16))) != SX_OK) return rc;
   }
-  if (r.n_fused) {
-    if ((rc = c->d_fused.ensure((size_t)r.n_fused)) != SX_OK) return rc;
-    if ((rc = c->d_fail_ctr.ensure(2)) != SX_OK) return rc;
-    if ((rc = c->d_fail_pairs.ensure((size_t)r.n_fused)) != SX_OK) return rc;
-    if ((rc = c->d_fail_sigs.ensure((size_t)2 * r.n_fused)) != SX_OK) return rc;
-    if ((rc = c->d_fused_scratch.ensure((size_t)c->fused_grid * (N / 2))) != SX_OK) return rc;
-  }
-  cudaStream_t st = c->stream;
-  if (nsp) CU(cudaMemcpyAsync(c->d_sps.p, c->h_sps[r.stage].p, sizeof(SpDesc) * nsp, cudaMemcpyHostToDevice, st));
-  if (r.n_fused) {
-    CU(cudaMemcpyAsync(c->d_fused.p, c->h_fused[r.stage].p, sizeof(FusedJob) * r.n_fused, cudaMemcpyHostToDevice, st));
-    c->stats.h2d_bytes += (int64_t)(sizeof(FusedJob) * r.n_fused);
-  }
-  if (r.n_pairlist + r.n_direct)
-    CU(cudaMemcpyAsync(c->d_lists.p, c->h_lists[r.stage].p, sizeof(uint32_t) * (r.n_pairlist + r.n_direct),
-                       cudaMemcpyHostToDevice, st));
-  c->stats.h2d_bytes += (int64_t)(sizeof(SpDesc) * nsp + sizeof(uint32_t) * (r.n_pairlist + r.n_direct));
   if (tap && tap->segs) {
     if ((rc = c->d_seg_tap.ensure((size_t)1 << 20)) != SX_OK) return rc;
     r.d_seg_tap = c->d_seg_tap.p;
@@ -988,31 +1053,41 @@ static int batch_wait(sx_ctx *c, Run &r) {
   if (!r.active) return SX_OK;
   r.active = false;
   const int nsig = r.nsig, nsp = r.nsp;
-  cudaStream_t st = c->stream;
   const bool prof = c->profiling;
   int rc;
   for (int attempt = 0; attempt < 8; attempt++) {
     if (attempt > 0 && (rc = batch_kernels(c, r)) != SX_OK) return rc;
-    CU(cudaStreamSynchronize(st));
+    CU(cudaEventSynchronize(c->ev_ctr[r.stage]));
     c->stats.d2h_bytes += (int64_t)sizeof(BatchCounters);
     if (prof) {
       float ms = 0;
       cudaEvent_t *ev = c->ev[r.stage];
-      // ev[0] .. ev[1] spans the encode kernel plus whatever the stream did before the rest of this batch was
-      // queued (nothing when the host keeps up: the encode kernel hides the host's turnaround)
-      if (r.need_encode) { cudaEventElapsedTime(&ms, ev[0], ev[1]); c->stats.ms_encode_fft += ms; }
-      if (nsp && r.need_xcorr) { cudaEventElapsedTime(&ms, ev[1], ev[2]); c->stats.ms_xcorr += ms; }
-      if (nsp) { cudaEventElapsedTime(&ms, ev[2], ev[3]); c->stats.ms_scan_score += ms; }
-      cudaEventElapsedTime(&ms, r.need_encode ? ev[0] : ev[1], ev[3]);
-      c->stats.ms_total += ms;
+      // ev[0] .. ev[1]: preparation + transform kernels; ev[1] .. ev[5]: the fused kernel (queued with them); ev[6] ..
+      // ev[2]: separate correlation kernels (and the fused one again when a batch is re-run); ev[2] .. ev[3]: scan
+      float tot = 0;
+      if (r.need_encode) { cudaEventElapsedTime(&ms, ev[0], ev[1]); c->stats.ms_encode_fft += ms; tot += ms; }
+      if (r.need_encode && r.n_fused) { cudaEventElapsedTime(&ms, ev[1], ev[5]); c->stats.ms_xcorr += ms; tot += ms; }
+      if (nsp && r.need_xcorr) { cudaEventElapsedTime(&ms, ev[6], ev[2]); c->stats.ms_xcorr += ms; tot += ms; }
+      if (nsp) { cudaEventElapsedTime(&ms, ev[2], ev[3]); c->stats.ms_scan_score += ms; tot += ms; }
+      c->stats.ms_total += tot;
+      if (getenv("SX_GAP_DEBUG") && attempt == 0) {  // where the stream idles between the kernels of consecutive batches
+        static double g_a = 0, g_b = 0, g_c = 0;
+        static int g_n = 0;
+        cudaEvent_t *pv = c->ev[r.stage ^ 1];
+        if (r.need_encode && cudaEventElapsedTime(&ms, pv[3], ev[0]) == cudaSuccess && ms > 0 && ms < 50) g_a += ms;
+        if (cudaEventElapsedTime(&ms, r.n_fused ? ev[5] : ev[1], ev[6]) == cudaSuccess) g_b += ms;
+        if (cudaEventElapsedTime(&ms, ev[0], ev[3]) == cudaSuccess) g_c += ms;
+        (void)cudaGetLastError();  // an event that was never recorded (first batch) makes cudaEventElapsedTime fail
+        if (++g_n % 64 == 0) fprintf(stderr, "[gap] batches %d: scan(b-1)->start(b) %.3f ms, early->rest %.3f ms, start->end %.3f ms (avg per batch)\n", g_n, g_a / g_n, g_b / g_n, g_c / g_n);
+      }
     }
     const BatchCounters ctr = *c->h_ctr.p;
     r.need_encode = false;  // spectra of this batch are in place now
     if (r.need_xcorr) r.n_cand_seen = ctr.cand_used;  // every candidate reserves one pool entry, overflowing or not
     if (ctr.status & ST_CAND_OVERFLOW) {
       // the candidate pool was too small: grow to what the kernel asked for and redo K2+K3
-      const size_t want = std::max<size_t>((size_t)ctr.cand_used + (ctr.cand_used >> 2), c->d_cand_pool.n * 2);
-      if ((rc = c->d_cand_pool.ensure(want)) != SX_OK) return rc;
+      const size_t want = std::max<size_t>((size_t)ctr.cand_used + (ctr.cand_used >> 2), c->d_cand_pool[r.stage].n * 2);
+      if ((rc = c->d_cand_pool[r.stage].ensure(want)) != SX_OK) return rc;
       c->stats.retries++;
       r.need_xcorr = true;
       continue;
@@ -1042,10 +1117,11 @@ static int batch_wait(sx_ctx *c, Run &r) {
     r.fetching = true;
     if (ctr.res_used) {
       if ((rc = c->h_res.ensure(ctr.res_used)) != SX_OK) return rc;
-      CU(cudaMemcpyAsync(c->h_res.p, c->d_res.p, sizeof(ResultRec) * ctr.res_used, cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(c->h_res.p, c->d_res.p, sizeof(ResultRec) * ctr.res_used, cudaMemcpyDeviceToHost, c->aux_stream));
       c->stats.d2h_bytes += (int64_t)(sizeof(ResultRec) * ctr.res_used);
     }
-    CU(cudaEventRecord(c->ev[r.stage][4], st));
+    CU(cudaEventRecord(c->ev[r.stage][4], c->aux_stream));
+    CU(cudaEventRecord(c->ev_res, c->aux_stream));
     return SX_OK;
   }
   return fail(SX_ERR_CUDA, "device pools kept overflowing after 8 attempts");
@@ -1087,12 +1163,12 @@ static int batch_collect(sx_ctx *c, Run &r, ResultSink *results) {
     }
     if (tap->cands && nsp) {
       std::vector<uint2> refs(nsp);
-      CU(cudaMemcpy(refs.data(), c->d_cand_ref.p, sizeof(uint2) * nsp, cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(refs.data(), c->d_cand_ref[r.stage].p, sizeof(uint2) * nsp, cudaMemcpyDeviceToHost));
       tap->cands->clear();
       for (int s2 = 0; s2 < nsp; s2++) {
         if (sel >= 0 && s2 != sel) continue;
         std::vector<uint16_t> tmp(refs[s2].y);
-        if (refs[s2].y) CU(cudaMemcpy(tmp.data(), c->d_cand_pool.p + refs[s2].x, sizeof(uint16_t) * refs[s2].y, cudaMemcpyDeviceToHost));
+        if (refs[s2].y) CU(cudaMemcpy(tmp.data(), c->d_cand_pool[r.stage].p + refs[s2].x, sizeof(uint16_t) * refs[s2].y, cudaMemcpyDeviceToHost));
         for (uint16_t v : tmp) tap->cands->push_back((int32_t)v);
       }
     }

@@ -771,12 +771,20 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
             }
           }
         }
+        // bases past the end of a chunk give zero samples: one mask per window instead of a test per sample
+        const uint32_t in0 = k0 + WIN <= len ? 0xffffffffu : (k0 < len ? (1u << (len - k0)) - 1u : 0u);
+        const uint32_t in1 = k0 + WIN <= len1 ? 0xffffffffu : (k0 < len1 ? (1u << (len1 - k0)) - 1u : 0u);
+        const bool full = (in0 & in1) == 0xffffffffu;
 #pragma unroll
         for (int j = 0; j < WIN; j++) {
           const int k = k0 + j;
           float2 v;
-          v.x = k < len ? (((sel0 >> j) & 1u) ? h0 : m0) : 0.f;
-          v.y = k < len1 ? (((sel1 >> j) & 1u) ? h1 : m1) : 0.f;
+          v.x = ((sel0 >> j) & 1u) ? h0 : m0;
+          v.y = ((sel1 >> j) & 1u) ? h1 : m1;
+          if (!full) {
+            if (!((in0 >> j) & 1u)) v.x = 0.f;
+            if (!((in1 >> j) & 1u)) v.y = 0.f;
+          }
           constexpr double ang = -2.0 * 3.14159265358979323846 / (double)N;
           const float2 st = make_float2((float)cx_cos_small(ang * j), (float)cx_sin_small(ang * j));
           const float2 wk = j == 0 ? wb : cmul(wb, st);
@@ -1528,12 +1536,21 @@ __global__ void __launch_bounds__(SX_FUSED_NT, 2)
         const uint32_t sel0 = ((c0 & 1u) ? lo0 : ~lo0) & ((c0 & 2u) ? hi0 : ~hi0);
         const uint32_t sel1 = ((c1 & 1u) ? lo1 : ~lo1) & ((c1 & 2u) ? hi1 : ~hi1);
         const float2 wb = half ? __ldg(wn + k0) : make_float2(1.f, 0.f);
+        // bases past the end of a chunk give zero samples: cut the selection masks once per window instead of
+        // testing every sample (zero = neither "hit" nor "miss": a second mask)
+        const uint32_t in0 = k0 + WIN <= len0 ? 0xffffffffu : (k0 < len0 ? (1u << (len0 - k0)) - 1u : 0u);
+        const uint32_t in1 = k0 + WIN <= len1 ? 0xffffffffu : (k0 < len1 ? (1u << (len1 - k0)) - 1u : 0u);
+        const bool full = (in0 & in1) == 0xffffffffu;
 #pragma unroll
         for (int j = 0; j < WIN; j++) {
           const int k = k0 + j;
           float2 v;
-          v.x = k < len0 ? (((sel0 >> j) & 1u) ? h0 : m0) : 0.f;
-          v.y = k < len1 ? (((sel1 >> j) & 1u) ? h1 : m1) : 0.f;
+          v.x = ((sel0 >> j) & 1u) ? h0 : m0;
+          v.y = ((sel1 >> j) & 1u) ? h1 : m1;
+          if (!full) {
+            if (!((in0 >> j) & 1u)) v.x = 0.f;
+            if (!((in1 >> j) & 1u)) v.y = 0.f;
+          }
           if (half) {
             constexpr double ang = -2.0 * 3.14159265358979323846 / (double)N;
             const float2 st = make_float2((float)cx_cos_small(ang * j), (float)cx_sin_small(ang * j));

@@ -933,7 +933,7 @@ def test_three_channel_form_equals_four_channels(sx):
 
 def test_fused_pair_kernel_equals_separate_kernels(sx):
     """Chunk pairs whose spectra nobody else in the batch needs go through ONE kernel (transforms, product, inverse,
-    FindTop; sx_kernels.cu pair_fused_kernel); debug_flags bit 3 keeps the separate transform and correlation kernels.
+    FindTop; sx_kernels.cu pair_fused_kernel) when sx_config::fuse_pairs is set; the default keeps the separate kernels.
     Identical records either way -- with pairs the fused kernel hands back (an IUPAC letter in one chunk), queries
     whose reverse strand needs its own signal (never fused), chunks shared between pairs (never fused), ragged
     lengths, several device batches, and with the target cache on and off."""
@@ -942,9 +942,9 @@ def test_fused_pair_kernel_equals_separate_kernels(sx):
     pairs = [(i, i) for i in range(n)] + [(i, i + 1) for i in range(0, 40, 2)]  # the first 40 chunks take part twice
     key = ["query_id", "target_id", "tstart", "qstart", "len", "reverse"]
     outs, fused = [], []
-    for flags in (0, 8):
+    for fuse in (1, 0):
         for cache in (0, 1):
-            with sx.XCorrEngine(target_total=50000.0, debug_flags=flags, max_batch_pairs=128, spectra_cache_bytes=cache) as eng:
+            with sx.XCorrEngine(target_total=50000.0, fuse_pairs=fuse, max_batch_pairs=128, spectra_cache_bytes=cache) as eng:
                 eng.set_targets(sx.ChunkSet.from_list(tl))
                 eng.set_queries(sx.ChunkSet.from_list(ql))
                 outs.append(np.sort(eng.align_pairs(pairs), order=key))
