@@ -65,7 +65,9 @@ typedef struct {
                               this context returns.  Batches start as soon as the bases they need have arrived. */
   int32_t debug_flags;     /* test hooks; bit 0: score every raw segment (no run-length pruning in the scan
                               kernel); bit 1: prepare every signal inside the transform kernel (no preparation kernel);
-                              bit 2: transform all four channels of every chunk (no three-channel form) */
+                              bit 2: transform all four channels of every chunk (no three-channel form);
+                              bit 3: N = 32768 through the three-kernel route (two half kernels + combine kernel over an
+                              HBM scratch buffer) instead of one kernel with a two-CTA cluster per strand-pair */
   int32_t fuse_pairs;      /* 1: chunk pairs whose spectra nobody else in the batch needs (independent pairs, the guided
                               refinement pass) go through ONE kernel -- transforms, product, inverse, peak scan -- and
                               their spectra never reach HBM.  Identical records.  Default 0: on B200 the separate

@@ -782,8 +782,9 @@ static int batch_kernels(sx_ctx *c, Run &r) {
     CU(launch_xcorr_findtop(c->log2n, c->d_sps[r.stage].p, c->d_lists[r.stage].p, r.n_pairlist, c->d_lists[r.stage].p + r.n_pairlist, r.n_direct, ws,
                             c->cfg.cutoff, c->cfg.cutoff_fast, c->d_cand_pool[r.stage].p,
                             (unsigned int)std::min<size_t>(c->d_cand_pool[r.stage].n, 0xfffffff0u), c->d_cand_ref[r.stage].p, c->d_ctr[r.stage].p,
-                            r.d_xc_tap, c->d_scratch.p, st));
-    c->stats.kernel_launches += log2n_split(c->log2n) ? 2 : (r.n_pairlist > 0) + (r.n_direct > 0);
+                            r.d_xc_tap, c->d_scratch.p, (c->cfg.debug_flags & 8) != 0, st));
+    const bool three = (c->cfg.debug_flags & 8) != 0 || r.n_pairlist > 0;  // split sizes: half kernels + combine kernel
+    c->stats.kernel_launches += log2n_split(c->log2n) ? (three ? 2 : 1) : (r.n_pairlist > 0) + (r.n_direct > 0);
   }
   r.fused_valid = false;  // any further attempt starts from zeroed counters
   if (prof) CU(cudaEventRecord(ev[2], st));
@@ -1008,7 +1009,8 @@ static int batch_launch(sx_ctx *c, Run &r) {
   const size_t N = (size_t)c->N;
   int rc;
   if ((rc = batch_launch_early(c, r)) != SX_OK) return rc;
-  if (log2n_split(c->log2n) && (rc = c->d_scratch.ensure((size_t)std::max(r.n_pairlist + r.n_direct, 1) * N)) != SX_OK)
+  if (log2n_split(c->log2n) && ((c->cfg.debug_flags & 8) != 0 || r.n_pairlist > 0) &&
+      (rc = c->d_scratch.ensure((size_t)std::max(r.n_pairlist + r.n_direct, 1) * N)) != SX_OK)
     return rc;
   if (c->cfg.debug_small_pools) {
     if (c->d_res.n == 0 && (rc = c->d_res.ensure(4)) != SX_OK) return rc;

@@ -25,6 +25,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -1783,6 +1784,150 @@ __global__ void __launch_bounds__(NT, 1)
   for (int n = tid; n < H; n += NT) out[n] = buf[swz(n)];
 }
 
+// ---- N = 32768 as ONE kernel: a cluster of two CTAs per strand-pair, one per half of the radix-2 split ----------
+// Product, quirk bins, drift pre-correction and the H-point inverse of its half as in xcorr_half_kernel; then the
+// radix-2 combine through DISTRIBUTED SHARED MEMORY: CTA 0 holds e[n], CTA 1 holds o[n]; index n is handled by exactly
+// one thread of the cluster (CTA 0 the lower half of the indices, CTA 1 the upper), which reads e[n] and o[n] -- one of
+// them from the other SM -- and writes x[n] = e[n] + w_N^{-n} o[n] over e[n] and x[n + H] = e[n] - w_N^{-n} o[n] over
+// o[n].  No scratch buffer, no second kernel.  After the rescale + half rotation lag i is x[(i + H) mod N], so CTA 1
+// now holds lags [0, H) and CTA 0 lags [H, N): each runs FindTop over its own lags (RMS envelope per 256 lags,
+// threshold, ballot mask) and the two compact into ONE ascending candidate list: they exchange their counts, the CTA
+// with the lower lags reserves the pool entries for both.
+template <int LOG2N, int NT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
+    xcorr_cluster_kernel(const uint32_t *__restrict__ direct_list, const SpDesc *__restrict__ sps, Slots ws, double cutoff,
+                         double cutoff_fast, uint16_t *__restrict__ cand_pool, unsigned int pool_cap,
+                         uint2 *__restrict__ cand_ref, BatchCounters *ctr, float *__restrict__ xc_tap) {
+  namespace cg = cooperative_groups;
+  constexpr int N = 1 << LOG2N, H = N / 2, NWL = H / 32, NBL = H / 256, NWARP = NT / 32;
+  static_assert(NWL <= NT, "one mask word per thread");
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *buf = reinterpret_cast<float2 *>(smem_raw);         // H complex: this CTA's half
+  float2 *s_tw = buf + H;                                      // TwTables<LOG2N>::TOTAL inverse-pass twiddles
+  uint32_t *mask = reinterpret_cast<uint32_t *>(s_tw + TwTables<LOG2N>::TOTAL);  // NWL words: this CTA's lags
+  __shared__ unsigned int s_wtot[NWARP];
+  __shared__ unsigned int s_peer_total, s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = (int)cluster.block_rank(), job = blockIdx.x >> 1;
+  TwTables<LOG2N>::template load<NT>(s_tw, tid);  // used after the barriers below
+  const int spi = (int)direct_list[job];
+  const SpDesc sp = sps[spi];
+  const SlotMeta tm = ws.meta[sp.t_slot];
+  {
+    // product of one strand: P = conj(U1) V1 + conj(U2) V2 over this half's bins (bin order is irrelevant here)
+    const float4 *u1 = reinterpret_cast<const float4 *>(ws.spec + ((size_t)sp.t_slot * 2) * N + (size_t)half * H), *u2 = u1 + N / 2;
+    const float4 *v1 = reinterpret_cast<const float4 *>(ws.spec + ((size_t)sp.q_slot * 2) * N + (size_t)half * H), *v2 = v1 + N / 2;
+    float4 *dst = reinterpret_cast<float4 *>(buf);
+#pragma unroll 2
+    for (int k = tid; k < H / 2; k += NT) {
+      const float4 a1 = __ldg(u1 + k), a2 = __ldg(u2 + k), b1 = __ldg(v1 + k), b2 = __ldg(v2 + k);
+      float4 p;
+      p.x = (b1.x * a1.x + b1.y * a1.y) + (b2.x * a2.x + b2.y * a2.y);
+      p.y = (b1.y * a1.x - b1.x * a1.y) + (b2.y * a2.x - b2.x * a2.y);
+      p.z = (b1.z * a1.z + b1.w * a1.w) + (b2.z * a2.z + b2.w * a2.w);
+      p.w = (b1.w * a1.z - b1.z * a1.w) + (b2.w * a2.z - b2.z * a2.w);
+      dst[k] = p;
+    }
+    __syncthreads();
+    if (tid == 0) {  // reference quirk (CrossCorr.cc:480-492): bins H-1 and H keep the TARGET spectrum
+      constexpr int PH1 = bin_slot<LOG2N>(H - 1) - H, PH2 = bin_slot<LOG2N>(H + 1) - H, PH = bin_slot<LOG2N>(H);
+      if (half == 1) {
+        buf[PH1] = make_float2(tm.q_re, tm.q_im);
+        buf[PH2] = make_float2(tm.q_re, -tm.q_im);
+      } else {
+        buf[PH] = make_float2(tm.q_nyq, 0.f);
+      }
+    }
+    __syncthreads();
+  }
+  if constexpr (LOG2N == 15) drift_correct_half<LOG2N, NT, true>(buf, ws.drift, half, tid);
+  fft_inverse_halves<LOG2N, H, NT>(buf, tid, s_tw);  // natural order, swizzled slots; ends with a barrier
+  cluster.sync();
+  {
+    float2 *peer = cluster.map_shared_rank(buf, half ^ 1);
+    float2 *eb = half == 0 ? buf : peer, *ob = half == 0 ? peer : buf;  // CTA 0's buffer: e -> x[0, H); CTA 1's: o -> x[H, N)
+    const float2 *__restrict__ wn = ws.wn;
+    for (int n = half * (H / 2) + tid; n < (half + 1) * (H / 2); n += NT) {
+      const int slot = swz(n);
+      const float2 e = eb[slot], o = ob[slot];
+      const float2 t = cmulc(o, __ldg(wn + n));
+      eb[slot] = cadd(e, t);
+      ob[slot] = csub(e, t);
+    }
+  }
+  cluster.sync();
+  // ---- FindTop over this CTA's lags: lag = lag0 + j with xc = Re buf[j] / N
+  const int lag0 = half == 1 ? 0 : H;
+  const float scale = 1.0f / (float)N;
+  const double co = (sp.flags & SP_FAST) ? cutoff_fast : cutoff;
+  auto xc_at = [&](int j) -> float { return buf[swz(j)].x * scale; };
+  if (xc_tap != nullptr) {
+    float *o = xc_tap + (size_t)spi * N + lag0;
+    for (int j = tid; j < H; j += NT) o[j] = xc_at(j);
+  }
+  for (int b = warp; b < NBL; b += NWARP) {  // see findtop_impl
+    float v[8];
+    double acc = 0.;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      v[r] = xc_at(b * 256 + r * 32 + lane);
+      acc += (double)__fmul_rn(v[r], v[r]);
+    }
+    acc = warp_sum(acc);
+    const double thr = __dadd_rn(__dmul_rn(__dsqrt_rn(__ddiv_rn(acc, 256.0)), co), 1.0);
+    const float thr_f = __double2float_rd(thr);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const uint32_t m = __ballot_sync(0xffffffffu, v[r] > thr_f);
+      if (lane == 0) mask[b * 8 + r] = m;
+    }
+  }
+  __syncthreads();
+  const unsigned int mine = tid < NWL ? __popc(mask[tid]) : 0u;
+  unsigned int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_wtot[warp] = incl;
+  __syncthreads();
+  unsigned int wbase = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < NWARP; w++) {
+    if (w < warp) wbase += s_wtot[w];
+    total += s_wtot[w];
+  }
+  if (tid == 0) *cluster.map_shared_rank(&s_peer_total, half ^ 1) = total;
+  cluster.sync();
+  if (half == 1 && tid == 0) {  // the CTA with the lower lags reserves for both
+    const unsigned int both = total + s_peer_total;
+    unsigned int base = 0;
+    if (both > 0) {
+      base = atomicAdd(&ctr->cand_used, both);
+      if (base + both > pool_cap) {
+        atomicOr(&ctr->status, (unsigned int)ST_CAND_OVERFLOW);
+        base = 0xffffffffu;
+      }
+    }
+    cand_ref[spi] = make_uint2(base, both);
+    s_base = base;
+    *cluster.map_shared_rank(&s_base, 0) = base == 0xffffffffu ? base : base + total;
+  }
+  cluster.sync();
+  const unsigned int base = s_base;
+  if (base != 0xffffffffu && mine > 0) {
+    unsigned int o = base + wbase + (incl - mine);
+    uint32_t m = mask[tid];
+    while (m) {
+      const int bit = __ffs(m) - 1;
+      m &= m - 1;
+      cand_pool[o++] = (uint16_t)(lag0 + tid * 32 + bit);
+    }
+  }
+}
+
 template <int LOG2N, int NT>
 __global__ void __launch_bounds__(NT, 1)
     combine_findtop_kernel(const uint32_t *__restrict__ pair_list, int n_pairs, const uint32_t *__restrict__ direct_list,
@@ -2105,9 +2250,17 @@ template <int LOG2N>
 static cudaError_t xcorr_launch(const SpDesc *sps, const uint32_t *pair_list, int n_pairs, const uint32_t *direct_list,
                                 int n_direct, Slots ws, double cutoff, double cutoff_fast, uint16_t *cand_pool,
                                 unsigned int pool_cap, uint2 *cand_ref, BatchCounters *ctr, float *xc_tap,
-                                float2 *scratch, cudaStream_t st) {
+                                float2 *scratch, bool split_three_kernels, cudaStream_t st) {
   constexpr int N = 1 << LOG2N, NT = Cfg<LOG2N>::NT;
   if constexpr (Cfg<LOG2N>::SPLIT) {
+    if (n_pairs == 0 && !split_three_kernels) {  // one cluster of two CTAs per strand-pair, combine through DSMEM
+      auto kc = xcorr_cluster_kernel<LOG2N, NT>;
+      const size_t smemc = (size_t)(N / 2) * 8 + (size_t)TwTables<LOG2N>::TOTAL * 8 + (size_t)(N / 64) * 4;
+      cudaError_t e = cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemc);
+      if (e != cudaSuccess) return e;
+      kc<<<2 * n_direct, NT, smemc, st>>>(direct_list, sps, ws, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, xc_tap);
+      return cudaGetLastError();
+    }
     if (scratch == nullptr) return cudaErrorInvalidValue;
     const int jobs = n_pairs + n_direct;
     auto k1 = xcorr_half_kernel<LOG2N, NT>;
@@ -2222,9 +2375,9 @@ cudaError_t launch_xcorr_findtop(int log2n, const SpDesc *sps, const uint32_t *p
                                  const uint32_t *direct_list, int n_direct, Slots ws, double cutoff,
                                  double cutoff_fast, uint16_t *cand_pool, unsigned int pool_cap,
                                  uint2 *cand_ref, BatchCounters *ctr, float *xc_tap, float2 *scratch,
-                                 cudaStream_t stream) {
+                                 bool split_three_kernels, cudaStream_t stream) {
   if (n_pairs <= 0 && n_direct <= 0) return cudaSuccess;
-#define CALL(L) xcorr_launch<L>(sps, pair_list, n_pairs, direct_list, n_direct, ws, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, xc_tap, scratch, stream)
+#define CALL(L) xcorr_launch<L>(sps, pair_list, n_pairs, direct_list, n_direct, ws, cutoff, cutoff_fast, cand_pool, pool_cap, cand_ref, ctr, xc_tap, scratch, split_three_kernels, stream)
   SX_DISPATCH(log2n, CALL)
 #undef CALL
 }

@@ -136,7 +136,9 @@ cudaError_t launch_xcorr_findtop(int log2n, const SpDesc *sps, const uint32_t *p
                                  const uint32_t *direct_list, int n_direct, Slots ws, double cutoff,
                                  double cutoff_fast, uint16_t *cand_pool, unsigned int pool_cap,
                                  uint2 *cand_ref, BatchCounters *ctr, float *xc_tap, float2 *scratch,
-                                 cudaStream_t stream);
+                                 bool split_three_kernels, cudaStream_t stream);  // split_three_kernels: N = 32768 through
+                                 // two half kernels + a combine kernel and the scratch buffer (the round-1 route, kept for
+                                 // comparison) instead of one kernel with a cluster of two CTAs per strand-pair
 // candidates of strand-pair `spi` from a correlation vector supplied by the caller (N floats, device memory)
 cudaError_t launch_findtop_external(int log2n, const float *xc, int spi, double cutoff, uint16_t *cand_pool,
                                     unsigned int pool_cap, uint2 *cand_ref, BatchCounters *ctr, cudaStream_t stream);

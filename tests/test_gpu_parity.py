@@ -931,6 +931,36 @@ def test_three_channel_form_equals_four_channels(sx):
     assert both.tobytes() == outs[0][2].tobytes()
 
 
+def test_cluster_kernel_equals_three_kernel_route_n32768(sx):
+    """N = 32768 (16384-base chunks): the correlation of a strand-pair is ONE kernel, a cluster of two CTAs that combine
+    their half transforms through distributed shared memory and share FindTop; debug_flags bit 3 takes the round-1 route
+    (two half kernels, an HBM scratch buffer, a combine kernel).  Same correlation vectors (1e-6 of the maximum), same
+    candidate lists, identical records, ragged lengths included."""
+    from satsuma2_b200 import synth
+
+    n, chunk = 24, 16384
+    T, Q, _ = synth.random_pairs(n, chunk, seed=77)
+    rng = np.random.default_rng(5)
+    tl = [(T[i, : (chunk if i % 3 else int(rng.integers(5000, chunk)))].tobytes(), 0, i, chunk) for i in range(n)]
+    ql = [(Q[i, : (chunk if i % 4 else int(rng.integers(5000, chunk)))].tobytes(), 0, i, chunk) for i in range(n)]
+    pairs = [(i, i) for i in range(n)] + [(i, (i + 1) % n) for i in range(0, n, 5)]
+    out = []
+    for flags in (0, 8):
+        with sx.XCorrEngine(t_chunk=chunk, q_chunk=chunk, target_total=float(n * chunk), debug_flags=flags, max_batch_pairs=10) as eng:
+            eng.set_targets(sx.ChunkSet.from_list(tl))
+            eng.set_queries(sx.ChunkSet.from_list(ql))
+            rec = np.sort(eng.align_pairs(pairs), order=["query_id", "target_id", "tstart", "qstart", "len", "reverse"])
+            xcs = [eng.tap_xcorr(i, i, st) for i in (0, 3, 4) for st in (0, 1)]
+            cands = [eng.tap_candidates(i, i, st) for i in (0, 3, 4) for st in (0, 1)]
+            out.append((rec, xcs, cands))
+    assert len(out[0][0]) >= 10
+    assert out[0][0].tobytes() == out[1][0].tobytes()
+    for a, b in zip(out[0][1], out[1][1]):
+        assert xc_rel_err(a, b) < 1e-6
+    for a, b in zip(out[0][2], out[1][2]):
+        assert len(a) > 100 and np.array_equal(a, b)
+
+
 def test_fused_pair_kernel_equals_separate_kernels(sx):
     """Chunk pairs whose spectra nobody else in the batch needs go through ONE kernel (transforms, product, inverse,
     FindTop; sx_kernels.cu pair_fused_kernel) when sx_config::fuse_pairs is set; the default keeps the separate kernels.
