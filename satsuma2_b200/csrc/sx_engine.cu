@@ -973,7 +973,7 @@ static int batch_launch_early(sx_ctx *c, Run &r) {
   if (c->profiling) CU(cudaEventRecord(c->ev[r.stage][0], st));
   if (nsig) {
     PrepBuf prep = {nullptr, nullptr, nullptr};
-    if (!log2n_split(c->log2n) && r.d_sig_tap == nullptr && !(c->cfg.debug_flags & 2)) {
+    if (r.d_sig_tap == nullptr && !(c->cfg.debug_flags & 2)) {
       if ((rc = c->d_prep_flag[r.stage].ensure((size_t)nsig)) != SX_OK) return rc;
       if ((rc = c->d_prep_went[r.stage].ensure((size_t)nsig * 256)) != SX_OK) return rc;
       if ((rc = c->d_prep_off[r.stage].ensure((size_t)nsig * 4)) != SX_OK) return rc;

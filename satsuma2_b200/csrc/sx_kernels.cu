@@ -522,17 +522,20 @@ __device__ __forceinline__ int encode_prepare(const SigDesc &sd, const Slots &ws
 template <int LOG2N>
 __global__ void __launch_bounds__(256) encode_prep_kernel(const SigDesc *__restrict__ sigs, int nsig, Slots ws, PrepBuf prep) {
   constexpr int N = 1 << LOG2N, H = N / 2, NW = N / 32, WIN = N / 512, WMAX = H / WIN;
-  static_assert(WIN <= 32, "one plane word per entropy window");
+  static_assert(WIN <= 64, "at most two plane words per entropy window");
   __shared__ uint32_t s_plw[8][2 * (NW / 2)];  // plane words of at most H bases, per warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sig = blockIdx.x * 8 + warp;
   if (sig >= nsig) return;
   const SigDesc sd = sigs[sig];
   const int len = sd.len;
-  if (sd.strand != 0 || len > H || len <= 0) {
+  if (len > H || len <= 0) {
     if (lane == 0) prep.flag[sig] = 0;
     return;
   }
+  // an explicit reverse-strand signal (a query whose reverse strand cannot be derived from its forward spectrum): its
+  // planes are the bit-reversed inverted forward planes, written to its slot first and read back for the window counts
+  const bool rc_sig = sd.strand != 0;
   constexpr int NWH = NW / 2;
   uint32_t *s_pl = s_plw[warp];
   const uint8_t *__restrict__ src = sd.src;
@@ -576,15 +579,15 @@ __global__ void __launch_bounds__(256) encode_prep_kernel(const SigDesc *__restr
     return;
   }
   __syncwarp();
-  {
-    uint32_t *planes = ws.planes + (size_t)sd.slot * 2 * NW;
+  uint32_t *own_planes = ws.planes + (size_t)sd.slot * 2 * NW;
+  if (!rc_sig) {
     for (int w = lane; w < NW; w += 32) {
-      planes[w] = w < nwords ? s_pl[w] : 0u;
-      planes[NW + w] = w < nwords ? s_pl[NWH + w] : 0u;
+      own_planes[w] = w < nwords ? s_pl[w] : 0u;
+      own_planes[NW + w] = w < nwords ? s_pl[NWH + w] : 0u;
     }
   }
-  if (sd.rc_slot1) {  // planes and meta of the other orientation (see encode_prepare)
-    const int oslot = sd.rc_slot1 - 1;
+  if (sd.rc_slot1 || rc_sig) {  // planes (and meta) of the other orientation (see encode_prepare)
+    const int oslot = rc_sig ? sd.slot : sd.rc_slot1 - 1;
     uint32_t *planes = ws.planes + (size_t)oslot * 2 * NW;
     const int q = (len - 1) >> 5, r = (len - 1) & 31;
     for (int j = lane; j < NW; j += 32) {
@@ -603,7 +606,7 @@ __global__ void __launch_bounds__(256) encode_prep_kernel(const SigDesc *__restr
       planes[j] = lo;
       planes[NW + j] = hi;
     }
-    if (lane == 0) {
+    if (lane == 0 && !rc_sig) {
       SlotMeta m;
       m.len = len;
       m.flags = 0;
@@ -613,7 +616,13 @@ __global__ void __launch_bounds__(256) encode_prep_kernel(const SigDesc *__restr
       m.pad = 0;
       ws.meta[oslot] = m;
     }
+    __syncwarp();  // rc_sig: the window counts below read these words back
   }
+  // plane word w of this signal's own orientation (zero past the chunk's last word)
+  auto plane_word = [&](int p, int w) -> uint32_t {
+    if (w >= nwords) return 0u;
+    return rc_sig ? own_planes[p * NW + w] : s_pl[p * NWH + w];
+  };
   // entropy weights per window and base totals (integer counts are the exact double sums of the reference)
   int totC = 0, totG = 0, totT = 0;
   const int nwin = (len + WIN - 1) / WIN;
@@ -622,9 +631,22 @@ __global__ void __launch_bounds__(256) encode_prep_kernel(const SigDesc *__restr
     float v = 0.f;
     if (w < nwin) {
       const int i0 = w * WIN, k = min(WIN, len - i0);
-      const uint32_t wm = k >= 32 ? 0xffffffffu : ((1u << k) - 1u);
-      const uint32_t lo = (s_pl[i0 >> 5] >> (i0 & 31)) & wm, hi = (s_pl[NWH + (i0 >> 5)] >> (i0 & 31)) & wm;
-      const int cntT = __popc(lo & hi), cntC = __popc(lo & ~hi), cntG = __popc(hi & ~lo);
+      int cntT = 0, cntC = 0, cntG = 0;
+      if (WIN <= 32) {
+        const uint32_t wm = k >= 32 ? 0xffffffffu : ((1u << k) - 1u);
+        const uint32_t lo = (plane_word(0, i0 >> 5) >> (i0 & 31)) & wm, hi = (plane_word(1, i0 >> 5) >> (i0 & 31)) & wm;
+        cntT = __popc(lo & hi);
+        cntC = __popc(lo & ~hi);
+        cntG = __popc(hi & ~lo);
+      } else {  // windows of 64 bases = two plane words (bits past the end of the chunk are zero)
+#pragma unroll
+        for (int h = 0; h < WIN / 32; h++) {
+          const uint32_t lo = plane_word(0, (i0 >> 5) + h), hi = plane_word(1, (i0 >> 5) + h);
+          cntT += __popc(lo & hi);
+          cntC += __popc(lo & ~hi);
+          cntG += __popc(hi & ~lo);
+        }
+      }
       const int cnt[4] = {k - cntT - cntC - cntG, cntC, cntG, cntT};
       totC += cntC;
       totG += cntG;
@@ -937,7 +959,7 @@ __device__ __forceinline__ void drift_correct_half(float2 *buf, const float2 *__
 // H-1 and H+1 are odd (half 1), bin H is even (half 0): the meta fields are written field by field.
 template <int LOG2N, int NT>
 __global__ void __launch_bounds__(NT, 1)
-    encode_fft_half_kernel(const SigDesc *__restrict__ sigs, Slots ws, float *__restrict__ tap) {
+    encode_fft_half_kernel(const SigDesc *__restrict__ sigs, Slots ws, float *__restrict__ tap, PrepBuf prep) {
   constexpr int N = 1 << LOG2N, H = N / 2, WIN = N / 512, NWARP = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *buf = reinterpret_cast<float2 *>(smem_raw);            // H complex (swizzled slots)
@@ -956,8 +978,22 @@ __global__ void __launch_bounds__(NT, 1)
   const int len = sd.len;
   const float2 *__restrict__ wn = ws.wn;
 
-  const int flags = encode_prepare<LOG2N, NT>(sd, ws, smem_raw, sb, went, s_fcode, s_comp, s_base2, s_red, s_off, &s_flags,
-                                              half == 0);
+  // prepared by encode_prep_kernel (pure A/C/G/T, at most H bases; either strand): pick up the oriented planes, window
+  // weights and means; otherwise both CTAs of the signal prepare it themselves
+  const bool prepared = prep.flag != nullptr && tap == nullptr && prep.flag[blockIdx.x] != 0;
+  uint32_t *s_pl2 = reinterpret_cast<uint32_t *>(sb);  // prepared: plane words [2][N/32] in place of the bases
+  int flags = 0;
+  if (prepared) {
+    constexpr int NWp = N / 32;
+    const uint32_t *pl = ws.planes + (size_t)sd.slot * 2 * NWp;
+    for (int w = tid; w < 2 * NWp; w += NT) s_pl2[w] = pl[w];
+    const float *wsrc = prep.went + (size_t)blockIdx.x * (H / WIN);
+    for (int w = tid; w < H / WIN; w += NT) went[w] = wsrc[w];
+    if (tid < 4) s_off[tid] = prep.off[(size_t)blockIdx.x * 4 + tid];
+    __syncthreads();
+  } else {
+    flags = encode_prepare<LOG2N, NT>(sd, ws, smem_raw, sb, went, s_fcode, s_comp, s_base2, s_red, s_off, &s_flags, half == 0);
+  }
   const bool flat = len < 1024;  // "Skip entropy": weight 1 everywhere (CrossCorr.cc:39-44)
   const bool pure = !(flags & SLOT_NONACGT);
   if (tap != nullptr && half == 0) {
@@ -999,9 +1035,44 @@ __global__ void __launch_bounds__(NT, 1)
         ts[N + k] = v.y;
       }
     }
-    for (int n = tid; n < H; n += NT) {
-      const float2 a = sample(n), b = sample(n + H);
-      buf[swz(n)] = half == 0 ? cadd(a, b) : cmul(csub(a, b), __ldg(wn + n));
+    if (prepared) {
+      // the chunk has at most H bases, so z[n + H] = 0: e[n] = z[n], o[n] = z[n] w_N^n.  One thread per 32 samples of
+      // a window: inside a window the sample is one of two floats per channel, rounded exactly as the per-base double
+      // product of the reference (see encode_fft_kernel); the base only selects between them.
+      constexpr int NWp = N / 32;
+      const uint32_t c0 = 2 * pr, c1 = 2 * pr + 1;
+      const double hit0 = __dsub_rn(1.0, off0), miss0 = __dsub_rn(0.0, off0);
+      const double hit1 = __dsub_rn(1.0, off1), miss1 = __dsub_rn(0.0, off1);
+      constexpr int SEG = WIN < 32 ? WIN : 32;  // samples per thread step
+      for (int sg = tid; sg < H / SEG; sg += NT) {
+        const int k0 = sg * SEG, w = k0 / WIN;
+        const double e = flat ? 1.0 : (double)went[w];
+        const float h0 = __double2float_rn(__dmul_rn(e, hit0)), m0 = __double2float_rn(__dmul_rn(e, miss0));
+        const float h1 = __double2float_rn(__dmul_rn(e, hit1)), m1 = __double2float_rn(__dmul_rn(e, miss1));
+        const uint32_t lo = s_pl2[k0 >> 5] >> (k0 & 31), hi = s_pl2[NWp + (k0 >> 5)] >> (k0 & 31);
+        const uint32_t sel0 = ((c0 & 1u) ? lo : ~lo) & ((c0 & 2u) ? hi : ~hi);
+        const uint32_t sel1 = ((c1 & 1u) ? lo : ~lo) & ((c1 & 2u) ? hi : ~hi);
+        const uint32_t in = k0 + SEG <= len ? 0xffffffffu : (k0 < len ? (1u << (len - k0)) - 1u : 0u);
+        const float2 wb = half ? __ldg(wn + k0) : make_float2(1.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < SEG; j++) {
+          float2 v;
+          v.x = ((sel0 >> j) & 1u) ? h0 : m0;
+          v.y = ((sel1 >> j) & 1u) ? h1 : m1;
+          if (!((in >> j) & 1u)) v = make_float2(0.f, 0.f);
+          if (half) {
+            constexpr double ang = -2.0 * 3.14159265358979323846 / (double)N;
+            const float2 st = make_float2((float)cx_cos_small(ang * j), (float)cx_sin_small(ang * j));
+            v = cmul(v, j == 0 ? wb : cmul(wb, st));
+          }
+          buf[swz(k0 + j)] = v;
+        }
+      }
+    } else {
+      for (int n = tid; n < H; n += NT) {
+        const float2 a = sample(n), b = sample(n + H);
+        buf[swz(n)] = half == 0 ? cadd(a, b) : cmul(csub(a, b), __ldg(wn + n));
+      }
     }
     __syncthreads();
     fft_forward_halves<LOG2N, H, NT>(buf, tid);
@@ -2228,7 +2299,12 @@ static cudaError_t encode_launch(const SigDesc *sigs, int nsig, Slots ws, float 
     auto k = encode_fft_half_kernel<LOG2N, NT>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<dim3(nsig, 2), NT, smem, st>>>(sigs, ws, tap);
+    if (tap != nullptr) prep.flag = nullptr;  // the signal tap shows the in-kernel route, stage by stage
+    if (prep.flag != nullptr) {
+      encode_prep_kernel<LOG2N><<<(nsig + 7) / 8, 256, 0, st>>>(sigs, nsig, ws, prep);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    k<<<dim3(nsig, 2), NT, smem, st>>>(sigs, ws, tap, prep);
     return cudaGetLastError();
   } else {
   const size_t smem = std::max((size_t)N * 8 + N + 512 * 4 + 128 * 2 + 256, fft_smem_floor());

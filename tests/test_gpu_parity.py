@@ -945,7 +945,7 @@ def test_cluster_kernel_equals_three_kernel_route_n32768(sx):
     ql = [(Q[i, : (chunk if i % 4 else int(rng.integers(5000, chunk)))].tobytes(), 0, i, chunk) for i in range(n)]
     pairs = [(i, i) for i in range(n)] + [(i, (i + 1) % n) for i in range(0, n, 5)]
     out = []
-    for flags in (0, 8):
+    for flags in (0, 8, 2):  # bit 1: every signal prepared inside the transform kernels (no preparation kernel)
         with sx.XCorrEngine(t_chunk=chunk, q_chunk=chunk, target_total=float(n * chunk), debug_flags=flags, max_batch_pairs=10) as eng:
             eng.set_targets(sx.ChunkSet.from_list(tl))
             eng.set_queries(sx.ChunkSet.from_list(ql))
@@ -954,11 +954,12 @@ def test_cluster_kernel_equals_three_kernel_route_n32768(sx):
             cands = [eng.tap_candidates(i, i, st) for i in (0, 3, 4) for st in (0, 1)]
             out.append((rec, xcs, cands))
     assert len(out[0][0]) >= 10
-    assert out[0][0].tobytes() == out[1][0].tobytes()
-    for a, b in zip(out[0][1], out[1][1]):
-        assert xc_rel_err(a, b) < 1e-6
-    for a, b in zip(out[0][2], out[1][2]):
-        assert len(a) > 100 and np.array_equal(a, b)
+    for other in out[1:]:
+        assert out[0][0].tobytes() == other[0].tobytes()
+        for a, b in zip(out[0][1], other[1]):
+            assert xc_rel_err(a, b) < 1e-6
+        for a, b in zip(out[0][2], other[2]):
+            assert len(a) > 100 and np.array_equal(a, b)
 
 
 def test_fused_pair_kernel_equals_separate_kernels(sx):
