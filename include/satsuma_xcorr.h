@@ -44,7 +44,8 @@ typedef struct sx_ctx sx_ctx;
 typedef struct {
   int32_t abi_version;     /* = SX_ABI_VERSION */
   int32_t device;          /* CUDA device ordinal */
-  int32_t t_chunk;         /* -t_chunk; FFT length N = 2*t_chunk, N in {2048..32768} */
+  int32_t t_chunk;         /* -t_chunk; FFT length N = 2*t_chunk, N in {2048..32768}; a target chunk holds at most
+                              t_chunk bases (ChunkManager never makes longer ones), a query chunk at most 2*t_chunk */
   int32_t q_chunk;         /* -q_chunk; <= 2*t_chunk; also the RC coordinate constant (Slave.cc:180) */
   double cutoff;           /* -cutoff      (1.8) */
   double cutoff_fast;      /* -cutoff_fast (2.9), used when sx_pair.fast != 0 (Slave.cc:237) */

@@ -457,7 +457,9 @@ extern "C" int sx_set_targets(sx_ctx *c, const char *bases, const int64_t *offse
   if (!c) return fail(SX_ERR_ARG, "sx_set_targets: null context");
   std::lock_guard<std::mutex> lk(c->mu);
   CU(cudaSetDevice(c->cfg.device));
-  int rc = set_store(c, c->T, bases, offsets, lens, starts, seq_ids, n, seq_sizes, n_seqs, c->N, "sx_set_targets");
+  // a target chunk holds at most t_chunk = N/2 bases (a query chunk up to N): the scan kernel sizes its per-warp lists
+  // for diagonals of at most N/2 target positions
+  int rc = set_store(c, c->T, bases, offsets, lens, starts, seq_ids, n, seq_sizes, n_seqs, c->N / 2, "sx_set_targets");
   if (rc != SX_OK) return rc;
   if (c->cfg.target_total <= 0) {  // Slave.cc:405-408
     double tot = 0;

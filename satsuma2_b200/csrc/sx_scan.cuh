@@ -38,9 +38,10 @@ struct ScanCfg {
   static constexpr int NW = (1 << LOG2N) / 32;                // words per plane
   static constexpr int PAD = 2;                               // zero words in front of every plane
   static constexpr int PW = NW + PAD + 2;                     // padded plane length (word NW + 1 is still readable)
-  static constexpr int NBW = (NW + 31) / 32;                  // words of a lane's survivor bitset
+  // a diagonal runs over target positions, at most N/2 of them: N/64 words
+  static constexpr int NBW = (NW / 2 + 31) / 32;              // words of a lane's survivor bitset
   static constexpr int SPC = LOG2N <= 14 ? 2 : 1;             // strand-pairs per CTA
-  static constexpr int ITEM_CAP = NW > 512 ? NW : 512;        // items listed per round (>= the most one lane can have)
+  static constexpr int ITEM_CAP = NW / 2 > 512 ? NW / 2 : 512;  // items listed per round (>= the most one lane can have)
   static constexpr size_t WARP_BYTES = (size_t)SX_RUN_CAP * 4 + (size_t)NBW * 32 * 4 + (size_t)ITEM_CAP * 4 +
                                        (size_t)ITEM_CAP * 2 + 32 * 4;
   static constexpr size_t SMEM = (size_t)SPC * 4 * PW * 4 + SX_SCAN_WARPS * WARP_BYTES;
