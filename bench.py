@@ -60,7 +60,7 @@ def load_peaks():
 def load_traffic(key="dram_bytes_per_launch"):
     """dram__bytes_read+write per launch (device batch of 16384 pairs) and the pipe utilisation figures of the same
     `ncu --set full` captures, from profiles/*_traffic.json (tools/make_profiles.py)."""
-    for name in ("r3_traffic.json", "r2_traffic.json", "r1_traffic.json"):
+    for name in ("r2_traffic.json", "r1_traffic.json"):
         try:
             d = json.load(open(os.path.join(ROOT, "profiles", name)))
             if key in d:
@@ -209,7 +209,7 @@ def parity_check(T, Q, n_sample, gpu_recs, cpu_recs, kind, target_total):
             "notes": unexplained}
 
 
-def pairs_workload(grp, local_rank, chunk, n, steps, warmup, batch, seed=7):
+def pairs_workload(grp, local_rank, chunk, n, steps, warmup, batch, seed=7, engine_kw=None, e2e=True):
     """configs[2]: independent random chunk pairs of a larger chunk size (FFT length 2 x chunk), one planted segment
     each -- the headline workload's shape at N = 16384 / 32768.  -> dict (device-resident value, e2e, kernel ms)."""
     import torch
@@ -224,8 +224,10 @@ def pairs_workload(grp, local_rank, chunk, n, steps, warmup, batch, seed=7):
     synth.random_pairs(n, chunk, seed=seed, out_t=T, out_q=Q)
     cs_t, cs_q = sx.ChunkSet.independent(T), sx.ChunkSet.independent(Q)
     pairs = np.ascontiguousarray(np.stack([np.arange(n), np.arange(n)], axis=1), dtype=np.int32)
-    eng = sx.XCorrEngine(device=local_rank, t_chunk=chunk, q_chunk=chunk, target_total=float(n) * chunk,
-                         max_batch_pairs=batch, spectra_cache_bytes=-1, async_upload=1)
+    kw = dict(device=local_rank, t_chunk=chunk, q_chunk=chunk, target_total=float(n) * chunk, max_batch_pairs=batch,
+              spectra_cache_bytes=-1, async_upload=1)
+    kw.update(engine_kw or {})
+    eng = sx.XCorrEngine(**kw)
     stream = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
     rec_buf = np.zeros(4 * n, dtype=sx.RESULT_DTYPE)
 
@@ -243,9 +245,15 @@ def pairs_workload(grp, local_rank, chunk, n, steps, warmup, batch, seed=7):
     ms_dev, clocks, rec, n_dev = _timed_steps(step_device, steps, warmup, stream, grp, local_rank, eng.reset_stats, 1.0)
     st = eng.stats()
     eng.set_profiling(False)
+    b = max(st["batches"], 1)
+    if not e2e:  # A/B leg: device-resident figures only
+        eng.close()
+        return {"value": n / (ms_dev / 1e3), "ms_per_step": ms_dev, "steps": n_dev,
+                "fused_pairs_per_step": int(st["fused_pairs"] / max(n_dev, 1)),
+                "kernel_ms_per_batch": {"encode_fft": st["ms_encode_fft"] / b, "xcorr_findtop": st["ms_xcorr"] / b,
+                                        "scan_score": st["ms_scan_score"] / b}, "records_per_step": int(len(rec))}
     ms_e2e, _, rec, n_e2e = _timed_steps(step_e2e, steps, 1, stream, grp, local_rank, eng.reset_stats, 1.0)
     st_e2e = eng.stats()
-    b = max(st["batches"], 1)
     out = {"workload": f"configs[2]: {n} random {chunk}x{chunk} chunk pairs (FFT length {2 * chunk}), one planted "
                        "segment each", "chunk": chunk, "fft_n": 2 * chunk, "pairs_per_step": n, "device_batch_pairs": batch,
            "metric": METRIC, "unit": UNIT, "value": n / (ms_dev / 1e3), "ms_per_step": ms_dev, "steps": n_dev,
@@ -604,14 +612,17 @@ def main():
     batches = max(st_dev["batches"], 1)
     traffic = load_traffic()  # dram bytes per launch from the committed ncu --set full captures
     ncu = load_traffic("ncu_per_launch")  # pipe utilisation of the same captures (counters, not a model)
+    # with --fuse-pairs 1 the fused kernel does the transforms of its pairs too (its time is under ms_xcorr) and their
+    # spectra never reach HBM: only the bases are read
+    ff = st_dev["fused_pairs"] / max(st_dev["chunk_pairs"], 1)
     kern = {
         "encode_fft": {"ms": st_dev["ms_encode_fft"], "launches": batches,
-                       "flop": FLOP_FWD_PER_SIGNAL * st_dev["signals"],
-                       "bytes": (SPECTRA_PER_CHUNK_PAIR * SPECTRUM_BYTES / 2 + CHUNK) * st_dev["signals"]},
+                       "flop": FLOP_FWD_PER_SIGNAL * st_dev["signals"] * (1 - ff),
+                       "bytes": (SPECTRA_PER_CHUNK_PAIR * SPECTRUM_BYTES / 2 * (1 - ff) + CHUNK) * st_dev["signals"]},
         "xcorr_findtop": {"ms": st_dev["ms_xcorr"], "launches": batches,
-                          "flop": FLOP_XCORR_PER_STRAND * st_dev["strand_pairs"],
+                          "flop": FLOP_XCORR_PER_STRAND * st_dev["strand_pairs"] + FLOP_FWD_PER_SIGNAL * st_dev["signals"] * ff,
                           # the spectra of a chunk pair read once (both strands derived from them)
-                          "bytes": SPECTRA_PER_CHUNK_PAIR * SPECTRUM_BYTES * st_dev["chunk_pairs"]},
+                          "bytes": SPECTRA_PER_CHUNK_PAIR * SPECTRUM_BYTES * st_dev["chunk_pairs"] * (1 - ff)},
         "scan_score": {"ms": st_dev["ms_scan_score"], "launches": batches, "flop": 0.0,
                        "bytes": (4 * (FFT_N // 32) * 4) * st_dev["strand_pairs"] + 2 * st_dev["candidates"],
                        "positions": float(st_dev["positions"])},
@@ -681,6 +692,21 @@ def main():
         if world == 1:
             extras["chunk8192"] = pairs_workload(grp, local_rank, 8192, 32768, args.steps, args.warmup, 8192)
             extras["chunk16384"] = pairs_workload(grp, local_rank, 16384, 8192, args.steps, args.warmup, 4096)
+            # A/B legs (device-resident, records must agree): N = 32768 through the round-1 route (two half kernels,
+            # HBM scratch, combine kernel) instead of the two-CTA cluster kernel; the headline shape through the fused
+            # transform + correlation kernel (sx_config::fuse_pairs) instead of the separate kernels
+            ab = pairs_workload(grp, local_rank, 16384, 8192, args.steps, args.warmup, 4096, engine_kw={"debug_flags": 8}, e2e=False)
+            ab["same_records"] = ab["records_per_step"] == extras["chunk16384"]["records_per_step"]
+            extras["chunk16384"]["three_kernel_route"] = ab
+            nf = min(n, 262144)
+            legs = {}
+            for name, fp in (("separate_kernels", 0), ("fused_kernel", 1)):
+                legs[name] = pairs_workload(grp, local_rank, CHUNK, nf, args.steps, args.warmup, args.batch, seed=1,
+                                            engine_kw={"fuse_pairs": fp, "target_total": target_total}, e2e=False)
+            legs["same_records"] = legs["separate_kernels"]["records_per_step"] == legs["fused_kernel"]["records_per_step"]
+            legs["note"] = ("sx_config::fuse_pairs = 1: transforms, product, inverse and FindTop of a chunk pair in one "
+                            "kernel, spectra never in HBM (its time is under xcorr_findtop); default 0, the faster one")
+            extras["fused_ab"] = legs
             extras["repeats"] = repeats_workload(grp, local_rank, 8.0, args.steps, args.warmup, args.batch)
 
     if rank == 0:
