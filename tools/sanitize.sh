@@ -8,3 +8,9 @@ SEL2='synthetic_edge or periodic_sequences_overflow_unit_list[4096] or split_tra
 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "$SEL2" > gpurun_out/sanitizer_racecheck_${tag}.log 2>&1
 echo "racecheck rc=$?" >> gpurun_out/sanitizer_racecheck_${tag}.log
 tail -n 4 gpurun_out/sanitizer_memcheck_${tag}.log; tail -n 4 gpurun_out/sanitizer_racecheck_${tag}.log
+# the routes added in the second session of round 2 (three-channel form, fused kernel + fall-back lists, cluster kernel)
+for tool in memcheck racecheck; do
+  compute-sanitizer --tool $tool --error-exitcode 9 python tools/sanitize_paths.py > gpurun_out/sanitizer_${tool}_paths_${tag}.log 2>&1
+  echo "$tool rc=$?" >> gpurun_out/sanitizer_${tool}_paths_${tag}.log
+  tail -n 4 gpurun_out/sanitizer_${tool}_paths_${tag}.log
+done
