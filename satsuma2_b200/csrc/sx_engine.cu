@@ -885,8 +885,12 @@ static void propose_g_partners(const sx_ctx *c, Batch &b, bool enable) {
     if ((size_t)b.sigs[m].slot < c->n_persist && (size_t)b.sigs[o].slot >= c->n_persist) std::swap(o, m);
     b.sigs[o].g_mode = G_OWNER;
     b.sigs[o].g_partner = m;
+    b.sigs[o].g_pslot = b.sigs[m].slot;
+    b.sigs[o].g_plen = b.sigs[m].len;
     b.sigs[m].g_mode = G_MEMBER;
     b.sigs[m].g_partner = o;
+    b.sigs[m].g_pslot = b.sigs[o].slot;
+    b.sigs[m].g_plen = b.sigs[o].len;
     open = -1;
   }
 }

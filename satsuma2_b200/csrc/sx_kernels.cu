@@ -720,9 +720,8 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
     for (int w = tid; w < H / WIN; w += NT) went[w] = wsrc[w];
     if (tid < 4) s_off[tid] = prep.off[(size_t)sig * 4 + tid];
     if (partner >= 0) {  // the partner's planes, weights and G mean behind this signal's
-      const SigDesc pd = sigs[partner];
-      plen = pd.len;
-      const uint32_t *ppl = ws.planes + (size_t)pd.slot * 2 * NWp;
+      plen = sd.g_plen;
+      const uint32_t *ppl = ws.planes + (size_t)sd.g_pslot * 2 * NWp;
       for (int w = tid; w < 2 * NWp; w += NT) s_pl2[2 * NWp + w] = ppl[w];
       const float *pw = prep.went + (size_t)partner * (H / WIN);
       for (int w = tid; w < H / WIN; w += NT) went[H / WIN + w] = pw[w];
@@ -892,7 +891,7 @@ __global__ void __launch_bounds__(NT, (LOG2N <= 13 ? 3 : 1))
     m.q_im = zmode == ZM_FOUR ? acc_im : 0.f;
     m.q_nyq = zmode == ZM_FOUR ? acc_ny : 0.f;
     m.zmode = zmode;
-    m.zslot = zmode == ZM_IM ? sigs[sd.g_partner].slot : sd.slot;
+    m.zslot = zmode == ZM_IM ? sd.g_pslot : sd.slot;
     m.pad = 0;
     ws.meta[sd.slot] = m;
   }

@@ -51,6 +51,8 @@ struct SigDesc {  // one chunk signal to encode + transform
   // into its own spec[.][1], G_MEMBER skips its second transform when its owner is pure too
   int32_t g_mode = 0;      // G_NONE / G_OWNER / G_MEMBER
   int32_t g_partner = -1;  // index of the partner in the same descriptor array (-1: none)
+  int32_t g_pslot = 0;     // the partner's slot and length (copied here by the host: one dependent load less at the
+  int32_t g_plen = 0;      // start of the transform kernel's CTA)
 };
 enum { G_NONE = 0, G_OWNER = 1, G_MEMBER = 2, G_FUSED = 3 };  // G_FUSED: handled by pair_fused_kernel (g_partner = the
                                                                // other chunk of the pair); the transform kernel skips it
