@@ -341,6 +341,8 @@ extern "C" void sx_destroy(sx_ctx *c) {
 }
 
 // ------------------------------------------------------------------------------------------------
+static int upload_pieces(sx_ctx *c, ChunkStore &S, size_t upto);
+
 static int set_store(sx_ctx *c, ChunkStore &S, const char *bases, const int64_t *offsets, const int32_t *lens,
                      const int32_t *starts, const int32_t *seq_ids, int32_t n, const int32_t *seq_sizes,
                      int32_t n_seqs, int max_len, const char *what) {
@@ -379,7 +381,8 @@ static int set_store(sx_ctx *c, ChunkStore &S, const char *bases, const int64_t 
   if (blob > 0) {
     S.async_pending = false;
     if (c->cfg.async_upload) {
-      // nothing travels yet: upload_pieces() enqueues the pieces as the batches ask for them
+      // the first pieces (what the first device batches read) start travelling right away, while the caller is still
+      // preparing its next call; upload_pieces() enqueues the rest as the batches ask for them
       CU(cudaStreamSynchronize(c->copy_stream));
       S.piece_bytes = (size_t)16 << 20;
       S.n_pieces = (blob + S.piece_bytes - 1) / S.piece_bytes;
@@ -391,6 +394,9 @@ static int set_store(sx_ctx *c, ChunkStore &S, const char *bases, const int64_t 
         S.piece_ev.push_back(e);
       }
       S.async_pending = true;
+      const size_t first = ((size_t)2 * (size_t)c->cfg.max_batch_pairs * (size_t)c->cfg.t_chunk) / S.piece_bytes + 1;
+      int rc = upload_pieces(c, S, first);
+      if (rc != SX_OK) return rc;
     } else {
       CU(cudaMemcpyAsync(S.d_bases, bases, blob, cudaMemcpyHostToDevice, c->stream));
       CU(cudaStreamSynchronize(c->stream));
