@@ -511,9 +511,10 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
           const bool inside = match_word(kw, full, m);
           // byte j of pre: matches in bytes 0 .. j of the word (three masks, four popcounts, packed by
           // multiply-adds, which run beside the logic pipe); c = pre - (pre << 8): the bytes' own counts
-          uint32_t pre = (uint32_t)__popc(m & 0xffu);
-          pre = mad_u32((uint32_t)__popc(m & 0xffffu), 0x100u, pre);
-          pre = mad_u32((uint32_t)__popc(m & 0xffffffu), 0x10000u, pre);
+          // (the low bytes are isolated by multiplications -- left shifts on the FMA pipe -- instead of AND masks)
+          uint32_t pre = (uint32_t)__popc(mad_u32(m, 0x1000000u, 0u));
+          pre = mad_u32((uint32_t)__popc(mad_u32(m, 0x10000u, 0u)), 0x100u, pre);
+          pre = mad_u32((uint32_t)__popc(mad_u32(m, 0x100u, 0u)), 0x10000u, pre);
           pre = mad_u32((uint32_t)__popc(m), 0x1000000u, pre);
           const uint32_t c = pre * 0xffffff01u;
           const uint32_t s6 = pre + bn + (cpp >> 24);               // byte j: counts of bytes g-5 .. g
