@@ -525,8 +525,11 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
           const uint32_t t6 = (s6 + 0x6d6d6d6du) & 0x80808080u;     // bytes with S6 >= 19
           const uint32_t t7 = (s7 - c + 0x6e6e6e6eu) & 0x80808080u;  // bytes with S7 - c >= 18
           if (inside && (t6 & t7)) accF |= bit;
-          if (inside && (t6 >> 31)) accH |= bit;
-          if (inside && ((s7 + 0x6du) & 0x80u)) accL |= bit;
+          // H and L are single bits of words that exist anyway: they are shifted in from the top, one funnel shift each
+          // (the block's words end up in reversed order; put right after the loop), instead of a test and a predicated OR
+          const uint32_t l31 = mad_u32(s7, 0x1000000u, 0x6d000000u);  // bit 31: S7 of the bottom byte >= 19
+          accH = __funnelshift_l(inside ? t6 : 0u, accH, 1);
+          accL = __funnelshift_l(inside ? l31 : 0u, accL, 1);
           bit <<= 1;
           const uint32_t tot = pre >> 24;
           bn = tot * 0x01010101u - (pre << 16);
@@ -552,6 +555,11 @@ __global__ void __launch_bounds__(SX_SCAN_NT)
           for (; kw < kw_full; kw++) step(kw, true);  // warp-uniform trip counts
 #pragma unroll 2
           for (; kw < kw_end; kw++) step(kw, false);
+          {
+            const int n_steps = kw_end - w * 32;  // 1 .. 32: word k of the block sits at bit n_steps - 1 - k
+            accH = __brev(accH) >> (32 - n_steps);
+            accL = __brev(accL) >> (32 - n_steps);
+          }
           const uint32_t x = accH & (accL >> 1);  // crossings between words of this block
           uint32_t acc = accF | (x & (accF >> 1)) | ((x & accF) << 1);
           if (carryH & accL & 1u) {  // a run may cross from the previous block's last word into this block's first
