@@ -988,6 +988,40 @@ def test_fused_pair_kernel_equals_separate_kernels(sx):
         assert outs[k + 1].tobytes() == outs[1].tobytes(), k
 
 
+@pytest.mark.parametrize("chunk", [1024, 2048])
+def test_fused_pair_kernel_small_transform_sizes(sx, oracle_lib, chunk):
+    """The fused kernel at N = 2048 / 4096 (radix plans 16-8-8 and 16-16-8): identical records to the separate kernels,
+    and both against the oracle."""
+    from satsuma2_b200 import synth
+
+    n, NN = 160, 2 * chunk
+    T, Q, _ = synth.random_pairs(n, chunk, seed=31 + chunk)
+    rng = np.random.default_rng(chunk)
+    tl = [(T[i, : (chunk if i % 3 else int(rng.integers(200, chunk)))].tobytes(), 0, i, chunk) for i in range(n)]
+    ql = [(Q[i, : (chunk if i % 2 else int(rng.integers(13, chunk // 16)) * 16)].tobytes(), 0, i, chunk) for i in range(n)]
+    pairs = [(i, i) for i in range(n)]
+    total = float(n * chunk)
+    outs, fused = [], []
+    for fuse in (1, 0):
+        with sx.XCorrEngine(t_chunk=chunk, q_chunk=chunk, target_total=total, fuse_pairs=fuse, max_batch_pairs=64) as eng:
+            eng.set_targets(sx.ChunkSet.from_list(tl))
+            eng.set_queries(sx.ChunkSet.from_list(ql))
+            outs.append(eng.align_pairs(pairs))
+            fused.append(eng.stats()["fused_pairs"])
+    assert fused[0] == n and fused[1] == 0
+    key = ["query_id", "target_id", "tstart", "qstart", "len", "reverse"]
+    assert np.sort(outs[0], order=key).tobytes() == np.sort(outs[1], order=key).tobytes()
+    exp = oracle_lib.align_pairs(oracle_lib.make_params(t_chunk=chunk, q_chunk=chunk, target_total=total), tl, ql, pairs,
+                                 threads=os.cpu_count() or 1)
+    assert len(exp) > 20
+    listed = []
+    for i in range(n):
+        compare_pair_records(oracle_lib, outs[0][outs[0]["query_id"] == i], exp[exp["query_id"] == i], tl[i][0], ql[i][0], 0, 0,
+                             chunk, chunk, NN, 1.8, 0.99, total, listed)
+    _log_listed(f"fused_small_{chunk}", listed)
+    assert len(listed) <= 3, listed
+
+
 @pytest.mark.parametrize("min_len,total", [(100, 1.6e6), (300, 4294967296.0), (47, 2.0e4)])
 def test_min_length_flag(sx, oracle_lib, min_len, total):
     """`-l` (Slave.cc:172): segments shorter than min_len are dropped whatever their probability -- also the shortest
