@@ -882,7 +882,7 @@ static void propose_g_partners(const sx_ctx *c, Batch &b, bool enable) {
   for (size_t i = 0; i < b.sigs.size(); i++) {
     SigDesc &s = b.sigs[i];
     if (s.g_mode == G_FUSED) continue;
-    if (!enable || s.strand != 0 || s.len <= 0 || s.len > H) continue;
+    if (!enable || s.len <= 0 || s.len > H) continue;  // either strand: the preparation kernel does both
     if (open < 0) {
       open = (int)i;
       continue;
@@ -909,8 +909,9 @@ static int batch_stage(sx_ctx *c, Run &r, Batch &b, TapRequest *tap, int stage) 
   r.stage = stage;
   const int nsig = r.nsig = (int)b.sigs.size(), nsp = r.nsp = (int)b.sps.size();
   // the three-channel form and the fused kernel both build on the preparation kernel (batch_launch_early)
-  const bool prep_on = !log2n_split(c->log2n) && !(c->cfg.debug_flags & 2) && !(tap && tap->sig5n);
-  const bool three = prep_on && !(c->cfg.debug_flags & 4);
+  const bool prep_on = !(c->cfg.debug_flags & 2) && !(tap && tap->sig5n);
+  // (the round-1 three-kernel route of N = 32768, debug_flags bit 3, multiplies the packed four-channel spectra)
+  const bool three = prep_on && !(c->cfg.debug_flags & 4) && !(log2n_split(c->log2n) && (c->cfg.debug_flags & 8));
   propose_fused(c, b, three && c->cfg.fuse_pairs == 1 && log2n_fusable(c->log2n) && tap == nullptr && c->fused_grid > 0);
   propose_g_partners(c, b, three);
   int rc;

@@ -969,6 +969,7 @@ __global__ void __launch_bounds__(NT, 1)
   uint8_t *s_base2 = s_comp + 128;                                // 128
   __shared__ double s_red[4][NWARP];
   __shared__ double s_off[4];
+  __shared__ double s_poff;  // three-channel form: the partner's G mean
   __shared__ int s_flags;
 
   const int tid = threadIdx.x;
@@ -982,13 +983,29 @@ __global__ void __launch_bounds__(NT, 1)
   const bool prepared = prep.flag != nullptr && tap == nullptr && prep.flag[blockIdx.x] != 0;
   uint32_t *s_pl2 = reinterpret_cast<uint32_t *>(sb);  // prepared: plane words [2][N/32] in place of the bases
   int flags = 0;
+  // three-channel form, as in encode_fft_kernel: the second transform carries G of this signal and G of its partner
+  int zmode = ZM_FOUR, partner = -1, plen = 0;
   if (prepared) {
+    if (sd.g_mode == G_OWNER) {
+      zmode = ZM_RE;
+      if (sd.g_partner >= 0 && prep.flag[sd.g_partner] != 0) partner = sd.g_partner;
+    } else if (sd.g_mode == G_MEMBER && sd.g_partner >= 0) {
+      zmode = prep.flag[sd.g_partner] != 0 ? ZM_IM : ZM_RE;
+    }
     constexpr int NWp = N / 32;
     const uint32_t *pl = ws.planes + (size_t)sd.slot * 2 * NWp;
     for (int w = tid; w < 2 * NWp; w += NT) s_pl2[w] = pl[w];
     const float *wsrc = prep.went + (size_t)blockIdx.x * (H / WIN);
     for (int w = tid; w < H / WIN; w += NT) went[w] = wsrc[w];
     if (tid < 4) s_off[tid] = prep.off[(size_t)blockIdx.x * 4 + tid];
+    if (partner >= 0) {
+      plen = sd.g_plen;
+      const uint32_t *ppl = ws.planes + (size_t)sd.g_pslot * 2 * NWp;
+      for (int w = tid; w < 2 * NWp; w += NT) s_pl2[2 * NWp + w] = ppl[w];
+      const float *pw = prep.went + (size_t)partner * (H / WIN);
+      for (int w = tid; w < H / WIN; w += NT) went[H / WIN + w] = pw[w];
+      if (tid == 4) s_poff = prep.off[(size_t)partner * 4 + 2];
+    }
     __syncthreads();
   } else {
     flags = encode_prepare<LOG2N, NT>(sd, ws, smem_raw, sb, went, s_fcode, s_comp, s_base2, s_red, s_off, &s_flags, half == 0);
@@ -1003,9 +1020,11 @@ __global__ void __launch_bounds__(NT, 1)
   float acc_re = 0.f, acc_im = 0.f, acc_ny = 0.f;
   // slots inside this CTA's half
   constexpr int PH1 = bin_slot<LOG2N>(H - 1) - H, PH2 = bin_slot<LOG2N>(H + 1) - H, PH = bin_slot<LOG2N>(H);
+  const int rounds = zmode == ZM_IM ? 1 : 2;
 #pragma unroll 1
-  for (int pr = 0; pr < 2; pr++) {
-    const double off0 = s_off[2 * pr], off1 = s_off[2 * pr + 1];
+  for (int pr = 0; pr < rounds; pr++) {
+    const bool g_round = pr == 1 && zmode != ZM_FOUR;  // (G of this signal) + i (G of the partner, or nothing)
+    const double off0 = s_off[2 * pr], off1 = g_round ? (partner >= 0 ? s_poff : 0.0) : s_off[2 * pr + 1];
     // sample k of the packed signal: (float)(weight * (fraction - mean)) per channel (SeqToPCM), 0 past the end
     auto sample = [&](int k) -> float2 {
       float2 v = make_float2(0.f, 0.f);
@@ -1039,26 +1058,34 @@ __global__ void __launch_bounds__(NT, 1)
       // a window: inside a window the sample is one of two floats per channel, rounded exactly as the per-base double
       // product of the reference (see encode_fft_kernel); the base only selects between them.
       constexpr int NWp = N / 32;
-      const uint32_t c0 = 2 * pr, c1 = 2 * pr + 1;
+      const uint32_t c0 = 2 * pr, c1 = g_round ? 2u : 2 * pr + 1;
+      const int len1 = g_round ? plen : len;  // plen = 0 without a partner: imaginary part all zero
+      const bool flat1 = g_round ? plen < 1024 : flat;
+      const int src1 = (g_round && partner >= 0) ? 1 : 0;  // whose planes / weights feed the imaginary part
       const double hit0 = __dsub_rn(1.0, off0), miss0 = __dsub_rn(0.0, off0);
       const double hit1 = __dsub_rn(1.0, off1), miss1 = __dsub_rn(0.0, off1);
       constexpr int SEG = WIN < 32 ? WIN : 32;  // samples per thread step
       for (int sg = tid; sg < H / SEG; sg += NT) {
         const int k0 = sg * SEG, w = k0 / WIN;
         const double e = flat ? 1.0 : (double)went[w];
+        const double e1 = flat1 ? 1.0 : (double)went[src1 * (H / WIN) + w];
         const float h0 = __double2float_rn(__dmul_rn(e, hit0)), m0 = __double2float_rn(__dmul_rn(e, miss0));
-        const float h1 = __double2float_rn(__dmul_rn(e, hit1)), m1 = __double2float_rn(__dmul_rn(e, miss1));
+        const float h1 = __double2float_rn(__dmul_rn(e1, hit1)), m1 = __double2float_rn(__dmul_rn(e1, miss1));
         const uint32_t lo = s_pl2[k0 >> 5] >> (k0 & 31), hi = s_pl2[NWp + (k0 >> 5)] >> (k0 & 31);
+        const uint32_t *p1 = s_pl2 + src1 * 2 * NWp;
+        const uint32_t lo1 = p1[k0 >> 5] >> (k0 & 31), hi1 = p1[NWp + (k0 >> 5)] >> (k0 & 31);
         const uint32_t sel0 = ((c0 & 1u) ? lo : ~lo) & ((c0 & 2u) ? hi : ~hi);
-        const uint32_t sel1 = ((c1 & 1u) ? lo : ~lo) & ((c1 & 2u) ? hi : ~hi);
+        const uint32_t sel1 = ((c1 & 1u) ? lo1 : ~lo1) & ((c1 & 2u) ? hi1 : ~hi1);
         const uint32_t in = k0 + SEG <= len ? 0xffffffffu : (k0 < len ? (1u << (len - k0)) - 1u : 0u);
+        const uint32_t in1 = k0 + SEG <= len1 ? 0xffffffffu : (k0 < len1 ? (1u << (len1 - k0)) - 1u : 0u);
         const float2 wb = half ? __ldg(wn + k0) : make_float2(1.f, 0.f);
 #pragma unroll
         for (int j = 0; j < SEG; j++) {
           float2 v;
           v.x = ((sel0 >> j) & 1u) ? h0 : m0;
           v.y = ((sel1 >> j) & 1u) ? h1 : m1;
-          if (!((in >> j) & 1u)) v = make_float2(0.f, 0.f);
+          if (!((in >> j) & 1u)) v.x = 0.f;
+          if (!((in1 >> j) & 1u)) v.y = 0.f;
           if (half) {
             constexpr double ang = -2.0 * 3.14159265358979323846 / (double)N;
             const float2 st = make_float2((float)cx_cos_small(ang * j), (float)cx_sin_small(ang * j));
@@ -1095,16 +1122,17 @@ __global__ void __launch_bounds__(NT, 1)
   }
   if (tid == 0) {
     SlotMeta *m = ws.meta + sd.slot;
+    const bool four = zmode == ZM_FOUR;  // three-channel form: the channel sum of the spectrum is zero by construction
     if (half == 0) {
       m->len = len;
       m->flags = flags & SLOT_NONACGT;
-      m->q_nyq = acc_ny;
-      m->zmode = ZM_FOUR;
-      m->zslot = 0;
+      m->q_nyq = four ? acc_ny : 0.f;
+      m->zmode = zmode;
+      m->zslot = zmode == ZM_IM ? sd.g_pslot : sd.slot;
       m->pad = 0;
     } else {
-      m->q_re = acc_re;
-      m->q_im = acc_im;
+      m->q_re = four ? acc_re : 0.f;
+      m->q_im = four ? acc_im : 0.f;
     }
   }
 }
@@ -1854,6 +1882,51 @@ __global__ void __launch_bounds__(NT, 1)
   for (int n = tid; n < H; n += NT) out[n] = buf[swz(n)];
 }
 
+// spectral_product for ONE half of the bins (a CTA that holds one H-point transform): slot indices inside the half,
+// 8-byte loads, one strand.  Half 0 (even bins): m <-> (H - m) mod H; half 1 (odd bins): scrambled position r <-> H-1-r.
+// Slot LR/2 of the first block (bin H) is left to the quirk code, bin 0 mirrors itself.
+template <int LOG2N, int NT, int TM, int QM>
+__device__ __forceinline__ void half_product_m(float2 *buf, const SpecSrc T, const SpecSrc Q, int half, int tid) {
+  constexpr int N = 1 << LOG2N, H = N / 2;
+  constexpr int LR = last_radix<LOG2N>();
+  const float2 *T1 = T.z1 + (size_t)half * H, *T3 = T.z3 + (size_t)half * H;
+  const float2 *Q1 = Q.z1 + (size_t)half * H, *Q3 = Q.z3 + (size_t)half * H;
+#pragma unroll 2
+  for (int it = tid; it < H / 2; it += NT) {
+    int pa, pb;
+    if (half == 0) {
+      const int r = (it / (LR / 2)) * LR + (it % (LR / 2));
+      const int m2 = (H - natural_bin<LOG2N>(r)) & (H - 1);
+      pa = swz(r);
+      pb = swz(scrambled_pos<LOG2N>(m2));
+    } else {
+      pa = swz(it);
+      pb = swz(H - 1 - it);
+    }
+    float2 oa, ob;
+    pair_product<false>(channels2<TM>(__ldg(T1 + pa), __ldg(T1 + pb), __ldg(T3 + pa), __ldg(T3 + pb)),
+                        channels2<QM>(__ldg(Q1 + pa), __ldg(Q1 + pb), __ldg(Q3 + pa), __ldg(Q3 + pb)), oa, ob);
+    buf[pa] = oa;
+    buf[pb] = ob;
+  }
+}
+template <int LOG2N, int NT>
+__device__ __forceinline__ void half_product(float2 *buf, const SpecSrc T, const SpecSrc Q, int half, int tid) {
+#define SX_PM(TM, QM) half_product_m<LOG2N, NT, TM, QM>(buf, T, Q, half, tid)
+  switch (T.mode * 3 + Q.mode) {
+    case ZM_FOUR * 3 + ZM_FOUR: SX_PM(ZM_FOUR, ZM_FOUR); break;
+    case ZM_FOUR * 3 + ZM_RE: SX_PM(ZM_FOUR, ZM_RE); break;
+    case ZM_FOUR * 3 + ZM_IM: SX_PM(ZM_FOUR, ZM_IM); break;
+    case ZM_RE * 3 + ZM_FOUR: SX_PM(ZM_RE, ZM_FOUR); break;
+    case ZM_RE * 3 + ZM_RE: SX_PM(ZM_RE, ZM_RE); break;
+    case ZM_RE * 3 + ZM_IM: SX_PM(ZM_RE, ZM_IM); break;
+    case ZM_IM * 3 + ZM_FOUR: SX_PM(ZM_IM, ZM_FOUR); break;
+    case ZM_IM * 3 + ZM_RE: SX_PM(ZM_IM, ZM_RE); break;
+    default: SX_PM(ZM_IM, ZM_IM); break;
+  }
+#undef SX_PM
+}
+
 // ---- N = 32768 as ONE kernel: a cluster of two CTAs per strand-pair, one per half of the radix-2 split ----------
 // Product, quirk bins, drift pre-correction and the H-point inverse of its half as in xcorr_half_kernel; then the
 // radix-2 combine through DISTRIBUTED SHARED MEMORY: CTA 0 holds e[n], CTA 1 holds o[n]; index n is handled by exactly
@@ -1885,28 +1958,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
   const SpDesc sp = sps[spi];
   const SlotMeta tm = ws.meta[sp.t_slot];
   {
-    // product of one strand: P = conj(U1) V1 + conj(U2) V2 over this half's bins (bin order is irrelevant here)
-    const float4 *u1 = reinterpret_cast<const float4 *>(ws.spec + ((size_t)sp.t_slot * 2) * N + (size_t)half * H), *u2 = u1 + N / 2;
-    const float4 *v1 = reinterpret_cast<const float4 *>(ws.spec + ((size_t)sp.q_slot * 2) * N + (size_t)half * H), *v2 = v1 + N / 2;
-    float4 *dst = reinterpret_cast<float4 *>(buf);
-#pragma unroll 2
-    for (int k = tid; k < H / 2; k += NT) {
-      const float4 a1 = __ldg(u1 + k), a2 = __ldg(u2 + k), b1 = __ldg(v1 + k), b2 = __ldg(v2 + k);
-      float4 p;
-      p.x = (b1.x * a1.x + b1.y * a1.y) + (b2.x * a2.x + b2.y * a2.y);
-      p.y = (b1.y * a1.x - b1.x * a1.y) + (b2.y * a2.x - b2.x * a2.y);
-      p.z = (b1.z * a1.z + b1.w * a1.w) + (b2.z * a2.z + b2.w * a2.w);
-      p.w = (b1.w * a1.z - b1.z * a1.w) + (b2.w * a2.z - b2.z * a2.w);
-      dst[k] = p;
-    }
+    // product of one strand over this half's bins, bin pair (k, N - k) by bin pair (both in this half), from the
+    // three- or four-channel spectra of the two chunks: 4 Pf, the spectrum of a real sequence (see spectral_product)
+    half_product<LOG2N, NT>(buf, spec_src(ws, sp.t_slot, tm, N), spec_src(ws, sp.q_slot, ws.meta[sp.q_slot], N), half, tid);
     __syncthreads();
     if (tid == 0) {  // reference quirk (CrossCorr.cc:480-492): bins H-1 and H keep the TARGET spectrum
       constexpr int PH1 = bin_slot<LOG2N>(H - 1) - H, PH2 = bin_slot<LOG2N>(H + 1) - H, PH = bin_slot<LOG2N>(H);
       if (half == 1) {
-        buf[PH1] = make_float2(tm.q_re, tm.q_im);
-        buf[PH2] = make_float2(tm.q_re, -tm.q_im);
+        buf[PH1] = make_float2(4.f * tm.q_re, 4.f * tm.q_im);
+        buf[PH2] = make_float2(4.f * tm.q_re, -4.f * tm.q_im);
       } else {
-        buf[PH] = make_float2(tm.q_nyq, 0.f);
+        buf[PH] = make_float2(4.f * tm.q_nyq, 0.f);
       }
     }
     __syncthreads();
@@ -1929,7 +1991,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
   cluster.sync();
   // ---- FindTop over this CTA's lags: lag = lag0 + j with xc = Re buf[j] / N
   const int lag0 = half == 1 ? 0 : H;
-  const float scale = 1.0f / (float)N;
+  const float scale = 0.25f / (float)N;  // the factor 4 of the product
   const double co = (sp.flags & SP_FAST) ? cutoff_fast : cutoff;
   auto xc_at = [&](int j) -> float { return buf[swz(j)].x * scale; };
   if (xc_tap != nullptr) {
