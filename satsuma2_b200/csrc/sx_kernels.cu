@@ -1331,18 +1331,22 @@ __device__ __forceinline__ void pair_product(const Chan4 &t, const Chan4 &q, flo
 // step with 16-byte loads: their mirror slots are neighbours too (even bins: top digit d <-> R - 1 - d while the
 // lower digits are not all zero; odd bins: r <-> H - 1 - r), and the swizzle only XORs the low four bits with a
 // per-block constant, so pairs stay pairs.  The caller synchronises.
+// half = -1: both halves into a buffer of N slots; 0 / 1: only the even / odd bins, into a buffer of H slots (a CTA that
+// holds one H-point transform, N = 32768)
 template <int LOG2N, int NT, bool BOTH, int TM, int QM>
-__device__ __forceinline__ void spectral_product_m(float2 *buf, const SpecSrc T, const SpecSrc Q, int tid) {
+__device__ __forceinline__ void spectral_product_m(float2 *buf, const SpecSrc T, const SpecSrc Q, int tid, int half) {
   constexpr int N = 1 << LOG2N, H = N / 2;
   constexpr int LR = last_radix<LOG2N>();
   constexpr int PPB = LR / 4;  // slot pairs per block of LR slots with top digit < LR / 2
+  const int it0 = half == 1 ? H / 4 : 0, it1 = half == 0 ? H / 4 : H / 2;
+  const int boff = half == 1 ? H : 0;  // slot offset of the buffer's first element
   const bool same3 = T.z3 == Q.z3;  // partners: one shared G transform
   const float4 *T1 = reinterpret_cast<const float4 *>(T.z1), *T3 = reinterpret_cast<const float4 *>(T.z3);
   const float4 *Q1 = reinterpret_cast<const float4 *>(Q.z1), *Q3 = reinterpret_cast<const float4 *>(Q.z3);
   auto lo = [](const float4 &v) { return make_float2(v.x, v.y); };
   auto hi = [](const float4 &v) { return make_float2(v.z, v.w); };
 #pragma unroll 2
-  for (int it = tid; it < H / 2; it += NT) {
+  for (int it = it0 + tid; it < it1; it += NT) {
     int pa0, pb0;
     if (it < H / 4) {  // even bins: m <-> (H - m) mod H; m < H/2 <=> top digit (last in scrambled order) < LR/2
       const int r = (it / PPB) * LR + 2 * (it % PPB);
@@ -1379,9 +1383,10 @@ __device__ __forceinline__ void spectral_product_m(float2 *buf, const SpecSrc T,
                        oa0, ob0);
     pair_product<BOTH>(channels2<TM>(hi(t1a), hi(t1b), hi(t3a), hi(t3b)), channels2<QM>(hi(q1a), hi(q1b), hi(q3a), hi(q3b)),
                        oa1, ob1);
-    reinterpret_cast<float4 *>(buf)[qa] = make_float4(oa0.x, oa0.y, oa1.x, oa1.y);
-    reinterpret_cast<float4 *>(buf)[qb] = x ? make_float4(ob1.x, ob1.y, ob0.x, ob0.y) : make_float4(ob0.x, ob0.y, ob1.x, ob1.y);
+    reinterpret_cast<float4 *>(buf - boff)[qa] = make_float4(oa0.x, oa0.y, oa1.x, oa1.y);
+    reinterpret_cast<float4 *>(buf - boff)[qb] = x ? make_float4(ob1.x, ob1.y, ob0.x, ob0.y) : make_float4(ob0.x, ob0.y, ob1.x, ob1.y);
   }
+  if (half == 1) return;
   for (int r = tid; r < LR / 2; r += NT) {  // first block of the even bins, slot by slot (bins 0 and H/2 mirror themselves)
     const int m2 = (H - natural_bin<LOG2N>(r)) & (H - 1);
     const int pa = swz(r), pb = swz(scrambled_pos<LOG2N>(m2));
@@ -1394,8 +1399,8 @@ __device__ __forceinline__ void spectral_product_m(float2 *buf, const SpecSrc T,
 }
 // the loop specialised for the forms of both chunks (uniform over the CTA)
 template <int LOG2N, int NT, bool BOTH>
-__device__ __forceinline__ void spectral_product(float2 *buf, const SpecSrc T, const SpecSrc Q, int tid) {
-#define SX_PM(TM, QM) spectral_product_m<LOG2N, NT, BOTH, TM, QM>(buf, T, Q, tid)
+__device__ __forceinline__ void spectral_product(float2 *buf, const SpecSrc T, const SpecSrc Q, int tid, int half = -1) {
+#define SX_PM(TM, QM) spectral_product_m<LOG2N, NT, BOTH, TM, QM>(buf, T, Q, tid, half)
   switch (T.mode * 3 + Q.mode) {
     case ZM_FOUR * 3 + ZM_FOUR: SX_PM(ZM_FOUR, ZM_FOUR); break;
     case ZM_FOUR * 3 + ZM_RE: SX_PM(ZM_FOUR, ZM_RE); break;
@@ -1882,51 +1887,6 @@ __global__ void __launch_bounds__(NT, 1)
   for (int n = tid; n < H; n += NT) out[n] = buf[swz(n)];
 }
 
-// spectral_product for ONE half of the bins (a CTA that holds one H-point transform): slot indices inside the half,
-// 8-byte loads, one strand.  Half 0 (even bins): m <-> (H - m) mod H; half 1 (odd bins): scrambled position r <-> H-1-r.
-// Slot LR/2 of the first block (bin H) is left to the quirk code, bin 0 mirrors itself.
-template <int LOG2N, int NT, int TM, int QM>
-__device__ __forceinline__ void half_product_m(float2 *buf, const SpecSrc T, const SpecSrc Q, int half, int tid) {
-  constexpr int N = 1 << LOG2N, H = N / 2;
-  constexpr int LR = last_radix<LOG2N>();
-  const float2 *T1 = T.z1 + (size_t)half * H, *T3 = T.z3 + (size_t)half * H;
-  const float2 *Q1 = Q.z1 + (size_t)half * H, *Q3 = Q.z3 + (size_t)half * H;
-#pragma unroll 2
-  for (int it = tid; it < H / 2; it += NT) {
-    int pa, pb;
-    if (half == 0) {
-      const int r = (it / (LR / 2)) * LR + (it % (LR / 2));
-      const int m2 = (H - natural_bin<LOG2N>(r)) & (H - 1);
-      pa = swz(r);
-      pb = swz(scrambled_pos<LOG2N>(m2));
-    } else {
-      pa = swz(it);
-      pb = swz(H - 1 - it);
-    }
-    float2 oa, ob;
-    pair_product<false>(channels2<TM>(__ldg(T1 + pa), __ldg(T1 + pb), __ldg(T3 + pa), __ldg(T3 + pb)),
-                        channels2<QM>(__ldg(Q1 + pa), __ldg(Q1 + pb), __ldg(Q3 + pa), __ldg(Q3 + pb)), oa, ob);
-    buf[pa] = oa;
-    buf[pb] = ob;
-  }
-}
-template <int LOG2N, int NT>
-__device__ __forceinline__ void half_product(float2 *buf, const SpecSrc T, const SpecSrc Q, int half, int tid) {
-#define SX_PM(TM, QM) half_product_m<LOG2N, NT, TM, QM>(buf, T, Q, half, tid)
-  switch (T.mode * 3 + Q.mode) {
-    case ZM_FOUR * 3 + ZM_FOUR: SX_PM(ZM_FOUR, ZM_FOUR); break;
-    case ZM_FOUR * 3 + ZM_RE: SX_PM(ZM_FOUR, ZM_RE); break;
-    case ZM_FOUR * 3 + ZM_IM: SX_PM(ZM_FOUR, ZM_IM); break;
-    case ZM_RE * 3 + ZM_FOUR: SX_PM(ZM_RE, ZM_FOUR); break;
-    case ZM_RE * 3 + ZM_RE: SX_PM(ZM_RE, ZM_RE); break;
-    case ZM_RE * 3 + ZM_IM: SX_PM(ZM_RE, ZM_IM); break;
-    case ZM_IM * 3 + ZM_FOUR: SX_PM(ZM_IM, ZM_FOUR); break;
-    case ZM_IM * 3 + ZM_RE: SX_PM(ZM_IM, ZM_RE); break;
-    default: SX_PM(ZM_IM, ZM_IM); break;
-  }
-#undef SX_PM
-}
-
 // ---- N = 32768 as ONE kernel: a cluster of two CTAs per strand-pair, one per half of the radix-2 split ----------
 // Product, quirk bins, drift pre-correction and the H-point inverse of its half as in xcorr_half_kernel; then the
 // radix-2 combine through DISTRIBUTED SHARED MEMORY: CTA 0 holds e[n], CTA 1 holds o[n]; index n is handled by exactly
@@ -1960,7 +1920,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
   {
     // product of one strand over this half's bins, bin pair (k, N - k) by bin pair (both in this half), from the
     // three- or four-channel spectra of the two chunks: 4 Pf, the spectrum of a real sequence (see spectral_product)
-    half_product<LOG2N, NT>(buf, spec_src(ws, sp.t_slot, tm, N), spec_src(ws, sp.q_slot, ws.meta[sp.q_slot], N), half, tid);
+    spectral_product<LOG2N, NT, false>(buf, spec_src(ws, sp.t_slot, tm, N), spec_src(ws, sp.q_slot, ws.meta[sp.q_slot], N), tid, half);
     __syncthreads();
     if (tid == 0) {  // reference quirk (CrossCorr.cc:480-492): bins H-1 and H keep the TARGET spectrum
       constexpr int PH1 = bin_slot<LOG2N>(H - 1) - H, PH2 = bin_slot<LOG2N>(H + 1) - H, PH = bin_slot<LOG2N>(H);
