@@ -15,8 +15,18 @@
 //        (analysis/ProbTable.cc:58-74, 105-140) and the filter of FilterMatches
 //        (analysis/HomologyByXCorrSlave.cc:168-219)
 //
-//   N = 32768 (more complex points than one CTA's shared memory holds): encode_fft_half_kernel,
-//        xcorr_half_kernel + combine_findtop_kernel -- two CTAs per transform, one per half of the radix-2 split
+//   K0 encode_prep_kernel     one warp per chunk signal ahead of K1: validation, 2-bit planes, entropy weights, means
+//   pair_fused_kernel         K1 + K2 in one kernel for chunk pairs whose spectra nobody else needs
+//        (sx_config::fuse_pairs; the spectra never reach HBM)
+//
+//   N = 32768 (more complex points than one CTA's shared memory holds): encode_fft_half_kernel -- two CTAs per
+//        transform, one per half of the radix-2 split; xcorr_cluster_kernel -- a cluster of two CTAs per strand-pair,
+//        halves combined through distributed shared memory (xcorr_half_kernel + combine_findtop_kernel: the same
+//        through an HBM scratch buffer, kept for comparison)
+//
+// Pure A/C/G/T chunks are transformed in THREE-CHANNEL form (sx_kernels.h): T = -(A + C + G) sample by sample, the G
+// channels of two chunks share one complex transform; the correlation kernels recover the per-channel spectra from
+// bin pairs (k, N - k).
 //
 // No tensor cores (nothing here is a dense contraction), no cuFFT, no CPU fallback.
 #include "sx_kernels.h"
