@@ -267,7 +267,7 @@ __device__ __forceinline__ uint32_t eval_word(const PlanePtrs &P, const Diag &d,
 }
 
 template <int LOG2N>
-__global__ void __launch_bounds__(SX_SCAN_NT)
+__global__ void __launch_bounds__(SX_SCAN_NT, 8)
     scan_score_kernel(const SpDesc *__restrict__ sps, int nsp, Slots ws, const uint16_t *__restrict__ cand_pool,
                       const uint2 *__restrict__ cand_ref, ScoreParams prm, ResultRec *__restrict__ res_pool,
                       unsigned int res_cap, SegRec *__restrict__ seg_tap, unsigned int seg_tap_cap, BatchCounters *ctr) {
